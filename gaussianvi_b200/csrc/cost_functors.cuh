@@ -1,0 +1,133 @@
+// Device cost functors psi(x): the reference's factor cost functions as
+// plain structs evaluated inside the fused sigma-point kernel.  Each functor provides
+//   XD                 number of leading coordinates of x it reads (rows of sqrt(Sigma) needed)
+//   eval(x, f)         psi up to the constant factor scale()
+//   scale()            constant folded into the epilogue (e.g. the hinge weight sigma)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gvib200 {
+
+// src/1d_example.cpp:25-35 (and tests/test_GH.cpp:21-34 with y_offset = +0.05)
+struct CostStereo1D {
+    static constexpr int XD = 1;
+    double mu_p, fb, sig_p_sq, sig_r_sq, y;  // fb = f*b, y = f*b/mu_p + y_offset
+    __device__ __forceinline__ double eval(const double* x, int) const {
+        const double a = x[0] - mu_p;
+        const double r = y - fb / x[0];
+        // (x-mu_p)^2 / sig_p_sq / 2 + (y - f b / x)^2 / sig_r_sq / 2, same operation order
+        return a * a / sig_p_sq / 2.0 + r * r / sig_r_sq / 2.0;
+    }
+    __device__ __forceinline__ double scale() const { return 1.0; }
+};
+
+// CudaOperation_PlanarPR::cost_obstacle_planar (helpers/CudaOperation.h:491-508, n_balls = 1,
+// slope = 1) over PlanarSDF::getSignedDistance (:51-103, :123-125):
+//   psi(x) = sigma * max(0, eps + r - sd(x0, x1))^2,   sd = bilinear lookup, point clamped to the field.
+// The field is stored as one 32-byte record per cell {v(r,c), v(r+1,c), v(r,c+1), v(r+1,c+1)} (upper
+// indices clamped: the reference reads one past the edge with weight exactly 0 there), so a lookup is
+// a single sector instead of four scattered doubles.
+struct CostPlanarHinge {
+    static constexpr int XD = 2;
+    const double4* __restrict__ rec;  // [cols][rows]
+    int rows, cols;
+    double ox, oy, xmax, ymax, inv_cell, thr, sigma;
+    __device__ __forceinline__ double eval(const double* x, int) const {
+        const double xin = fmin(fmax(x[0], ox), xmax);
+        const double yin = fmin(fmax(x[1], oy), ymax);
+        const double col = (xin - ox) * inv_cell;
+        const double row = (yin - oy) * inv_cell;
+        // floor() through the 2^52 trick (coordinates are in [0, 2^31)); at exact integers either
+        // neighbouring cell gives the same bilinear value, so round-half-even is harmless.
+        const double M = 6755399441055744.0;
+        const double uc = (col - 0.5) + M;
+        const double ur = (row - 0.5) + M;
+        const int lci = __double2loint(uc);
+        const int lri = __double2loint(ur);
+        const double fc = col - (uc - M);
+        const double fr = row - (ur - M);
+        // one 256-bit read-only load (SASS LDG.E.256.CONSTANT; records are 32-byte aligned)
+        double4 v;
+        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+            : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+            : "l"(rec + (size_t)lci * rows + lri));
+        const double a = fma(fr, v.y - v.x, v.x);
+        const double b = fma(fr, v.w - v.z, v.z);
+        const double sd = fma(fc, b - a, a);
+        const double h = fmax(thr - sd, 0.0);
+        return h * h;
+    }
+    __device__ __forceinline__ double scale() const { return sigma; }
+};
+
+// cost_linear_gp (gp/cost_functions.h:36-39 -> MinimumAccGP::cost gp/minimum_acc_prior.h:103-106,
+// LTV_GP::cost gp/LTV_prior.h:217-220): 1/2 (Phi th1 - th2)^T Qinv (Phi th1 - th2).
+// Per-factor parameters: Phi[DS*DS], Qinv[DS*DS] column-major.
+template <int DS>
+struct CostLinearGP {
+    static constexpr int XD = 2 * DS;
+    const double* __restrict__ params;  // [n][2*DS*DS]
+    __device__ __forceinline__ double eval(const double* x, int f) const {
+        const double* Phi = params + (size_t)f * 2 * DS * DS;
+        const double* Qi = Phi + DS * DS;
+        double r[DS];
+#pragma unroll
+        for (int i = 0; i < DS; ++i) {
+            double s = -x[DS + i];
+#pragma unroll
+            for (int k = 0; k < DS; ++k) s = fma(__ldg(Phi + i + k * DS), x[k], s);
+            r[i] = s;
+        }
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < DS; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < DS; ++i) t = fma(__ldg(Qi + i + j * DS), r[i], t);
+            q = fma(t, r[j], q);
+        }
+        return q;
+    }
+    __device__ __forceinline__ double scale() const { return 0.5; }
+};
+
+// cost_fixed_gp (gp/cost_functions.h:25-27 -> FixedPriorGP::fixed_factor_cost gp/fixed_prior.h:28-30):
+// (x - mu)^T Kinv (x - mu).  Per-factor parameters: Kinv[DIM*DIM], mu[DIM].
+template <int DIM>
+struct CostFixedGP {
+    static constexpr int XD = DIM;
+    const double* __restrict__ params;  // [n][DIM*DIM + DIM]
+    __device__ __forceinline__ double eval(const double* x, int f) const {
+        const double* Ki = params + (size_t)f * (DIM * DIM + DIM);
+        const double* mu = Ki + DIM * DIM;
+        double r[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) r[i] = x[i] - __ldg(mu + i);
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) t = fma(__ldg(Ki + i + j * DIM), r[i], t);
+            q = fma(t, r[j], q);
+        }
+        return q;
+    }
+    __device__ __forceinline__ double scale() const { return 1.0; }
+};
+
+// x^T (c I) x: the integrand gx_1d of tests/test_gh_spgh.cpp:21-25 (known-answer tests).
+template <int DIM>
+struct CostQuadratic {
+    static constexpr int XD = DIM;
+    double c;
+    __device__ __forceinline__ double eval(const double* x, int) const {
+        double q = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) q = fma(x[i], x[i], q);
+        return q;
+    }
+    __device__ __forceinline__ double scale() const { return c; }
+};
+
+}  // namespace gvib200

@@ -1,0 +1,1396 @@
+// libgvib200.so -- C-ABI implementation (include/gvib200.h) and host control of the device-resident
+// NGD-GVI iteration.  Host code mirrors GVIGH::optimize (gvibase/GVI-GH-GBP-impl.h:33-130) and
+// NGDGH (ngd/NGD-GH-impl.h); all arithmetic of the hot path runs in the kernels of kernels.cuh.
+#include "../../include/gvib200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "bt_plan.h"
+#include "kernels.cuh"
+#include "spgh_table.h"
+
+using namespace gvib200;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(GVIB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct Table {
+    int dim = 0, deg = 0, n = 0, row = 0;
+    std::vector<double> nodes, w;  // host
+    double* d_rows = nullptr;      // device [n][row]
+};
+
+struct gvib200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::map<std::pair<int, int>, std::unique_ptr<Table>> tables;
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    long long launches = 0;  // kernels launched through this ctx
+};
+
+struct GhGroup {
+    int kind = 0, dim = 0, deg = 0, n = 0, first_id = 0;
+    size_t voff = 0, moff = 0;  // offsets (doubles) of this group in fVdmu / fVdd
+    std::vector<int> start;
+    std::vector<double> T, Thigh;
+    std::vector<char> params;
+    const Table* table = nullptr;
+    int* d_start = nullptr;
+    double* d_T = nullptr;
+    double* d_Thigh = nullptr;
+    void* d_params = nullptr;
+    double* d_SR[2] = {nullptr, nullptr};
+    double* d_raw = nullptr;
+};
+
+struct LinGroup {
+    int dim = 0, m = 0, kdim = 0, n = 0, first_id = 0;
+    size_t voff = 0;
+    std::vector<int> start;
+    std::vector<double> Lambda, psi, Kinv, A, C, T, Thigh;
+    int* d_start = nullptr;
+    double *d_Lambda = nullptr, *d_psi = nullptr, *d_Kinv = nullptr, *d_A = nullptr, *d_C = nullptr, *d_T = nullptr;
+};
+
+struct FactorRef {
+    bool linear;
+    int group;
+    int index;
+};
+
+struct gvib200_problem {
+    gvib200_ctx* ctx = nullptr;
+    int S = 0, d = 0;
+    cudaStream_t stream = nullptr;
+    bool finalized = false, has_state = false;
+    std::vector<GhGroup> gh;
+    std::vector<LinGroup> lin;
+    std::vector<FactorRef> factors;  // id order
+    int n_factors = 0;
+    size_t nV = 0, nM = 0;  // sizes of fVdmu / fVdd
+    // SDF
+    double4* d_sdf_rec = nullptr;
+    int sdf_rows = 0, sdf_cols = 0;
+    double sdf_ox = 0, sdf_oy = 0, sdf_cell = 0;
+    // state, double buffered (cur / candidate)
+    int cur = 0;
+    double *mu[2] = {}, *LD[2] = {}, *LO[2] = {}, *CD[2] = {}, *CO[2] = {};
+    double *fcost[2] = {}, *fVdmu[2] = {}, *fVdd[2] = {};
+    double* scal = nullptr;    // device scalars: [0..1] logdet cur/cand slots, [2..3] cost slots, [4] tmp
+    double* h_scal = nullptr;  // pinned mirror
+    int* d_flag = nullptr;     // not-SPD flag
+    int* h_flag = nullptr;
+    double *Vdmu = nullptr, *VD = nullptr, *VO = nullptr, *rhs = nullptr, *dmu = nullptr;
+    double *KlinD = nullptr, *KlinO = nullptr;
+    // adjacency
+    int *vptr = nullptr, *voff = nullptr, *dptr = nullptr, *doff = nullptr, *dld = nullptr, *optr = nullptr,
+        *ooff = nullptr, *old = nullptr;
+    // chain engine
+    BtPlan plan;
+    double* ws = nullptr;
+    // schedule (GVIGH::optimize locals)
+    int iter = 0;
+    bool is_lowtemp = true, converged = false;
+    bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
+    bool grads_valid = false;
+    // profiling
+    bool profile = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+template <class T>
+static int dev_upload(T** p, const std::vector<T>& v, cudaStream_t st) {
+    TRY(dev_alloc(p, v.size()));
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define LAUNCH(prob, kern, grid, block, smem, ...)                                   \
+    do {                                                                             \
+        kern<<<(grid), (block), (smem), (prob)->stream>>>(__VA_ARGS__);              \
+        (prob)->ctx->launches++;                                                     \
+    } while (0)
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GVIB200_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
+    auto key = std::make_pair(dim, deg);
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        std::unique_ptr<Table> t(new Table);
+        t->dim = dim;
+        t->deg = deg;
+        try {
+            generate_spgh_table(dim, deg, t->nodes, t->w);
+        } catch (const std::exception& e) {
+            return fail(GVIB200_ENOTABLE, std::string("sparse GH table: ") + e.what());
+        }
+        t->n = (int)t->w.size();
+        it = ctx->tables.emplace(key, std::move(t)).first;
+    }
+    Table* t = it->second.get();
+    if (t->d_rows == nullptr) {
+        t->row = (dim + 2) & ~1;
+        std::vector<double> rows((size_t)t->n * t->row, 0.0);
+        for (int i = 0; i < t->n; ++i) {
+            for (int c = 0; c < dim; ++c) rows[(size_t)i * t->row + c] = t->nodes[(size_t)i * dim + c];
+            rows[(size_t)i * t->row + dim] = t->w[i];
+        }
+        CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(t->d_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    *out = t;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain engine drivers
+// ------------------------------------------------------------------------------------------------
+template <int D>
+static int chain_forward(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs) {
+    const size_t nl = p->plan.levels.size();
+    for (size_t l = 0; l + 1 < nl; ++l) {
+        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
+        const int block = 128;
+        if (rhs) LAUNCH(p, (k_bt_forward<D, true>), cdiv(lv.K, block), block, 0, lv);
+        else LAUNCH(p, (k_bt_forward<D, false>), cdiv(lv.K, block), block, 0, lv);
+    }
+    return check_launch("bt_forward");
+}
+
+// selected inverse + log det of the block-tridiagonal (Dg, Og) -> (cD, cO), logdet scalar (device)
+template <int D>
+static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet) {
+    TRY(chain_forward<D>(p, Dg, Og, nullptr));
+    const size_t nl = p->plan.levels.size();
+    {
+        BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, nullptr, p->d_flag);
+        double* tD = (nl == 1) ? cD : p->ws + p->plan.levels[nl - 1].cD;
+        double* tO = (nl == 1) ? cO : p->ws + p->plan.levels[nl - 1].cO;
+        LAUNCH(p, (k_bt_top<D, false>), 1, 32, 0, top, nullptr, tD, tO);
+    }
+    for (int l = (int)nl - 2; l >= 0; --l) {
+        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, nullptr, p->d_flag);
+        const auto& up = p->plan.levels[l + 1];
+        double* lD = (l == 0) ? cD : p->ws + p->plan.levels[l].cD;
+        double* lO = (l == 0) ? cO : p->ws + p->plan.levels[l].cO;
+        const int block = 128;
+        LAUNCH(p, (k_bt_selinv<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.cD, p->ws + up.cO, lD, lO);
+    }
+    LAUNCH(p, k_sum, 1, 256, 0, p->plan.ld_count, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+    return check_launch("bt_selinv");
+}
+
+template <int D>
+static int chain_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x,
+                       double* d_logdet) {
+    TRY(chain_forward<D>(p, Dg, Og, rhs));
+    const size_t nl = p->plan.levels.size();
+    {
+        BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, rhs, p->d_flag);
+        double* tx = (nl == 1) ? x : p->ws + p->plan.levels[nl - 1].x;
+        LAUNCH(p, (k_bt_top<D, true>), 1, 32, 0, top, tx, nullptr, nullptr);
+    }
+    for (int l = (int)nl - 2; l >= 0; --l) {
+        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
+        const auto& up = p->plan.levels[l + 1];
+        double* lx = (l == 0) ? x : p->ws + p->plan.levels[l].x;
+        const int block = 128;
+        LAUNCH(p, (k_bt_backsolve<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.x, lx);
+    }
+    if (d_logdet)
+        LAUNCH(p, k_sum, 1, 256, 0, p->plan.ld_count, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+    return check_launch("bt_solve");
+}
+
+#define DISPATCH_D(d, CALL)                                                              \
+    switch (d) {                                                                         \
+        case 1: { constexpr int D_ = 1; CALL; } break;                                   \
+        case 2: { constexpr int D_ = 2; CALL; } break;                                   \
+        case 3: { constexpr int D_ = 3; CALL; } break;                                   \
+        case 4: { constexpr int D_ = 4; CALL; } break;                                   \
+        case 6: { constexpr int D_ = 6; CALL; } break;                                   \
+        default: return fail(GVIB200_EINVAL, "unsupported state dimension (1, 2, 3, 4, 6)"); \
+    }
+
+static int do_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet) {
+    int rc = 0;
+    DISPATCH_D(p->d, rc = chain_selinv<D_>(p, Dg, Og, cD, cO, d_logdet));
+    return rc;
+}
+static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x, double* d_logdet) {
+    int rc = 0;
+    DISPATCH_D(p->d, rc = chain_solve<D_>(p, Dg, Og, rhs, x, d_logdet));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// quadrature sweeps
+// ------------------------------------------------------------------------------------------------
+template <int DIM, int SD>
+static int launch_prologue(gvib200_problem* p, const GhGroup& g, const double* cD, const double* cO, double* SR) {
+    const int block = (DIM <= 4) ? 128 : 32;
+    LAUNCH(p, (k_prologue<DIM, SD>), cdiv(g.n, block), block, 0, g.n, g.d_start, cD, cO, SR);
+    return 0;
+}
+
+template <int DIM, class Cost>
+static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
+                          double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+    constexpr int XD = Cost::XD;
+    constexpr int ROW = (DIM + 2) & ~1;
+    constexpr int THREADS = K1Cfg<DIM>::THREADS;
+    constexpr int WARPS = THREADS / 32;
+    const size_t scratch = (size_t)WARPS * K1Scratch<DIM, XD>::DOUBLES * sizeof(double);
+    const size_t budget = std::min<size_t>(p->ctx->smem_optin, 227 * 1024) - 1024;
+    int chunk = g.table->n;
+    // prefer two resident CTAs when the table is small
+    size_t need = (size_t)chunk * ROW * sizeof(double) + scratch;
+    if (need > budget) {
+        chunk = (int)((budget - scratch) / (ROW * sizeof(double)));
+        chunk &= ~31;
+        need = (size_t)chunk * ROW * sizeof(double) + scratch;
+    }
+    MomentArgs<Cost> a;
+    a.n = g.n;
+    a.n_nodes = g.table->n;
+    a.chunk = chunk;
+    a.state_dim = p->d;
+    a.table = g.table->d_rows;
+    a.start = g.d_start;
+    a.mu = mu;
+    a.SR = SR;
+    a.T = g.d_T;
+    a.fcost = fcost + g.first_id;
+    a.fVdmu = fVdmu + g.voff;
+    a.fVdd = fVdd + g.moff;
+    a.raw = raw;
+    a.cost = cost;
+    auto kfull = k_moments<DIM, Cost, true>;
+    auto kcost = k_moments<DIM, Cost, false>;
+    auto kern = full ? kfull : kcost;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, need));
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min(cdiv(g.n, WARPS), p->ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    kern<<<grid, THREADS, need, p->stream>>>(a);
+    p->ctx->launches++;
+    return check_launch("k_moments");
+}
+
+struct SweepTarget {
+    const double* mu;
+    const double* cD;
+    const double* cO;
+    int which;  // buffer index for SR / fcost / fVdmu / fVdd
+};
+
+template <int DIM, int SD>
+static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bool prologue, bool sweep, bool full,
+                        double* raw) {
+    double* SR = g.d_SR[t.which];
+    if (prologue) TRY((launch_prologue<DIM, SD>(p, g, t.cD, t.cO, SR)));
+    if (!sweep) return check_launch("k_prologue");
+    double* fc = p->fcost[t.which];
+    double* fv = p->fVdmu[t.which];
+    double* fm = p->fVdd[t.which];
+    switch (g.kind) {
+        case GVIB200_COST_STEREO_1D: {
+            if constexpr (DIM == 1) {
+                const auto* hp = reinterpret_cast<const gvib200_stereo1d_params*>(g.params.data());
+                CostStereo1D c;
+                c.mu_p = hp->mu_p;
+                c.fb = hp->f * hp->b;
+                c.sig_p_sq = hp->sig_p_sq;
+                c.sig_r_sq = hp->sig_r_sq;
+                c.y = hp->f * hp->b / hp->mu_p + hp->y_offset;
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        case GVIB200_COST_PLANAR_HINGE: {
+            if constexpr (DIM >= 2 && DIM <= 4) {
+                if (p->d_sdf_rec == nullptr) return fail(GVIB200_ESTATE, "planar hinge cost needs gvib200_set_planar_sdf");
+                const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
+                CostPlanarHinge c;
+                c.rec = p->d_sdf_rec;
+                c.rows = p->sdf_rows;
+                c.cols = p->sdf_cols;
+                c.ox = p->sdf_ox;
+                c.oy = p->sdf_oy;
+                c.xmax = p->sdf_ox + (p->sdf_cols - 1.0) * p->sdf_cell;
+                c.ymax = p->sdf_oy + (p->sdf_rows - 1.0) * p->sdf_cell;
+                c.inv_cell = 1.0 / p->sdf_cell;
+                c.thr = hp->epsilon + hp->radius;
+                c.sigma = hp->sigma;
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        case GVIB200_COST_LINEAR_GP: {
+            if constexpr (DIM % 2 == 0 && DIM == 2 * SD) {
+                CostLinearGP<DIM / 2> c;
+                c.params = reinterpret_cast<const double*>(g.d_params);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        case GVIB200_COST_FIXED_GP: {
+            if constexpr (DIM == SD) {
+                CostFixedGP<DIM> c;
+                c.params = reinterpret_cast<const double*>(g.d_params);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        case GVIB200_COST_QUADRATIC: {
+            if constexpr (DIM <= 4) {
+                CostQuadratic<DIM> c;
+                c.c = *reinterpret_cast<const double*>(g.params.data());
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        default: break;
+    }
+    return fail(GVIB200_EINVAL, "unsupported (cost kind, factor dim, state dim) combination");
+}
+
+static int gh_group_dispatch(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bool prologue, bool sweep, bool full,
+                             double* raw) {
+    const int dim = g.dim, sd = p->d;
+#define GH_CASE(DIM_, SD_) \
+    if (dim == DIM_ && sd == SD_) return gh_group_run<DIM_, SD_>(p, g, t, prologue, sweep, full, raw);
+    GH_CASE(1, 1)
+    GH_CASE(2, 1)
+    GH_CASE(2, 2)
+    GH_CASE(3, 3)
+    GH_CASE(4, 2)
+    GH_CASE(4, 4)
+    GH_CASE(6, 6)
+    GH_CASE(8, 4)
+    GH_CASE(12, 6)
+#undef GH_CASE
+    return fail(GVIB200_EINVAL, "unsupported (factor dim, state dim) combination");
+}
+
+template <int DIM>
+static void launch_raw_to_x(gvib200_problem* p, const GhGroup& g, const double* SR, double* E0, double* E1, double* E2) {
+    LAUNCH(p, (k_raw_to_x<DIM>), cdiv(g.n, 128), 128, 0, g.n, g.d_raw, SR, E0, E1, E2);
+}
+
+static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
+    for (auto& g : p->lin) {
+        LinearArgs a;
+        a.n = g.n;
+        a.dim = g.dim;
+        a.m = g.m;
+        a.state_dim = p->d;
+        a.start = g.d_start;
+        a.Lambda = g.d_Lambda;
+        a.psi = g.d_psi;
+        a.Kinv = g.d_Kinv;
+        a.A = g.d_A;
+        a.C = g.d_C;
+        a.T = g.d_T;
+        a.mu = t.mu;
+        a.covD = t.cD;
+        a.covO = t.cO;
+        a.fcost = p->fcost[t.which] + g.first_id;
+        a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
+        LAUNCH(p, k_linear, cdiv(g.n, 128), 128, 0, a);
+    }
+    return check_launch("k_linear");
+}
+
+// prologue + sweep over every factor at (mu, cov) of buffer `which`
+static int run_sweep(gvib200_problem* p, int which, bool prologue, bool full, bool want_raw) {
+    SweepTarget t{p->mu[which], p->CD[which], p->CO[which], which};
+    for (auto& g : p->gh) {
+        double* raw = nullptr;
+        if (want_raw) {
+            if (g.d_raw == nullptr) TRY(dev_alloc(&g.d_raw, (size_t)g.n * (1 + g.dim + g.dim * g.dim)));
+            raw = g.d_raw;
+        }
+        TRY(gh_group_dispatch(p, g, t, prologue, true, full, raw));
+    }
+    TRY(run_linear(p, t, full));
+    return 0;
+}
+
+static int run_prologue_only(gvib200_problem* p, int which) {
+    SweepTarget t{p->mu[which], p->CD[which], p->CO[which], which};
+    for (auto& g : p->gh) TRY(gh_group_dispatch(p, g, t, true, false, false, nullptr));
+    return 0;
+}
+
+// total cost of buffer `which`: sum of factor costs + logdet/2 (GVI-GH-GBP-impl.h:217-239) -> scal[2 + which]
+static void run_total(gvib200_problem* p, int which) {
+    LAUNCH(p, k_sum, 1, 1024, 0, (size_t)p->n_factors, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
+}
+
+template <int D>
+static void launch_assemble(gvib200_problem* p, int which) {
+    LAUNCH(p, (k_assemble<D>), cdiv(p->S, 128), 128, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
+           p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, p->Vdmu, p->VD, p->VO, p->rhs);
+}
+
+static int read_flag(gvib200_problem* p, int* flag) {
+    CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    *flag = *p->h_flag;
+    return 0;
+}
+static int clear_flag(gvib200_problem* p) {
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: context / tables
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* gvib200_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* gvib200_version(void) { return "gvib200 0.1 sm_100a"; }
+
+extern "C" int gvib200_ctx_create(int device, gvib200_ctx** out) {
+    if (!out) return fail(GVIB200_EINVAL, "ctx_create: null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GVIB200_ECUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(GVIB200_EINVAL, "ctx_create: bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<gvib200_ctx> c(new gvib200_ctx);
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = c.release();
+    return 0;
+}
+
+extern "C" int gvib200_ctx_destroy(gvib200_ctx* ctx) {
+    if (!ctx) return 0;
+    for (auto& kv : ctx->tables)
+        if (kv.second->d_rows) cudaFree(kv.second->d_rows);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(GVIB200_EINVAL, "ctx_set_comm: bad arguments");
+    ctx->nccl_comm = nccl_comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return 0;
+}
+
+extern "C" int gvib200_table_size(int dim, int deg) {
+    std::vector<double> n, w;
+    try {
+        generate_spgh_table(dim, deg, n, w);
+    } catch (const std::exception& e) {
+        return fail(GVIB200_ENOTABLE, e.what());
+    }
+    return (int)w.size();
+}
+
+extern "C" int gvib200_table_generate(int dim, int deg, double* nodes_rowmajor, double* weights, int capacity) {
+    std::vector<double> n, w;
+    try {
+        generate_spgh_table(dim, deg, n, w);
+    } catch (const std::exception& e) {
+        return fail(GVIB200_ENOTABLE, e.what());
+    }
+    if ((int)w.size() > capacity) return fail(GVIB200_EINVAL, "table_generate: capacity too small");
+    if (nodes_rowmajor) std::memcpy(nodes_rowmajor, n.data(), n.size() * sizeof(double));
+    if (weights) std::memcpy(weights, w.data(), w.size() * sizeof(double));
+    return (int)w.size();
+}
+
+extern "C" int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, const double* nodes_rowmajor,
+                                 const double* weights) {
+    if (!ctx || dim < 1 || n < 1 || !nodes_rowmajor || !weights) return fail(GVIB200_EINVAL, "table_set: bad arguments");
+    std::unique_ptr<Table> t(new Table);
+    t->dim = dim;
+    t->deg = deg;
+    t->n = n;
+    t->nodes.assign(nodes_rowmajor, nodes_rowmajor + (size_t)n * dim);
+    t->w.assign(weights, weights + n);
+    auto key = std::make_pair(dim, deg);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end() && it->second->d_rows) cudaFree(it->second->d_rows);
+    ctx->tables[key] = std::move(t);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: problem definition
+// ------------------------------------------------------------------------------------------------
+extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_state, gvib200_problem** out) {
+    if (!ctx || !out || num_states < 1) return fail(GVIB200_EINVAL, "problem_create: bad arguments");
+    if (!(dim_state == 1 || dim_state == 2 || dim_state == 3 || dim_state == 4 || dim_state == 6))
+        return fail(GVIB200_EINVAL, "problem_create: state dimension must be 1, 2, 3, 4 or 6");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::unique_ptr<gvib200_problem> p(new gvib200_problem);
+    p->ctx = ctx;
+    p->S = num_states;
+    p->d = dim_state;
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    *out = p.release();
+    return 0;
+}
+
+static void free_problem(gvib200_problem* p) {
+    auto F = [](void* q) {
+        if (q) cudaFree(q);
+    };
+    for (auto& g : p->gh) {
+        F(g.d_start); F(g.d_T); F(g.d_Thigh); F(g.d_params); F(g.d_SR[0]); F(g.d_SR[1]); F(g.d_raw);
+    }
+    for (auto& g : p->lin) {
+        F(g.d_start); F(g.d_Lambda); F(g.d_psi); F(g.d_Kinv); F(g.d_A); F(g.d_C); F(g.d_T);
+    }
+    F(p->d_sdf_rec);
+    for (int i = 0; i < 2; ++i) {
+        F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
+    }
+    F(p->scal); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
+    F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws);
+    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->h_flag) cudaFreeHost(p->h_flag);
+    if (p->stream) cudaStreamDestroy(p->stream);
+}
+
+extern "C" int gvib200_problem_destroy(gvib200_problem* prob) {
+    if (!prob) return 0;
+    cudaSetDevice(prob->ctx->device);
+    free_problem(prob);
+    delete prob;
+    return 0;
+}
+
+extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, double ox, double oy, double cell,
+                                      const double* data) {
+    if (!p || rows < 2 || cols < 2 || !(cell > 0) || !data) return fail(GVIB200_EINVAL, "set_planar_sdf: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (p->d_sdf_rec) cudaFree(p->d_sdf_rec);
+    double* d_data = nullptr;
+    const size_t n = (size_t)rows * cols;
+    CUDA_TRY(cudaMalloc((void**)&d_data, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&p->d_sdf_rec, n * sizeof(double4)));
+    CUDA_TRY(cudaMemcpyAsync(d_data, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    LAUNCH(p, k_build_sdf_records, cdiv((long long)n, 256), 256, 0, rows, cols, d_data, p->d_sdf_rec);
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    cudaFree(d_data);
+    p->sdf_rows = rows;
+    p->sdf_cols = cols;
+    p->sdf_ox = ox;
+    p->sdf_oy = oy;
+    p->sdf_cell = cell;
+    return check_launch("k_build_sdf_records");
+}
+
+static size_t cost_param_record(int kind, int dim) {
+    switch (kind) {
+        case GVIB200_COST_LINEAR_GP: return (size_t)2 * (dim / 2) * (dim / 2) * sizeof(double);
+        case GVIB200_COST_FIXED_GP: return (size_t)(dim * dim + dim) * sizeof(double);
+        default: return 0;
+    }
+}
+
+extern "C" int gvib200_add_gh_factors(gvib200_problem* p, int kind, int dim, int deg, int n, const int32_t* start,
+                                      const double* T, const double* Thigh, const void* params, size_t bytes,
+                                      int* first_id) {
+    if (!p || n < 1 || !start) return fail(GVIB200_EINVAL, "add_gh_factors: bad arguments");
+    if (p->finalized) return fail(GVIB200_ESTATE, "add_gh_factors: problem already finalized");
+    if (dim % p->d != 0 || (dim / p->d != 1 && dim / p->d != 2))
+        return fail(GVIB200_EINVAL, "add_gh_factors: factor dim must span 1 or 2 states");
+    const int nst = dim / p->d;
+    for (int i = 0; i < n; ++i)
+        if (start[i] < 0 || start[i] + nst > p->S) return fail(GVIB200_EINVAL, "add_gh_factors: start_index out of range");
+    size_t want = 0;
+    switch (kind) {
+        case GVIB200_COST_STEREO_1D: want = sizeof(gvib200_stereo1d_params); break;
+        case GVIB200_COST_PLANAR_HINGE: want = sizeof(gvib200_hinge_params); break;
+        case GVIB200_COST_QUADRATIC: want = sizeof(double); break;
+        case GVIB200_COST_LINEAR_GP:
+        case GVIB200_COST_FIXED_GP: want = cost_param_record(kind, dim) * n; break;
+        default: return fail(GVIB200_EINVAL, "add_gh_factors: unknown cost kind");
+    }
+    if (bytes != want || !params) return fail(GVIB200_EINVAL, "add_gh_factors: cost_params size mismatch");
+    GhGroup g;
+    g.kind = kind;
+    g.dim = dim;
+    g.deg = deg;
+    g.n = n;
+    g.first_id = p->n_factors;
+    g.start.assign(start, start + n);
+    g.T.assign(n, 1.0);
+    g.Thigh.assign(n, 10.0);
+    if (T) g.T.assign(T, T + n);
+    if (Thigh) g.Thigh.assign(Thigh, Thigh + n);
+    g.params.assign((const char*)params, (const char*)params + bytes);
+    TRY(get_table(p->ctx, dim, deg, &g.table));
+    for (int i = 0; i < n; ++i) p->factors.push_back(FactorRef{false, (int)p->gh.size(), i});
+    p->n_factors += n;
+    if (first_id) *first_id = g.first_id;
+    p->gh.push_back(std::move(g));
+    return 0;
+}
+
+extern "C" int gvib200_add_linear_factors(gvib200_problem* p, int dim, int m, int kdim, int n, const int32_t* start,
+                                          const double* Lambda, const double* Psi, const double* mu_t,
+                                          const double* Kinv, const double* C, const double* T, const double* Thigh,
+                                          int* first_id) {
+    if (!p || n < 1 || !start || !Lambda || !Psi || !mu_t || !Kinv || !C)
+        return fail(GVIB200_EINVAL, "add_linear_factors: bad arguments");
+    if (p->finalized) return fail(GVIB200_ESTATE, "add_linear_factors: problem already finalized");
+    if (dim % p->d != 0 || (dim / p->d != 1 && dim / p->d != 2) || dim > LIN_MAX_DIM || m > LIN_MAX_DIM || m < 1)
+        return fail(GVIB200_EINVAL, "add_linear_factors: unsupported dimensions");
+    const int nst = dim / p->d;
+    for (int i = 0; i < n; ++i)
+        if (start[i] < 0 || start[i] + nst > p->S) return fail(GVIB200_EINVAL, "add_linear_factors: start_index out of range");
+    LinGroup g;
+    g.dim = dim;
+    g.m = m;
+    g.kdim = kdim;
+    g.n = n;
+    g.first_id = p->n_factors;
+    g.start.assign(start, start + n);
+    g.Lambda.assign(Lambda, Lambda + (size_t)n * m * dim);
+    g.Kinv.assign(Kinv, Kinv + (size_t)n * m * m);
+    g.C.assign(C, C + n);
+    g.T.assign(n, 1.0);
+    g.Thigh.assign(n, 10.0);
+    if (T) g.T.assign(T, T + n);
+    if (Thigh) g.Thigh.assign(Thigh, Thigh + n);
+    g.psi.assign((size_t)n * m, 0.0);
+    g.A.assign((size_t)n * dim * dim, 0.0);
+    std::vector<double> KL((size_t)m * dim);
+    for (int f = 0; f < n; ++f) {
+        const double* L = Lambda + (size_t)f * m * dim;
+        const double* P = Psi + (size_t)f * m * kdim;
+        const double* mt = mu_t + (size_t)f * kdim;
+        const double* K = Kinv + (size_t)f * m * m;
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < kdim; ++k) s += P[i + (size_t)k * m] * mt[k];
+            g.psi[(size_t)f * m + i] = s;
+        }
+        // A = Lambda^T Kinv Lambda
+        for (int j = 0; j < dim; ++j)
+            for (int i = 0; i < m; ++i) {
+                double s = 0.0;
+                for (int k = 0; k < m; ++k) s += K[i + (size_t)k * m] * L[k + (size_t)j * m];
+                KL[i + (size_t)j * m] = s;
+            }
+        double* A = g.A.data() + (size_t)f * dim * dim;
+        for (int j = 0; j < dim; ++j)
+            for (int i = 0; i < dim; ++i) {
+                double s = 0.0;
+                for (int k = 0; k < m; ++k) s += L[k + (size_t)i * m] * KL[k + (size_t)j * m];
+                A[i + (size_t)j * dim] = s;
+            }
+    }
+    for (int i = 0; i < n; ++i) p->factors.push_back(FactorRef{true, (int)p->lin.size(), i});
+    p->n_factors += n;
+    if (first_id) *first_id = g.first_id;
+    p->lin.push_back(std::move(g));
+    return 0;
+}
+
+// constant part of Vddmu contributed by the linear factors: sum_k scatter(2 C_k A_k / T_k)
+static int upload_klin(gvib200_problem* p) {
+    const int d = p->d, S = p->S;
+    const size_t dd = (size_t)d * d;
+    std::vector<double> KD((size_t)S * dd, 0.0), KO((size_t)std::max(S - 1, 1) * dd, 0.0);
+    for (auto& g : p->lin) {
+        for (int f = 0; f < g.n; ++f) {
+            const double sc = 2.0 * g.C[f] / g.T[f];
+            const double* A = g.A.data() + (size_t)f * g.dim * g.dim;
+            const int s = g.start[f];
+            const int nst = g.dim / d;
+            for (int bj = 0; bj < nst; ++bj)
+                for (int bi = 0; bi <= bj; ++bi) {
+                    double* dst = (bi == bj) ? KD.data() + (size_t)(s + bi) * dd : KO.data() + (size_t)s * dd;
+                    for (int j = 0; j < d; ++j)
+                        for (int i = 0; i < d; ++i)
+                            dst[i + (size_t)j * d] += sc * A[(bi * d + i) + (size_t)(bj * d + j) * g.dim];
+                }
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->KlinD, KD.data(), (size_t)S * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (S > 1)
+        CUDA_TRY(cudaMemcpyAsync(p->KlinO, KO.data(), (size_t)(S - 1) * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
+    if (!p) return fail(GVIB200_EINVAL, "finalize: null problem");
+    if (p->finalized) return 0;
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const int S = p->S, d = p->d;
+    const size_t dd = (size_t)d * d;
+    // offsets of per-factor outputs
+    size_t nV = 0, nM = 0;
+    for (auto& g : p->gh) {
+        g.voff = nV;
+        g.moff = nM;
+        nV += (size_t)g.n * g.dim;
+        nM += (size_t)g.n * g.dim * g.dim;
+    }
+    for (auto& g : p->lin) {
+        g.voff = nV;
+        nV += (size_t)g.n * g.dim;
+    }
+    p->nV = nV;
+    p->nM = nM;
+    // adjacency (id order within each state => fixed summation order)
+    std::vector<std::vector<int>> vl(S), dl(S), dll(S), ol(S), oll(S);
+    for (auto& fr : p->factors) {
+        if (!fr.linear) {
+            auto& g = p->gh[fr.group];
+            const int s = g.start[fr.index], nst = g.dim / d;
+            const size_t vo = g.voff + (size_t)fr.index * g.dim, mo = g.moff + (size_t)fr.index * g.dim * g.dim;
+            for (int b = 0; b < nst; ++b) {
+                vl[s + b].push_back((int)(vo + (size_t)b * d));
+                dl[s + b].push_back((int)(mo + (size_t)b * d + (size_t)b * d * g.dim));
+                dll[s + b].push_back(g.dim);
+            }
+            if (nst == 2) {
+                ol[s].push_back((int)(mo + (size_t)d * g.dim));
+                oll[s].push_back(g.dim);
+            }
+        } else {
+            auto& g = p->lin[fr.group];
+            const int s = g.start[fr.index], nst = g.dim / d;
+            const size_t vo = g.voff + (size_t)fr.index * g.dim;
+            for (int b = 0; b < nst; ++b) vl[s + b].push_back((int)(vo + (size_t)b * d));
+        }
+    }
+    if (nV > 0x7fffffffULL || nM > 0x7fffffffULL) return fail(GVIB200_EINVAL, "finalize: problem too large for int32 offsets");
+    auto flatten = [&](const std::vector<std::vector<int>>& ll, std::vector<int>& ptr, std::vector<int>& val) {
+        ptr.assign(S + 1, 0);
+        val.clear();
+        for (int s = 0; s < S; ++s) {
+            ptr[s] = (int)val.size();
+            val.insert(val.end(), ll[s].begin(), ll[s].end());
+        }
+        ptr[S] = (int)val.size();
+    };
+    std::vector<int> ptr, val, val2;
+    flatten(vl, ptr, val);
+    TRY(dev_upload(&p->vptr, ptr, p->stream));
+    TRY(dev_upload(&p->voff, val, p->stream));
+    flatten(dl, ptr, val);
+    flatten(dll, ptr, val2);
+    TRY(dev_upload(&p->dptr, ptr, p->stream));
+    TRY(dev_upload(&p->doff, val, p->stream));
+    TRY(dev_upload(&p->dld, val2, p->stream));
+    flatten(ol, ptr, val);
+    flatten(oll, ptr, val2);
+    TRY(dev_upload(&p->optr, ptr, p->stream));
+    TRY(dev_upload(&p->ooff, val, p->stream));
+    TRY(dev_upload(&p->old, val2, p->stream));
+    // factor groups
+    for (auto& g : p->gh) {
+        TRY(dev_upload(&g.d_start, g.start, p->stream));
+        TRY(dev_upload(&g.d_T, g.T, p->stream));
+        TRY(dev_upload(&g.d_Thigh, g.Thigh, p->stream));
+        if (g.kind == GVIB200_COST_LINEAR_GP || g.kind == GVIB200_COST_FIXED_GP) {
+            CUDA_TRY(cudaMalloc(&g.d_params, g.params.size()));
+            CUDA_TRY(cudaMemcpyAsync(g.d_params, g.params.data(), g.params.size(), cudaMemcpyHostToDevice, p->stream));
+        }
+        for (int i = 0; i < 2; ++i) TRY(dev_alloc(&g.d_SR[i], (size_t)g.n * 2 * g.dim * g.dim));
+    }
+    for (auto& g : p->lin) {
+        TRY(dev_upload(&g.d_start, g.start, p->stream));
+        TRY(dev_upload(&g.d_Lambda, g.Lambda, p->stream));
+        TRY(dev_upload(&g.d_psi, g.psi, p->stream));
+        TRY(dev_upload(&g.d_Kinv, g.Kinv, p->stream));
+        TRY(dev_upload(&g.d_A, g.A, p->stream));
+        TRY(dev_upload(&g.d_C, g.C, p->stream));
+        TRY(dev_upload(&g.d_T, g.T, p->stream));
+    }
+    // state
+    for (int i = 0; i < 2; ++i) {
+        TRY(dev_alloc(&p->mu[i], (size_t)S * d));
+        TRY(dev_alloc(&p->LD[i], (size_t)S * dd));
+        TRY(dev_alloc(&p->LO[i], (size_t)S * dd));
+        TRY(dev_alloc(&p->CD[i], (size_t)S * dd));
+        TRY(dev_alloc(&p->CO[i], (size_t)S * dd));
+        TRY(dev_alloc(&p->fcost[i], (size_t)p->n_factors));
+        TRY(dev_alloc(&p->fVdmu[i], nV));
+        TRY(dev_alloc(&p->fVdd[i], nM));
+        CUDA_TRY(cudaMemsetAsync(p->LO[i], 0, (size_t)S * dd * sizeof(double), p->stream));
+        CUDA_TRY(cudaMemsetAsync(p->CO[i], 0, (size_t)S * dd * sizeof(double), p->stream));
+    }
+    TRY(dev_alloc(&p->scal, 8));
+    CUDA_TRY(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_scal, 8 * sizeof(double)));
+    TRY(dev_alloc(&p->d_flag, 1));
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_flag, sizeof(int)));
+    TRY(dev_alloc(&p->Vdmu, (size_t)S * d));
+    TRY(dev_alloc(&p->rhs, (size_t)S * d));
+    TRY(dev_alloc(&p->dmu, (size_t)S * d));
+    TRY(dev_alloc(&p->VD, (size_t)S * dd));
+    TRY(dev_alloc(&p->VO, (size_t)S * dd));
+    TRY(dev_alloc(&p->KlinD, (size_t)S * dd));
+    TRY(dev_alloc(&p->KlinO, (size_t)S * dd));
+    TRY(upload_klin(p));
+    // chain plan
+    p->plan = bt_make_plan(S, d, 4, 8, false);
+    TRY(dev_alloc(&p->ws, p->plan.ws_doubles + 16));
+    CUDA_TRY(cudaMemsetAsync(p->ws, 0, (p->plan.ws_doubles + 16) * sizeof(double), p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: state
+// ------------------------------------------------------------------------------------------------
+static int recompute_from_precision(gvib200_problem* p, int which) {
+    TRY(clear_flag(p));
+    TRY(do_selinv(p, p->LD[which], p->LO[which], p->CD[which], p->CO[which], p->scal + which));
+    TRY(run_prologue_only(p, which));
+    int flag = 0;
+    TRY(read_flag(p, &flag));
+    if (flag) return fail(GVIB200_ENOTSPD, "precision matrix is not positive definite");
+    return 0;
+}
+
+extern "C" int gvib200_set_state(gvib200_problem* p, const double* mu, const double* pd, const double* po) {
+    if (!p || !p->finalized) return fail(GVIB200_ESTATE, "set_state: problem not finalized");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const int S = p->S, d = p->d, c = p->cur;
+    const size_t dd = (size_t)d * d;
+    if (mu) CUDA_TRY(cudaMemcpyAsync(p->mu[c], mu, (size_t)S * d * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (pd) {
+        CUDA_TRY(cudaMemcpyAsync(p->LD[c], pd, (size_t)S * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        if (S > 1) {
+            if (po) CUDA_TRY(cudaMemcpyAsync(p->LO[c], po, (size_t)(S - 1) * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            else CUDA_TRY(cudaMemsetAsync(p->LO[c], 0, (size_t)(S - 1) * dd * sizeof(double), p->stream));
+        }
+    }
+    p->sweep_valid = false;
+    p->grads_valid = false;
+    if (pd || !p->has_state) {
+        if (!pd) return fail(GVIB200_ESTATE, "set_state: the first call must provide a precision");
+        TRY(recompute_from_precision(p, c));
+    }
+    p->has_state = true;
+    return 0;
+}
+
+static int download(gvib200_problem* p, double* dst, const double* src, size_t n) {
+    if (!dst || n == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    return 0;
+}
+
+extern "C" int gvib200_get_mean(gvib200_problem* p, double* mu) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_mean: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    TRY(download(p, mu, p->mu[p->cur], (size_t)p->S * p->d));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+extern "C" int gvib200_get_prec_blocks(gvib200_problem* p, double* diag, double* off) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_prec_blocks: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const size_t dd = (size_t)p->d * p->d;
+    TRY(download(p, diag, p->LD[p->cur], p->S * dd));
+    TRY(download(p, off, p->LO[p->cur], (p->S - 1) * dd));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+extern "C" int gvib200_get_cov_blocks(gvib200_problem* p, double* diag, double* off) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_cov_blocks: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const size_t dd = (size_t)p->d * p->d;
+    TRY(download(p, diag, p->CD[p->cur], p->S * dd));
+    TRY(download(p, off, p->CO[p->cur], (p->S - 1) * dd));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: moments / cost / gradients
+// ------------------------------------------------------------------------------------------------
+static int ensure_sweep(gvib200_problem* p, bool want_raw) {
+    if (p->sweep_valid && !want_raw) return 0;
+    TRY(run_sweep(p, p->cur, false, true, want_raw));
+    run_total(p, p->cur);
+    p->sweep_valid = true;
+    return check_launch("sweep");
+}
+
+extern "C" int gvib200_moments(gvib200_problem* p, double* E0, double* E1, double* E2) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "moments: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    TRY(ensure_sweep(p, true));
+    size_t o0 = 0, o1 = 0, o2 = 0;
+    for (auto& g : p->gh) {
+        double *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+        TRY(dev_alloc(&d0, (size_t)g.n));
+        TRY(dev_alloc(&d1, (size_t)g.n * g.dim));
+        TRY(dev_alloc(&d2, (size_t)g.n * g.dim * g.dim));
+        const double* SR = g.d_SR[p->cur];
+        switch (g.dim) {
+            case 1: launch_raw_to_x<1>(p, g, SR, d0, d1, d2); break;
+            case 2: launch_raw_to_x<2>(p, g, SR, d0, d1, d2); break;
+            case 3: launch_raw_to_x<3>(p, g, SR, d0, d1, d2); break;
+            case 4: launch_raw_to_x<4>(p, g, SR, d0, d1, d2); break;
+            case 6: launch_raw_to_x<6>(p, g, SR, d0, d1, d2); break;
+            case 8: launch_raw_to_x<8>(p, g, SR, d0, d1, d2); break;
+            case 12: launch_raw_to_x<12>(p, g, SR, d0, d1, d2); break;
+            default: return fail(GVIB200_EINVAL, "moments: unsupported factor dim");
+        }
+        if (E0) TRY(download(p, E0 + o0, d0, (size_t)g.n));
+        if (E1) TRY(download(p, E1 + o1, d1, (size_t)g.n * g.dim));
+        if (E2) TRY(download(p, E2 + o2, d2, (size_t)g.n * g.dim * g.dim));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        cudaFree(d0);
+        cudaFree(d1);
+        cudaFree(d2);
+        o0 += g.n;
+        o1 += (size_t)g.n * g.dim;
+        o2 += (size_t)g.n * g.dim * g.dim;
+    }
+    return check_launch("moments");
+}
+
+extern "C" int gvib200_cost(gvib200_problem* p, const double* mu, const double* pd, const double* po, double* cost,
+                            double* fac_costs) {
+    if (!p || !p->finalized) return fail(GVIB200_ESTATE, "cost: problem not finalized");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const int S = p->S, d = p->d;
+    const size_t dd = (size_t)d * d;
+    int which;
+    if (!mu && !pd) {
+        if (!p->has_state) return fail(GVIB200_ESTATE, "cost: no state");
+        TRY(ensure_sweep(p, false));
+        which = p->cur;
+    } else {
+        if (!p->has_state && (!mu || !pd)) return fail(GVIB200_ESTATE, "cost: no state to take defaults from");
+        which = 1 - p->cur;
+        const int c = p->cur;
+        if (mu) CUDA_TRY(cudaMemcpyAsync(p->mu[which], mu, (size_t)S * d * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        else CUDA_TRY(cudaMemcpyAsync(p->mu[which], p->mu[c], (size_t)S * d * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        if (pd) {
+            CUDA_TRY(cudaMemcpyAsync(p->LD[which], pd, S * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            if (S > 1) {
+                if (po) CUDA_TRY(cudaMemcpyAsync(p->LO[which], po, (S - 1) * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                else CUDA_TRY(cudaMemsetAsync(p->LO[which], 0, (S - 1) * dd * sizeof(double), p->stream));
+            }
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(p->LD[which], p->LD[c], S * dd * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CUDA_TRY(cudaMemcpyAsync(p->LO[which], p->LO[c], S * dd * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        }
+        TRY(clear_flag(p));
+        TRY(do_selinv(p, p->LD[which], p->LO[which], p->CD[which], p->CO[which], p->scal + which));
+        TRY(run_sweep(p, which, true, false, false));
+        run_total(p, which);
+        int flag = 0;
+        TRY(read_flag(p, &flag));
+        if (flag) return fail(GVIB200_ENOTSPD, "cost: precision matrix is not positive definite");
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (fac_costs) TRY(download(p, fac_costs, p->fcost[which], (size_t)p->n_factors));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (cost) *cost = p->h_scal[2 + which];
+    return check_launch("cost");
+}
+
+// gradients at the current state: assemble + dmu solve; leaves Vdmu/VD/VO/dmu on the device
+static int compute_gradients(gvib200_problem* p) {
+    TRY(ensure_sweep(p, false));
+    switch (p->d) {
+        case 1: launch_assemble<1>(p, p->cur); break;
+        case 2: launch_assemble<2>(p, p->cur); break;
+        case 3: launch_assemble<3>(p, p->cur); break;
+        case 4: launch_assemble<4>(p, p->cur); break;
+        case 6: launch_assemble<6>(p, p->cur); break;
+        default: return fail(GVIB200_EINVAL, "unsupported state dim");
+    }
+    TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr));
+    p->grads_valid = true;
+    return check_launch("gradients");
+}
+
+extern "C" int gvib200_gradients(gvib200_problem* p, double* dmu, double* dD, double* dO) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "gradients: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const int S = p->S, d = p->d;
+    const size_t dd = (size_t)d * d;
+    TRY(clear_flag(p));
+    TRY(compute_gradients(p));
+    int flag = 0;
+    TRY(read_flag(p, &flag));
+    TRY(download(p, dmu, p->dmu, (size_t)S * d));
+    if (dD || dO) {
+        // dprecision = Vddmu - precision, staged through the candidate precision buffers
+        const int w = 1 - p->cur;
+        LAUNCH(p, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VD, p->LD[p->cur], p->LD[w]);
+        LAUNCH(p, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VO, p->LO[p->cur], p->LO[w]);
+        TRY(download(p, dD, p->LD[w], S * dd));
+        TRY(download(p, dO, p->LO[w], (S - 1) * dd));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (flag) return fail(GVIB200_ENOTSPD, "gradients: Vddmu is not positive definite (the reference would hand it to CG)");
+    return check_launch("gradients");
+}
+
+extern "C" int gvib200_get_V(gvib200_problem* p, double* Vdmu, double* VD, double* VO) {
+    if (!p || !p->grads_valid) return fail(GVIB200_ESTATE, "get_V: call gradients first");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const size_t dd = (size_t)p->d * p->d;
+    TRY(download(p, Vdmu, p->Vdmu, (size_t)p->S * p->d));
+    TRY(download(p, VD, p->VD, p->S * dd));
+    TRY(download(p, VO, p->VO, (p->S - 1) * dd));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: optimizer
+// ------------------------------------------------------------------------------------------------
+extern "C" void gvib200_default_opts(gvib200_opts* o) {
+    if (!o) return;
+    o->step_size_base = 0.55;
+    o->backtrack_ratio = 0.75;
+    o->max_backtrack = 10;
+    o->niters_lowtemp = 10;
+    o->reuse_accepted_sweep = 0;
+}
+
+// GVIGH::switch_to_high_temperature (gvibase/GVI-GH-GBP-impl.h:18-27)
+static int switch_to_high_temperature(gvib200_problem* p) {
+    for (auto& g : p->gh) {
+        g.T = g.Thigh;
+        CUDA_TRY(cudaMemcpyAsync(g.d_T, g.T.data(), g.T.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    for (auto& g : p->lin) {
+        g.T = g.Thigh;
+        CUDA_TRY(cudaMemcpyAsync(g.d_T, g.T.data(), g.T.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    TRY(upload_klin(p));
+    p->sweep_valid = false;
+    p->grads_valid = false;
+    return 0;
+}
+
+static int launch_candidate(gvib200_problem* p, double alpha) {
+    const int S = p->S, d = p->d, c = p->cur, w = 1 - p->cur;
+    const size_t dd = (size_t)d * d;
+    const size_t nmu = (size_t)S * d, nD = S * dd, nO = (S - 1) * dd;
+    LAUNCH(p, k_candidate, cdiv(nD, 256), 256, 0, nmu, nD, nO, alpha, p->mu[c], p->dmu, p->LD[c], p->LO[c], p->VD,
+           p->VO, p->mu[w], p->LD[w], p->LO[w]);
+    return 0;
+}
+
+extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_in, gvib200_iter_stats* st) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "ngd_iterate: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    gvib200_opts o;
+    if (opts_in) o = *opts_in;
+    else gvib200_default_opts(&o);
+    gvib200_iter_stats s;
+    std::memset(&s, 0, sizeof(s));
+    if (p->converged) {
+        s.converged = 1;
+        if (st) *st = s;
+        return 0;
+    }
+    // temperature switch at iteration niters_lowtemp (GVI-GH-GBP-impl.h:49-58)
+    if (p->iter == o.niters_lowtemp && p->is_lowtemp) {
+        TRY(switch_to_high_temperature(p));
+        p->is_lowtemp = false;
+        s.switched_high_T = 1;
+    }
+    TRY(clear_flag(p));
+    // cost_iter + factor costs + gradients from ONE full-moment sweep at the current state
+    if (!p->sweep_valid) s.n_moment_sweeps++;
+    TRY(compute_gradients(p));
+    CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    int flag = 0;
+    TRY(read_flag(p, &flag));
+    const double cost_iter = p->h_scal[2 + p->cur];
+    s.cost = cost_iter;
+    if (flag) {
+        s.status = GVIB200_ENOTSPD;
+        if (st) *st = s;
+        p->iter++;
+        return fail(GVIB200_ENOTSPD, "ngd_iterate: Vddmu is not positive definite");
+    }
+    // back-tracking (GVI-GH-GBP-impl.h:82-124)
+    int cnt = 0;
+    double step = o.step_size_base;
+    while (true) {
+        step *= o.backtrack_ratio;
+        const int w = 1 - p->cur;
+        TRY(launch_candidate(p, step));
+        TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w));
+        TRY(run_sweep(p, w, true, o.reuse_accepted_sweep != 0, false));
+        if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
+        else s.n_cost_sweeps++;
+        run_total(p, w);
+        CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        TRY(read_flag(p, &flag));
+        const double new_cost = p->h_scal[2 + w];
+        s.new_cost = new_cost;
+        // a candidate precision that is not SPD has no finite cost: treat as a rejected trial
+        const bool ok = (flag == 0) && (new_cost < cost_iter);
+        if (flag) TRY(clear_flag(p));
+        if (ok) {
+            // update_proposal (ngd/NGD-GH-impl.h:151-156): the candidate's mu, precision, covariance and factor
+            // marginals become current -- a buffer flip, everything is already on the device
+            p->cur = w;
+            p->sweep_valid = (o.reuse_accepted_sweep != 0);
+            p->grads_valid = false;
+            s.accepted = 1;
+            s.step = step;
+            s.n_backtrack = cnt;
+            break;
+        }
+        cnt++;
+        if (cnt > o.max_backtrack) {
+            if (p->is_lowtemp) {
+                TRY(switch_to_high_temperature(p));
+                p->is_lowtemp = false;
+                s.switched_high_T = 1;
+            } else {
+                p->converged = true;
+                s.converged = 1;
+            }
+            s.n_backtrack = cnt;
+            break;
+        }
+    }
+    p->iter++;
+    if (st) *st = s;
+    return 0;
+}
+
+extern "C" int gvib200_optimize(gvib200_problem* p, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats,
+                                int* n_done, double* fac_costs_trace, double* mean_trace) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "optimize: no state");
+    int done = 0;
+    for (int it = 0; it < n_iters; ++it) {
+        if (p->converged) break;
+        gvib200_iter_stats s;
+        if (mean_trace) TRY(gvib200_get_mean(p, mean_trace + (size_t)it * p->S * p->d));
+        int rc = gvib200_ngd_iterate(p, opts, &s);
+        if (stats) stats[it] = s;
+        if (rc != 0) {
+            if (n_done) *n_done = done;
+            return rc;
+        }
+        // factor costs recorded at the start of the iteration: still in the pre-flip buffer
+        if (fac_costs_trace) {
+            const int src = s.accepted ? 1 - p->cur : p->cur;
+            TRY(download(p, fac_costs_trace + (size_t)it * p->n_factors, p->fcost[src], (size_t)p->n_factors));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        done++;
+    }
+    if (n_done) *n_done = done;
+    return 0;
+}
+
+extern "C" int gvib200_reset_schedule(gvib200_problem* p) {
+    if (!p) return fail(GVIB200_EINVAL, "reset_schedule: null");
+    p->iter = 0;
+    p->converged = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: stand-alone block-tridiagonal engine
+// ------------------------------------------------------------------------------------------------
+static int standalone(gvib200_ctx* ctx, int S, int d, const double* diag, const double* off, const double* rhs,
+                      double* x, double* cD, double* cO, double* logdet) {
+    if (!ctx || S < 1 || !diag || (S > 1 && !off)) return fail(GVIB200_EINVAL, "blocktri: bad arguments");
+    gvib200_problem* p = nullptr;
+    TRY(gvib200_problem_create(ctx, S, d, &p));
+    int rc = gvib200_problem_finalize(p);
+    const size_t dd = (size_t)d * d;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(p->LD[0], diag, S * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        if (S > 1) CUDA_TRY(cudaMemcpyAsync(p->LO[0], off, (S - 1) * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        TRY(clear_flag(p));
+        if (rhs) {
+            CUDA_TRY(cudaMemcpyAsync(p->rhs, rhs, (size_t)S * d * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            TRY(do_solve(p, p->LD[0], p->LO[0], p->rhs, p->dmu, p->scal));
+            TRY(download(p, x, p->dmu, (size_t)S * d));
+        } else {
+            TRY(do_selinv(p, p->LD[0], p->LO[0], p->CD[0], p->CO[0], p->scal));
+            TRY(download(p, cD, p->CD[0], S * dd));
+            TRY(download(p, cO, p->CO[0], (S - 1) * dd));
+        }
+        CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        int flag = 0;
+        TRY(read_flag(p, &flag));
+        if (logdet) *logdet = p->h_scal[0];
+        if (flag) return fail(GVIB200_ENOTSPD, "blocktri: matrix is not positive definite");
+        return 0;
+    };
+    if (rc == 0) rc = body();
+    gvib200_problem_destroy(p);
+    return rc;
+}
+
+extern "C" int gvib200_selected_inverse(gvib200_ctx* ctx, int S, int d, const double* diag, const double* off,
+                                        double* cov_diag, double* cov_off, double* logdet) {
+    return standalone(ctx, S, d, diag, off, nullptr, nullptr, cov_diag, cov_off, logdet);
+}
+extern "C" int gvib200_blocktri_solve(gvib200_ctx* ctx, int S, int d, const double* diag, const double* off,
+                                      const double* rhs, double* x, double* logdet) {
+    if (!rhs || !x) return fail(GVIB200_EINVAL, "blocktri_solve: null rhs/x");
+    return standalone(ctx, S, d, diag, off, rhs, x, nullptr, nullptr, logdet);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: measurement hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int gvib200_time_stage(gvib200_problem* p, int stage, int reps, const gvib200_opts* opts, float* ms_per_rep,
+                                  long long* kernel_launches) {
+    if (!p || !p->has_state || reps < 1) return fail(GVIB200_ESTATE, "time_stage: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    gvib200_opts o;
+    if (opts) o = *opts;
+    else gvib200_default_opts(&o);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int c = p->cur, w = 1 - p->cur;
+    // make sure gradients exist so that stages 2/3 have inputs
+    if (stage == 2 || stage == 3) TRY(compute_gradients(p));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    const long long l0 = p->ctx->launches;
+    CUDA_TRY(cudaEventRecord(e0, p->stream));
+    for (int r = 0; r < reps; ++r) {
+        switch (stage) {
+            case 0: TRY(run_sweep(p, c, true, true, false)); break;
+            case 1: TRY(run_sweep(p, c, true, false, false)); break;
+            case 2: {
+                switch (p->d) {
+                    case 1: launch_assemble<1>(p, c); break;
+                    case 2: launch_assemble<2>(p, c); break;
+                    case 3: launch_assemble<3>(p, c); break;
+                    case 4: launch_assemble<4>(p, c); break;
+                    case 6: launch_assemble<6>(p, c); break;
+                }
+                TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr));
+                break;
+            }
+            case 3: {
+                TRY(launch_candidate(p, o.step_size_base * o.backtrack_ratio));
+                TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w));
+                break;
+            }
+            default: cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(GVIB200_EINVAL, "time_stage: bad stage");
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1, p->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_rep) *ms_per_rep = ms / reps;
+    if (kernel_launches) *kernel_launches = (p->ctx->launches - l0) / reps;
+    if (stage <= 1) {
+        // the sweep overwrote fcost[cur] consistently (same state), totals need refreshing
+        run_total(p, c);
+        p->sweep_valid = (stage == 0);
+    }
+    return check_launch("time_stage");
+}
+
+extern "C" int gvib200_fp64_peak(gvib200_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(GVIB200_EINVAL, "fp64_peak: bad arguments");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 14, block = 256, grid = ctx->sm_count * 8;
+    k_fp64_peak<<<grid, block>>>(1024, d_out);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_fp64_peak<<<grid, block>>>(iters, d_out);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * block * (double)grid;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return check_launch("k_fp64_peak");
+}
+
+extern "C" long long gvib200_launch_count(gvib200_ctx* ctx) { return ctx ? ctx->launches : 0; }

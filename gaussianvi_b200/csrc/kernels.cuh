@@ -1,0 +1,563 @@
+// CUDA kernels of the factorized NGD-GVI iteration (sm_100a, FP64).
+//   k_prologue   K2  per-factor marginal extraction + PSD sqrt / inverse sqrt (Jacobi in registers)
+//   k_moments    K1  fused sigma points + cost functor + moment reduction + Vdmu/Vddmu epilogue
+//   k_linear         closed-form linear-Gaussian factors (gradient + cost)
+//   k_assemble   K3  deterministic gather of factor blocks into the block-tridiagonal joint
+//   k_bt_*       K4  partitioned block-tridiagonal Cholesky / solve / selected inverse / log det
+//   k_candidate      line-search candidate (mu + a dmu, Lambda + a dLambda)
+//   k_total_cost     sum of factor costs + 1/2 log det, fixed summation order
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bt_chain.h"
+#include "cost_functors.cuh"
+#include "smallmat.h"
+
+namespace gvib200 {
+
+// ------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: per-factor prologue.  Extract Sigma_k from the block-tridiagonal covariance
+// (GVIFactorizedBase::update_precision_from_joint, gvibase/GVIFactorizedBase.h:111-114 +
+// TrajectoryBlock::extract helpers/MatrixHelper.h:132-134) and form S = Sigma^1/2 (symmetric PSD root,
+// quadrature/SparseGaussHermite.h:231-233) and R = Sigma^-1/2 (so that P_k = R R).
+// One thread per factor; SR[f] = {S[DIM*DIM], R[DIM*DIM]} column-major.
+// ------------------------------------------------------------------------------------------
+template <int DIM, int SD>
+__global__ void k_prologue(int n, const int* __restrict__ start, const double* __restrict__ covD,
+                           const double* __restrict__ covO, double* __restrict__ SR) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    constexpr int NS = DIM / SD;  // states spanned (1 or 2)
+    static_assert(NS == 1 || NS == 2, "factors span one or two consecutive states");
+    const int s = start[f];
+    Mat<DIM> Sig, S, R;
+#pragma unroll
+    for (int j = 0; j < SD; ++j)
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            Sig(i, j) = covD[(size_t)s * SD * SD + i + j * SD];
+            if (NS == 2) {
+                Sig(SD + i, SD + j) = covD[(size_t)(s + 1) * SD * SD + i + j * SD];
+                const double o = covO[(size_t)s * SD * SD + i + j * SD];  // block (s, s+1)
+                Sig(i, SD + j) = o;
+                Sig(SD + j, i) = o;
+            }
+        }
+    sqrt_and_invsqrt<DIM>(S, R, Sig);
+    double* out = SR + (size_t)f * 2 * DIM * DIM;
+#pragma unroll
+    for (int e = 0; e < DIM * DIM; ++e) {
+        out[e] = S.a[e];
+        out[DIM * DIM + e] = R.a[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: fused sigma-point / cost / moment kernel.  One warp per factor, lanes stride the nodes.
+//   x_i = mu_k + S_k xi_i                      quadrature/SparseGaussHermite.h:242
+//   e0 = sum w psi, e1 = sum w psi xi, e2 = sum w psi xi xi^T   (xi-space; E1 = S e1, E2 = S e2 S,
+//        identical to the x-space sums of ngd/NGDFactorizedBaseGH.h:46-48)
+//   Vdmu = P E1 / T = R e1 / T;  Vddmu = (P E2 P - P E0)/T = R (e2 - e0 I) R / T  (:61-73)
+//   cost = E0 / T                                                                    (:122-129)
+// The node table (xi | w rows) is staged into shared memory with a TMA bulk copy; when it does not fit
+// it is streamed in chunks.  The warp reduction is a fixed xor-butterfly, so results are reproducible.
+// ------------------------------------------------------------------------------------------
+template <class Cost>
+struct MomentArgs {
+    int n;                 // factors in this group
+    int n_nodes;           // quadrature nodes
+    int chunk;             // nodes per shared-memory chunk (>= n_nodes: single stage)
+    int state_dim;
+    const double* table;   // [n_nodes][ROW] rows (xi_0..xi_{DIM-1}, w, pad), ROW = even(DIM + 1)
+    const int* start;      // [n] start state
+    const double* mu;      // joint mean
+    const double* SR;      // [n][2*DIM*DIM]
+    const double* T;       // [n] temperatures
+    double* fcost;         // [n] E0 / T
+    double* fVdmu;         // [n][DIM]
+    double* fVdd;          // [n][DIM*DIM]
+    double* raw;           // optional [n][1 + DIM + DIM*DIM]: e0, e1, e2 (xi-space, times scale)
+    Cost cost;
+};
+
+template <int DIM>
+struct MomentAcc {
+    static constexpr int NE2 = DIM * (DIM + 1) / 2;
+    double e0;
+    double e1[DIM];
+    double e2[NE2];  // packed upper triangle, (a, b) a <= b at index a*DIM - a(a-1)/2 + (b - a)
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// threads per CTA: small factors keep everything in registers; big ones trade occupancy for registers
+template <int DIM>
+struct K1Cfg {
+    static constexpr int THREADS = (DIM <= 4) ? 512 : (DIM <= 8 ? 256 : 128);
+};
+// per-warp scratch: epilogue totals (+ the S rows when they do not fit in registers)
+template <int DIM, int XD>
+struct K1Scratch {
+    static constexpr bool S_IN_SMEM = (XD * DIM > 32);
+    static constexpr int NOUT = 1 + DIM + DIM * DIM;
+    static constexpr int DOUBLES = NOUT + (S_IN_SMEM ? XD * DIM : 0);
+};
+
+template <int DIM, class Cost, bool FULL>
+__global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArgs<Cost> a) {
+    constexpr int ROW = (DIM + 2) & ~1;
+    constexpr int XD = Cost::XD;
+    constexpr int NE2 = DIM * (DIM + 1) / 2;
+    constexpr int NOUT = 1 + DIM + DIM * DIM;
+    constexpr bool S_IN_SMEM = K1Scratch<DIM, XD>::S_IN_SMEM;
+    constexpr int NSREG = S_IN_SMEM ? 1 : XD;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    double* tab = smem;                                                // [chunk][ROW]
+    double* scratch = smem + (size_t)a.chunk * ROW;                   // [warps][K1Scratch::DOUBLES]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    double* my = scratch + warp * K1Scratch<DIM, XD>::DOUBLES;
+    double* sS = my + NOUT;  // [XD][DIM] row r at sS[r*DIM + c] (only when S_IN_SMEM)
+
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    const bool single = a.n_nodes <= a.chunk;
+    if (single) {
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)(a.n_nodes * ROW * sizeof(double));
+            mbar_expect_tx(&mbar, bytes);
+            bulk_copy_g2s(tab, a.table, bytes, &mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+    }
+
+    const int stride = gridDim.x * nwarps;
+    for (int base = blockIdx.x * nwarps; base < a.n; base += stride) {
+        const int f = base + warp;
+        const bool active = f < a.n;
+        // factor data: mu_k and the first XD rows of S_k
+        double mu[XD], S[NSREG][DIM];
+        if (active) {
+            const double* Sp = a.SR + (size_t)f * 2 * DIM * DIM;
+            const double* mp = a.mu + (size_t)a.start[f] * a.state_dim;
+#pragma unroll
+            for (int r = 0; r < XD; ++r) mu[r] = __ldg(mp + r);
+            if (S_IN_SMEM) {
+                __syncwarp();
+                for (int e = lane; e < XD * DIM; e += 32) sS[e] = __ldg(Sp + (e / DIM) + (e % DIM) * DIM);
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int r = 0; r < NSREG; ++r)
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) S[r][c] = __ldg(Sp + r + c * DIM);
+            }
+        }
+        MomentAcc<DIM> acc;
+        acc.e0 = 0.0;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) acc.e1[c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NE2; ++c) acc.e2[c] = 0.0;
+
+        for (int c0 = 0; c0 < a.n_nodes; c0 += a.chunk) {
+            const int cn = min(a.chunk, a.n_nodes - c0);
+            if (!single) {
+                __syncthreads();  // every warp is done with the previous chunk
+                if (threadIdx.x == 0) {
+                    const unsigned bytes = (unsigned)(cn * ROW * sizeof(double));
+                    mbar_expect_tx(&mbar, bytes);
+                    bulk_copy_g2s(tab, a.table + (size_t)c0 * ROW, bytes, &mbar);
+                }
+                mbar_wait(&mbar, parity);
+                parity ^= 1;
+            }
+            if (active) {
+#pragma unroll 2
+                for (int i = lane; i < cn; i += 32) {
+                    const double* row = tab + (size_t)i * ROW;
+                    double xi[DIM];
+#pragma unroll
+                    for (int c = 0; c < DIM; c += 2) {
+                        if (c + 1 < DIM) {
+                            const double2 v = *reinterpret_cast<const double2*>(row + c);
+                            xi[c] = v.x;
+                            xi[c + 1] = v.y;
+                        } else {
+                            xi[c] = row[c];
+                        }
+                    }
+                    const double w = row[DIM];
+                    double x[XD];
+#pragma unroll
+                    for (int r = 0; r < XD; ++r) {
+                        double s = mu[r];
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) s = fma(S_IN_SMEM ? sS[r * DIM + c] : S[S_IN_SMEM ? 0 : r][c], xi[c], s);
+                        x[r] = s;
+                    }
+                    const double p = w * a.cost.eval(x, f);
+                    acc.e0 += p;
+                    if (FULL) {
+                        int idx = 0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
+                            const double q = p * xi[c];
+                            acc.e1[c] += q;
+#pragma unroll
+                            for (int d2 = c; d2 < DIM; ++d2) {
+                                acc.e2[idx] = fma(q, xi[d2], acc.e2[idx]);
+                                ++idx;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!active) continue;  // whole warp
+        // ---- fixed-order butterfly reduction ----
+        const double sc = a.cost.scale();
+        acc.e0 = warp_sum(acc.e0) * sc;
+        if (FULL) {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) acc.e1[c] = warp_sum(acc.e1[c]) * sc;
+#pragma unroll
+            for (int c = 0; c < NE2; ++c) acc.e2[c] = warp_sum(acc.e2[c]) * sc;
+        }
+        const double invT = 1.0 / __ldg(a.T + f);
+        if (!FULL) {
+            if (lane == 0) a.fcost[f] = acc.e0 * invT;
+            continue;
+        }
+        // ---- epilogue: lane 0 publishes the totals, lanes split the small products ----
+        if (lane == 0) {
+            my[0] = acc.e0;
+            int idx = 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                my[1 + c] = acc.e1[c];
+#pragma unroll
+                for (int d2 = c; d2 < DIM; ++d2) {
+                    my[1 + DIM + c + d2 * DIM] = acc.e2[idx];
+                    my[1 + DIM + d2 + c * DIM] = acc.e2[idx];
+                    ++idx;
+                }
+            }
+        }
+        __syncwarp();
+        if (a.raw != nullptr) {
+            for (int e = lane; e < NOUT; e += 32) a.raw[(size_t)f * NOUT + e] = my[e];
+        }
+        const double* R = a.SR + (size_t)f * 2 * DIM * DIM + DIM * DIM;
+        const double e0 = my[0];
+        for (int e = lane; e < DIM * DIM + DIM + 1; e += 32) {
+            if (e < DIM * DIM) {
+                int i = e % DIM, j = e / DIM;
+                if (i > j) {  // upper triangle mirrored (ngd/NGDFactorizedBaseGH.h:71-72)
+                    const int t = i;
+                    i = j;
+                    j = t;
+                }
+                // (R (e2 - e0 I) R)_{ij} = sum_b (sum_a R_ai M_ab) R_bj
+                double v = 0.0;
+                for (int b = 0; b < DIM; ++b) {
+                    double t = 0.0;
+                    for (int aa = 0; aa < DIM; ++aa) {
+                        const double m = my[1 + DIM + aa + b * DIM] - (aa == b ? e0 : 0.0);
+                        t = fma(__ldg(R + aa + i * DIM), m, t);
+                    }
+                    v = fma(t, __ldg(R + b + j * DIM), v);
+                }
+                a.fVdd[(size_t)f * DIM * DIM + e] = v * invT;
+            } else if (e < DIM * DIM + DIM) {
+                const int i = e - DIM * DIM;
+                double v = 0.0;
+                for (int aa = 0; aa < DIM; ++aa) v = fma(__ldg(R + i + aa * DIM), my[1 + aa], v);
+                a.fVdmu[(size_t)f * DIM + i] = v * invT;
+            } else {
+                a.fcost[f] = e0 * invT;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// x-space moments for the parity probe (gvib200_moments): E1 = S e1, E2 = S e2 S.
+template <int DIM>
+__global__ void k_raw_to_x(int n, const double* __restrict__ raw, const double* __restrict__ SR, double* __restrict__ E0,
+                           double* __restrict__ E1, double* __restrict__ E2) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    constexpr int NOUT = 1 + DIM + DIM * DIM;
+    const double* r = raw + (size_t)f * NOUT;
+    const double* S = SR + (size_t)f * 2 * DIM * DIM;
+    if (E0) E0[f] = r[0];
+    if (E1) {
+        for (int i = 0; i < DIM; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < DIM; ++k) s = fma(S[i + k * DIM], r[1 + k], s);
+            E1[(size_t)f * DIM + i] = s;
+        }
+    }
+    if (E2) {
+        for (int j = 0; j < DIM; ++j)
+            for (int i = 0; i < DIM; ++i) {
+                double v = 0.0;
+                for (int b = 0; b < DIM; ++b) {
+                    double t = 0.0;
+                    for (int aa = 0; aa < DIM; ++aa) t = fma(S[i + aa * DIM], r[1 + DIM + aa + b * DIM], t);
+                    v = fma(t, S[b + j * DIM], v);
+                }
+                E2[(size_t)f * DIM * DIM + i + j * DIM] = v;
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Closed-form linear-Gaussian factors (ngd/NGDFactorizedLinear.h:93-129).  One thread per factor.
+//   r = Lambda mu_k - Psi mu_t;  Vdmu = 2 C Lambda^T Kinv r / T
+//   cost = C (tr(A Sigma_k) + r^T Kinv r) / T,  A = Lambda^T Kinv Lambda
+// Vddmu = 2 C A / T is state independent (the reference evaluates it through a 4-th moment loop that is
+// algebraically the same, :107-119) and is pre-assembled once into the constant block-tridiagonal Klin.
+// ------------------------------------------------------------------------------------------
+constexpr int LIN_MAX_DIM = 12;
+struct LinearArgs {
+    int n, dim, m, state_dim;
+    const int* start;
+    const double* Lambda;  // [n][m*dim]
+    const double* psi;     // [n][m] = Psi mu_t
+    const double* Kinv;    // [n][m*m]
+    const double* A;       // [n][dim*dim]
+    const double* C;       // [n]
+    const double* T;       // [n]
+    const double* mu;      // joint mean
+    const double* covD;
+    const double* covO;
+    double* fcost;   // [n]
+    double* fVdmu;   // [n][dim] or null (cost only)
+};
+
+__global__ void k_linear(const LinearArgs a) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n) return;
+    const int dim = a.dim, m = a.m, sd = a.state_dim;
+    const int s = a.start[f];
+    const double* L = a.Lambda + (size_t)f * m * dim;
+    const double* Ki = a.Kinv + (size_t)f * m * m;
+    const double* mu = a.mu + (size_t)s * sd;
+    double r[LIN_MAX_DIM], kr[LIN_MAX_DIM];
+    for (int i = 0; i < m; ++i) {
+        double v = -a.psi[(size_t)f * m + i];
+        for (int k = 0; k < dim; ++k) v = fma(L[i + k * m], mu[k], v);
+        r[i] = v;
+    }
+    double q = 0.0;
+    for (int i = 0; i < m; ++i) {
+        double v = 0.0;
+        for (int k = 0; k < m; ++k) v = fma(Ki[i + k * m], r[k], v);
+        kr[i] = v;
+        q = fma(v, r[i], q);
+    }
+    const double c_over_t = a.C[f] / a.T[f];
+    if (a.fVdmu != nullptr) {
+        for (int k = 0; k < dim; ++k) {
+            double v = 0.0;
+            for (int i = 0; i < m; ++i) v = fma(L[i + k * m], kr[i], v);
+            a.fVdmu[(size_t)f * dim + k] = 2.0 * v * c_over_t;
+        }
+    }
+    // tr(A Sigma_k): Sigma_k assembled from the covariance blocks
+    const double* A = a.A + (size_t)f * dim * dim;
+    const int ns = dim / sd;
+    double tr = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        const int bj = j / sd, jj = j % sd;
+        for (int i = 0; i < dim; ++i) {
+            const int bi = i / sd, ii = i % sd;
+            double sij;
+            if (bi == bj) sij = a.covD[(size_t)(s + bi) * sd * sd + ii + jj * sd];
+            else if (bi < bj) sij = a.covO[(size_t)s * sd * sd + ii + jj * sd];
+            else sij = a.covO[(size_t)s * sd * sd + jj + ii * sd];
+            tr = fma(A[j + i * dim], sij, tr);  // A symmetric: sum_ij A_ji Sigma_ij
+        }
+    }
+    (void)ns;
+    a.fcost[f] = (tr + q) * c_over_t;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: assembly (local2joint_* + the sums of NGDGH::compute_gradients, ngd/NGD-GH-impl.h:36-57).
+// One thread per state gathers, in a fixed order, the factor blocks that touch it:
+//   Vdmu[s]   = sum of fVdmu pieces;   VD[s] = KlinD[s] + sum of diag pieces;   VO[s] = KlinO[s] + off pieces
+// ------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_assemble(int S, const int* __restrict__ vptr, const int* __restrict__ voff,
+                           const int* __restrict__ dptr, const int* __restrict__ doff, const int* __restrict__ dld,
+                           const int* __restrict__ optr, const int* __restrict__ ooff, const int* __restrict__ old,
+                           const double* __restrict__ fVdmu, const double* __restrict__ fVdd,
+                           const double* __restrict__ KlinD, const double* __restrict__ KlinO,
+                           double* __restrict__ Vdmu, double* __restrict__ VD, double* __restrict__ VO,
+                           double* __restrict__ rhs) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    Vec<D> v;
+    vec_zero<D>(v);
+    for (int e = vptr[s]; e < vptr[s + 1]; ++e) {
+        const double* p = fVdmu + voff[e];
+#pragma unroll
+        for (int i = 0; i < D; ++i) v.a[i] += p[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        Vdmu[(size_t)s * D + i] = v.a[i];
+        rhs[(size_t)s * D + i] = -v.a[i];
+    }
+    Mat<D> M;
+    mat_load<D>(M, KlinD + (size_t)s * D * D);
+    for (int e = dptr[s]; e < dptr[s + 1]; ++e) {
+        const double* p = fVdd + doff[e];
+        const int ld = dld[e];
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int i = 0; i < D; ++i) M(i, j) += p[i + j * ld];
+    }
+    mat_store<D>(VD + (size_t)s * D * D, M);
+    if (s < S - 1) {
+        mat_load<D>(M, KlinO + (size_t)s * D * D);
+        for (int e = optr[s]; e < optr[s + 1]; ++e) {
+            const double* p = fVdd + ooff[e];
+            const int ld = old[e];
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+#pragma unroll
+                for (int i = 0; i < D; ++i) M(i, j) += p[i + j * ld];
+        }
+        mat_store<D>(VO + (size_t)s * D * D, M);
+    }
+}
+
+// Line-search candidate (NGDGH::onestep_linesearch, ngd/NGD-GH-impl.h:129-148):
+//   mu' = mu + a dmu,  Lambda' = Lambda + a (Vddmu - Lambda)
+__global__ void k_candidate(size_t nmu, size_t nD, size_t nO, double alpha, const double* __restrict__ mu,
+                            const double* __restrict__ dmu, const double* __restrict__ LD,
+                            const double* __restrict__ LO, const double* __restrict__ VD,
+                            const double* __restrict__ VO, double* __restrict__ mu_c, double* __restrict__ LD_c,
+                            double* __restrict__ LO_c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nmu) mu_c[i] = mu[i] + alpha * dmu[i];
+    if (i < nD) LD_c[i] = LD[i] + alpha * (VD[i] - LD[i]);
+    if (i < nO) LO_c[i] = LO[i] + alpha * (VO[i] - LO[i]);
+}
+
+// dprecision = Vddmu - Lambda (ngd/NGD-GH-impl.h:57), only materialised for gvib200_gradients()
+__global__ void k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+// Deterministic single-block sum: out[0] = sum(v[0..n)) (+ half * extra[0] if extra != null)
+__global__ void k_sum(size_t n, const double* __restrict__ v, const double* __restrict__ extra, double half,
+                      double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0] + (extra ? half * extra[0] : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: block-tridiagonal engine -- thin thread-per-segment wrappers over bt_chain.h
+// ------------------------------------------------------------------------------------------
+template <int D, bool RHS>
+__global__ void k_bt_forward(const BtLevel<D> lv) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < lv.K) bt_forward_segment<D, RHS>(lv, k);
+}
+template <int D, bool RHS>
+__global__ void k_bt_top(const BtLevel<D> lv, double* x, double* cD, double* cO) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) bt_serial_top<D, RHS>(lv, x, cD, cO);
+}
+template <int D>
+__global__ void k_bt_backsolve(const BtLevel<D> lv, const double* xr, double* x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < lv.K) bt_backsolve_segment<D>(lv, k, xr, x);
+}
+template <int D>
+__global__ void k_bt_selinv(const BtLevel<D> lv, const double* cDr, const double* cOr, double* cD, double* cO) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < lv.K) bt_selinv_segment<D>(lv, k, cDr, cOr, cD, cO);
+}
+
+// cell records for CostPlanarHinge from the column-major field
+__global__ void k_build_sdf_records(int rows, int cols, const double* __restrict__ data, double4* __restrict__ rec) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int r = idx % rows, c = idx / rows;
+    const int hr = min(r + 1, rows - 1), hc = min(c + 1, cols - 1);
+    double4 v;
+    v.x = data[r + (size_t)c * rows];
+    v.y = data[hr + (size_t)c * rows];
+    v.z = data[r + (size_t)hc * rows];
+    v.w = data[hr + (size_t)hc * rows];
+    rec[idx] = v;
+}
+
+// FP64 FMA micro-benchmark: the FP64 roofline denominator (not in MEASURED_PEAKS.json)
+__global__ void k_fp64_peak(int iters, double* out) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
+}  // namespace gvib200

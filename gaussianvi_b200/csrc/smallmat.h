@@ -1,0 +1,306 @@
+// Fixed-size dense helpers for the d x d blocks of the chain (d = state dim) and the
+// dim x dim factor marginals.  Column-major (Eigen's default), everything unrolled so the
+// matrices live in registers.  __host__ __device__ so the host test harness
+// (tests/cpp/bt_host_emu.cpp) exercises exactly the arithmetic the kernels run.
+#pragma once
+
+#ifdef __CUDACC__
+#define GVI_HD __host__ __device__ __forceinline__
+#else
+#define GVI_HD inline
+#endif
+
+#include <math.h>
+
+namespace gvib200 {
+
+template <int N>
+struct Mat {
+    double a[N * N];
+    GVI_HD double& operator()(int i, int j) { return a[i + j * N]; }
+    GVI_HD double operator()(int i, int j) const { return a[i + j * N]; }
+};
+
+template <int N>
+struct Vec {
+    double a[N];
+    GVI_HD double& operator()(int i) { return a[i]; }
+    GVI_HD double operator()(int i) const { return a[i]; }
+};
+
+template <int N>
+GVI_HD void mat_zero(Mat<N>& A) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) A.a[i] = 0.0;
+}
+
+template <int N>
+GVI_HD void vec_zero(Vec<N>& v) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v.a[i] = 0.0;
+}
+
+template <int N>
+GVI_HD void mat_load(Mat<N>& A, const double* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) A.a[i] = p[i];
+}
+
+template <int N>
+GVI_HD void mat_store(double* __restrict__ p, const Mat<N>& A) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) p[i] = A.a[i];
+}
+
+template <int N>
+GVI_HD void vec_load(Vec<N>& v, const double* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v.a[i] = p[i];
+}
+
+template <int N>
+GVI_HD void vec_store(double* __restrict__ p, const Vec<N>& v) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = v.a[i];
+}
+
+// C = A * B
+template <int N>
+GVI_HD void mm(Mat<N>& C, const Mat<N>& A, const Mat<N>& B) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s = fma(A(i, k), B(k, j), s);
+            C(i, j) = s;
+        }
+}
+
+// C = A^T * B
+template <int N>
+GVI_HD void mtm(Mat<N>& C, const Mat<N>& A, const Mat<N>& B) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s = fma(A(k, i), B(k, j), s);
+            C(i, j) = s;
+        }
+}
+
+// C = A * B^T
+template <int N>
+GVI_HD void mmt(Mat<N>& C, const Mat<N>& A, const Mat<N>& B) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) s = fma(A(i, k), B(j, k), s);
+            C(i, j) = s;
+        }
+}
+
+// y = A x
+template <int N>
+GVI_HD void mv(Vec<N>& y, const Mat<N>& A, const Vec<N>& x) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) s = fma(A(i, k), x(k), s);
+        y(i) = s;
+    }
+}
+
+// y = A^T x
+template <int N>
+GVI_HD void mtv(Vec<N>& y, const Mat<N>& A, const Vec<N>& x) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) s = fma(A(k, i), x(k), s);
+        y(i) = s;
+    }
+}
+
+template <int N>
+GVI_HD void mat_transpose(Mat<N>& B, const Mat<N>& A) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) B(i, j) = A(j, i);
+}
+
+template <int N>
+GVI_HD void symmetrize(Mat<N>& A) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double s = 0.5 * (A(i, j) + A(j, i));
+            A(i, j) = s;
+            A(j, i) = s;
+        }
+}
+
+// Inverse of an SPD matrix through its Cholesky factor: A = L L^T, Ainv = L^-T L^-1.
+// Returns log det(A) in *logdet; returns false (and leaves Ainv unspecified, possibly NaN) when a
+// pivot is not strictly positive -- the caller raises GVIB200_ENOTSPD.  Only the lower triangle of
+// A is read.
+template <int N>
+GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, double* logdet) {
+    Mat<N> L;
+    bool ok = true;
+    double ld = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = A(j, j);
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L(j, k), L(j, k), s);
+        ok = ok && (s > 0.0);
+        ld += log(s);
+        const double r = 1.0 / sqrt(s);
+        L(j, j) = s * r;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double t = A(i, j);
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L(i, k), L(j, k), t);
+            L(i, j) = t * r;
+        }
+    }
+    // M = L^-1 (lower triangular)
+    Mat<N> M;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        M(j, j) = 1.0 / L(j, j);
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k) t = fma(-L(i, k), M(k, j), t);
+            M(i, j) = t / L(i, i);
+        }
+    }
+    // Ainv = M^T M (symmetric)
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j; i < N; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = i; k < N; ++k) t = fma(M(k, i), M(k, j), t);
+            Ainv(i, j) = t;
+            Ainv(j, i) = t;
+        }
+    *logdet = ld;
+    return ok;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (classical threshold variant).
+// On return A's diagonal holds the eigenvalues (in lam) and V the orthonormal eigenvectors in its
+// columns.  Used for the symmetric PSD square root S = V sqrt(lam) V^T that the reference takes with
+// SelfAdjointEigenSolver::operatorSqrt() (quadrature/SparseGaussHermite.h:231-243) and for
+// P_k = Sigma_k^-1 (gvibase/GVIFactorizedBase.h:111-114).
+template <int N>
+GVI_HD void jacobi_eig(Mat<N>& A, Mat<N>& V, Vec<N>& lam) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) V(i, j) = (i == j) ? 1.0 : 0.0;
+    if (N == 1) {
+        lam(0) = A(0, 0);
+        return;
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            diag += fabs(A(j, j));
+#pragma unroll
+            for (int i = 0; i < j; ++i) off += fabs(A(i, j));
+        }
+        if (off <= 1e-300 || off <= 1e-22 * diag) break;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A(p, q);
+                const double app = A(p, p), aqq = A(q, q);
+                // skip when the rotation would not change app/aqq at all
+                if (fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq)) || apq == 0.0) {
+                    A(p, q) = 0.0;
+                    A(q, p) = 0.0;
+                    continue;
+                }
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0);
+                const double s = t * c;
+                const double tau = s / (1.0 + c);
+                A(p, p) = app - t * apq;
+                A(q, q) = aqq + t * apq;
+                A(p, q) = 0.0;
+                A(q, p) = 0.0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    if (r != p && r != q) {
+                        const double arp = A(r, p), arq = A(r, q);
+                        const double nrp = arp - s * (arq + tau * arp);
+                        const double nrq = arq + s * (arp - tau * arq);
+                        A(r, p) = nrp;
+                        A(p, r) = nrp;
+                        A(r, q) = nrq;
+                        A(q, r) = nrq;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const double vrp = V(r, p), vrq = V(r, q);
+                    V(r, p) = vrp - s * (vrq + tau * vrp);
+                    V(r, q) = vrq + s * (vrp - tau * vrq);
+                }
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) lam(j) = A(j, j);
+}
+
+// S = V diag(f(lam)) V^T for f = sqrt and f = 1/sqrt: the PSD square root of Sigma and its inverse.
+template <int N>
+GVI_HD void sqrt_and_invsqrt(Mat<N>& S, Mat<N>& R, const Mat<N>& Sigma) {
+    Mat<N> A = Sigma, V;
+    Vec<N> lam;
+    jacobi_eig<N>(A, V, lam);
+    Vec<N> sq, isq;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        sq(k) = sqrt(lam(k));
+        isq(k) = 1.0 / sq(k);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j; i < N; ++i) {
+            double s = 0.0, r = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double vv = V(i, k) * V(j, k);
+                s = fma(vv, sq(k), s);
+                r = fma(vv, isq(k), r);
+            }
+            S(i, j) = s;
+            S(j, i) = s;
+            R(i, j) = r;
+            R(j, i) = r;
+        }
+}
+
+}  // namespace gvib200

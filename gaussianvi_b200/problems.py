@@ -1,0 +1,289 @@
+"""Synthetic trajectory problems of the shapes BASELINE.json names and the glue that
+turns a neutral ProblemSpec into a device problem.  Host-side set-up only (runs once per problem): the
+prior models follow gp/fixed_prior.h, gp/minimum_acc_prior.h and gp/LTV_prior.h of the reference; the
+numbers produced here are fed unchanged to both the GPU path and (in tests/bench) the CPU oracle.
+NumPy only -- this module must not import anything under oracle/."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class GhGroupSpec:
+    kind: int
+    dim: int
+    deg: int
+    start: np.ndarray                 # [n] int32
+    params: object                    # ctypes struct or float64 array [n, rec]
+    T: float = 1.0
+    T_high: float = 10.0
+
+
+@dataclass
+class LinGroupSpec:
+    start: np.ndarray                 # [n]
+    Lambda: np.ndarray                # [n, m, dim]
+    Psi: np.ndarray                   # [n, m, kdim]
+    mu_t: np.ndarray                  # [n, kdim]
+    Kinv: np.ndarray                  # [n, m, m]
+    C: np.ndarray                     # [n]
+    T: float = 1.0
+    T_high: float = 10.0
+
+
+@dataclass
+class ProblemSpec:
+    S: int
+    d: int
+    groups: List[object] = field(default_factory=list)   # GhGroupSpec | LinGroupSpec, id order
+    sdf: Optional[Tuple[np.ndarray, Tuple[float, float], float]] = None  # (data [rows, cols], origin, cell)
+    mu0: Optional[np.ndarray] = None
+    prec0_D: Optional[np.ndarray] = None   # [S, d, d]
+    prec0_O: Optional[np.ndarray] = None   # [S-1, d, d]
+    meta: Dict[str, object] = field(default_factory=dict)
+
+    @property
+    def n_gh(self) -> int:
+        return sum(len(g.start) for g in self.groups if isinstance(g, GhGroupSpec))
+
+    @property
+    def n_factors(self) -> int:
+        return sum(len(g.start) for g in self.groups)
+
+
+def build_device_problem(ctx: "capi.Context", spec: ProblemSpec, set_state: bool = True) -> "capi.Problem":
+    p = capi.Problem(ctx, spec.S, spec.d)
+    if spec.sdf is not None:
+        data, origin, cell = spec.sdf
+        p.set_planar_sdf(data, origin, cell)
+    for g in spec.groups:
+        if isinstance(g, GhGroupSpec):
+            p.add_gh_factors(g.kind, g.dim, g.deg, g.start, g.params, g.T, g.T_high)
+        else:
+            p.add_linear_factors(g.start, g.Lambda, g.Psi, g.mu_t, g.Kinv, g.C, g.T, g.T_high)
+    p.finalize()
+    if set_state and spec.mu0 is not None:
+        p.set_state(spec.mu0, spec.prec0_D, spec.prec0_O)
+    return p
+
+
+# ----------------------------------------------------------------------------------------------
+# batched matrix exponential (Taylor + scaling and squaring) for the LTV prior set-up
+# ----------------------------------------------------------------------------------------------
+def expm_batch(X: np.ndarray) -> np.ndarray:
+    """exp of a batch of small matrices [..., n, n]."""
+    X = np.asarray(X, dtype=np.float64)
+    nrm = np.max(np.sum(np.abs(X), axis=-1), axis=-1)
+    s = int(max(0, np.ceil(np.log2(max(float(nrm.max()), 1e-300) / 0.25))))
+    Y = X / (2.0 ** s)
+    n = X.shape[-1]
+    E = np.broadcast_to(np.eye(n), X.shape).copy()
+    term = E.copy()
+    for k in range(1, 19):
+        term = term @ Y / k
+        E = E + term
+    for _ in range(s):
+        E = E @ E
+    return E
+
+
+def ltv_transition_batch(A: np.ndarray, B: np.ndarray, delta_t: float):
+    """Phi(dt), Q(dt) of Phi' = A Phi, Q' = A Q + Q A^T + B B^T with A [n, 4, ds, ds], B [n, 4, ds, nb]
+    piece-wise constant on the four quarter intervals (gp/LTV_prior.h:123-197; exact per-piece integration by
+    Van Loan's block exponential instead of GSL rkf45 at tol 1e-12)."""
+    n, _, ds, _ = A.shape
+    h = delta_t / 4.0
+    Phi = np.broadcast_to(np.eye(ds), (n, ds, ds)).copy()
+    Q = np.zeros((n, ds, ds))
+    for k in range(4):
+        M = np.zeros((n, 2 * ds, 2 * ds))
+        M[:, :ds, :ds] = -A[:, k]
+        M[:, :ds, ds:] = B[:, k] @ np.transpose(B[:, k], (0, 2, 1))
+        M[:, ds:, ds:] = np.transpose(A[:, k], (0, 2, 1))
+        E = expm_batch(M * h)
+        Phik = np.transpose(E[:, ds:, ds:], (0, 2, 1))
+        Qk = Phik @ E[:, :ds, ds:]
+        Qk = 0.5 * (Qk + np.transpose(Qk, (0, 2, 1)))
+        Q = Phik @ Q @ np.transpose(Phik, (0, 2, 1)) + Qk
+        Phi = Phik @ Phi
+    return Phi, 0.5 * (Q + np.transpose(Q, (0, 2, 1)))
+
+
+# ----------------------------------------------------------------------------------------------
+# ingredients
+# ----------------------------------------------------------------------------------------------
+def disc_sdf(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
+    """Analytic signed distance to `n_discs` discs on a rows x cols grid."""
+    rng = np.random.default_rng(seed)
+    cx = rng.uniform(origin[0], origin[0] + (cols - 1) * cell, n_discs)
+    cy = rng.uniform(origin[1], origin[1] + (rows - 1) * cell, n_discs)
+    rad = rng.uniform(1.0, 3.0, n_discs)
+    xs = origin[0] + cell * np.arange(cols)
+    ys = origin[1] + cell * np.arange(rows)
+    X, Y = np.meshgrid(xs, ys)  # [rows, cols]
+    sd = np.full((rows, cols), np.inf)
+    for k in range(n_discs):
+        sd = np.minimum(sd, np.hypot(X - cx[k], Y - cy[k]) - rad[k])
+    return sd, (float(origin[0]), float(origin[1])), float(cell)
+
+
+def lissajous_nominal(S: int, delta_t: float) -> np.ndarray:
+    """Nominal 2-D point-robot trajectory [S, 4] = (x, y, vx, vy): constant phase step per state, so every
+    problem size sees the same obstacle density."""
+    i = np.arange(S, dtype=np.float64)
+    x = 15.0 * np.sin(14.0 * np.pi * i / 1002.0)
+    y = 5.0 + 9.0 * np.sin(22.0 * np.pi * i / 1002.0)
+    vx = np.gradient(x, delta_t) if S > 1 else np.zeros(S)
+    vy = np.gradient(y, delta_t) if S > 1 else np.zeros(S)
+    return np.stack([x, y, vx, vy], axis=1)
+
+
+def fixed_prior_group(states, mus, K, d, T=1.0, T_high=10.0) -> LinGroupSpec:
+    """FixedPriorGP(K, mu): Lambda = Psi = I, C = 1 (gp/fixed_prior.h:19-50)."""
+    n = len(states)
+    Kinv = np.linalg.inv(K)
+    return LinGroupSpec(start=np.asarray(states, np.int32), Lambda=np.tile(np.eye(d), (n, 1, 1)),
+                        Psi=np.tile(np.eye(d), (n, 1, 1)), mu_t=np.asarray(mus, float).reshape(n, d),
+                        Kinv=np.tile(Kinv, (n, 1, 1)), C=np.ones(n), T=T, T_high=T_high)
+
+
+def minacc_group(S: int, Qc: np.ndarray, delta_t: float, T=1.0, T_high=10.0) -> LinGroupSpec:
+    """MinimumAccGP(Qc, i, dt, mu0) for i = 0..S-2 (gp/minimum_acc_prior.h:39-80,110-116)."""
+    Qc = np.atleast_2d(np.asarray(Qc, float))
+    dim = Qc.shape[0]
+    ds = 2 * dim
+    I = np.eye(dim)
+    Phi = np.block([[I, delta_t * I], [np.zeros((dim, dim)), I]])
+    iq = np.linalg.inv(Qc)
+    invQ = np.block([[12 * iq / delta_t ** 3, -6 * iq / delta_t ** 2], [-6 * iq / delta_t ** 2, 4 * iq / delta_t]])
+    Lam = np.hstack([-Phi, np.eye(ds)])
+    n = S - 1
+    return LinGroupSpec(start=np.arange(n, dtype=np.int32), Lambda=np.tile(Lam, (n, 1, 1)),
+                        Psi=np.zeros((n, ds, 2 * ds)), mu_t=np.zeros((n, 2 * ds)), Kinv=np.tile(invQ, (n, 1, 1)),
+                        C=np.full(n, 0.5), T=T, T_high=T_high)
+
+
+def ltv_group(S: int, delta_t: float, nominal: np.ndarray, seed=3, T=1.0, T_high=10.0):
+    """LTV_GP prior for i = 0..S-2 with the damped-oscillator dynamics of SURVEY 8(d) cfg3:
+    A(t) = [[0, I], [-w(t)^2 I, -c(t) I]], B = [0; I], w, c ~ U(1, 2) per quarter interval.
+    target_mean = -nominal (sign quirk of gp/LTV_prior.h:87-94: the prior is centred on -target_mean)."""
+    n = S - 1
+    dim = 2
+    ds = 4
+    rng = np.random.default_rng(seed)
+    nq = 4 * n + 1
+    w = rng.uniform(1.0, 2.0, nq)
+    c = rng.uniform(1.0, 2.0, nq)
+    hA = np.zeros((nq, ds, ds))
+    hA[:, :dim, dim:] = np.eye(dim)
+    hA[:, dim:, :dim] = -(w ** 2)[:, None, None] * np.eye(dim)
+    hA[:, dim:, dim:] = -c[:, None, None] * np.eye(dim)
+    hB = np.zeros((nq, ds, dim))
+    hB[:, dim:, :] = np.eye(dim)
+    idx = 4 * np.arange(n)[:, None] + np.arange(4)[None, :]
+    Phi, Q = ltv_transition_batch(hA[idx], hB[idx], delta_t)
+    Kinv = np.linalg.inv(Q)
+    Kinv = 0.5 * (Kinv + np.transpose(Kinv, (0, 2, 1)))
+    Lam = np.concatenate([-Phi, np.broadcast_to(np.eye(ds), (n, ds, ds))], axis=2)
+    Psi = -Lam
+    target = -nominal
+    mu_t = np.concatenate([target[:-1], target[1:]], axis=1)
+    g = LinGroupSpec(start=np.arange(n, dtype=np.int32), Lambda=Lam, Psi=Psi, mu_t=mu_t, Kinv=Kinv,
+                     C=np.full(n, 0.5), T=T, T_high=T_high)
+    return g, Phi, Q, (hA, hB)
+
+
+# ----------------------------------------------------------------------------------------------
+# the configurations of BASELINE.json
+# ----------------------------------------------------------------------------------------------
+def make_cfg1() -> ProblemSpec:
+    """src/1d_example.cpp: one 1-D nonlinear factor, GH degree 10, mu0 = 20, precision0 = 1/9."""
+    prm = capi.Stereo1DParams(20.0, 400.0, 0.1, 0.09, 9.0, -0.8)
+    spec = ProblemSpec(S=1, d=1)
+    spec.groups.append(GhGroupSpec(capi.COST_STEREO_1D, 1, 10, np.zeros(1, np.int32), prm, 1.0, 10.0))
+    spec.mu0 = np.array([20.0])
+    spec.prec0_D = np.array([[[1.0 / 9.0]]])
+    spec.prec0_O = np.zeros((0, 1, 1))
+    spec.meta = dict(name="cfg1", step_size_base=0.75, niters=10, niters_lowtemp=10)
+    return spec
+
+
+def make_cfg2(S: int = 1000, delta_t: float = 0.1, anchors_every: int = 10, prec0: float = 10.0) -> ProblemSpec:
+    """All-linear 2-D point robot (d = 4): fixed priors at both ends, minimum-acceleration GP prior, weak anchor
+    priors every `anchors_every` states (keeps kappa(Vddmu) ~ 3e5)."""
+    d = 4
+    start = np.array([-15.0, -5.0, 0.0, 0.0])
+    goal = np.array([15.0, 14.0, 0.0, 0.0])
+    tt = np.linspace(0.0, 1.0, S)[:, None]
+    vel = (goal[:2] - start[:2]) / (max(S - 1, 1) * delta_t)
+    mu0 = start[None, :] * (1 - tt) + goal[None, :] * tt
+    mu0[:, 2:] = vel
+    spec = ProblemSpec(S=S, d=d)
+    spec.groups.append(fixed_prior_group([0, S - 1], np.stack([start, goal]), 1e-4 * np.eye(d), d))
+    spec.groups.append(minacc_group(S, 0.8 * np.eye(2), delta_t))
+    if anchors_every > 0:
+        st = np.arange(anchors_every, S - 1, anchors_every)
+        if len(st):
+            spec.groups.append(fixed_prior_group(st, mu0[st], np.eye(d), d))
+    spec.mu0 = mu0.reshape(-1)
+    spec.prec0_D = np.tile(prec0 * np.eye(d), (S, 1, 1))
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(name="cfg2", step_size_base=0.55, niters=10, niters_lowtemp=10)
+    return spec
+
+
+def make_cfg3(N: int = 100_000, delta_t: float = 0.2, deg: int = 6, sigma: float = 0.1, prec0: float = 100.0,
+              seed: int = 3) -> ProblemSpec:
+    """Headline shape: S = N + 2 states, N single-state planar hinge-SDF factors (d = 4, sparse GH degree `deg`)
+    at states 1..S-2, N + 1 LTV GP factors, two fixed priors."""
+    d = 4
+    S = N + 2
+    nominal = lissajous_nominal(S, delta_t)
+    spec = ProblemSpec(S=S, d=d)
+    spec.sdf = disc_sdf()
+    spec.groups.append(fixed_prior_group([0, S - 1], np.stack([nominal[0], nominal[-1]]), 1e-4 * np.eye(d), d))
+    g, _, _, _ = ltv_group(S, delta_t, nominal, seed=seed)
+    spec.groups.append(g)
+    spec.groups.append(GhGroupSpec(capi.COST_PLANAR_HINGE, d, deg, np.arange(1, S - 1, dtype=np.int32),
+                                   capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
+    spec.mu0 = nominal.reshape(-1).copy()
+    spec.prec0_D = np.tile(prec0 * np.eye(d), (S, 1, 1))
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(name="cfg3", step_size_base=0.55, niters=10, niters_lowtemp=10, n_nodes=None)
+    return spec
+
+
+def make_factor_batch(N: int = 100_000, deg: int = 6, sigma: float = 0.1, seed: int = 11) -> ProblemSpec:
+    """Factor-batch micro-input for the 1e-10 moment parity: N independent single-state hinge
+    factors, mu_k ~ U(field), Sigma_k = R diag(lam) R^T, lam log-uniform in [1e-3, 1], R Haar."""
+    d = 4
+    rng = np.random.default_rng(seed)
+    sdf = disc_sdf()
+    data, origin, cell = sdf
+    rows, cols = data.shape
+    mu = np.zeros((N, d))
+    mu[:, 0] = rng.uniform(origin[0], origin[0] + (cols - 1) * cell, N)
+    mu[:, 1] = rng.uniform(origin[1], origin[1] + (rows - 1) * cell, N)
+    mu[:, 2:] = rng.standard_normal((N, 2))
+    lam = np.exp(rng.uniform(np.log(1e-3), np.log(1.0), (N, d)))
+    G = rng.standard_normal((N, d, d))
+    Qm, Rm = np.linalg.qr(G)
+    Qm = Qm * np.sign(np.diagonal(Rm, axis1=1, axis2=2))[:, None, :]
+    Sigma = (Qm * lam[:, None, :]) @ np.transpose(Qm, (0, 2, 1))
+    Sigma = 0.5 * (Sigma + np.transpose(Sigma, (0, 2, 1)))
+    prec = np.linalg.inv(Sigma)
+    prec = 0.5 * (prec + np.transpose(prec, (0, 2, 1)))
+    spec = ProblemSpec(S=N, d=d)
+    spec.sdf = sdf
+    spec.groups.append(GhGroupSpec(capi.COST_PLANAR_HINGE, d, deg, np.arange(N, dtype=np.int32),
+                                   capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
+    spec.mu0 = mu.reshape(-1)
+    spec.prec0_D = prec
+    spec.prec0_O = np.zeros((N - 1, d, d))
+    spec.meta = dict(name="factor_batch", Sigma=Sigma)
+    return spec

@@ -1,0 +1,197 @@
+/* gvib200 -- C-ABI of the B200-native factorized NGD-GVI hot path (libgvib200.so).
+ *
+ * The reference (hzyu17/GaussianVI) has no FFI boundary: callers are C++ translation units
+ * that include its header-only templates.  This header is therefore the
+ * boundary a maintainer would bind to; each entry point names the reference interface it
+ * replaces (paths relative to the reference root).  The C++ facade in
+ * gaussianvi_b200/cpp/gvi/ re-exposes the reference's class names on top of these calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative GVIB200_E* code; the message of the last
+ *     failure on the calling thread is gvib200_last_error().
+ *   - all array arguments are caller-owned HOST pointers; doubles, column-major for matrices
+ *     (Eigen's default), int32 for indices.  Copies are synchronous.  The library owns all device
+ *     memory behind the opaque handles.
+ *   - block-tridiagonal matrices (the sparsity pattern fixed at gvibase/GVI-GH.h:214-230) are
+ *     passed as  diag[S][d*d]  (block (i,i)) and  off[S-1][d*d]  (block (i,i+1), column-major).
+ *   - one ctx per GPU, one CUDA stream per problem; handles are not thread-safe, distinct
+ *     handles may be driven from distinct host threads.
+ *   - there is no CPU fallback: without a usable CUDA device ctx_create fails with GVIB200_ECUDA.
+ */
+#ifndef GVIB200_H
+#define GVIB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVIB200_OK 0
+#define GVIB200_EINVAL (-1)   /* bad argument                                         */
+#define GVIB200_ECUDA (-2)    /* CUDA runtime error / no device                        */
+#define GVIB200_ESTATE (-3)   /* call order violated (e.g. iterate before set_state)   */
+#define GVIB200_ENOTSPD (-4)  /* a block-tridiagonal matrix had a non-positive pivot   */
+#define GVIB200_ENOTABLE (-5) /* (dim, deg) quadrature table unavailable               */
+#define GVIB200_ENCCL (-6)    /* collective failure                                    */
+
+typedef struct gvib200_ctx gvib200_ctx;
+typedef struct gvib200_problem gvib200_problem;
+
+/* ---- cost functors psi(x) evaluated at sigma points ------------- */
+enum {
+    /* src/1d_example.cpp:25-35 (params: gvib200_stereo1d_params; tests/test_GH.cpp:21-34 uses y_offset=+0.05) */
+    GVIB200_COST_STEREO_1D = 1,
+    /* CudaOperation_PlanarPR::cost_obstacle_planar, helpers/CudaOperation.h:491-508 over PlanarSDF :27-128
+       (params: gvib200_hinge_params; field set with gvib200_set_planar_sdf) */
+    GVIB200_COST_PLANAR_HINGE = 2,
+    /* cost_linear_gp, gp/cost_functions.h:36-39 / gp/cost_functions_LTV.h:34-37:
+       1/2 (Phi th1 - th2)^T Qinv (Phi th1 - th2); per-factor params: Phi[ds*ds], Qinv[ds*ds] column-major */
+    GVIB200_COST_LINEAR_GP = 3,
+    /* cost_fixed_gp, gp/cost_functions.h:25-27: (x-mu)^T Kinv (x-mu); per-factor params: Kinv[dim*dim], mu[dim] */
+    GVIB200_COST_FIXED_GP = 4,
+    /* x^T (c I) x  -- the test integrand gx_1d of tests/test_gh_spgh.cpp:21-25 (params: one double c) */
+    GVIB200_COST_QUADRATIC = 5
+};
+
+typedef struct {
+    double mu_p, f, b, sig_r_sq, sig_p_sq, y_offset; /* y = f*b/mu_p + y_offset; 1d_example: -0.8 */
+} gvib200_stereo1d_params;
+
+typedef struct {
+    double sigma, epsilon, radius; /* helpers/CudaOperation.h:456 defaults 15.5, 0.5, 1 */
+} gvib200_hinge_params;
+
+/* ---- context ---------------------------------------------------------------------- */
+int gvib200_ctx_create(int device, gvib200_ctx** out);
+int gvib200_ctx_destroy(gvib200_ctx* ctx);
+const char* gvib200_last_error(void);
+/* library build identification: "gvib200 <version> sm_100a" */
+const char* gvib200_version(void);
+
+/* Multi-GPU (one process per GPU): attach an already-initialised NCCL communicator
+   (ncclComm_t passed as void*) plus this rank's index / world size.  The chain of every problem
+   created afterwards on this ctx is partitioned along the time axis.           */
+int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world);
+
+/* ---- sparse Gauss-Hermite tables (replaces the cereal map consumed at
+        quadrature/SparseGaussHermite.h:138-166 and its MATLAB generator
+        quadrature/generateSpGHWeights.h:23-84) -------------------------------------------- */
+/* number of nodes of the (dim, deg) rule, or a negative error */
+int gvib200_table_size(int dim, int deg);
+/* host-side generation into caller buffers: nodes_rowmajor[n*dim], weights[n] */
+int gvib200_table_generate(int dim, int deg, double* nodes_rowmajor, double* weights, int capacity);
+/* override the generated table of (dim, deg) with an externally loaded one (e.g. read from the
+   reference's SparseGHQuadratureWeights_cereal.bin) */
+int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, const double* nodes_rowmajor, const double* weights);
+
+/* ---- problem definition (replaces the construction of GVIGH<Factor>, gvibase/GVI-GH-GBP.h:41-64,
+        from a vector of factor optimizers) --------------------------------------------------- */
+int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_state, gvib200_problem** out);
+int gvib200_problem_destroy(gvib200_problem* prob);
+
+/* signed-distance field used by GVIB200_COST_PLANAR_HINGE: PlanarSDF(origin, cell_size, data)
+   helpers/CudaOperation.h:40-45; data column-major rows x cols */
+int gvib200_set_planar_sdf(gvib200_problem* prob, int rows, int cols, double origin_x, double origin_y,
+                           double cell_size, const double* data_colmajor);
+
+/* n nonlinear factors NGDFactorizedBaseGH<CostClass>(dimension, state_dim, gh_degree, function, cost_class,
+   num_states, start_index, temperature, high_temperature) -- ngd/NGDFactorizedBaseGH.h:37-41.
+   dim must be a multiple of dim_state (1 or 2 consecutive states).  temperature/high_temperature: n
+   values each, or NULL for the reference defaults 1.0 / 10.0.  cost_params: one struct for
+   STEREO_1D / PLANAR_HINGE / QUADRATIC, n packed per-factor records for LINEAR_GP / FIXED_GP.
+   Returns (through first_id) the global id of the first factor added; ids are consecutive and fix
+   the order of factor_costs. */
+int gvib200_add_gh_factors(gvib200_problem* prob, int cost_kind, int dim, int deg, int n, const int32_t* start_index,
+                           const double* temperature, const double* high_temperature, const void* cost_params,
+                           size_t cost_params_bytes, int* first_id);
+
+/* n closed-form linear-Gaussian factors NGDFactorizedLinear<Factor>(dimension, dim_state, function,
+   linear_factor, num_states, start_indx, temperature, high_temperature) -- ngd/NGDFactorizedLinear.h:28-47,
+   where linear_factor supplies get_Lambda() [m x dim], get_Psi() [m x kdim], get_mu() [kdim],
+   get_precision() [m x m], get_Constant() (gp/linear_factor.h:18-31).  Per-factor packed, column-major. */
+int gvib200_add_linear_factors(gvib200_problem* prob, int dim, int m, int kdim, int n, const int32_t* start_index,
+                               const double* Lambda, const double* Psi, const double* mu_t, const double* Kinv,
+                               const double* C, const double* temperature, const double* high_temperature,
+                               int* first_id);
+
+/* freeze the factor set, build the state<->factor adjacency, upload tables */
+int gvib200_problem_finalize(gvib200_problem* prob);
+
+/* ---- state (GVIGH::set_initial_values / set_mu / set_precision, gvibase/GVI-GH-GBP.h:201-233,
+        GVI-GH-GBP-impl.h:169-183: also recomputes the covariance blocks and every factor marginal) */
+int gvib200_set_state(gvib200_problem* prob, const double* mu, const double* prec_diag, const double* prec_off);
+int gvib200_get_mean(gvib200_problem* prob, double* mu);                                 /* GVIGH::mean()       */
+int gvib200_get_prec_blocks(gvib200_problem* prob, double* diag, double* off);           /* GVIGH::precision()  */
+int gvib200_get_cov_blocks(gvib200_problem* prob, double* diag, double* off);            /* GVIGH::covariance() */
+
+/* ---- per-factor quadrature moments at the current state: E_Phis / E_xMuPhis / E_xMuxMuTPhis
+        (gvibase/GVI-GH-GBP.h:348-378; SparseGaussHermite::Integrate quadrature/SparseGaussHermite.h:197-221).
+        Output order: GH factors in id order; E1 packed [dim] and E2 packed [dim*dim] per factor using each
+        factor's own dim.  Any pointer may be NULL. ------------------------------------------------------- */
+int gvib200_moments(gvib200_problem* prob, double* E0, double* E1, double* E2);
+
+/* GVIGH::cost_value(mean, Precision) and factor_cost_vector(mean, Precision), GVI-GH-GBP-impl.h:188-239.
+   NULL mu/diag/off = the current state.  fac_costs (n_factors, id order) may be NULL. */
+int gvib200_cost(gvib200_problem* prob, const double* mu, const double* prec_diag, const double* prec_off,
+                 double* cost, double* fac_costs);
+
+/* NGDGH::compute_gradients, ngd/NGD-GH-impl.h:20-63: dmu[S*d], dprecision as blocks.  The mean step is
+   solved by a direct block-tridiagonal Cholesky (the reference calls Eigen CG capped at 2n iterations). */
+int gvib200_gradients(gvib200_problem* prob, double* dmu, double* dprec_diag, double* dprec_off);
+/* joint Vdmu / Vddmu of the last gradients call (NGDGH::Vdmu()/Vddmu(), ngd/NGD-GH.h:90-92) */
+int gvib200_get_V(gvib200_problem* prob, double* Vdmu, double* Vddmu_diag, double* Vddmu_off);
+
+typedef struct {
+    double step_size_base;   /* GVIGH::_step_size_base, default 0.55 (gvibase/GVI-GH-GBP.h:94) */
+    double backtrack_ratio;  /* 0.75, hard-coded at gvibase/GVI-GH-GBP-impl.h:89                */
+    int max_backtrack;       /* _niters_backtrack, default 10                                   */
+    int niters_lowtemp;      /* _niters_lowtemp, default 10                                     */
+    int reuse_accepted_sweep;/* 0: faithful schedule (1 moment sweep + T_ls cost sweeps / iteration);
+                                1: line-search sweeps compute full moments and the accepted trial's
+                                   moments seed the next iteration (identical results, fewer sweeps) */
+} gvib200_opts;
+void gvib200_default_opts(gvib200_opts* opts);
+
+typedef struct {
+    double cost;          /* cost_iter at the start of the iteration (recorded by the reference) */
+    double new_cost;      /* cost of the accepted trial (or of the last rejected one)            */
+    double step;          /* accepted step size                                                   */
+    int n_backtrack;      /* rejected trials                                                      */
+    int accepted;         /* 1 if a trial was accepted                                            */
+    int switched_high_T;  /* 1 if the optimizer switched to the high temperature this iteration   */
+    int converged;        /* 1 if back-tracking was exhausted at high temperature                 */
+    int status;           /* 0 or GVIB200_ENOTSPD                                                 */
+    int n_moment_sweeps;  /* quadrature sweeps executed (full moments)                            */
+    int n_cost_sweeps;    /* quadrature sweeps executed (cost only)                               */
+} gvib200_iter_stats;
+
+/* the whole GVIGH::optimize loop (gvibase/GVI-GH-GBP-impl.h:33-130) with state resident in HBM:
+   runs up to n_iters iterations, fills stats[0..n_done).  fac_costs_trace (n_iters x n_factors) and
+   the per-iteration snapshots the reference's recorder keeps are optional (NULL to skip). */
+int gvib200_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats,
+                     int* n_done, double* fac_costs_trace, double* mean_trace);
+/* one iteration (same code path; iteration index is kept inside the problem for the temperature switch) */
+int gvib200_ngd_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats);
+/* reset the iteration counter / temperature phase (keeps the state) */
+int gvib200_reset_schedule(gvib200_problem* prob);
+
+/* ---- stand-alone block-tridiagonal engine (GVIGH::inverse_GBP, GVI-GH-GBP-impl.h:245-305;
+        EigenWrapper::inv_sparse helpers/EigenWrapper.h:336-381; SparseLDLT log det :234-238) -------- */
+int gvib200_selected_inverse(gvib200_ctx* ctx, int S, int d, const double* diag, const double* off, double* cov_diag,
+                             double* cov_off, double* logdet);
+int gvib200_blocktri_solve(gvib200_ctx* ctx, int S, int d, const double* diag, const double* off, const double* rhs,
+                           double* x, double* logdet);
+
+/* ---- measurement hooks (bench.py): device-resident timing of the stages with CUDA events on the
+        problem's stream.  stage: 0 = moment sweep (K2+K1), 1 = cost sweep, 2 = assemble + dmu solve,
+        3 = candidate + selected inverse + log det, 4 = one full iteration.  Returns milliseconds per repetition. */
+int gvib200_time_stage(gvib200_problem* prob, int stage, int reps, const gvib200_opts* opts, float* ms_per_rep,
+                       long long* kernel_launches);
+int gvib200_fp64_peak(gvib200_ctx* ctx, double* tflops);   /* DFMA micro-benchmark: the FP64 roofline denominator */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVIB200_H */

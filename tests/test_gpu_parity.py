@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances are BASELINE.json's: per-factor quadrature moments 1e-10 relative (tensor-wise
+max norm), final mu / Sigma after the reference's iteration count 1e-7 relative."""
+import numpy as np
+import pytest
+
+import gvi_oracle as o
+import oracle_bridge as ob
+from gaussianvi_b200 import capi, problems
+
+pytestmark = pytest.mark.gpu
+
+MOMENT_TOL = 1e-10
+FINAL_TOL = 1e-7
+GOLDEN = ob.ROOT / "tests" / "golden"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def rand_spd_chain(rng, S, d):
+    D = np.zeros((S, d, d))
+    O = np.zeros((max(S - 1, 0), d, d))
+    for i in range(S):
+        A = rng.standard_normal((d, d))
+        D[i] += 0.1 * A @ A.T + np.eye(d)
+    for i in range(S - 1):
+        B = rng.standard_normal((2 * d, 2 * d))
+        M = B @ B.T
+        D[i] += M[:d, :d]
+        D[i + 1] += M[d:, d:]
+        O[i] += M[:d, d:]
+    return D, O
+
+
+# ---------------------------------------------------------------- block-tridiagonal engine (a9, a10)
+@pytest.mark.parametrize("S,d", [(1, 4), (2, 4), (3, 1), (9, 4), (33, 2), (100, 4), (257, 3), (1000, 4), (40, 6)])
+def test_selected_inverse_matches_dense(gpu_ctx, S, d):
+    rng = np.random.default_rng(S * 10 + d)
+    D, O = rand_spd_chain(rng, S, d)
+    cD, cO, ld = gpu_ctx.selected_inverse(D, O)
+    A = o.BlockTri(D, O).dense()
+    Ai = np.linalg.inv(A)
+    eD = np.array([Ai[i * d:(i + 1) * d, i * d:(i + 1) * d] for i in range(S)])
+    assert rel(cD, eD) < 1e-12
+    if S > 1:
+        eO = np.array([Ai[i * d:(i + 1) * d, (i + 1) * d:(i + 2) * d] for i in range(S - 1)])
+        assert rel(cO, eO) < 1e-12
+    assert abs(ld - np.linalg.slogdet(A)[1]) < 1e-10 * max(1.0, abs(ld))
+
+
+def test_selected_inverse_matches_gbp_oracle_long_chain(gpu_ctx):
+    """src/GBP.cpp:133-158 property at a size the dense inverse cannot reach: GBP marginals == selected inverse."""
+    rng = np.random.default_rng(5)
+    S, d = 20000, 4
+    D, O = rand_spd_chain(rng, S, d)
+    cD, cO, ld = gpu_ctx.selected_inverse(D, O)
+    ref = o.inverse_gbp(o.BlockTri(D, O))
+    assert rel(cD, ref.D) < 1e-11
+    assert rel(cO, ref.O) < 1e-11
+    assert abs(ld - o.logdet(o.BlockTri(D, O))) < 1e-9 * abs(ld)
+
+
+@pytest.mark.parametrize("S,d", [(1, 2), (7, 4), (300, 4), (5000, 4)])
+def test_blocktri_solve(gpu_ctx, S, d):
+    rng = np.random.default_rng(S + d)
+    D, O = rand_spd_chain(rng, S, d)
+    rhs = rng.standard_normal(S * d)
+    x, ld = gpu_ctx.blocktri_solve(D, O, rhs)
+    xe = o.block_solve(o.BlockTri(D, O), rhs)
+    assert rel(x, xe) < 1e-11
+
+
+def test_not_spd_is_reported(gpu_ctx):
+    D = np.tile(np.eye(2), (5, 1, 1))
+    D[3] = -np.eye(2)
+    O = np.zeros((4, 2, 2))
+    with pytest.raises(capi.GviError) as e:
+        gpu_ctx.selected_inverse(D, O)
+    assert e.value.code == capi.E_NOTSPD
+
+
+# ---------------------------------------------------------------- quadrature known answers (a1, a2)
+def single_factor_problem(ctx, kind, dim, deg, params, mean, cov):
+    spec = problems.ProblemSpec(S=1, d=dim)
+    spec.groups.append(problems.GhGroupSpec(kind, dim, deg, np.zeros(1, np.int32), params, 1.0, 10.0))
+    spec.mu0 = np.asarray(mean, float)
+    spec.prec0_D = np.linalg.inv(np.atleast_2d(np.asarray(cov, float)))[None]
+    spec.prec0_O = np.zeros((0, dim, dim))
+    return spec, problems.build_device_problem(ctx, spec)
+
+
+def test_kat_stereo_1d_deg6(gpu_ctx):
+    """tests/test_GH.cpp:134-161: E[phi] = 1.1129, E[(x-mu) phi] = -1.2144 (1e-4), sparse deg 6, mu=20, Sigma=9."""
+    prm = capi.Stereo1DParams(20.0, 400.0, 0.1, 0.09, 9.0, 0.05)
+    spec, p = single_factor_problem(gpu_ctx, capi.COST_STEREO_1D, 1, 6, prm, [20.0], [[9.0]])
+    (E0, E1, E2), = p.moments()
+    assert abs(E0[0] - 1.1129) < 1e-4 and abs(E1[0, 0] + 1.2144) < 1e-4
+    f = ob.build_factors(spec, fast=False)[0]
+    r0, r1, r2 = o.moments(f.psi, [20.0], [[9.0]], f.Z, f.w)
+    assert rel(E0[0], r0) < MOMENT_TOL and rel(E1[0], r1) < MOMENT_TOL and rel(E2[0], r2) < MOMENT_TOL
+
+
+@pytest.mark.parametrize("dim,deg,mean,cov,c,expected,tol", [
+    (4, 3, np.zeros(4), 1e-4 * np.eye(4), 1e4, 4.0, 1e-10),                                  # test_gh_spgh.cpp:76-90
+    (3, 8, np.ones(3), np.eye(3), 1e4, 6.00e4, 1e-7),                                         # :194-220
+    (2, 10, np.ones(2), np.linalg.inv(np.array([[1, -0.74], [-0.74, 1.0]])), 1e4, 6.420866489831914e4, 1e-5),  # :92-124
+])
+def test_kat_quadratic(gpu_ctx, dim, deg, mean, cov, c, expected, tol):
+    spec, p = single_factor_problem(gpu_ctx, capi.COST_QUADRATIC, dim, deg, np.array([c]), mean, cov)
+    (E0, E1, E2), = p.moments()
+    assert abs(E0[0] - expected) < tol
+    f = ob.build_factors(spec, fast=False)[0]
+    r0, r1, r2 = o.moments(f.psi, mean, cov, f.Z, f.w)
+    # E1 vanishes by symmetry for a centred quadratic: compare against the natural scale sqrt(|Sigma|) |E0|
+    scale1 = max(np.abs(r1).max(), np.sqrt(np.abs(cov).max()) * abs(r0))
+    assert rel(E0[0], r0) < MOMENT_TOL and np.abs(E1[0] - r1).max() < MOMENT_TOL * scale1 and rel(E2[0], r2) < MOMENT_TOL
+
+
+def test_moments_hinge_factor_batch(gpu_ctx):
+    """SURVEY 8(d) factor-batch micro-input (seed 11) at a size the NumPy oracle finishes in seconds."""
+    N = 1500
+    spec = problems.make_factor_batch(N=N)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    (E0, E1, E2), = p.moments()
+    covD, _ = p.covariance()
+    g = spec.groups[0]
+    psi = ob.psi_for_group(spec, g, 0)
+    Z, w = o.table(4, 6)
+    mu = spec.mu0.reshape(N, 4)
+    worst = [0.0, 0.0, 0.0]
+    nz = 0
+    for k in range(N):
+        r0, r1, r2 = o.moments_fast(psi, mu[k], covD[k], Z, w)
+        if r0 == 0.0:  # free space: the hinge is 0 at every node -> exactly 0 on the GPU too
+            assert E0[k] == 0.0 and not E1[k].any() and not E2[k].any()
+            continue
+        nz += 1
+        worst[0] = max(worst[0], rel(E0[k], r0))
+        worst[1] = max(worst[1], rel(E1[k], r1))
+        worst[2] = max(worst[2], rel(E2[k], r2))
+    print("hinge factor batch: non-zero factors", nz, "worst rel err", worst)
+    assert nz > N // 10
+    assert max(worst) < MOMENT_TOL
+
+
+def test_linear_gp_quadrature_equals_closed_form(gpu_ctx):
+    """Closed form == quadrature for linear factors (gp/factorized_opts_linear.h:12-14 'for comparison'):
+    GH of a quadratic is exact, so a LINEAR_GP GH factor and the closed-form factor must agree to rounding."""
+    S, d, dt = 6, 4, 0.1
+    lin = problems.minacc_group(S, 0.8 * np.eye(2), dt)
+    rng = np.random.default_rng(1)
+    D, O = rand_spd_chain(rng, S, d)
+    mu = rng.standard_normal(S * d)
+    Phi = -lin.Lambda[0][:, :d]
+    rec = np.concatenate([np.tile(Phi.T.reshape(-1), (S - 1, 1)), np.tile(lin.Kinv[0].T.reshape(-1), (S - 1, 1))], axis=1)
+    anchor = problems.fixed_prior_group([0, S - 1], np.zeros((2, d)), np.eye(d), d)  # makes Vddmu SPD
+    a = problems.ProblemSpec(S=S, d=d, groups=[anchor, lin], mu0=mu, prec0_D=D, prec0_O=O)
+    b = problems.ProblemSpec(S=S, d=d, groups=[anchor, problems.GhGroupSpec(capi.COST_LINEAR_GP, 2 * d, 4, lin.start, rec)],
+                             mu0=mu, prec0_D=D, prec0_O=O)
+    pa, pb = problems.build_device_problem(gpu_ctx, a), problems.build_device_problem(gpu_ctx, b)
+    ca, fa = pa.cost()
+    cb, fb = pb.cost()
+    assert rel(fb, fa) < 1e-10
+    pa.gradients(), pb.gradients()
+    va, vb = pa.get_V(), pb.get_V()
+    for x, y in zip(va, vb):
+        assert rel(y, x) < 1e-9
+
+
+# ---------------------------------------------------------------- end-to-end traces (a3..a12)
+def test_cfg1_golden_trace(gpu_ctx):
+    """src/1d_example.cpp against the reference's committed outputs data/1d/*.csv (10 iterations)."""
+    spec = problems.make_cfg1()
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = 0.75
+    opts.niters_lowtemp = 10
+    g = lambda n: np.loadtxt(GOLDEN / "ref_1d" / f"{n}.csv", delimiter=",").reshape(-1)
+    means, covs, precs, costs, fcs = [], [], [], [], []
+    for it in range(10):
+        means.append(p.mean()[0])
+        covs.append(p.covariance()[0][0, 0, 0])
+        precs.append(p.precision()[0][0, 0, 0])
+        st = p.iterate(opts)
+        costs.append(st.cost)
+        assert st.accepted == 1 and st.n_backtrack == 0
+    assert rel(means, g("mean")) < 1e-10
+    assert rel(covs, g("cov")) < 1e-10
+    assert rel(precs, g("precision")) < 1e-10
+    assert rel(costs, g("cost")) < 1e-10
+
+
+def test_cfg1_factor_costs_and_costmap(gpu_ctx):
+    spec = problems.make_cfg1()
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = 0.75
+    stats, fc, mt = p.optimize(10, opts, want_traces=True)
+    g = np.loadtxt(GOLDEN / "ref_1d" / "factor_costs.csv", delimiter=",").reshape(-1)
+    assert rel(fc[:, 0], g) < 1e-10
+    # data/1d/costmap.csv: cost_value over mu in [18,25), precision in [0.05,1) (gvibase/GVI-GH.h:385-412)
+    cm = np.loadtxt(GOLDEN / "ref_1d" / "costmap.csv", delimiter=",")
+    nm = 40
+    for i in (0, 7, 19, 39):
+        for j in (0, 11, 26, 39):
+            c, _ = p.cost(np.array([18 + i * 7.0 / nm]), np.array([[[0.05 + j * 0.95 / nm]]]), None)
+            assert abs(c - cm[j, i]) < 1e-9 * max(1.0, abs(cm[j, i]))
+
+
+def run_pair(gpu_ctx, spec, niters, reuse=0, **okw):
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = spec.meta.get("step_size_base", 0.55)
+    opts.niters_lowtemp = spec.meta.get("niters_lowtemp", 10)
+    opts.reuse_accepted_sweep = reuse
+    stats = p.optimize(niters, opts)
+    ref = ob.build_oracle(spec, niters=niters, **okw)
+    recs = ref.optimize()
+    return p, stats, ref, recs
+
+
+def check_final(p, stats, ref, recs):
+    assert len(stats) == len(recs)
+    for s, r in zip(stats, recs):
+        assert bool(s.accepted) == r.accepted and s.n_backtrack == r.n_backtrack
+        assert abs(s.cost - r.cost) < 1e-8 * max(1.0, abs(r.cost))
+    cD, cO = p.covariance()
+    e_mu = rel(p.mean(), ref.mean())
+    e_cov = rel(np.concatenate([cD.reshape(-1), cO.reshape(-1)]),
+                np.concatenate([ref.cov.D.reshape(-1), ref.cov.O.reshape(-1)]))
+    return e_mu, e_cov
+
+
+@pytest.mark.parametrize("reuse", [0, 1])
+def test_cfg2_small_all_linear(gpu_ctx, reuse):
+    spec = problems.make_cfg2(S=60)
+    p, stats, ref, recs = run_pair(gpu_ctx, spec, 10, reuse)
+    e_mu, e_cov = check_final(p, stats, ref, recs)
+    print("cfg2 S=60: rel err mu", e_mu, "cov", e_cov, "kappa(Vddmu)", np.linalg.cond(ref.Vddmu.dense()))
+    assert e_mu < FINAL_TOL and e_cov < FINAL_TOL
+
+
+@pytest.mark.parametrize("reuse", [0, 1])
+def test_cfg3_small_hinge_ltv(gpu_ctx, reuse):
+    spec = problems.make_cfg3(N=80)
+    p, stats, ref, recs = run_pair(gpu_ctx, spec, 10, reuse)
+    e_mu, e_cov = check_final(p, stats, ref, recs)
+    print("cfg3 N=80: rel err mu", e_mu, "cov", e_cov, "kappa(Vddmu)", np.linalg.cond(ref.Vddmu.dense()))
+    assert e_mu < FINAL_TOL and e_cov < FINAL_TOL
+
+
+def test_cfg3_gradients_match_oracle(gpu_ctx):
+    spec = problems.make_cfg3(N=200)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    ref = ob.build_oracle(spec)
+    dmu, dD, dO = p.gradients()
+    Vd, VD, VO = p.get_V()
+    rdmu, rdp = ref.compute_gradients()
+    assert rel(Vd, ref.Vdmu) < 1e-9
+    assert rel(VD, ref.Vddmu.D) < 1e-9 and rel(VO, ref.Vddmu.O) < 1e-9
+    assert rel(dmu, rdmu) < 1e-8
+    assert rel(dD, rdp.D) < 1e-9
+    c, fc = p.cost()
+    assert rel(fc, ref.factor_cost_vector()) < 1e-10
+    assert abs(c - ref.cost_value()) < 1e-9 * abs(c)
