@@ -95,7 +95,7 @@ GVI_HD void bt_forward_segment(const BtLevel<D>& lv, int k) {
     Vec<D> glacc, gcur, yv, tv;
     mat_zero<D>(CLacc);
     vec_zero<D>(glacc);
-    double ld = 0.0;
+    LogDetAcc ld;
     bool ok = true;
     // reduced node k keeps the (summed) diagonal / rhs of separator a
     bt_load_diag<D>(T, lv, a);
@@ -127,9 +127,7 @@ GVI_HD void bt_forward_segment(const BtLevel<D>& lv, int k) {
     bt_load_diag<D>(Dt, lv, a + 1);
     if (RHS) bt_load_rhs<D>(gcur, lv, a + 1);
     for (int j = a + 1; j < b; ++j) {
-        double l;
-        ok = spd_inverse<D>(Dinv, Dt, &l) && ok;
-        ld += l;
+        ok = spd_inverse<D>(Dinv, Dt, ld) && ok;
         mat_load<D>(Oj, lv.O + (size_t)j * DD);  // block (j, j+1)
         mm<D>(G, Dinv, Oj);
         mmt<D>(H, Dinv, W);  // Dinv * W^T
@@ -180,7 +178,7 @@ GVI_HD void bt_forward_segment(const BtLevel<D>& lv, int k) {
     mat_store<D>(lv.rCL + (size_t)k * DD, CLacc);
     mat_store<D>(lv.rO + (size_t)k * DD, W);  // block (a, b) of the reduced system
     if (RHS) vec_store<D>(lv.rgl + (size_t)k * D, glacc);
-    lv.ld[k] = ld;
+    lv.ld[k] = ld.value();
     if (!ok) *lv.notspd = 1;
 }
 
@@ -261,14 +259,12 @@ GVI_HD void bt_serial_top(const BtLevel<D>& lv, double* __restrict__ x, double* 
     const int n = lv.n;
     Mat<D> Dt, Dinv, Oj, G, T, Snn, Sjn;
     Vec<D> gcur, yv, tv, xn;
-    double ld = 0.0;
+    LogDetAcc ld;
     bool ok = true;
     bt_load_diag<D>(Dt, lv, 0);
     if (RHS) bt_load_rhs<D>(gcur, lv, 0);
     for (int j = 0; j < n; ++j) {
-        double l;
-        ok = spd_inverse<D>(Dinv, Dt, &l) && ok;
-        ld += l;
+        ok = spd_inverse<D>(Dinv, Dt, ld) && ok;
         mat_store<D>(lv.Dinv + (size_t)j * DD, Dinv);
         if (RHS) {
             mv<D>(yv, Dinv, gcur);
@@ -291,7 +287,7 @@ GVI_HD void bt_serial_top(const BtLevel<D>& lv, double* __restrict__ x, double* 
             }
         }
     }
-    lv.ld[0] = ld;
+    lv.ld[0] = ld.value();
     if (!ok) *lv.notspd = 1;
     if (RHS && x != nullptr) {
         vec_load<D>(xn, lv.y + (size_t)(n - 1) * D);

@@ -1,16 +1,36 @@
 // Device cost functors psi(x): the reference's factor cost functions as
 // plain structs evaluated inside the fused sigma-point kernel.  Each functor provides
 //   XD                 number of leading coordinates of x it reads (rows of sqrt(Sigma) needed)
-//   eval(x, f)         psi up to the constant factor scale()
+//   Pending            state carried between the two halves of an evaluation
+//   begin<FAST>(x, f)  first half: everything up to (and including) issuing the long-latency loads
+//   finish(pending)    second half: psi up to the constant factor scale()
+//   fast_ok(lo, hi)    per-factor, warp-uniform: may the FAST variant be used for sigma points whose
+//                      leading coordinates lie in the box [lo, hi]?  (FAST must give identical results)
 //   scale()            constant folded into the epilogue (e.g. the hinge weight sigma)
+// The split lets the kernel keep the gather of node i+32 in flight while it finishes node i.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace gvib200 {
 
+// functors without long-latency loads evaluate everything in begin()
+#define GVIB200_SIMPLE_FUNCTOR_INTERFACE()                                                        \
+    struct Pending {                                                                              \
+        double psi;                                                                               \
+    };                                                                                            \
+    template <bool FAST>                                                                          \
+    __device__ __forceinline__ Pending begin(const double* x, int f) const {                     \
+        Pending p;                                                                                \
+        p.psi = eval(x, f);                                                                       \
+        return p;                                                                                 \
+    }                                                                                             \
+    __device__ __forceinline__ double finish(const Pending& p) const { return p.psi; }            \
+    __device__ __forceinline__ bool fast_ok(const double*, const double*) const { return false; }
+
 // src/1d_example.cpp:25-35 (and tests/test_GH.cpp:21-34 with y_offset = +0.05)
 struct CostStereo1D {
     static constexpr int XD = 1;
+    GVIB200_SIMPLE_FUNCTOR_INTERFACE()
     double mu_p, fb, sig_p_sq, sig_r_sq, y;  // fb = f*b, y = f*b/mu_p + y_offset
     __device__ __forceinline__ double eval(const double* x, int) const {
         const double a = x[0] - mu_p;
@@ -32,28 +52,50 @@ struct CostPlanarHinge {
     const double4* __restrict__ rec;  // [cols][rows]
     int rows, cols;
     double ox, oy, xmax, ymax, inv_cell, thr, sigma;
-    __device__ __forceinline__ double eval(const double* x, int) const {
-        const double xin = fmin(fmax(x[0], ox), xmax);
-        const double yin = fmin(fmax(x[1], oy), ymax);
-        const double col = (xin - ox) * inv_cell;
-        const double row = (yin - oy) * inv_cell;
-        // floor() through the 2^52 trick (coordinates are in [0, 2^31)); at exact integers either
-        // neighbouring cell gives the same bilinear value, so round-half-even is harmless.
+    double cx0, cy0;  // -ox*inv_cell, -oy*inv_cell
+    struct Pending {
+        double4 v;
+        double fc, fr;
+    };
+    // FAST: the factor's whole sigma-point box lies inside the field, so the clamp is the identity
+    __device__ __forceinline__ bool fast_ok(const double* lo, const double* hi) const {
+        // one cell of margin keeps the cell coordinate safely positive / below the last node under rounding
+        const double cell = 1.0 / inv_cell;
+        return lo[0] >= ox + cell && hi[0] <= xmax - cell && lo[1] >= oy + cell && hi[1] <= ymax - cell;
+    }
+    template <bool FAST>
+    __device__ __forceinline__ Pending begin(const double* x, int) const {
+        double xin = x[0], yin = x[1];
+        if (!FAST) {
+            xin = fmin(fmax(xin, ox), xmax);
+            yin = fmin(fmax(yin, oy), ymax);
+        }
+        double col = fma(xin, inv_cell, cx0);
+        double row = fma(yin, inv_cell, cy0);
+        if (!FAST) {  // x == origin may round to -tiny: keep floor() at cell 0
+            col = fmax(col, 0.0);
+            row = fmax(row, 0.0);
+        }
+        // floor() by adding 1.5*2^52 with round-toward-minus-infinity (one DADD.RM); the low word of the
+        // sum is the integer cell index, the difference back is floor(col) as a double.
         const double M = 6755399441055744.0;
-        const double uc = (col - 0.5) + M;
-        const double ur = (row - 0.5) + M;
+        const double uc = __dadd_rd(col, M);
+        const double ur = __dadd_rd(row, M);
         const int lci = __double2loint(uc);
         const int lri = __double2loint(ur);
-        const double fc = col - (uc - M);
-        const double fr = row - (ur - M);
+        Pending p;
+        p.fc = col - (uc - M);
+        p.fr = row - (ur - M);
         // one 256-bit read-only load (SASS LDG.E.256.CONSTANT; records are 32-byte aligned)
-        double4 v;
-        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
-            : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
-            : "l"(rec + (size_t)lci * rows + lri));
-        const double a = fma(fr, v.y - v.x, v.x);
-        const double b = fma(fr, v.w - v.z, v.z);
-        const double sd = fma(fc, b - a, a);
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                     : "=d"(p.v.x), "=d"(p.v.y), "=d"(p.v.z), "=d"(p.v.w)
+                     : "l"(rec + (size_t)lci * rows + lri));
+        return p;
+    }
+    __device__ __forceinline__ double finish(const Pending& p) const {
+        const double a = fma(p.fr, p.v.y - p.v.x, p.v.x);
+        const double b = fma(p.fr, p.v.w - p.v.z, p.v.z);
+        const double sd = fma(p.fc, b - a, a);
         const double h = fmax(thr - sd, 0.0);
         return h * h;
     }
@@ -66,6 +108,7 @@ struct CostPlanarHinge {
 template <int DS>
 struct CostLinearGP {
     static constexpr int XD = 2 * DS;
+    GVIB200_SIMPLE_FUNCTOR_INTERFACE()
     const double* __restrict__ params;  // [n][2*DS*DS]
     __device__ __forceinline__ double eval(const double* x, int f) const {
         const double* Phi = params + (size_t)f * 2 * DS * DS;
@@ -96,6 +139,7 @@ struct CostLinearGP {
 template <int DIM>
 struct CostFixedGP {
     static constexpr int XD = DIM;
+    GVIB200_SIMPLE_FUNCTOR_INTERFACE()
     const double* __restrict__ params;  // [n][DIM*DIM + DIM]
     __device__ __forceinline__ double eval(const double* x, int f) const {
         const double* Ki = params + (size_t)f * (DIM * DIM + DIM);
@@ -120,6 +164,7 @@ struct CostFixedGP {
 template <int DIM>
 struct CostQuadratic {
     static constexpr int XD = DIM;
+    GVIB200_SIMPLE_FUNCTOR_INTERFACE()
     double c;
     __device__ __forceinline__ double eval(const double* x, int) const {
         double q = 0.0;

@@ -45,9 +45,10 @@ static int fail(int code, const std::string& msg) {
 // handles
 // ------------------------------------------------------------------------------------------------
 struct Table {
-    int dim = 0, deg = 0, n = 0, row = 0;
+    int dim = 0, deg = 0, n = 0, n_pad = 0;
     std::vector<double> nodes, w;  // host
-    double* d_rows = nullptr;      // device [n][row]
+    double ximax[12] = {};         // max |xi_c|
+    double* d_rows = nullptr;      // device planes: NP x [n_pad] double2, then [n_pad] weights
 };
 
 struct gvib200_ctx {
@@ -108,6 +109,7 @@ struct gvib200_problem {
     int cur = 0;
     double *mu[2] = {}, *LD[2] = {}, *LO[2] = {}, *CD[2] = {}, *CO[2] = {};
     double *fcost[2] = {}, *fVdmu[2] = {}, *fVdd[2] = {};
+    double* partial = nullptr; // per-block partial sums of the factor costs
     double* scal = nullptr;    // device scalars: [0..1] logdet cur/cand slots, [2..3] cost slots, [4] tmp
     double* h_scal = nullptr;  // pinned mirror
     int* d_flag = nullptr;     // not-SPD flag
@@ -179,11 +181,18 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
     }
     Table* t = it->second.get();
     if (t->d_rows == nullptr) {
-        t->row = (dim + 2) & ~1;
-        std::vector<double> rows((size_t)t->n * t->row, 0.0);
+        // padded with zero-weight nodes at xi = 0 to a multiple of 32: the node loop needs no tail handling
+        t->n_pad = (t->n + 31) & ~31;
+        const int NP = (dim + 1) / 2;
+        std::vector<double> rows((size_t)t->n_pad * (2 * NP + 1), 0.0);
+        for (int c = 0; c < 12; ++c) t->ximax[c] = 0.0;
         for (int i = 0; i < t->n; ++i) {
-            for (int c = 0; c < dim; ++c) rows[(size_t)i * t->row + c] = t->nodes[(size_t)i * dim + c];
-            rows[(size_t)i * t->row + dim] = t->w[i];
+            for (int c = 0; c < dim; ++c) {
+                const double v = t->nodes[(size_t)i * dim + c];
+                rows[(size_t)(c / 2) * 2 * t->n_pad + (size_t)2 * i + (c & 1)] = v;
+                if (c < 12) t->ximax[c] = std::max(t->ximax[c], std::fabs(v));
+            }
+            rows[(size_t)2 * NP * t->n_pad + i] = t->w[i];
         }
         CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(t->d_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -207,6 +216,17 @@ static int chain_forward(gvib200_problem* p, const double* Dg, const double* Og,
     return check_launch("bt_forward");
 }
 
+static void sum_logdet(gvib200_problem* p, double* d_logdet) {
+    const size_t n = p->plan.ld_count;
+    if (n > 8192) {
+        const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
+        LAUNCH(p, k_partial_sum, nb, 256, 0, n, p->ws + p->plan.ld_offset, p->partial);
+        LAUNCH(p, k_sum, 1, 256, 0, (size_t)nb, p->partial, nullptr, 0.0, d_logdet);
+    } else {
+        LAUNCH(p, k_sum, 1, 256, 0, n, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+    }
+}
+
 // selected inverse + log det of the block-tridiagonal (Dg, Og) -> (cD, cO), logdet scalar (device)
 template <int D>
 static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet) {
@@ -226,7 +246,7 @@ static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, 
         const int block = 128;
         LAUNCH(p, (k_bt_selinv<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.cD, p->ws + up.cO, lD, lO);
     }
-    LAUNCH(p, k_sum, 1, 256, 0, p->plan.ld_count, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+    sum_logdet(p, d_logdet);
     return check_launch("bt_selinv");
 }
 
@@ -247,8 +267,7 @@ static int chain_solve(gvib200_problem* p, const double* Dg, const double* Og, c
         const int block = 128;
         LAUNCH(p, (k_bt_backsolve<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.x, lx);
     }
-    if (d_logdet)
-        LAUNCH(p, k_sum, 1, 256, 0, p->plan.ld_count, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+    if (d_logdet) sum_logdet(p, d_logdet);
     return check_launch("bt_solve");
 }
 
@@ -287,13 +306,13 @@ template <int DIM, class Cost>
 static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
                           double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
     constexpr int XD = Cost::XD;
-    constexpr int ROW = (DIM + 2) & ~1;
+    constexpr int ROW = 2 * ((DIM + 1) / 2) + 1;  // doubles per node over all planes
     constexpr int THREADS = K1Cfg<DIM>::THREADS;
     constexpr int WARPS = THREADS / 32;
     const size_t scratch = (size_t)WARPS * K1Scratch<DIM, XD>::DOUBLES * sizeof(double);
-    const size_t budget = std::min<size_t>(p->ctx->smem_optin, 227 * 1024) - 1024;
-    int chunk = g.table->n;
-    // prefer two resident CTAs when the table is small
+    // leave room for K1Cfg::MIN_BLOCKS resident CTAs when the whole table fits, else stream it in chunks
+    const size_t budget = (std::min<size_t>(p->ctx->smem_optin, 227 * 1024) - 2048) / K1Cfg<DIM>::MIN_BLOCKS;
+    int chunk = g.table->n_pad;
     size_t need = (size_t)chunk * ROW * sizeof(double) + scratch;
     if (need > budget) {
         chunk = (int)((budget - scratch) / (ROW * sizeof(double)));
@@ -302,8 +321,9 @@ static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost
     }
     MomentArgs<Cost> a;
     a.n = g.n;
-    a.n_nodes = g.table->n;
+    a.n_nodes = g.table->n_pad;
     a.chunk = chunk;
+    for (int c = 0; c < 12; ++c) a.ximax[c] = g.table->ximax[c];
     a.state_dim = p->d;
     a.table = g.table->d_rows;
     a.start = g.d_start;
@@ -372,6 +392,8 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.xmax = p->sdf_ox + (p->sdf_cols - 1.0) * p->sdf_cell;
                 c.ymax = p->sdf_oy + (p->sdf_rows - 1.0) * p->sdf_cell;
                 c.inv_cell = 1.0 / p->sdf_cell;
+                c.cx0 = -p->sdf_ox * c.inv_cell;
+                c.cy0 = -p->sdf_oy * c.inv_cell;
                 c.thr = hp->epsilon + hp->radius;
                 c.sigma = hp->sigma;
                 return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
@@ -477,7 +499,14 @@ static int run_prologue_only(gvib200_problem* p, int which) {
 
 // total cost of buffer `which`: sum of factor costs + logdet/2 (GVI-GH-GBP-impl.h:217-239) -> scal[2 + which]
 static void run_total(gvib200_problem* p, int which) {
-    LAUNCH(p, k_sum, 1, 1024, 0, (size_t)p->n_factors, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
+    const size_t n = (size_t)p->n_factors;
+    if (n > 8192) {
+        const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
+        LAUNCH(p, k_partial_sum, nb, 256, 0, n, p->fcost[which], p->partial);
+        LAUNCH(p, k_sum, 1, 256, 0, (size_t)nb, p->partial, p->scal + which, 0.5, p->scal + 2 + which);
+    } else {
+        LAUNCH(p, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
+    }
 }
 
 template <int D>
@@ -607,7 +636,7 @@ static void free_problem(gvib200_problem* p) {
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
-    F(p->scal); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
+    F(p->scal); F(p->partial); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
     F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->h_flag) cudaFreeHost(p->h_flag);
@@ -880,6 +909,7 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
         CUDA_TRY(cudaMemsetAsync(p->CO[i], 0, (size_t)S * dd * sizeof(double), p->stream));
     }
     TRY(dev_alloc(&p->scal, 8));
+    TRY(dev_alloc(&p->partial, 1024));
     CUDA_TRY(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
     CUDA_TRY(cudaMallocHost((void**)&p->h_scal, 8 * sizeof(double)));
     TRY(dev_alloc(&p->d_flag, 1));

@@ -98,10 +98,10 @@ __global__ void k_prologue(int n, const int* __restrict__ start, const double* _
 template <class Cost>
 struct MomentArgs {
     int n;                 // factors in this group
-    int n_nodes;           // quadrature nodes
-    int chunk;             // nodes per shared-memory chunk (>= n_nodes: single stage)
+    int n_nodes;           // quadrature nodes, padded with zero-weight nodes to a multiple of 32
+    int chunk;             // nodes per shared-memory chunk (multiple of 32; >= n_nodes: single stage)
     int state_dim;
-    const double* table;   // [n_nodes][ROW] rows (xi_0..xi_{DIM-1}, w, pad), ROW = even(DIM + 1)
+    const double* table;   // planes: NP x [n_nodes] double2 (xi_2p, xi_2p+1), then [n_nodes] weights
     const int* start;      // [n] start state
     const double* mu;      // joint mean
     const double* SR;      // [n][2*DIM*DIM]
@@ -110,6 +110,7 @@ struct MomentArgs {
     double* fVdmu;         // [n][DIM]
     double* fVdd;          // [n][DIM*DIM]
     double* raw;           // optional [n][1 + DIM + DIM*DIM]: e0, e1, e2 (xi-space, times scale)
+    double ximax[12];      // max |xi_c| over the table (bounding box of the sigma points)
     Cost cost;
 };
 
@@ -127,10 +128,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// threads per CTA: small factors keep everything in registers; big ones trade occupancy for registers
+// threads per CTA / minimum resident CTAs: small factors keep everything in registers
 template <int DIM>
 struct K1Cfg {
-    static constexpr int THREADS = (DIM <= 4) ? 512 : (DIM <= 8 ? 256 : 128);
+    static constexpr int THREADS = (DIM <= 4) ? 256 : 128;
+    static constexpr int MIN_BLOCKS = (DIM <= 4) ? 2 : 1;
 };
 // per-warp scratch: epilogue totals (+ the S rows when they do not fit in registers)
 template <int DIM, int XD>
@@ -140,9 +142,82 @@ struct K1Scratch {
     static constexpr int DOUBLES = NOUT + (S_IN_SMEM ? XD * DIM : 0);
 };
 
+// One node: xi (from the shared planes), x = mu + S xi, first half of the cost evaluation.
+template <int DIM, class Cost, bool FAST, bool S_IN_SMEM, int NSREG>
+__device__ __forceinline__ typename Cost::Pending k1_begin(const double2* __restrict__ planes, const double* __restrict__ wts,
+                                                           int plane_stride, int i, const double (&mu)[Cost::XD],
+                                                           const double (&S)[NSREG][DIM], const double* __restrict__ sS,
+                                                           const Cost& cost, int f, double (&xi)[DIM], double& w) {
+    constexpr int NP = (DIM + 1) / 2;
+    constexpr int XD = Cost::XD;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double2 v = planes[(size_t)p * plane_stride + i];
+        xi[2 * p] = v.x;
+        if (2 * p + 1 < DIM) xi[2 * p + 1] = v.y;
+    }
+    w = wts[i];
+    double x[XD];
+#pragma unroll
+    for (int r = 0; r < XD; ++r) {
+        double s = mu[r];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) s = fma(S_IN_SMEM ? sS[r * DIM + c] : S[S_IN_SMEM ? 0 : r][c], xi[c], s);
+        x[r] = s;
+    }
+    return cost.template begin<FAST>(x, f);
+}
+
+template <int DIM, bool FULL>
+__device__ __forceinline__ void k1_accumulate(MomentAcc<DIM>& acc, bool& nz, const double (&xi)[DIM], double w,
+                                              double psi) {
+    const double p = w * psi;
+    acc.e0 += p;
+    if (FULL) {
+        // whole-warp skip of free-space nodes (psi == 0 for every lane): exact, the terms are zeros
+        if (__any_sync(0xffffffffu, p != 0.0)) {
+            nz = true;
+            int idx = 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                const double q = p * xi[c];
+                acc.e1[c] += q;
+#pragma unroll
+                for (int d2 = c; d2 < DIM; ++d2) {
+                    acc.e2[idx] = fma(q, xi[d2], acc.e2[idx]);
+                    ++idx;
+                }
+            }
+        }
+    }
+}
+
+// Software-pipelined node loop over one shared-memory chunk: the gather of node i+32 is issued
+// before node i is finished.  cn is a multiple of 32, so the loop is warp-uniform.
+template <int DIM, class Cost, bool FULL, bool FAST, bool S_IN_SMEM, int NSREG>
+__device__ __forceinline__ void k1_node_loop(MomentAcc<DIM>& acc, bool& nz, const double2* __restrict__ planes,
+                                             const double* __restrict__ wts, int plane_stride, int cn, int lane,
+                                             const double (&mu)[Cost::XD], const double (&S)[NSREG][DIM],
+                                             const double* __restrict__ sS, const Cost& cost, int f) {
+    double xiA[DIM], wA;
+    typename Cost::Pending pa =
+        k1_begin<DIM, Cost, FAST, S_IN_SMEM, NSREG>(planes, wts, plane_stride, lane, mu, S, sS, cost, f, xiA, wA);
+    for (int i = lane + 32; i < cn; i += 32) {
+        double xiB[DIM], wB;
+        typename Cost::Pending pb =
+            k1_begin<DIM, Cost, FAST, S_IN_SMEM, NSREG>(planes, wts, plane_stride, i, mu, S, sS, cost, f, xiB, wB);
+        k1_accumulate<DIM, FULL>(acc, nz, xiA, wA, cost.finish(pa));
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) xiA[c] = xiB[c];
+        wA = wB;
+        pa = pb;
+    }
+    k1_accumulate<DIM, FULL>(acc, nz, xiA, wA, cost.finish(pa));
+}
+
 template <int DIM, class Cost, bool FULL>
-__global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArgs<Cost> a) {
-    constexpr int ROW = (DIM + 2) & ~1;
+__global__ void __launch_bounds__(K1Cfg<DIM>::THREADS, K1Cfg<DIM>::MIN_BLOCKS) k_moments(const MomentArgs<Cost> a) {
+    constexpr int NP = (DIM + 1) / 2;
     constexpr int XD = Cost::XD;
     constexpr int NE2 = DIM * (DIM + 1) / 2;
     constexpr int NOUT = 1 + DIM + DIM * DIM;
@@ -150,8 +225,9 @@ __global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArg
     constexpr int NSREG = S_IN_SMEM ? 1 : XD;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t mbar;
-    double* tab = smem;                                                // [chunk][ROW]
-    double* scratch = smem + (size_t)a.chunk * ROW;                   // [warps][K1Scratch::DOUBLES]
+    const double2* planes = reinterpret_cast<const double2*>(smem);   // [NP][chunk]
+    const double* wts = smem + (size_t)2 * NP * a.chunk;              // [chunk]
+    double* scratch = smem + (size_t)(2 * NP + 1) * a.chunk;          // [warps][K1Scratch::DOUBLES]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -162,15 +238,21 @@ __global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArg
     __syncthreads();
     unsigned parity = 0;
     const bool single = a.n_nodes <= a.chunk;
-    if (single) {
+    // stage nodes [c0, c0 + cn) of every plane: NP + 1 bulk copies completing on one mbarrier
+    auto stage_chunk = [&](int c0, int cn) {
         if (threadIdx.x == 0) {
-            const unsigned bytes = (unsigned)(a.n_nodes * ROW * sizeof(double));
-            mbar_expect_tx(&mbar, bytes);
-            bulk_copy_g2s(tab, a.table, bytes, &mbar);
+            mbar_expect_tx(&mbar, (unsigned)(cn * (2 * NP + 1) * sizeof(double)));
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+                bulk_copy_g2s(smem + (size_t)2 * p * a.chunk, a.table + (size_t)2 * p * a.n_nodes + (size_t)2 * c0,
+                              (unsigned)(cn * 2 * sizeof(double)), &mbar);
+            bulk_copy_g2s(smem + (size_t)2 * NP * a.chunk, a.table + (size_t)2 * NP * a.n_nodes + c0,
+                          (unsigned)(cn * sizeof(double)), &mbar);
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
-    }
+    };
+    if (single) stage_chunk(0, a.n_nodes);
 
     const int stride = gridDim.x * nwarps;
     for (int base = blockIdx.x * nwarps; base < a.n; base += stride) {
@@ -178,6 +260,7 @@ __global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArg
         const bool active = f < a.n;
         // factor data: mu_k and the first XD rows of S_k
         double mu[XD], S[NSREG][DIM];
+        bool fast = false;
         if (active) {
             const double* Sp = a.SR + (size_t)f * 2 * DIM * DIM;
             const double* mp = a.mu + (size_t)a.start[f] * a.state_dim;
@@ -188,13 +271,23 @@ __global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArg
                 for (int e = lane; e < XD * DIM; e += 32) sS[e] = __ldg(Sp + (e / DIM) + (e % DIM) * DIM);
                 __syncwarp();
             } else {
+                double lo[XD], hi[XD];
 #pragma unroll
-                for (int r = 0; r < NSREG; ++r)
+                for (int r = 0; r < NSREG; ++r) {
+                    double rad = 0.0;
 #pragma unroll
-                    for (int c = 0; c < DIM; ++c) S[r][c] = __ldg(Sp + r + c * DIM);
+                    for (int c = 0; c < DIM; ++c) {
+                        S[r][c] = __ldg(Sp + r + c * DIM);
+                        rad = fma(fabs(S[r][c]), a.ximax[c], rad);
+                    }
+                    lo[r] = mu[r] - rad;
+                    hi[r] = mu[r] + rad;
+                }
+                fast = a.cost.fast_ok(lo, hi);
             }
         }
         MomentAcc<DIM> acc;
+        bool nz = false;  // warp-uniform: some node of this factor had psi != 0
         acc.e0 = 0.0;
 #pragma unroll
         for (int c = 0; c < DIM; ++c) acc.e1[c] = 0.0;
@@ -205,71 +298,39 @@ __global__ void __launch_bounds__(K1Cfg<DIM>::THREADS) k_moments(const MomentArg
             const int cn = min(a.chunk, a.n_nodes - c0);
             if (!single) {
                 __syncthreads();  // every warp is done with the previous chunk
-                if (threadIdx.x == 0) {
-                    const unsigned bytes = (unsigned)(cn * ROW * sizeof(double));
-                    mbar_expect_tx(&mbar, bytes);
-                    bulk_copy_g2s(tab, a.table + (size_t)c0 * ROW, bytes, &mbar);
-                }
-                mbar_wait(&mbar, parity);
-                parity ^= 1;
+                stage_chunk(c0, cn);
             }
             if (active) {
-#pragma unroll 2
-                for (int i = lane; i < cn; i += 32) {
-                    const double* row = tab + (size_t)i * ROW;
-                    double xi[DIM];
-#pragma unroll
-                    for (int c = 0; c < DIM; c += 2) {
-                        if (c + 1 < DIM) {
-                            const double2 v = *reinterpret_cast<const double2*>(row + c);
-                            xi[c] = v.x;
-                            xi[c + 1] = v.y;
-                        } else {
-                            xi[c] = row[c];
-                        }
-                    }
-                    const double w = row[DIM];
-                    double x[XD];
-#pragma unroll
-                    for (int r = 0; r < XD; ++r) {
-                        double s = mu[r];
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c) s = fma(S_IN_SMEM ? sS[r * DIM + c] : S[S_IN_SMEM ? 0 : r][c], xi[c], s);
-                        x[r] = s;
-                    }
-                    const double p = w * a.cost.eval(x, f);
-                    acc.e0 += p;
-                    if (FULL) {
-                        int idx = 0;
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c) {
-                            const double q = p * xi[c];
-                            acc.e1[c] += q;
-#pragma unroll
-                            for (int d2 = c; d2 < DIM; ++d2) {
-                                acc.e2[idx] = fma(q, xi[d2], acc.e2[idx]);
-                                ++idx;
-                            }
-                        }
-                    }
-                }
+                if (fast)
+                    k1_node_loop<DIM, Cost, FULL, true, S_IN_SMEM, NSREG>(acc, nz, planes, wts, a.chunk, cn, lane, mu, S, sS,
+                                                                           a.cost, f);
+                else
+                    k1_node_loop<DIM, Cost, FULL, false, S_IN_SMEM, NSREG>(acc, nz, planes, wts, a.chunk, cn, lane, mu, S, sS,
+                                                                            a.cost, f);
             }
         }
         if (!active) continue;  // whole warp
         // ---- fixed-order butterfly reduction ----
         const double sc = a.cost.scale();
         acc.e0 = warp_sum(acc.e0) * sc;
-        if (FULL) {
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) acc.e1[c] = warp_sum(acc.e1[c]) * sc;
-#pragma unroll
-            for (int c = 0; c < NE2; ++c) acc.e2[c] = warp_sum(acc.e2[c]) * sc;
-        }
         const double invT = 1.0 / __ldg(a.T + f);
         if (!FULL) {
             if (lane == 0) a.fcost[f] = acc.e0 * invT;
             continue;
         }
+        if (!nz && a.raw == nullptr) {
+            // free space: psi vanished at every node, so every moment is exactly zero
+            for (int e = lane; e < DIM * DIM + DIM + 1; e += 32) {
+                if (e < DIM * DIM) a.fVdd[(size_t)f * DIM * DIM + e] = 0.0;
+                else if (e < DIM * DIM + DIM) a.fVdmu[(size_t)f * DIM + (e - DIM * DIM)] = 0.0;
+                else a.fcost[f] = 0.0;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) acc.e1[c] = warp_sum(acc.e1[c]) * sc;
+#pragma unroll
+        for (int c = 0; c < NE2; ++c) acc.e2[c] = warp_sum(acc.e2[c]) * sc;
         // ---- epilogue: lane 0 publishes the totals, lanes split the small products ----
         if (lane == 0) {
             my[0] = acc.e0;
@@ -495,6 +556,23 @@ __global__ void k_candidate(size_t nmu, size_t nD, size_t nO, double alpha, cons
 __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] - b[i];
+}
+
+// Stage 1 of the deterministic two-stage sum: block b reduces a fixed contiguous slice of v.
+__global__ void k_partial_sum(size_t n, const double* __restrict__ v, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    const size_t per = (n + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = (lo + per < n) ? lo + per : n;
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
 // Deterministic single-block sum: out[0] = sum(v[0..n)) (+ half * extra[0] if extra != null)

@@ -150,23 +150,63 @@ GVI_HD void symmetrize(Mat<N>& A) {
         }
 }
 
+// 1/sqrt(x): the device path uses the hardware-seeded rsqrt (no DSQRT + DDIV slow paths on the
+// serial critical path of the chain engine); the host harness uses the plain expression.
+GVI_HD double gvi_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// Running log-determinant as (mantissa product, binary exponent): one multiply per pivot on the
+// serial path instead of one log(); log() is taken once per worker at the end.
+struct LogDetAcc {
+    double m;
+    int e;
+    GVI_HD LogDetAcc() : m(1.0), e(0) {}
+    GVI_HD void mul(double s) { m *= s; }
+    // renormalise the mantissa into [1, 2); call at least every few multiplies (each pivot may span
+    // ~1e+-70 before the product leaves the double range)
+    GVI_HD void normalize() {
+#ifdef __CUDA_ARCH__
+        const int hi = __double2hiint(m);
+        const int ex = ((hi >> 20) & 0x7ff) - 1023;
+        if (m > 0.0 && ex > -1022 && ex < 1024) {
+            m = __hiloint2double(hi - (ex << 20), __double2loint(m));
+            e += ex;
+        }
+#else
+        if (m > 0.0 && isfinite(m)) {
+            int ex;
+            m = frexp(m, &ex) * 2.0;
+            e += ex - 1;
+        }
+#endif
+    }
+    GVI_HD double value() const { return log(m) + (double)e * 0.69314718055994530942; }
+};
+
 // Inverse of an SPD matrix through its Cholesky factor: A = L L^T, Ainv = L^-T L^-1.
-// Returns log det(A) in *logdet; returns false (and leaves Ainv unspecified, possibly NaN) when a
-// pivot is not strictly positive -- the caller raises GVIB200_ENOTSPD.  Only the lower triangle of
-// A is read.
+// The pivots are multiplied into `ld` (log det accumulator); returns false (and leaves Ainv
+// unspecified, possibly NaN) when a pivot is not strictly positive -- the caller raises
+// GVIB200_ENOTSPD.  Only the lower triangle of A is read.  Division free: every 1/L_jj is the
+// rsqrt of the pivot.
 template <int N>
-GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, double* logdet) {
+GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, LogDetAcc& ld) {
     Mat<N> L;
+    double rd[N];
     bool ok = true;
-    double ld = 0.0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         double s = A(j, j);
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L(j, k), L(j, k), s);
         ok = ok && (s > 0.0);
-        ld += log(s);
-        const double r = 1.0 / sqrt(s);
+        ld.mul(s);
+        const double r = gvi_rsqrt(s);
+        rd[j] = r;
         L(j, j) = s * r;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
@@ -176,17 +216,18 @@ GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, double* logdet) {
             L(i, j) = t * r;
         }
     }
+    ld.normalize();
     // M = L^-1 (lower triangular)
     Mat<N> M;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        M(j, j) = 1.0 / L(j, j);
+        M(j, j) = rd[j];
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             double t = 0.0;
 #pragma unroll
             for (int k = j; k < i; ++k) t = fma(-L(i, k), M(k, j), t);
-            M(i, j) = t / L(i, i);
+            M(i, j) = t * rd[i];
         }
     }
     // Ainv = M^T M (symmetric)
@@ -200,7 +241,6 @@ GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, double* logdet) {
             Ainv(i, j) = t;
             Ainv(j, i) = t;
         }
-    *logdet = ld;
     return ok;
 }
 

@@ -117,12 +117,17 @@ def ltv_transition_batch(A: np.ndarray, B: np.ndarray, delta_t: float):
 # ----------------------------------------------------------------------------------------------
 # ingredients
 # ----------------------------------------------------------------------------------------------
-def disc_sdf(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
-    """Analytic signed distance to `n_discs` discs on a rows x cols grid (SURVEY 8(d) cfg3)."""
+def disc_layout(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
     rng = np.random.default_rng(seed)
     cx = rng.uniform(origin[0], origin[0] + (cols - 1) * cell, n_discs)
     cy = rng.uniform(origin[1], origin[1] + (rows - 1) * cell, n_discs)
     rad = rng.uniform(1.0, 3.0, n_discs)
+    return cx, cy, rad
+
+
+def disc_sdf(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
+    """Analytic signed distance to `n_discs` discs on a rows x cols grid (SURVEY 8(d) cfg3)."""
+    cx, cy, rad = disc_layout(rows, cols, origin, cell, n_discs, seed)
     xs = origin[0] + cell * np.arange(cols)
     ys = origin[1] + cell * np.arange(rows)
     X, Y = np.meshgrid(xs, ys)  # [rows, cols]
@@ -132,12 +137,27 @@ def disc_sdf(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, se
     return sd, (float(origin[0]), float(origin[1])), float(cell)
 
 
-def lissajous_nominal(S: int, delta_t: float) -> np.ndarray:
+def lissajous_nominal(S: int, delta_t: float, clearance: Optional[float] = None, discs=None) -> np.ndarray:
     """Nominal 2-D point-robot trajectory [S, 4] = (x, y, vx, vy): constant phase step per state, so every
-    problem size sees the same obstacle density."""
+    problem size sees the same obstacle density.  With `clearance` the path is pushed radially
+    out of every disc to distance radius + clearance: a collision-free initial plan that still runs through the
+    hinge band.  (A dense Lissajous at N = 100k otherwise passes through disc CENTRES, where the distance field
+    has curvature -2 sigma h / rho -> -inf and Vddmu stops being positive definite, see DESIGN.md.)"""
     i = np.arange(S, dtype=np.float64)
     x = 15.0 * np.sin(14.0 * np.pi * i / 1002.0)
     y = 5.0 + 9.0 * np.sin(22.0 * np.pi * i / 1002.0)
+    if clearance is not None and discs is not None:
+        cx, cy, rad = discs
+        for _ in range(4):
+            for k in range(len(rad)):
+                dx, dy = x - cx[k], y - cy[k]
+                rho = np.hypot(dx, dy)
+                inside = rho < rad[k] + clearance
+                rho_s = np.where(rho < 1e-9, 1.0, rho)
+                ux = np.where(rho < 1e-9, 1.0, dx / rho_s)
+                uy = np.where(rho < 1e-9, 0.0, dy / rho_s)
+                x = np.where(inside, cx[k] + (rad[k] + clearance) * ux, x)
+                y = np.where(inside, cy[k] + (rad[k] + clearance) * uy, y)
     vx = np.gradient(x, delta_t) if S > 1 else np.zeros(S)
     vy = np.gradient(y, delta_t) if S > 1 else np.zeros(S)
     return np.stack([x, y, vx, vy], axis=1)
@@ -238,12 +258,12 @@ def make_cfg2(S: int = 1000, delta_t: float = 0.1, anchors_every: int = 10, prec
 
 
 def make_cfg3(N: int = 100_000, delta_t: float = 0.2, deg: int = 6, sigma: float = 0.1, prec0: float = 100.0,
-              seed: int = 3) -> ProblemSpec:
+              seed: int = 3, clearance: Optional[float] = 0.6) -> ProblemSpec:
     """Headline shape: S = N + 2 states, N single-state planar hinge-SDF factors (d = 4, sparse GH degree `deg`)
     at states 1..S-2, N + 1 LTV GP factors, two fixed priors."""
     d = 4
     S = N + 2
-    nominal = lissajous_nominal(S, delta_t)
+    nominal = lissajous_nominal(S, delta_t, clearance, disc_layout())
     spec = ProblemSpec(S=S, d=d)
     spec.sdf = disc_sdf()
     spec.groups.append(fixed_prior_group([0, S - 1], np.stack([nominal[0], nominal[-1]]), 1e-4 * np.eye(d), d))
