@@ -1,0 +1,142 @@
+"""CPU tests of the product's host side: libgvib200.so loads and exports every symbol include/gvib200.h declares,
+the native sparse-GH table generator is bit-identical to the oracle's restatement of nwspgr.m, the chain engine's
+__host__ __device__ arithmetic (run by tests/cpp/libbt_host_emu.so) matches the oracle, and the library fails loudly
+without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import gvi_oracle as o
+import oracle_bridge as ob
+from gaussianvi_b200 import capi
+
+ROOT = ob.ROOT
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def test_header_symbols_are_exported():
+    hdr = (ROOT / "include" / "gvib200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(gvib200_[A-Za-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    lib = capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gvib200.h but not exported by libgvib200.so"
+    assert set(declared) == set(capi.EXPORTS), set(declared) ^ set(capi.EXPORTS)
+    assert b"sm_100a" in lib.gvib200_version()
+
+
+def test_no_cpu_fallback():
+    """Without a usable CUDA device the product refuses to run (this container has no GPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the refusal path cannot be exercised")
+    with pytest.raises(capi.GviError) as e:
+        capi.Context(0)
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("dim,deg", [(1, 10), (1, 6), (2, 10), (3, 8), (4, 3), (4, 6), (5, 2), (8, 4), (12, 4)])
+def test_native_table_generator_bit_exact(dim, deg):
+    """gvib200_table_generate (gaussianvi_b200/csrc/spgh_table.cpp) vs the oracle's nwspgr restatement: same node
+    count, same ROW ORDER, bit-identical nodes and weights."""
+    Z, w = o.table(dim, deg)
+    Zc, wc = capi.table_generate(dim, deg)
+    assert Zc.shape == Z.shape
+    assert np.array_equal(Zc, Z)
+    assert np.array_equal(wc, w)
+
+
+def test_table_unavailable_is_an_error():
+    lib = capi.load_library()
+    assert lib.gvib200_table_size(4, 99) < 0
+
+
+# ------------------------------------------------------------------ chain engine on the host
+def _emu():
+    lib = C.CDLL(str(ROOT / "tests" / "cpp" / "libbt_host_emu.so"))
+    return lib
+
+
+def rand_spd_chain(rng, S, d):
+    D = np.zeros((S, d, d))
+    O = np.zeros((max(S - 1, 0), d, d))
+    for i in range(S):
+        A = rng.standard_normal((d, d))
+        D[i] += 0.1 * A @ A.T + np.eye(d)
+    for i in range(S - 1):
+        B = rng.standard_normal((2 * d, 2 * d))
+        M = B @ B.T
+        D[i] += M[:d, :d]
+        D[i + 1] += M[d:, d:]
+        O[i] += M[:d, d:]
+    return D, O
+
+
+def emu_run(S, d, D, O, rhs, seg, nserial):
+    lib = _emu()
+    dp = C.POINTER(C.c_double)
+    Dc = np.ascontiguousarray(np.transpose(D, (0, 2, 1)))
+    Oc = np.ascontiguousarray(np.transpose(O, (0, 2, 1))) if S > 1 else np.zeros((1, d, d))
+    x = np.zeros(S * d)
+    cD = np.zeros((S, d, d))
+    cO = np.zeros((max(S - 1, 1), d, d))
+    ld = C.c_double()
+    p = lambda a: a.ctypes.data_as(dp)
+    rc = lib.emu_blocktri(S, d, p(Dc), p(Oc), p(rhs), p(x), None, None, C.byref(ld), seg, nserial)
+    assert rc == 0
+    rc = lib.emu_blocktri(S, d, p(Dc), p(Oc), None, None, p(cD), p(cO), C.byref(ld), seg, nserial)
+    assert rc == 0
+    return x, np.transpose(cD, (0, 2, 1)), np.transpose(cO[:S - 1], (0, 2, 1)), ld.value
+
+
+@pytest.mark.parametrize("S,d,seg,nserial", [(1, 4, 4, 8), (2, 4, 4, 8), (9, 4, 4, 8), (10, 4, 4, 2), (33, 2, 4, 8), (100, 4, 4, 8),
+                                             (257, 3, 8, 4), (1000, 4, 16, 8), (1002, 4, 32, 16), (40, 6, 4, 8), (77, 1, 5, 3)])
+def test_chain_engine_host_matches_oracle(S, d, seg, nserial):
+    rng = np.random.default_rng(S * 10 + d)
+    D, O = rand_spd_chain(rng, S, d)
+    rhs = rng.standard_normal(S * d)
+    x, cD, cO, ld = emu_run(S, d, D, O, rhs, seg, nserial)
+    bt = o.BlockTri(D, O)
+    ref = o.inverse_gbp(bt)
+    assert rel(x, o.block_solve(bt, rhs)) < 1e-11
+    assert rel(cD, ref.D) < 1e-11
+    if S > 1:
+        assert rel(cO, ref.O) < 1e-11
+    assert abs(ld - o.logdet(bt)) < 1e-10 * max(1.0, abs(ld))
+
+
+def test_chain_engine_reports_indefinite():
+    lib = _emu()
+    dp = C.POINTER(C.c_double)
+    D = np.tile(np.eye(2), (5, 1, 1))
+    D[3] = -np.eye(2)
+    O = np.zeros((4, 2, 2))
+    cD, cO = np.zeros_like(D), np.zeros_like(O)
+    ld = C.c_double()
+    p = lambda a: a.ctypes.data_as(dp)
+    assert lib.emu_blocktri(5, 2, p(D), p(O), None, None, p(cD), p(cO), C.byref(ld), 4, 2) == -4
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 12])
+def test_jacobi_sqrt_matches_eigh(n):
+    """The device prologue's symmetric PSD root (quadrature/SparseGaussHermite.h:231-233) vs numpy eigh."""
+    lib = _emu()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(n)
+    for trial in range(20):
+        lam = np.exp(rng.uniform(np.log(1e-6), np.log(10.0), n))
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        Sig = (Q * lam) @ Q.T
+        Sig = 0.5 * (Sig + Sig.T)
+        S, R = np.zeros((n, n)), np.zeros((n, n))
+        assert lib.emu_sqrt_invsqrt(n, Sig.ctypes.data_as(dp), S.ctypes.data_as(dp), R.ctypes.data_as(dp)) == 0
+        ref = o.sqrtm_psd(Sig)
+        assert rel(S, ref) < 1e-12
+        assert rel(R @ R, np.linalg.inv(Sig)) < 1e-9
