@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json: NGD iterations / s (and sigma-point evaluations / s) of the
+factorized NGD-GVI hot path at N = 100 000 nonlinear factors, d = 4, sparse Gauss-Hermite degree 6 (953 nodes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gvib200|reference]
+
+One "step" = one full NGD iteration (quadrature sweep(s) + precision assembly + block-tridiagonal solve + candidate +
+selected inverse / log det + line-search cost) of the synthetic cfg3 trajectory.
+
+  value     whole-job NGD iterations / s with all state resident in HBM (gvib200_ngd_iterate), CUDA-event timed on the
+            problem's stream, max over ranks.  At N > 1 every rank owns its own contiguous 100k-factor time segment
+            (weak scaling); value = N_ranks * 100k-factor iterations / s, i.e. normalised to 100k factors.
+  e2e       the same iteration through the C-ABI with HOST buffers: per step set_state(mu, Lambda) from pinned host
+            memory, one iteration, mean + covariance blocks read back.
+  roofline  dominant kernel (the fused sigma-point / cost / moment kernel K1): algorithmic FP64 flops per launch
+            (89 per sigma point) / average launch duration from per-launch CUDA events, against the FP64
+            FMA peak measured live by a DFMA micro-benchmark (MEASURED_PEAKS.json carries no FP64 figure).
+  cpu_baseline  the oracle's C restatement (oracle/gvi_oracle_c.c, OpenMP) on a bounded sample of the same workload.
+
+--impl reference times the CPU path alone (rank 0), with the reference's own schedule of one iteration.
+"""
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_FACTORS = 100_000
+DEG = 6
+N_NODES = 953
+FLOPS_FULL = 89     # per sigma point, full-moment sweep, d = 4, planar hinge
+FLOPS_COST = 61     # per sigma point, cost-only sweep
+METRIC = "NGD iters/sec & sigma-pt evals/sec at N=100k factors, d=4, SpGH deg 6"
+UNIT = "NGD iters/s"
+CPU_SAMPLE_FACTORS = 10_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="gvib200", choices=["gvib200", "reference"])
+    ap.add_argument("--schedule", default="reuse", choices=["reuse", "faithful"],
+                    help="reuse: the accepted trial's full-moment sweep seeds the next iteration (identical results); "
+                         "faithful: 1 moment sweep + T_ls cost sweeps per iteration")
+    ap.add_argument("--factors", type=int, default=N_FACTORS, help="(development only) factors per GPU")
+    ap.add_argument("--rewind-every", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(n_factors, steps, warmup, schedule):
+    """Time the oracle's C restatement on a bounded sample of cfg3 (n_factors factors); returns
+    (iterations / s normalised to 100k factors, seconds per sample iteration, threads, T_ls, psi sweeps / iteration)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import gvi_oracle as o          # table generator of the oracle
+    import gvi_oracle_c as oc       # the C restatement (CPU baseline; never part of the product path)
+    from gaussianvi_b200 import problems
+    spec = problems.make_cfg3(N=n_factors)
+    c = oc.COracle(spec, o.table)
+    for _ in range(warmup):
+        c.iterate(schedule=schedule)
+    times, nb, sweeps = [], [], []
+    for _ in range(steps):
+        t = time.perf_counter()
+        st = c.iterate(schedule=schedule)
+        times.append(time.perf_counter() - t)
+        nb.append(st.n_backtrack + 1)
+        sweeps.append(st.n_psi_sweeps)
+        if st.status != 0 or not st.accepted:
+            raise RuntimeError("CPU oracle iteration failed")
+    t_iter = sum(times) / len(times)
+    scale = n_factors / N_FACTORS
+    return scale / t_iter, t_iter, oc.num_threads(), statistics.mean(nb), statistics.mean(sweeps)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    value, t_iter, threads, tls, sweeps = cpu_arm(CPU_SAMPLE_FACTORS, steps, warmup, schedule=0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * t_iter * (N_FACTORS / CPU_SAMPLE_FACTORS), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: NGD-GH hinge-SDF factors + LTV GP prior, d=4, N=100k factors, sparse-GH degree 6 (953 nodes)",
+                   "factors": N_FACTORS, "states": N_FACTORS + 2, "dim_state": 4, "gh_degree": DEG, "nodes": N_NODES},
+        "sigma_pt_evals_per_s": value * N_FACTORS * N_NODES * sweeps,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"one NGD iteration per step of the cfg3 generator at {CPU_SAMPLE_FACTORS} factors "
+                                   f"({CPU_SAMPLE_FACTORS + 2} states), the reference's own schedule "
+                                   f"({sweeps:.0f} psi sweeps, (3+T_ls) chain inversions per iteration, T_ls={tls:.2f}); "
+                                   f"work is linear in the factor count, value scaled by {CPU_SAMPLE_FACTORS}/{N_FACTORS}",
+                         "seconds_per_sample_iteration": t_iter,
+                         "why_port": "the reference is header-only C++ on Eigen 3.4 + GSL + a MATLAB-generated table; none "
+                                     "is in this image, so oracle/_ref cannot be built"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import gaussianvi_b200 as gv
+    from gaussianvi_b200 import problems
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    N = args.factors
+    ctx = gv.Context(local_rank)
+    # every rank owns one contiguous time segment of N factors (its own LTV coefficients: seed 3 + rank)
+    spec = problems.make_cfg3(N=N, deg=DEG, seed=3 + rank)
+    prob = problems.build_device_problem(ctx, spec)
+    info = prob.info()
+    pts = int(info.sigma_points_per_sweep)
+    opts = gv.Problem.default_opts()
+    opts.niters_lowtemp = 1 << 30          # no temperature switch inside the timed run
+    opts.reuse_accepted_sweep = 1 if args.schedule == "reuse" else 0
+    fp64_peak = ctx.fp64_peak_tflops()
+
+    # ---- warm-up, then snapshot the steady state the timed blocks rewind to
+    prob.iterate(opts)
+    prob.snapshot_save()
+    for _ in range(W):
+        prob.iterate(opts)
+    prob.snapshot_restore()
+
+    def run_steps(k, collect=None):
+        for i in range(k):
+            if i and i % args.rewind_every == 0:
+                prob.snapshot_restore()     # device-to-device rewind, keeps every step's work identical
+            st = prob.iterate(opts)
+            if collect is not None:
+                collect.append(st)
+
+    # ---- device-resident timed region
+    sampler = ClockSampler(local_rank)
+    stats = []
+    barrier()
+    l0 = ctx.launch_count()
+    sampler.start()
+    t_wall = time.perf_counter()
+    prob.timer_start()
+    run_steps(K, stats)
+    ms = prob.timer_stop()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ms = max_over_ranks(ms)
+    tls = statistics.mean(s.n_backtrack + 1 for s in stats)
+    n_full = sum(s.n_moment_sweeps for s in stats)
+    n_cost = sum(s.n_cost_sweeps for s in stats)
+    if not all(s.accepted for s in stats):
+        raise SystemExit("bench.py: a timed NGD iteration was not accepted")
+    ms_per_step = ms / K
+    value = world * (N / N_FACTORS) * 1e3 / ms_per_step
+    evals = sum_over_ranks(pts * (n_full + n_cost)) / (ms * 1e-3)
+
+    # ---- per-launch profile of the same K steps (event pair per launch; separate pass, not the timed one)
+    prob.snapshot_restore()
+    prob.profile_begin()
+    run_steps(K)
+    prof = prob.profile_end()
+    k1 = prof.get("k_moments<full>", (0, 0.0))
+    k1_ms = k1[1] / max(k1[0], 1)
+    k1_tflops = pts * FLOPS_FULL / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+    prof_total = sum(v[1] for v in prof.values())
+    # chain engine: algorithmic HBM bytes per block-tridiagonal pass (~8*8*d^2 per state per inversion)
+    S, d = info.num_states, info.dim_state
+    chain_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("k_bt_forward", "k_bt_top", "k_bt_back"))
+    chain_passes = 2 * K  # one dmu solve + one selected inverse per iteration (T_ls = 1)
+    chain_bytes = 8 * 8 * d * d * S
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (6650 GB/s)"
+    flops_iter = pts * (FLOPS_FULL * n_full + FLOPS_COST * n_cost) / K
+
+    # ---- end to end through the C-ABI with host buffers (pinned), every step: H2D state, iterate, D2H result
+    mu_h = torch.from_numpy(np.ascontiguousarray(spec.mu0)).pin_memory().numpy()
+    pD_h = torch.from_numpy(np.ascontiguousarray(spec.prec0_D)).pin_memory().numpy()
+    pO_h = torch.from_numpy(np.ascontiguousarray(spec.prec0_O)).pin_memory().numpy()
+    e2e_steps = max(3, min(K, 12))
+    h2d = mu_h.nbytes + pD_h.nbytes + pO_h.nbytes
+    d2h = h2d
+    prob.set_state(mu_h, pD_h, pO_h); prob.iterate(opts); prob.mean(); prob.covariance()   # warm the path
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prob.set_state(mu_h, pD_h, pO_h)
+        st = prob.iterate(opts)
+        m = prob.mean()
+        cD, cO = prob.covariance()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * (N / N_FACTORS) * e2e_steps / e2e_s
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v_ref, t_ref, threads, tls_c, sw_ref = cpu_arm(CPU_SAMPLE_FACTORS, 2, 1, schedule=0)
+            v_lean, t_lean, _, _, sw_lean = cpu_arm(CPU_SAMPLE_FACTORS, 2, 1, schedule=1)
+            cpu = {"value": v_ref, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"2 NGD iterations of the cfg3 generator at {CPU_SAMPLE_FACTORS} factors after 1 warm-up, "
+                             f"reference schedule ({sw_ref:.0f} psi sweeps / iteration); scaled by "
+                             f"{CPU_SAMPLE_FACTORS}/{N_FACTORS} (work is linear in the factor count)",
+                   "lean_schedule_value": v_lean, "lean_psi_sweeps": sw_lean}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg3: NGD-GH hinge-SDF factors + LTV GP prior, d=4, N=100k factors, sparse-GH degree 6 (953 nodes)",
+                       "factors_per_gpu": N, "states_per_gpu": S, "dim_state": d, "gh_degree": DEG, "nodes": N_NODES,
+                       "linear_factors_per_gpu": int(info.n_linear_factors), "schedule": args.schedule,
+                       "T_ls_mean": tls, "parallelism": "1 GPU" if world == 1 else
+                       f"{world} ranks, one contiguous 100k-factor time segment per rank (weak), no data-path collective",
+                       "l2": "working set per iteration (state, factor marginals, chain workspace, SDF: ~0.25 GB) exceeds the "
+                             "126 MB L2; no flush",
+                       "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)"},
+            "sigma_pt_evals_per_s": evals,
+            "wall_ms_per_step": 1e3 * t_wall / K,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "call": "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks"},
+            "roofline": {"bound": "fp64", "kernel": "k_moments<4, CostPlanarHinge, full> (K1)",
+                         "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak); MEASURED_PEAKS.json "
+                                        "has no FP64 figure",
+                         "algorithmic_flops_per_launch": pts * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],
+                         "share_of_step": k1[1] / prof_total if prof_total else None,
+                         "whole_iteration": {"flops": flops_iter, "achieved": flops_iter / (ms_per_step * 1e-3) / 1e12,
+                                             "frac": flops_iter / (ms_per_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},
+                         "chain_engine_hbm": {"bound": "hbm", "achieved": chain_bytes * chain_passes / (chain_ms * 1e-3) / 1e9 if chain_ms else None,
+                                              "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                                              "frac": chain_bytes * chain_passes / (chain_ms * 1e-3) / 1e9 / hbm_peak if chain_ms else None,
+                                              "algorithmic_bytes_per_pass": chain_bytes}},
+            "kernel_ms_per_step": {k: v[1] / K for k, v in sorted(prof.items())},
+            "kernel_launches_per_step": {k: v[0] / K for k, v in sorted(prof.items())},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    prob.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,8 @@ EXPORTS = [
     "gvib200_get_cov_blocks", "gvib200_moments", "gvib200_cost", "gvib200_gradients", "gvib200_get_V",
     "gvib200_default_opts", "gvib200_optimize", "gvib200_ngd_iterate", "gvib200_reset_schedule",
     "gvib200_selected_inverse", "gvib200_blocktri_solve", "gvib200_time_stage", "gvib200_fp64_peak",
+    "gvib200_launch_count", "gvib200_timer_start", "gvib200_timer_stop", "gvib200_profile_begin", "gvib200_profile_end",
+    "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
 ]
 
 
@@ -50,6 +52,15 @@ class IterStats(C.Structure):
     _fields_ = [("cost", C.c_double), ("new_cost", C.c_double), ("step", C.c_double), ("n_backtrack", C.c_int),
                 ("accepted", C.c_int), ("switched_high_T", C.c_int), ("converged", C.c_int), ("status", C.c_int),
                 ("n_moment_sweeps", C.c_int), ("n_cost_sweeps", C.c_int)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("n_classes", C.c_int), ("count", C.c_longlong * 16), ("ms", C.c_double * 16)]
+
+
+class Info(C.Structure):
+    _fields_ = [("num_states", C.c_int), ("dim_state", C.c_int), ("n_factors", C.c_int), ("n_gh_factors", C.c_int),
+                ("n_linear_factors", C.c_int), ("chain_levels", C.c_int), ("sigma_points_per_sweep", C.c_longlong)]
 
 
 class Stereo1DParams(C.Structure):
@@ -79,6 +90,7 @@ def load_library() -> C.CDLL:
     lib.gvib200_version.restype = C.c_char_p
     lib.gvib200_launch_count.restype = C.c_longlong
     lib.gvib200_launch_count.argtypes = [C.c_void_p]
+    lib.gvib200_kernel_class_name.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -332,6 +344,35 @@ class Problem:
 
     def reset_schedule(self):
         _check(self.lib.gvib200_reset_schedule(self.h))
+
+    def timer_start(self):
+        _check(self.lib.gvib200_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(self.lib.gvib200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_begin(self):
+        _check(self.lib.gvib200_profile_begin(self.h))
+
+    def profile_end(self) -> dict:
+        """{kernel class name: (launches, summed device ms)} for the launches since profile_begin()."""
+        pr = Profile()
+        _check(self.lib.gvib200_profile_end(self.h, C.byref(pr)))
+        return {self.lib.gvib200_kernel_class_name(k).decode(): (int(pr.count[k]), float(pr.ms[k]))
+                for k in range(pr.n_classes) if pr.count[k]}
+
+    def info(self) -> Info:
+        out = Info()
+        _check(self.lib.gvib200_problem_info(self.h, C.byref(out)))
+        return out
+
+    def snapshot_save(self):
+        _check(self.lib.gvib200_snapshot_save(self.h))
+
+    def snapshot_restore(self):
+        _check(self.lib.gvib200_snapshot_restore(self.h))
 
     def time_stage(self, stage: int, reps: int, opts: Optional[Opts] = None):
         ms = C.c_float()

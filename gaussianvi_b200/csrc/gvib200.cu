@@ -85,6 +85,17 @@ struct LinGroup {
     double *d_Lambda = nullptr, *d_psi = nullptr, *d_Kinv = nullptr, *d_A = nullptr, *d_C = nullptr, *d_T = nullptr;
 };
 
+// kernel classes for the per-launch profile (gvib200_profile_begin / _end)
+enum { KC_MOMENTS_FULL = 0, KC_MOMENTS_COST, KC_PROLOGUE, KC_LINEAR, KC_ASSEMBLE, KC_BT_FORWARD, KC_BT_TOP, KC_BT_BACK,
+       KC_SUM, KC_CANDIDATE, KC_OTHER, KC_COUNT };
+static const char* const KC_NAMES[KC_COUNT] = {"k_moments<full>", "k_moments<cost>", "k_prologue", "k_linear", "k_assemble",
+                                               "k_bt_forward",   "k_bt_top",        "k_bt_back",  "k_sum",    "k_candidate",
+                                               "other"};
+struct ProfRec {
+    int kc;
+    cudaEvent_t a, b;
+};
+
 struct FactorRef {
     bool linear;
     int group;
@@ -127,8 +138,16 @@ struct gvib200_problem {
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
     bool grads_valid = false;
-    // profiling
+    // profiling: one CUDA event pair per launch while enabled
     bool profile = false;
+    std::vector<ProfRec> prof;
+    // timer (gvib200_timer_start / _stop)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // snapshot (gvib200_snapshot_save / _restore)
+    double* snap = nullptr;
+    size_t snap_doubles = 0;
+    int snap_iter = 0, snap_cur = 0;
+    bool snap_lowtemp = true, snap_sweep_valid = false;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -149,11 +168,25 @@ static int dev_upload(T** p, const std::vector<T>& v, cudaStream_t st) {
 }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-#define LAUNCH(prob, kern, grid, block, smem, ...)                                   \
+static inline void prof_begin(gvib200_problem* p, int kc);
+static inline void prof_end(gvib200_problem* p);
+#define LAUNCH(prob, kc, kern, grid, block, smem, ...)                               \
     do {                                                                             \
+        if ((prob)->profile) prof_begin((prob), (kc));                               \
         kern<<<(grid), (block), (smem), (prob)->stream>>>(__VA_ARGS__);              \
+        if ((prob)->profile) prof_end((prob));                                       \
         (prob)->ctx->launches++;                                                     \
     } while (0)
+
+static inline void prof_begin(gvib200_problem* p, int kc) {
+    ProfRec r;
+    r.kc = kc;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, p->stream);
+    p->prof.push_back(r);
+}
+static inline void prof_end(gvib200_problem* p) { cudaEventRecord(p->prof.back().b, p->stream); }
 
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -210,8 +243,8 @@ static int chain_forward(gvib200_problem* p, const double* Dg, const double* Og,
     for (size_t l = 0; l + 1 < nl; ++l) {
         BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
         const int block = 128;
-        if (rhs) LAUNCH(p, (k_bt_forward<D, true>), cdiv(lv.K, block), block, 0, lv);
-        else LAUNCH(p, (k_bt_forward<D, false>), cdiv(lv.K, block), block, 0, lv);
+        if (rhs) LAUNCH(p, KC_BT_FORWARD, (k_bt_forward<D, true>), cdiv(lv.K, block), block, 0, lv);
+        else LAUNCH(p, KC_BT_FORWARD, (k_bt_forward<D, false>), cdiv(lv.K, block), block, 0, lv);
     }
     return check_launch("bt_forward");
 }
@@ -220,10 +253,10 @@ static void sum_logdet(gvib200_problem* p, double* d_logdet) {
     const size_t n = p->plan.ld_count;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
-        LAUNCH(p, k_partial_sum, nb, 256, 0, n, p->ws + p->plan.ld_offset, p->partial);
-        LAUNCH(p, k_sum, 1, 256, 0, (size_t)nb, p->partial, nullptr, 0.0, d_logdet);
+        LAUNCH(p, KC_SUM, k_partial_sum, nb, 256, 0, n, p->ws + p->plan.ld_offset, p->partial);
+        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)nb, p->partial, nullptr, 0.0, d_logdet);
     } else {
-        LAUNCH(p, k_sum, 1, 256, 0, n, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, n, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
     }
 }
 
@@ -236,7 +269,7 @@ static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, 
         BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, nullptr, p->d_flag);
         double* tD = (nl == 1) ? cD : p->ws + p->plan.levels[nl - 1].cD;
         double* tO = (nl == 1) ? cO : p->ws + p->plan.levels[nl - 1].cO;
-        LAUNCH(p, (k_bt_top<D, false>), 1, 32, 0, top, nullptr, tD, tO);
+        LAUNCH(p, KC_BT_TOP, (k_bt_top<D, false>), 1, 32, 0, top, nullptr, tD, tO);
     }
     for (int l = (int)nl - 2; l >= 0; --l) {
         BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, nullptr, p->d_flag);
@@ -244,7 +277,7 @@ static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, 
         double* lD = (l == 0) ? cD : p->ws + p->plan.levels[l].cD;
         double* lO = (l == 0) ? cO : p->ws + p->plan.levels[l].cO;
         const int block = 128;
-        LAUNCH(p, (k_bt_selinv<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.cD, p->ws + up.cO, lD, lO);
+        LAUNCH(p, KC_BT_BACK, (k_bt_selinv<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.cD, p->ws + up.cO, lD, lO);
     }
     sum_logdet(p, d_logdet);
     return check_launch("bt_selinv");
@@ -258,14 +291,14 @@ static int chain_solve(gvib200_problem* p, const double* Dg, const double* Og, c
     {
         BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, rhs, p->d_flag);
         double* tx = (nl == 1) ? x : p->ws + p->plan.levels[nl - 1].x;
-        LAUNCH(p, (k_bt_top<D, true>), 1, 32, 0, top, tx, nullptr, nullptr);
+        LAUNCH(p, KC_BT_TOP, (k_bt_top<D, true>), 1, 32, 0, top, tx, nullptr, nullptr);
     }
     for (int l = (int)nl - 2; l >= 0; --l) {
         BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
         const auto& up = p->plan.levels[l + 1];
         double* lx = (l == 0) ? x : p->ws + p->plan.levels[l].x;
         const int block = 128;
-        LAUNCH(p, (k_bt_backsolve<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.x, lx);
+        LAUNCH(p, KC_BT_BACK, (k_bt_backsolve<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.x, lx);
     }
     if (d_logdet) sum_logdet(p, d_logdet);
     return check_launch("bt_solve");
@@ -298,7 +331,7 @@ static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, cons
 template <int DIM, int SD>
 static int launch_prologue(gvib200_problem* p, const GhGroup& g, const double* cD, const double* cO, double* SR) {
     const int block = (DIM <= 4) ? 128 : 32;
-    LAUNCH(p, (k_prologue<DIM, SD>), cdiv(g.n, block), block, 0, g.n, g.d_start, cD, cO, SR);
+    LAUNCH(p, KC_PROLOGUE, (k_prologue<DIM, SD>), cdiv(g.n, block), block, 0, g.n, g.d_start, cD, cO, SR);
     return 0;
 }
 
@@ -344,7 +377,9 @@ static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(cdiv(g.n, WARPS), p->ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
+    if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
     kern<<<grid, THREADS, need, p->stream>>>(a);
+    if (p->profile) prof_end(p);
     p->ctx->launches++;
     return check_launch("k_moments");
 }
@@ -449,7 +484,7 @@ static int gh_group_dispatch(gvib200_problem* p, GhGroup& g, const SweepTarget& 
 
 template <int DIM>
 static void launch_raw_to_x(gvib200_problem* p, const GhGroup& g, const double* SR, double* E0, double* E1, double* E2) {
-    LAUNCH(p, (k_raw_to_x<DIM>), cdiv(g.n, 128), 128, 0, g.n, g.d_raw, SR, E0, E1, E2);
+    LAUNCH(p, KC_OTHER, (k_raw_to_x<DIM>), cdiv(g.n, 128), 128, 0, g.n, g.d_raw, SR, E0, E1, E2);
 }
 
 static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
@@ -471,7 +506,7 @@ static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
         a.covO = t.cO;
         a.fcost = p->fcost[t.which] + g.first_id;
         a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
-        LAUNCH(p, k_linear, cdiv(g.n, 128), 128, 0, a);
+        LAUNCH(p, KC_LINEAR, k_linear, cdiv(g.n, 128), 128, 0, a);
     }
     return check_launch("k_linear");
 }
@@ -502,16 +537,16 @@ static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
-        LAUNCH(p, k_partial_sum, nb, 256, 0, n, p->fcost[which], p->partial);
-        LAUNCH(p, k_sum, 1, 256, 0, (size_t)nb, p->partial, p->scal + which, 0.5, p->scal + 2 + which);
+        LAUNCH(p, KC_SUM, k_partial_sum, nb, 256, 0, n, p->fcost[which], p->partial);
+        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)nb, p->partial, p->scal + which, 0.5, p->scal + 2 + which);
     } else {
-        LAUNCH(p, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
+        LAUNCH(p, KC_SUM, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
     }
 }
 
 template <int D>
 static void launch_assemble(gvib200_problem* p, int which) {
-    LAUNCH(p, (k_assemble<D>), cdiv(p->S, 128), 128, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
+    LAUNCH(p, KC_ASSEMBLE, (k_assemble<D>), cdiv(p->S, 128), 128, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
            p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, p->Vdmu, p->VD, p->VO, p->rhs);
 }
 
@@ -638,6 +673,13 @@ static void free_problem(gvib200_problem* p) {
     }
     F(p->scal); F(p->partial); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
     F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws);
+    F(p->snap);
+    for (auto& r : p->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    if (p->t0) cudaEventDestroy(p->t0);
+    if (p->t1) cudaEventDestroy(p->t1);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->h_flag) cudaFreeHost(p->h_flag);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -661,7 +703,7 @@ extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, do
     CUDA_TRY(cudaMalloc((void**)&d_data, n * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&p->d_sdf_rec, n * sizeof(double4)));
     CUDA_TRY(cudaMemcpyAsync(d_data, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    LAUNCH(p, k_build_sdf_records, cdiv((long long)n, 256), 256, 0, rows, cols, d_data, p->d_sdf_rec);
+    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv((long long)n, 256), 256, 0, rows, cols, d_data, p->d_sdf_rec);
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     cudaFree(d_data);
     p->sdf_rows = rows;
@@ -1117,8 +1159,8 @@ extern "C" int gvib200_gradients(gvib200_problem* p, double* dmu, double* dD, do
     if (dD || dO) {
         // dprecision = Vddmu - precision, staged through the candidate precision buffers
         const int w = 1 - p->cur;
-        LAUNCH(p, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VD, p->LD[p->cur], p->LD[w]);
-        LAUNCH(p, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VO, p->LO[p->cur], p->LO[w]);
+        LAUNCH(p, KC_OTHER, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VD, p->LD[p->cur], p->LD[w]);
+        LAUNCH(p, KC_OTHER, k_sub, cdiv(S * dd, 256), 256, 0, S * dd, p->VO, p->LO[p->cur], p->LO[w]);
         TRY(download(p, dD, p->LD[w], S * dd));
         TRY(download(p, dO, p->LO[w], (S - 1) * dd));
     }
@@ -1170,7 +1212,7 @@ static int launch_candidate(gvib200_problem* p, double alpha) {
     const int S = p->S, d = p->d, c = p->cur, w = 1 - p->cur;
     const size_t dd = (size_t)d * d;
     const size_t nmu = (size_t)S * d, nD = S * dd, nO = (S - 1) * dd;
-    LAUNCH(p, k_candidate, cdiv(nD, 256), 256, 0, nmu, nD, nO, alpha, p->mu[c], p->dmu, p->LD[c], p->LO[c], p->VD,
+    LAUNCH(p, KC_CANDIDATE, k_candidate, cdiv(nD, 256), 256, 0, nmu, nD, nO, alpha, p->mu[c], p->dmu, p->LD[c], p->LO[c], p->VD,
            p->VO, p->mu[w], p->LD[w], p->LO[w]);
     return 0;
 }
@@ -1336,6 +1378,148 @@ extern "C" int gvib200_blocktri_solve(gvib200_ctx* ctx, int S, int d, const doub
     return standalone(ctx, S, d, diag, off, rhs, x, nullptr, nullptr, logdet);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: device-side snapshot of the optimizer state (bench.py rewinds the trajectory between blocks of
+// timed iterations so that every step does the same work)
+// ------------------------------------------------------------------------------------------------
+static size_t snapshot_size(const gvib200_problem* p) {
+    const size_t dd = (size_t)p->d * p->d, S = (size_t)p->S;
+    size_t n = S * p->d + 4 * S * dd + (size_t)p->n_factors + p->nV + p->nM + 8;
+    for (auto& g : p->gh) n += (size_t)g.n * 2 * g.dim * g.dim;
+    return n;
+}
+
+static int snapshot_copy(gvib200_problem* p, bool save) {
+    const size_t dd = (size_t)p->d * p->d, S = (size_t)p->S;
+    const int c = p->cur;
+    double* q = p->snap;
+    auto cp = [&](double* live, size_t n) -> int {
+        CUDA_TRY(cudaMemcpyAsync(save ? q : live, save ? live : q, n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        q += n;
+        return 0;
+    };
+    TRY(cp(p->mu[c], S * p->d));
+    TRY(cp(p->LD[c], S * dd));
+    TRY(cp(p->LO[c], S * dd));
+    TRY(cp(p->CD[c], S * dd));
+    TRY(cp(p->CO[c], S * dd));
+    for (auto& g : p->gh) TRY(cp(g.d_SR[c], (size_t)g.n * 2 * g.dim * g.dim));
+    // the factor sweep at the current state (valid when sweep_valid) and the device scalars
+    TRY(cp(p->fcost[c], (size_t)p->n_factors));
+    TRY(cp(p->fVdmu[c], p->nV));
+    TRY(cp(p->fVdd[c], p->nM));
+    TRY(cp(p->scal, 8));
+    return 0;
+}
+
+extern "C" int gvib200_snapshot_save(gvib200_problem* p) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "snapshot_save: no state");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    const size_t n = snapshot_size(p);
+    if (p->snap == nullptr || p->snap_doubles != n) {
+        if (p->snap) cudaFree(p->snap);
+        TRY(dev_alloc(&p->snap, n));
+        p->snap_doubles = n;
+    }
+    TRY(snapshot_copy(p, true));
+    p->snap_iter = p->iter;
+    p->snap_lowtemp = p->is_lowtemp;
+    p->snap_cur = p->cur;
+    p->snap_sweep_valid = p->sweep_valid;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int gvib200_snapshot_restore(gvib200_problem* p) {
+    if (!p || !p->snap) return fail(GVIB200_ESTATE, "snapshot_restore: nothing saved");
+    if (p->snap_lowtemp != p->is_lowtemp)
+        return fail(GVIB200_ESTATE, "snapshot_restore: the temperature phase changed since the snapshot");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (p->snap_cur != p->cur) {
+        // the scalars are slot-indexed (cur / candidate): restore into the slot layout of the snapshot
+        p->cur = p->snap_cur;
+    }
+    TRY(snapshot_copy(p, false));
+    p->iter = p->snap_iter;
+    p->converged = false;
+    p->sweep_valid = p->snap_sweep_valid;
+    p->grads_valid = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: timing on the problem's stream
+// ------------------------------------------------------------------------------------------------
+extern "C" int gvib200_timer_start(gvib200_problem* p) {
+    if (!p) return fail(GVIB200_EINVAL, "timer_start: null");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (!p->t0) {
+        CUDA_TRY(cudaEventCreate(&p->t0));
+        CUDA_TRY(cudaEventCreate(&p->t1));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaEventRecord(p->t0, p->stream));
+    return 0;
+}
+
+extern "C" int gvib200_timer_stop(gvib200_problem* p, float* ms) {
+    if (!p || !p->t0 || !ms) return fail(GVIB200_ESTATE, "timer_stop: timer not started");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    CUDA_TRY(cudaEventRecord(p->t1, p->stream));
+    CUDA_TRY(cudaEventSynchronize(p->t1));
+    CUDA_TRY(cudaEventElapsedTime(ms, p->t0, p->t1));
+    return 0;
+}
+
+extern "C" int gvib200_profile_begin(gvib200_problem* p) {
+    if (!p) return fail(GVIB200_EINVAL, "profile_begin: null");
+    for (auto& r : p->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    p->prof.clear();
+    p->profile = true;
+    return 0;
+}
+
+extern "C" int gvib200_profile_end(gvib200_problem* p, gvib200_profile* out) {
+    if (!p || !out) return fail(GVIB200_EINVAL, "profile_end: null");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    p->profile = false;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    std::memset(out, 0, sizeof(*out));
+    out->n_classes = KC_COUNT;
+    for (auto& r : p->prof) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        out->count[r.kc]++;
+        out->ms[r.kc] += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    p->prof.clear();
+    return 0;
+}
+
+extern "C" const char* gvib200_kernel_class_name(int kc) { return (kc >= 0 && kc < KC_COUNT) ? KC_NAMES[kc] : ""; }
+
+// algorithmic size of the problem, for the roofline arithmetic of bench.py
+extern "C" int gvib200_problem_info(gvib200_problem* p, gvib200_info* out) {
+    if (!p || !out) return fail(GVIB200_EINVAL, "problem_info: null");
+    std::memset(out, 0, sizeof(*out));
+    out->num_states = p->S;
+    out->dim_state = p->d;
+    out->n_factors = p->n_factors;
+    for (auto& g : p->gh) {
+        out->n_gh_factors += g.n;
+        out->sigma_points_per_sweep += (long long)g.n * g.table->n;
+    }
+    for (auto& g : p->lin) out->n_linear_factors += g.n;
+    out->chain_levels = (int)p->plan.levels.size();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI: measurement hooks
 // ------------------------------------------------------------------------------------------------
@@ -1359,6 +1543,13 @@ extern "C" int gvib200_time_stage(gvib200_problem* p, int stage, int reps, const
         switch (stage) {
             case 0: TRY(run_sweep(p, c, true, true, false)); break;
             case 1: TRY(run_sweep(p, c, true, false, false)); break;
+            case 5:  // K1 alone (full moments), prologue outputs reused
+            case 6:  // K1 alone (cost only)
+            {
+                SweepTarget t{p->mu[c], p->CD[c], p->CO[c], c};
+                for (auto& g : p->gh) TRY(gh_group_dispatch(p, g, t, false, true, stage == 5, nullptr));
+                break;
+            }
             case 2: {
                 switch (p->d) {
                     case 1: launch_assemble<1>(p, c); break;
@@ -1386,7 +1577,7 @@ extern "C" int gvib200_time_stage(gvib200_problem* p, int stage, int reps, const
     cudaEventDestroy(e1);
     if (ms_per_rep) *ms_per_rep = ms / reps;
     if (kernel_launches) *kernel_launches = (p->ctx->launches - l0) / reps;
-    if (stage <= 1) {
+    if (stage <= 1 || stage >= 5) {
         // the sweep overwrote fcost[cur] consistently (same state), totals need refreshing
         run_total(p, c);
         p->sweep_valid = (stage == 0);

@@ -186,10 +186,38 @@ int gvib200_blocktri_solve(gvib200_ctx* ctx, int S, int d, const double* diag, c
 
 /* ---- measurement hooks (bench.py): device-resident timing of the stages with CUDA events on the
         problem's stream.  stage: 0 = moment sweep (K2+K1), 1 = cost sweep, 2 = assemble + dmu solve,
-        3 = candidate + selected inverse + log det, 4 = one full iteration.  Returns milliseconds per repetition. */
+        3 = candidate + selected inverse + log det, 5 = the fused moment kernel K1 alone (full moments), 6 = K1 alone
+        (cost only).  Returns milliseconds per repetition. */
 int gvib200_time_stage(gvib200_problem* prob, int stage, int reps, const gvib200_opts* opts, float* ms_per_rep,
                        long long* kernel_launches);
 int gvib200_fp64_peak(gvib200_ctx* ctx, double* tflops);   /* DFMA micro-benchmark: the FP64 roofline denominator */
+long long gvib200_launch_count(gvib200_ctx* ctx);            /* kernels launched through this ctx so far */
+
+/* CUDA-event stopwatch on the problem's stream (the stream every kernel of the problem is launched on) */
+int gvib200_timer_start(gvib200_problem* prob);
+int gvib200_timer_stop(gvib200_problem* prob, float* ms);
+
+/* per-launch profile: between _begin and _end every kernel launch of the problem is bracketed by a CUDA event
+   pair; _end returns launch counts and summed device time per kernel class (gvib200_kernel_class_name). */
+typedef struct {
+    int n_classes;
+    long long count[16];
+    double ms[16];
+} gvib200_profile;
+int gvib200_profile_begin(gvib200_problem* prob);
+int gvib200_profile_end(gvib200_problem* prob, gvib200_profile* out);
+const char* gvib200_kernel_class_name(int kernel_class);
+
+typedef struct {
+    int num_states, dim_state, n_factors, n_gh_factors, n_linear_factors, chain_levels;
+    long long sigma_points_per_sweep; /* sum over GH factors of the nodes of their rule */
+} gvib200_info;
+int gvib200_problem_info(gvib200_problem* prob, gvib200_info* out);
+
+/* device-side snapshot / rewind of the optimizer state (mean, precision, covariance, factor marginals,
+   iteration counter); no host traffic */
+int gvib200_snapshot_save(gvib200_problem* prob);
+int gvib200_snapshot_restore(gvib200_problem* prob);
 
 #ifdef __cplusplus
 }
