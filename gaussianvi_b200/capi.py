@@ -60,7 +60,8 @@ class Profile(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("num_states", C.c_int), ("dim_state", C.c_int), ("n_factors", C.c_int), ("n_gh_factors", C.c_int),
-                ("n_linear_factors", C.c_int), ("chain_levels", C.c_int), ("sigma_points_per_sweep", C.c_longlong)]
+                ("n_linear_factors", C.c_int), ("chain_levels", C.c_int), ("chain_tiles", C.c_int), ("chain_tile_links", C.c_int),
+                ("sigma_points_per_sweep", C.c_longlong)]
 
 
 class Stereo1DParams(C.Structure):

@@ -1,0 +1,472 @@
+// Block-tridiagonal SPD engine, second generation: tile-wise block cyclic reduction.
+//
+// Replaces, for the joint precision pattern fixed at gvibase/GVI-GH.h:214-230:
+//   GVIGH::inverse_GBP + calculate_factor_message   gvibase/GVI-GH-GBP-impl.h:245-342
+//   EigenWrapper::inv_sparse (Takahashi on LDLT)     helpers/EigenWrapper.h:336-381
+//   SparseLDLT(Precision).vectorD().log().sum()      gvibase/GVI-GH-GBP-impl.h:234-238
+//   ConjugateGradient(Vddmu).solve(-Vdmu)            ngd/NGD-GH-impl.h:59-60 (direct solve instead)
+//
+// The chain of n nodes is cut into K tiles of T links; tile k owns the nodes n0 = kT .. n0 + Tk (local 0 .. Tk), its two
+// end nodes are separators shared with the neighbouring tiles.  One CTA holds a tile in shared memory and eliminates
+// its Tk - 1 interior nodes by block cyclic reduction: at level l every node j = (2t+1) 2^l < Tk is eliminated against
+// its alive neighbours i = j - 2^l and k = min(j + 2^l, Tk) -- a nested-dissection Cholesky, log2(T) dependent steps
+// instead of T.  What is left (Schur complements on the separators and their coupling) is a block-tridiagonal system of
+// K + 1 nodes which ONE CTA reduces the same way (the "top"), solves, and expands again; a last launch walks every tile
+// back down (solution and / or the Takahashi selected inverse: diagonal and first off-diagonal blocks of the inverse).
+// Three launches per solve, every global access coalesced.
+//
+// Storage inside a tile: node j lives in slot(j) -- 0 and Tk in slots 0 and 1, the nodes eliminated at level l
+// contiguously from off[l] -- so that the threads of one level touch consecutive slots; element e of slot s sits at
+// [e * NS + s] (structure of arrays: conflict-free shared-memory accesses).  The elimination record of node j (G, H,
+// Dinv, y) goes to global memory at record index base + slot(j) - 2 in a 32-record interleaved layout, written and
+// read back by the same lane pattern.
+//
+// Everything here is __host__ __device__ and free of CUDA intrinsics: tests/cpp/bt_host_emu.cpp runs the very same
+// arithmetic on the CPU against the oracle.
+#pragma once
+#include "smallmat.h"
+
+namespace gvib200 {
+
+constexpr int CR_MAX_LEVELS = 16;
+
+struct CrGeom {
+    int T;                       // local nodes 0 .. T
+    int levels;                  // cyclic-reduction levels until only {0, T} are alive
+    int off[CR_MAX_LEVELS + 1];  // first slot (minus 2) of the nodes eliminated at level l; off[levels] = T - 1
+};
+
+GVI_HD int cr_count(int T, int l) { return (((T - 1) >> l) + 1) >> 1; }  // nodes eliminated at level l
+
+GVI_HD void cr_make_geom(CrGeom& g, int T) {
+    g.T = T;
+    int lv = 0;
+    while ((1 << lv) < T) ++lv;
+    g.levels = lv;
+    int o = 0;
+    for (int l = 0; l <= CR_MAX_LEVELS; ++l) {
+        g.off[l] = o;
+        if (l < lv) o += cr_count(T, l);
+    }
+}
+
+GVI_HD int cr_ctz(int j) {
+    int c = 0;
+    while (((j >> c) & 1) == 0) ++c;
+    return c;
+}
+
+GVI_HD int cr_slot(const CrGeom& g, int j) {
+    if (j == 0) return 0;
+    if (j == g.T) return 1;
+    const int l = cr_ctz(j);
+    return 2 + g.off[l] + (j >> (l + 1));
+}
+
+// record r, element e of a [.. x NE] record array in the 32-record interleaved layout
+GVI_HD size_t cr_rec(size_t r, int e, int NE) { return (r >> 5) * (size_t)(32 * NE) + (size_t)e * 32 + (r & 31); }
+GVI_HD size_t cr_rec_capacity(size_t nrec, int NE) { return ((nrec + 31) >> 5) * (size_t)(32 * NE); }
+
+// working arrays of one tile (shared memory on the device), slot indexed, structure of arrays with stride NS
+template <int D>
+struct CrView {
+    int NS;
+    double* Dn;  // [D*D][NS] Schur-updated diagonal blocks; after the forward pass reused for the covariance diagonal
+    double* P;   // [D*D][NS] coupling of a node to its next alive node; reused for the covariance couplings
+    double* g;   // [D][NS] right-hand side; reused for the solution
+};
+
+template <int D>
+struct CrRec {
+    double* G;     // Dinv * A[j,k]
+    double* H;     // Dinv * A[i,j]^T
+    double* Dinv;  // inverse of the pivot block
+    double* y;     // Dinv * g_j
+};
+
+template <int D>
+GVI_HD void cr_ld(Mat<D>& A, const double* base, int NS, int s) {
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) A.a[e] = base[(size_t)e * NS + s];
+}
+template <int D>
+GVI_HD void cr_st(double* base, int NS, int s, const Mat<D>& A) {
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) base[(size_t)e * NS + s] = A.a[e];
+}
+template <int D>
+GVI_HD void cr_ldv(Vec<D>& v, const double* base, int NS, int s) {
+#pragma unroll
+    for (int e = 0; e < D; ++e) v.a[e] = base[(size_t)e * NS + s];
+}
+template <int D>
+GVI_HD void cr_stv(double* base, int NS, int s, const Vec<D>& v) {
+#pragma unroll
+    for (int e = 0; e < D; ++e) base[(size_t)e * NS + s] = v.a[e];
+}
+template <int D>
+GVI_HD void cr_rec_ld(Mat<D>& A, const double* base, size_t r) {
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) A.a[e] = base[cr_rec(r, e, D * D)];
+}
+template <int D>
+GVI_HD void cr_rec_st(double* base, size_t r, const Mat<D>& A) {
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) base[cr_rec(r, e, D * D)] = A.a[e];
+}
+template <int D>
+GVI_HD void cr_rec_ldv(Vec<D>& v, const double* base, size_t r) {
+#pragma unroll
+    for (int e = 0; e < D; ++e) v.a[e] = base[cr_rec(r, e, D)];
+}
+template <int D>
+GVI_HD void cr_rec_stv(double* base, size_t r, const Vec<D>& v) {
+#pragma unroll
+    for (int e = 0; e < D; ++e) base[cr_rec(r, e, D)] = v.a[e];
+}
+
+// what one elimination keeps between its two phases
+template <int D>
+struct CrElim {
+    int si, sj, sk;
+    Mat<D> Pi, G, H;
+    Vec<D> y;
+};
+
+// Forward elimination of node j = (2t+1) 2^l, phase A: pivot inverse, record, Schur update of the RIGHT neighbour
+// (every right neighbour is updated by exactly one elimination of the level, so phase A is race free).
+template <int D, bool RHS>
+GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t,
+                     CrElim<D>& c, LogDetAcc& ld) {
+    const int j = (2 * t + 1) << l;
+    const int i = j - (1 << l);
+    const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
+    c.sj = 2 + gm.off[l] + t;
+    c.si = cr_slot(gm, i);
+    c.sk = cr_slot(gm, k);
+    const size_t r = rec_base + (size_t)(c.sj - 2);
+    Mat<D> Dt, Pj, Dinv, Tm;
+    cr_ld<D>(Dt, v.Dn, v.NS, c.sj);
+    cr_ld<D>(c.Pi, v.P, v.NS, c.si);
+    cr_ld<D>(Pj, v.P, v.NS, c.sj);
+    symmetrize<D>(Dt);
+    const bool ok = spd_inverse<D>(Dinv, Dt, ld);
+    mm<D>(c.G, Dinv, Pj);
+    mmt<D>(c.H, Dinv, c.Pi);  // Dinv * Pi^T
+    cr_rec_st<D>(rec.G, r, c.G);
+    cr_rec_st<D>(rec.H, r, c.H);
+    cr_rec_st<D>(rec.Dinv, r, Dinv);
+    // right neighbour: Dn[k] -= Pj^T G
+    mtm<D>(Tm, Pj, c.G);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) v.Dn[(size_t)e * v.NS + c.sk] -= Tm.a[e];
+    if (RHS) {
+        Vec<D> gv, tv;
+        cr_ldv<D>(gv, v.g, v.NS, c.sj);
+        mv<D>(c.y, Dinv, gv);
+        cr_rec_stv<D>(rec.y, r, c.y);
+        mtv<D>(tv, Pj, c.y);
+#pragma unroll
+        for (int e = 0; e < D; ++e) v.g[(size_t)e * v.NS + c.sk] -= tv.a[e];
+    }
+    return ok;
+}
+
+// phase B: Schur update of the LEFT neighbour and its new coupling to k (again one writer per node)
+template <int D, bool RHS>
+GVI_HD void cr_fwd_B(const CrView<D>& v, const CrElim<D>& c) {
+    Mat<D> Tm;
+    mm<D>(Tm, c.Pi, c.H);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) v.Dn[(size_t)e * v.NS + c.si] -= Tm.a[e];
+    mm<D>(Tm, c.Pi, c.G);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) v.P[(size_t)e * v.NS + c.si] = -Tm.a[e];
+    if (RHS) {
+        Vec<D> tv;
+        mv<D>(tv, c.Pi, c.y);
+#pragma unroll
+        for (int e = 0; e < D; ++e) v.g[(size_t)e * v.NS + c.si] -= tv.a[e];
+    }
+}
+
+// Back substitution of node j at level l: x_j = y_j - G x_k - H x_i (x lives in v.g)
+template <int D>
+GVI_HD void cr_bwd_solve(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t) {
+    const int j = (2 * t + 1) << l;
+    const int i = j - (1 << l);
+    const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
+    const int sj = 2 + gm.off[l] + t, si = cr_slot(gm, i), sk = cr_slot(gm, k);
+    const size_t r = rec_base + (size_t)(sj - 2);
+    Mat<D> G, H;
+    Vec<D> xi, xk, y, t1, t2;
+    cr_rec_ld<D>(G, rec.G, r);
+    cr_rec_ld<D>(H, rec.H, r);
+    cr_rec_ldv<D>(y, rec.y, r);
+    cr_ldv<D>(xi, v.g, v.NS, si);
+    cr_ldv<D>(xk, v.g, v.NS, sk);
+    mv<D>(t1, G, xk);
+    mv<D>(t2, H, xi);
+#pragma unroll
+    for (int e = 0; e < D; ++e) y.a[e] -= t1.a[e] + t2.a[e];
+    cr_stv<D>(v.g, v.NS, sj, y);
+}
+
+// Takahashi recursion for node j at level l.  On entry v.Dn holds Sigma_ii, Sigma_kk and v.P[si] = Sigma_{i,k};
+// on exit v.Dn[sj] = Sigma_jj, v.P[si] = Sigma_{i,j}, v.P[sj] = Sigma_{j,k}.
+template <int D>
+GVI_HD void cr_bwd_selinv(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t) {
+    const int j = (2 * t + 1) << l;
+    const int i = j - (1 << l);
+    const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
+    const int sj = 2 + gm.off[l] + t, si = cr_slot(gm, i), sk = cr_slot(gm, k);
+    const size_t r = rec_base + (size_t)(sj - 2);
+    Mat<D> G, H, Dinv, Sii, Skk, Sik, Sjk, Sji, T1, T2;
+    cr_rec_ld<D>(G, rec.G, r);
+    cr_rec_ld<D>(H, rec.H, r);
+    cr_rec_ld<D>(Dinv, rec.Dinv, r);
+    cr_ld<D>(Sii, v.Dn, v.NS, si);
+    cr_ld<D>(Skk, v.Dn, v.NS, sk);
+    cr_ld<D>(Sik, v.P, v.NS, si);
+    // Sigma_{j,k} = -(G Sigma_kk + H Sigma_ik)
+    mm<D>(T1, G, Skk);
+    mm<D>(T2, H, Sik);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) Sjk.a[e] = -(T1.a[e] + T2.a[e]);
+    // Sigma_{j,i} = -(G Sigma_ki + H Sigma_ii),  Sigma_ki = Sigma_ik^T
+    mmt<D>(T1, G, Sik);
+    mm<D>(T2, H, Sii);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) Sji.a[e] = -(T1.a[e] + T2.a[e]);
+    // Sigma_jj = Dinv - Sigma_jk G^T - Sigma_ji H^T
+    mmt<D>(T1, Sjk, G);
+    mmt<D>(T2, Sji, H);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) Dinv.a[e] -= T1.a[e] + T2.a[e];
+    symmetrize<D>(Dinv);
+    cr_st<D>(v.Dn, v.NS, sj, Dinv);
+    cr_st<D>(v.P, v.NS, sj, Sjk);
+    mat_transpose<D>(T1, Sji);
+    cr_st<D>(v.P, v.NS, si, T1);
+}
+
+// The system left after all levels: nodes 0 and T (slots 0, 1) coupled by P[slot 0]; T == 0: a single node.
+// Solves it in place: v.g <- x (RHS), v.Dn <- Sigma diagonal blocks and v.P[0] <- Sigma_{0,T} (SELINV).
+template <int D, bool RHS, bool SELINV>
+GVI_HD bool cr_top2(const CrView<D>& v, int T, LogDetAcc& ld) {
+    Mat<D> A0, A1, P, I0, S1, G, Tm;
+    cr_ld<D>(A0, v.Dn, v.NS, 0);
+    symmetrize<D>(A0);
+    bool ok = spd_inverse<D>(I0, A0, ld);
+    Vec<D> g0, g1, y0, x1, tv;
+    if (RHS) {
+        cr_ldv<D>(g0, v.g, v.NS, 0);
+        mv<D>(y0, I0, g0);
+    }
+    if (T == 0) {
+        if (RHS) cr_stv<D>(v.g, v.NS, 0, y0);
+        if (SELINV) cr_st<D>(v.Dn, v.NS, 0, I0);
+        return ok;
+    }
+    cr_ld<D>(A1, v.Dn, v.NS, 1);
+    cr_ld<D>(P, v.P, v.NS, 0);
+    mm<D>(G, I0, P);  // A0^-1 P
+    mtm<D>(Tm, P, G);
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) A1.a[e] -= Tm.a[e];
+    symmetrize<D>(A1);
+    ok = spd_inverse<D>(S1, A1, ld) && ok;  // Sigma_TT
+    if (RHS) {
+        cr_ldv<D>(g1, v.g, v.NS, 1);
+        mtv<D>(tv, P, y0);
+#pragma unroll
+        for (int e = 0; e < D; ++e) g1.a[e] -= tv.a[e];
+        mv<D>(x1, S1, g1);
+        mv<D>(tv, G, x1);
+#pragma unroll
+        for (int e = 0; e < D; ++e) y0.a[e] -= tv.a[e];
+        cr_stv<D>(v.g, v.NS, 0, y0);
+        cr_stv<D>(v.g, v.NS, 1, x1);
+    }
+    if (SELINV) {
+        Mat<D> S01, S00;
+        mm<D>(Tm, G, S1);
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) S01.a[e] = -Tm.a[e];  // Sigma_{0,T} = -G Sigma_TT
+        mmt<D>(Tm, S01, G);
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) S00.a[e] = I0.a[e] - Tm.a[e];
+        symmetrize<D>(S00);
+        cr_st<D>(v.Dn, v.NS, 0, S00);
+        cr_st<D>(v.Dn, v.NS, 1, S1);
+        cr_st<D>(v.P, v.NS, 0, S01);
+    }
+    return ok;
+}
+
+}  // namespace gvib200
+
+// ------------------------------------------------------------------------------------------------------------------
+// Glue shared by the CUDA kernels (kernels.cuh) and the host harness: a "thread" tid of nthreads strides the copies.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gvib200 {
+
+template <int D>
+struct CrArgs {
+    int n;  // nodes of the chain
+    int T;  // links per tile (tile k owns nodes kT .. min((k+1)T, n-1))
+    int K;  // tiles; K == 0: the whole chain is handled by the top kernel alone
+    // the system: diag[n][D*D], off[n-1][D*D] (block (i, i+1)), rhs[n][D] (null without a right-hand side)
+    const double* Dg;
+    const double* Og;
+    const double* g;
+    CrRec<D> rec;  // elimination records of the tiles, K * (T - 1) records
+    // reduced system on the separators (input of the top), node k = separator kT:
+    //   diag(k) = rDn[k] + rCL[k] (k < K) + rCR[k-1] (k > 0), coupling rO[k], rhs rg + rgl + rgr likewise
+    double *rDn, *rCL, *rCR, *rO, *rg, *rgl, *rgr;
+    double *tD, *tO, *tx;  // results of the top on the separators: [K+1][DD], [K][DD], [K+1][D]
+    double *x, *cD, *cO;   // outputs: solution [n][D]; selected inverse diag [n][DD], off [n-1][DD]
+    double* ld;            // [K + 1] partial log determinants (tiles, then the top)
+    int* notspd;
+};
+
+GVI_HD int cr_pad_slots(int nodes) { return nodes | 1; }  // odd stride: conflict-free transposing copies
+
+// shared-memory doubles needed by one tile CTA / by the top CTA
+template <int D>
+GVI_HD size_t cr_tile_doubles(int T) { return (size_t)(2 * D * D + D) * cr_pad_slots(T + 1); }
+template <int D>
+GVI_HD size_t cr_top_doubles(int n_top) {
+    const size_t nrec = n_top > 2 ? (size_t)(n_top - 2) : 0;
+    return (size_t)(2 * D * D + D) * cr_pad_slots(n_top) + 3 * cr_rec_capacity(nrec, D * D) + cr_rec_capacity(nrec, D);
+}
+
+template <int D>
+GVI_HD CrView<D> cr_make_view(double* sm, int nodes) {
+    CrView<D> v;
+    v.NS = cr_pad_slots(nodes);
+    v.Dn = sm;
+    v.P = v.Dn + (size_t)D * D * v.NS;
+    v.g = v.P + (size_t)D * D * v.NS;
+    return v;
+}
+
+// tile -> working arrays.  Separator slots start from zero: they only collect this tile's Schur contributions.
+template <int D, bool RHS>
+GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int n0, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    const int Tk = gm.T;
+    for (int idx = tid; idx < (Tk + 1) * DD; idx += nthreads) {
+        const int node = idx / DD, e = idx - node * DD;
+        const int s = cr_slot(gm, node);
+        v.Dn[(size_t)e * v.NS + s] = (node == 0 || node == Tk) ? 0.0 : a.Dg[(size_t)(n0 + node) * DD + e];
+        if (node < Tk) v.P[(size_t)e * v.NS + s] = a.Og[(size_t)(n0 + node) * DD + e];
+    }
+    if (RHS) {
+        for (int idx = tid; idx < (Tk + 1) * D; idx += nthreads) {
+            const int node = idx / D, e = idx - node * D;
+            v.g[(size_t)e * v.NS + cr_slot(gm, node)] = (node == 0 || node == Tk) ? 0.0 : a.g[(size_t)(n0 + node) * D + e];
+        }
+    }
+}
+
+// what the tile hands to the top: its contributions to the two separators and their coupling
+template <int D, bool RHS>
+GVI_HD void cr_tile_store_reduced(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int tile, int n0, int tid,
+                                  int nthreads) {
+    constexpr int DD = D * D;
+    const bool last = (tile == a.K - 1);
+    for (int e = tid; e < DD; e += nthreads) {
+        a.rDn[(size_t)tile * DD + e] = a.Dg[(size_t)n0 * DD + e];
+        if (last) a.rDn[(size_t)a.K * DD + e] = a.Dg[(size_t)(a.n - 1) * DD + e];
+        a.rCL[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 0];
+        a.rCR[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 1];
+        a.rO[(size_t)tile * DD + e] = v.P[(size_t)e * v.NS + 0];
+    }
+    if (RHS) {
+        for (int e = tid; e < D; e += nthreads) {
+            a.rg[(size_t)tile * D + e] = a.g[(size_t)n0 * D + e];
+            if (last) a.rg[(size_t)a.K * D + e] = a.g[(size_t)(a.n - 1) * D + e];
+            a.rgl[(size_t)tile * D + e] = v.g[(size_t)e * v.NS + 0];
+            a.rgr[(size_t)tile * D + e] = v.g[(size_t)e * v.NS + 1];
+        }
+    }
+}
+
+// top: gather the separator system (or, K == 0, the chain itself) into the working arrays
+template <int D, bool RHS>
+GVI_HD void cr_top_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    const int nt = gm.T + 1;  // nodes of the top
+    for (int idx = tid; idx < nt * DD; idx += nthreads) {
+        const int node = idx / DD, e = idx - node * DD;
+        const int s = cr_slot(gm, node);
+        double dv;
+        if (a.K == 0) {
+            dv = a.Dg[(size_t)node * DD + e];
+            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = a.Og[(size_t)node * DD + e];
+        } else {
+            dv = a.rDn[(size_t)node * DD + e];
+            if (node < a.K) dv += a.rCL[(size_t)node * DD + e];
+            if (node > 0) dv += a.rCR[(size_t)(node - 1) * DD + e];
+            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = a.rO[(size_t)node * DD + e];
+        }
+        v.Dn[(size_t)e * v.NS + s] = dv;
+    }
+    if (RHS) {
+        for (int idx = tid; idx < nt * D; idx += nthreads) {
+            const int node = idx / D, e = idx - node * D;
+            double gv;
+            if (a.K == 0) {
+                gv = a.g[(size_t)node * D + e];
+            } else {
+                gv = a.rg[(size_t)node * D + e];
+                if (node < a.K) gv += a.rgl[(size_t)node * D + e];
+                if (node > 0) gv += a.rgr[(size_t)(node - 1) * D + e];
+            }
+            v.g[(size_t)e * v.NS + cr_slot(gm, node)] = gv;
+        }
+    }
+}
+
+// working arrays -> AoS results for nodes [0, count) (diag / solution) and couplings [0, ncoup), written at node offset n0
+template <int D, bool RHS, bool SELINV>
+GVI_HD void cr_store_results(const CrView<D>& v, const CrGeom& gm, int count, int ncoup, double* x, double* cD, double* cO,
+                             size_t n0, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    if (SELINV) {
+        for (int idx = tid; idx < count * DD; idx += nthreads) {
+            const int node = idx / DD, e = idx - node * DD;
+            const int s = cr_slot(gm, node);
+            cD[(n0 + node) * DD + e] = v.Dn[(size_t)e * v.NS + s];
+            if (node < ncoup) cO[(n0 + node) * DD + e] = v.P[(size_t)e * v.NS + s];
+        }
+    }
+    if (RHS) {
+        for (int idx = tid; idx < count * D; idx += nthreads) {
+            const int node = idx / D, e = idx - node * D;
+            x[(n0 + node) * D + e] = v.g[(size_t)e * v.NS + cr_slot(gm, node)];
+        }
+    }
+}
+
+// tile, backward: seed the two separators from the results of the top
+template <int D, bool RHS, bool SELINV>
+GVI_HD void cr_tile_seed(const CrArgs<D>& a, const CrView<D>& v, int tile, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    if (SELINV) {
+        for (int e = tid; e < DD; e += nthreads) {
+            v.Dn[(size_t)e * v.NS + 0] = a.tD[(size_t)tile * DD + e];
+            v.Dn[(size_t)e * v.NS + 1] = a.tD[(size_t)(tile + 1) * DD + e];
+            v.P[(size_t)e * v.NS + 0] = a.tO[(size_t)tile * DD + e];
+        }
+    }
+    if (RHS) {
+        for (int e = tid; e < D; e += nthreads) {
+            v.g[(size_t)e * v.NS + 0] = a.tx[(size_t)tile * D + e];
+            v.g[(size_t)e * v.NS + 1] = a.tx[(size_t)(tile + 1) * D + e];
+        }
+    }
+}
+
+}  // namespace gvib200

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "bt_plan.h"
+#include "bt_cr_plan.h"
 #include "kernels.cuh"
 #include "spgh_table.h"
 
@@ -130,9 +130,14 @@ struct gvib200_problem {
     // adjacency
     int *vptr = nullptr, *voff = nullptr, *dptr = nullptr, *doff = nullptr, *dld = nullptr, *optr = nullptr,
         *ooff = nullptr, *old = nullptr;
-    // chain engine
-    BtPlan plan;
-    double* ws = nullptr;
+    // chain engine (bt_cr.h): one plan, two workspaces so that the dmu solve and the candidate's selected inverse
+    // can run concurrently on the two streams
+    CrPlan plan;
+    double* ws[2] = {nullptr, nullptr};
+    double* ldsum[2] = {nullptr, nullptr};
+    cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
+    cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // schedule (GVIGH::optimize locals)
     int iter = 0;
     bool is_lowtemp = true, converged = false;
@@ -173,7 +178,7 @@ static inline void prof_end(gvib200_problem* p);
 #define LAUNCH(prob, kc, kern, grid, block, smem, ...)                               \
     do {                                                                             \
         if ((prob)->profile) prof_begin((prob), (kc));                               \
-        kern<<<(grid), (block), (smem), (prob)->stream>>>(__VA_ARGS__);              \
+        kern<<<(grid), (block), (smem), (prob)->ls>>>(__VA_ARGS__);              \
         if ((prob)->profile) prof_end((prob));                                       \
         (prob)->ctx->launches++;                                                     \
     } while (0)
@@ -183,10 +188,10 @@ static inline void prof_begin(gvib200_problem* p, int kc) {
     r.kc = kc;
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
-    cudaEventRecord(r.a, p->stream);
+    cudaEventRecord(r.a, p->ls);
     p->prof.push_back(r);
 }
-static inline void prof_end(gvib200_problem* p) { cudaEventRecord(p->prof.back().b, p->stream); }
+static inline void prof_end(gvib200_problem* p) { cudaEventRecord(p->prof.back().b, p->ls); }
 
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -235,73 +240,44 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// chain engine drivers
+// chain engine drivers (tile-wise block cyclic reduction, bt_cr.h): three launches per pass
 // ------------------------------------------------------------------------------------------------
-template <int D>
-static int chain_forward(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs) {
-    const size_t nl = p->plan.levels.size();
-    for (size_t l = 0; l + 1 < nl; ++l) {
-        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
-        const int block = 128;
-        if (rhs) LAUNCH(p, KC_BT_FORWARD, (k_bt_forward<D, true>), cdiv(lv.K, block), block, 0, lv);
-        else LAUNCH(p, KC_BT_FORWARD, (k_bt_forward<D, false>), cdiv(lv.K, block), block, 0, lv);
-    }
-    return check_launch("bt_forward");
+template <class K>
+static int cr_allow_smem(K kern, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
 }
 
-static void sum_logdet(gvib200_problem* p, double* d_logdet) {
-    const size_t n = p->plan.ld_count;
-    if (n > 8192) {
-        const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
-        LAUNCH(p, KC_SUM, k_partial_sum, nb, 256, 0, n, p->ws + p->plan.ld_offset, p->partial);
-        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)nb, p->partial, nullptr, 0.0, d_logdet);
-    } else {
-        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, n, p->ws + p->plan.ld_offset, nullptr, 0.0, d_logdet);
+template <int D, bool RHS, bool SELINV>
+static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const double* Og, const double* rhs, double* x,
+                      double* cD, double* cO, double* d_logdet, int* d_flag) {
+    const CrPlan& pl = p->plan;
+    CrArgs<D> a = cr_bind<D>(pl, p->ws[slot], Dg, Og, rhs, x, cD, cO, d_flag);
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        TRY(cr_allow_smem(k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 4096));
+        TRY(cr_allow_smem(k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 4096));
+        TRY(cr_allow_smem(k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 4096));
+        configured = true;
     }
+    if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
+    if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    if (d_logdet) LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)pl.ld_count, a.ld, nullptr, 0.0, d_logdet);
+    return check_launch("chain_pass");
 }
 
 // selected inverse + log det of the block-tridiagonal (Dg, Og) -> (cD, cO), logdet scalar (device)
 template <int D>
-static int chain_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet) {
-    TRY(chain_forward<D>(p, Dg, Og, nullptr));
-    const size_t nl = p->plan.levels.size();
-    {
-        BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, nullptr, p->d_flag);
-        double* tD = (nl == 1) ? cD : p->ws + p->plan.levels[nl - 1].cD;
-        double* tO = (nl == 1) ? cO : p->ws + p->plan.levels[nl - 1].cO;
-        LAUNCH(p, KC_BT_TOP, (k_bt_top<D, false>), 1, 32, 0, top, nullptr, tD, tO);
-    }
-    for (int l = (int)nl - 2; l >= 0; --l) {
-        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, nullptr, p->d_flag);
-        const auto& up = p->plan.levels[l + 1];
-        double* lD = (l == 0) ? cD : p->ws + p->plan.levels[l].cD;
-        double* lO = (l == 0) ? cO : p->ws + p->plan.levels[l].cO;
-        const int block = 128;
-        LAUNCH(p, KC_BT_BACK, (k_bt_selinv<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.cD, p->ws + up.cO, lD, lO);
-    }
-    sum_logdet(p, d_logdet);
-    return check_launch("bt_selinv");
+static int chain_selinv(gvib200_problem* p, int slot, const double* Dg, const double* Og, double* cD, double* cO,
+                        double* d_logdet, int* d_flag) {
+    return chain_pass<D, false, true>(p, slot, Dg, Og, nullptr, nullptr, cD, cO, d_logdet, d_flag);
 }
 
 template <int D>
-static int chain_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x,
-                       double* d_logdet) {
-    TRY(chain_forward<D>(p, Dg, Og, rhs));
-    const size_t nl = p->plan.levels.size();
-    {
-        BtLevel<D> top = bt_bind_level<D>(p->plan, nl - 1, p->ws, Dg, Og, rhs, p->d_flag);
-        double* tx = (nl == 1) ? x : p->ws + p->plan.levels[nl - 1].x;
-        LAUNCH(p, KC_BT_TOP, (k_bt_top<D, true>), 1, 32, 0, top, tx, nullptr, nullptr);
-    }
-    for (int l = (int)nl - 2; l >= 0; --l) {
-        BtLevel<D> lv = bt_bind_level<D>(p->plan, l, p->ws, Dg, Og, rhs, p->d_flag);
-        const auto& up = p->plan.levels[l + 1];
-        double* lx = (l == 0) ? x : p->ws + p->plan.levels[l].x;
-        const int block = 128;
-        LAUNCH(p, KC_BT_BACK, (k_bt_backsolve<D>), cdiv(lv.K, block), block, 0, lv, p->ws + up.x, lx);
-    }
-    if (d_logdet) sum_logdet(p, d_logdet);
-    return check_launch("bt_solve");
+static int chain_solve(gvib200_problem* p, int slot, const double* Dg, const double* Og, const double* rhs, double* x,
+                       double* d_logdet, int* d_flag) {
+    return chain_pass<D, true, false>(p, slot, Dg, Og, rhs, x, nullptr, nullptr, d_logdet, d_flag);
 }
 
 #define DISPATCH_D(d, CALL)                                                              \
@@ -314,14 +290,17 @@ static int chain_solve(gvib200_problem* p, const double* Dg, const double* Og, c
         default: return fail(GVIB200_EINVAL, "unsupported state dimension (1, 2, 3, 4, 6)"); \
     }
 
-static int do_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet) {
+// slot: which workspace (0: main stream, 1: side stream); the not-SPD flag of slot s is d_flag[s]
+static int do_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet,
+                     int slot = 0) {
     int rc = 0;
-    DISPATCH_D(p->d, rc = chain_selinv<D_>(p, Dg, Og, cD, cO, d_logdet));
+    DISPATCH_D(p->d, rc = chain_selinv<D_>(p, slot, Dg, Og, cD, cO, d_logdet, p->d_flag + slot));
     return rc;
 }
-static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x, double* d_logdet) {
+static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x, double* d_logdet,
+                    int slot = 0) {
     int rc = 0;
-    DISPATCH_D(p->d, rc = chain_solve<D_>(p, Dg, Og, rhs, x, d_logdet));
+    DISPATCH_D(p->d, rc = chain_solve<D_>(p, slot, Dg, Og, rhs, x, d_logdet, p->d_flag + slot));
     return rc;
 }
 
@@ -378,7 +357,7 @@ static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost
     int grid = std::min(cdiv(g.n, WARPS), p->ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
     if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
-    kern<<<grid, THREADS, need, p->stream>>>(a);
+    kern<<<grid, THREADS, need, p->ls>>>(a);
     if (p->profile) prof_end(p);
     p->ctx->launches++;
     return check_launch("k_moments");
@@ -550,14 +529,22 @@ static void launch_assemble(gvib200_problem* p, int which) {
            p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, p->Vdmu, p->VD, p->VO, p->rhs);
 }
 
-static int read_flag(gvib200_problem* p, int* flag) {
-    CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+// d_flag[0] / d_flag[1]: not-SPD flags of the chain passes run in workspace slot 0 / 1
+static int read_flags(gvib200_problem* p, int* flag0, int* flag1) {
+    CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    *flag = *p->h_flag;
+    *flag0 = p->h_flag[0];
+    *flag1 = p->h_flag[1];
+    return 0;
+}
+static int read_flag(gvib200_problem* p, int* flag) {
+    int f0 = 0, f1 = 0;
+    TRY(read_flags(p, &f0, &f1));
+    *flag = f0 | f1;
     return 0;
 }
 static int clear_flag(gvib200_problem* p) {
-    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), p->stream));
     return 0;
 }
 
@@ -653,6 +640,10 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     p->S = num_states;
     p->d = dim_state;
     CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    p->ls = p->stream;
     *out = p.release();
     return 0;
 }
@@ -672,7 +663,7 @@ static void free_problem(gvib200_problem* p) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
     F(p->scal); F(p->partial); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
-    F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws);
+    F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
     F(p->snap);
     for (auto& r : p->prof) {
         cudaEventDestroy(r.a);
@@ -682,6 +673,9 @@ static void free_problem(gvib200_problem* p) {
     if (p->t1) cudaEventDestroy(p->t1);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->h_flag) cudaFreeHost(p->h_flag);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream) cudaStreamDestroy(p->stream);
 }
 
@@ -954,9 +948,9 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     TRY(dev_alloc(&p->partial, 1024));
     CUDA_TRY(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
     CUDA_TRY(cudaMallocHost((void**)&p->h_scal, 8 * sizeof(double)));
-    TRY(dev_alloc(&p->d_flag, 1));
-    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
-    CUDA_TRY(cudaMallocHost((void**)&p->h_flag, sizeof(int)));
+    TRY(dev_alloc(&p->d_flag, 2));
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), p->stream));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_flag, 2 * sizeof(int)));
     TRY(dev_alloc(&p->Vdmu, (size_t)S * d));
     TRY(dev_alloc(&p->rhs, (size_t)S * d));
     TRY(dev_alloc(&p->dmu, (size_t)S * d));
@@ -966,9 +960,23 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     TRY(dev_alloc(&p->KlinO, (size_t)S * dd));
     TRY(upload_klin(p));
     // chain plan
-    p->plan = bt_make_plan(S, d, 4, 8, false);
-    TRY(dev_alloc(&p->ws, p->plan.ws_doubles + 16));
-    CUDA_TRY(cudaMemsetAsync(p->ws, 0, (p->plan.ws_doubles + 16) * sizeof(double), p->stream));
+    {
+        // dynamic shared memory left for the chain kernels next to their static arrays
+        const size_t smem = p->ctx->smem_optin - 4096;
+        bool ok = false;
+        switch (d) {
+            case 1: ok = cr_make_plan<1>(p->plan, S, p->ctx->sm_count, smem); break;
+            case 2: ok = cr_make_plan<2>(p->plan, S, p->ctx->sm_count, smem); break;
+            case 3: ok = cr_make_plan<3>(p->plan, S, p->ctx->sm_count, smem); break;
+            case 4: ok = cr_make_plan<4>(p->plan, S, p->ctx->sm_count, smem); break;
+            case 6: ok = cr_make_plan<6>(p->plan, S, p->ctx->sm_count, smem); break;
+        }
+        if (!ok) return fail(GVIB200_EINVAL, "finalize: the chain is too long for the two-level block-tridiagonal plan");
+    }
+    for (int i = 0; i < 2; ++i) {
+        TRY(dev_alloc(&p->ws[i], p->plan.ws_doubles + 16));
+        CUDA_TRY(cudaMemsetAsync(p->ws[i], 0, (p->plan.ws_doubles + 16) * sizeof(double), p->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->finalized = true;
     return 0;
@@ -1130,17 +1138,22 @@ extern "C" int gvib200_cost(gvib200_problem* p, const double* mu, const double* 
     return check_launch("cost");
 }
 
+static int dispatch_assemble(gvib200_problem* p, int which) {
+    switch (p->d) {
+        case 1: launch_assemble<1>(p, which); break;
+        case 2: launch_assemble<2>(p, which); break;
+        case 3: launch_assemble<3>(p, which); break;
+        case 4: launch_assemble<4>(p, which); break;
+        case 6: launch_assemble<6>(p, which); break;
+        default: return fail(GVIB200_EINVAL, "unsupported state dim");
+    }
+    return 0;
+}
+
 // gradients at the current state: assemble + dmu solve; leaves Vdmu/VD/VO/dmu on the device
 static int compute_gradients(gvib200_problem* p) {
     TRY(ensure_sweep(p, false));
-    switch (p->d) {
-        case 1: launch_assemble<1>(p, p->cur); break;
-        case 2: launch_assemble<2>(p, p->cur); break;
-        case 3: launch_assemble<3>(p, p->cur); break;
-        case 4: launch_assemble<4>(p, p->cur); break;
-        case 6: launch_assemble<6>(p, p->cur); break;
-        default: return fail(GVIB200_EINVAL, "unsupported state dim");
-    }
+    TRY(dispatch_assemble(p, p->cur));
     TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr));
     p->grads_valid = true;
     return check_launch("gradients");
@@ -1208,12 +1221,14 @@ static int switch_to_high_temperature(gvib200_problem* p) {
     return 0;
 }
 
-static int launch_candidate(gvib200_problem* p, double alpha) {
+// which: 1 = mean, 2 = precision, 3 = both
+static int launch_candidate(gvib200_problem* p, double alpha, int which = 3) {
     const int S = p->S, d = p->d, c = p->cur, w = 1 - p->cur;
     const size_t dd = (size_t)d * d;
-    const size_t nmu = (size_t)S * d, nD = S * dd, nO = (S - 1) * dd;
-    LAUNCH(p, KC_CANDIDATE, k_candidate, cdiv(nD, 256), 256, 0, nmu, nD, nO, alpha, p->mu[c], p->dmu, p->LD[c], p->LO[c], p->VD,
-           p->VO, p->mu[w], p->LD[w], p->LO[w]);
+    const size_t nmu = (which & 1) ? (size_t)S * d : 0, nD = (which & 2) ? S * dd : 0, nO = (which & 2) ? (S - 1) * dd : 0;
+    const size_t nmax = nD > nmu ? nD : nmu;
+    LAUNCH(p, KC_CANDIDATE, k_candidate, cdiv(nmax, 256), 256, 0, nmu, nD, nO, alpha, p->mu[c], p->dmu, p->LD[c], p->LO[c],
+           p->VD, p->VO, p->mu[w], p->LD[w], p->LO[w]);
     return 0;
 }
 
@@ -1239,37 +1254,56 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     TRY(clear_flag(p));
     // cost_iter + factor costs + gradients from ONE full-moment sweep at the current state
     if (!p->sweep_valid) s.n_moment_sweeps++;
-    TRY(compute_gradients(p));
-    CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    int flag = 0;
-    TRY(read_flag(p, &flag));
-    const double cost_iter = p->h_scal[2 + p->cur];
-    s.cost = cost_iter;
-    if (flag) {
-        s.status = GVIB200_ENOTSPD;
-        if (st) *st = s;
-        p->iter++;
-        return fail(GVIB200_ENOTSPD, "ngd_iterate: Vddmu is not positive definite");
-    }
-    // back-tracking (GVI-GH-GBP-impl.h:82-124)
+    TRY(ensure_sweep(p, false));
+    TRY(dispatch_assemble(p, p->cur));
+    // back-tracking (GVI-GH-GBP-impl.h:82-124).  The first trial's candidate precision Lambda + a (Vddmu - Lambda) does
+    // not depend on dmu, so its selected inverse runs on the side stream while the main stream solves for dmu.
     int cnt = 0;
+    int flag_solve = 0, flag_inv = 0;
     double step = o.step_size_base;
+    double cost_iter = 0.0;
     while (true) {
         step *= o.backtrack_ratio;
         const int w = 1 - p->cur;
-        TRY(launch_candidate(p, step));
-        TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w));
+        if (cnt == 0) {
+            CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
+            p->ls = p->stream2;
+            int rc = launch_candidate(p, step, 2);
+            if (rc == 0) rc = do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1);
+            p->ls = p->stream;
+            if (rc != 0) return rc;
+            CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
+            TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0));
+            p->grads_valid = true;
+            TRY(launch_candidate(p, step, 1));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+        } else {
+            TRY(launch_candidate(p, step, 3));
+            TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1));
+        }
         TRY(run_sweep(p, w, true, o.reuse_accepted_sweep != 0, false));
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
         run_total(p, w);
         CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-        TRY(read_flag(p, &flag));
+        TRY(read_flags(p, &flag_solve, &flag_inv));
+        if (cnt == 0) {
+            cost_iter = p->h_scal[2 + p->cur];
+            s.cost = cost_iter;
+            if (flag_solve) {
+                s.status = GVIB200_ENOTSPD;
+                if (st) *st = s;
+                p->iter++;
+                TRY(clear_flag(p));
+                return fail(GVIB200_ENOTSPD, "ngd_iterate: Vddmu is not positive definite");
+            }
+        }
         const double new_cost = p->h_scal[2 + w];
         s.new_cost = new_cost;
         // a candidate precision that is not SPD has no finite cost: treat as a rejected trial
-        const bool ok = (flag == 0) && (new_cost < cost_iter);
-        if (flag) TRY(clear_flag(p));
+        const bool ok = (flag_inv == 0) && (new_cost < cost_iter);
+        if (flag_inv) TRY(clear_flag(p));
         if (ok) {
             // update_proposal (ngd/NGD-GH-impl.h:151-156): the candidate's mu, precision, covariance and factor
             // marginals become current -- a buffer flip, everything is already on the device
@@ -1516,7 +1550,9 @@ extern "C" int gvib200_problem_info(gvib200_problem* p, gvib200_info* out) {
         out->sigma_points_per_sweep += (long long)g.n * g.table->n;
     }
     for (auto& g : p->lin) out->n_linear_factors += g.n;
-    out->chain_levels = (int)p->plan.levels.size();
+    out->chain_levels = p->plan.K > 0 ? 2 : 1;
+    out->chain_tiles = p->plan.K;
+    out->chain_tile_links = p->plan.T;
     return 0;
 }
 
@@ -1551,13 +1587,7 @@ extern "C" int gvib200_time_stage(gvib200_problem* p, int stage, int reps, const
                 break;
             }
             case 2: {
-                switch (p->d) {
-                    case 1: launch_assemble<1>(p, c); break;
-                    case 2: launch_assemble<2>(p, c); break;
-                    case 3: launch_assemble<3>(p, c); break;
-                    case 4: launch_assemble<4>(p, c); break;
-                    case 6: launch_assemble<6>(p, c); break;
-                }
+                TRY(dispatch_assemble(p, c));
                 TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr));
                 break;
             }

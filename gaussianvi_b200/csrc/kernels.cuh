@@ -3,14 +3,14 @@
 //   k_moments    K1  fused sigma points + cost functor + moment reduction + Vdmu/Vddmu epilogue
 //   k_linear         closed-form linear-Gaussian factors (gradient + cost)
 //   k_assemble   K3  deterministic gather of factor blocks into the block-tridiagonal joint
-//   k_bt_*       K4  partitioned block-tridiagonal Cholesky / solve / selected inverse / log det
+//   k_cr_*       K4  tile-wise block cyclic reduction: block-tridiagonal Cholesky / solve / selected inverse / log det
 //   k_candidate      line-search candidate (mu + a dmu, Lambda + a dLambda)
 //   k_total_cost     sum of factor costs + 1/2 log det, fixed summation order
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "bt_chain.h"
+#include "bt_cr.h"
 #include "cost_functors.cuh"
 #include "smallmat.h"
 
@@ -591,26 +591,123 @@ __global__ void k_sum(size_t n, const double* __restrict__ v, const double* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: block-tridiagonal engine -- thin thread-per-segment wrappers over bt_chain.h
+// K4: tile-wise block cyclic reduction, see bt_cr.h.  Three launches per solve:
+//   k_cr_tile_forward   one CTA per tile: load the tile into shared memory, eliminate its interior level by level,
+//                       stream the elimination records to HBM, hand the separator Schur complements to the top
+//   k_cr_top            ONE CTA: cyclic reduction of the separator chain (records stay in shared memory), 2-node
+//                       solve, expansion back to every separator (or, K == 0, the whole chain at once)
+//   k_cr_tile_backward  one CTA per tile: back substitution and / or Takahashi selected inverse, level by level
 // ------------------------------------------------------------------------------------------
+constexpr int CR_THREADS = 256;
+
+// deterministic block sum of one double per thread (fixed tree), result valid in thread 0
+__device__ __forceinline__ double cr_block_sum(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+
 template <int D, bool RHS>
-__global__ void k_bt_forward(const BtLevel<D> lv) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < lv.K) bt_forward_segment<D, RHS>(lv, k);
+__device__ __forceinline__ bool cr_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm,
+                                                  LogDetAcc& ld) {
+    bool ok = true;
+    for (int l = 0; l < gm.levels; ++l) {
+        const int cnt = cr_count(gm.T, l);
+        for (int base = 0; base < cnt; base += blockDim.x) {
+            const int t = base + threadIdx.x;
+            CrElim<D> c;
+            if (t < cnt) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, t, c, ld) && ok;
+            __syncthreads();
+            if (t < cnt) cr_fwd_B<D, RHS>(v, c);
+            __syncthreads();
+        }
+    }
+    return ok;
 }
+
+template <int D, bool RHS, bool SELINV>
+__device__ __forceinline__ void cr_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base,
+                                                   const CrGeom& gm) {
+    for (int l = gm.levels - 1; l >= 0; --l) {
+        const int cnt = cr_count(gm.T, l);
+        for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+            if (SELINV) cr_bwd_selinv<D>(v, rec, rec_base, gm, l, t);
+            if (RHS) cr_bwd_solve<D>(v, rec, rec_base, gm, l, t);
+        }
+        __syncthreads();
+    }
+}
+
 template <int D, bool RHS>
-__global__ void k_bt_top(const BtLevel<D> lv, double* x, double* cD, double* cO) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) bt_serial_top<D, RHS>(lv, x, cD, cO);
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    const int tile = blockIdx.x;
+    const int n0 = tile * a.T;
+    const int Tk = min(a.T, a.n - 1 - n0);
+    if (threadIdx.x == 0) cr_make_geom(gm, Tk);
+    __syncthreads();
+    const CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    cr_tile_load<D, RHS>(a, v, gm, n0, threadIdx.x, blockDim.x);
+    __syncthreads();
+    LogDetAcc ld;
+    const bool ok = cr_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld);
+    cr_tile_store_reduced<D, RHS>(a, v, gm, tile, n0, threadIdx.x, blockDim.x);
+    const double s = cr_block_sum(ld.value(), red);
+    if (threadIdx.x == 0) a.ld[tile] = s;
+    if (!ok) *a.notspd = 1;
 }
-template <int D>
-__global__ void k_bt_backsolve(const BtLevel<D> lv, const double* xr, double* x) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < lv.K) bt_backsolve_segment<D>(lv, k, xr, x);
+
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    const int nt = (a.K == 0) ? a.n : a.K + 1;  // nodes of the top chain
+    if (threadIdx.x == 0) cr_make_geom(gm, nt - 1);
+    __syncthreads();
+    const CrView<D> v = cr_make_view<D>(smem, nt);
+    // elimination records of the top stay in shared memory
+    const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
+    CrRec<D> rec;
+    rec.G = v.g + (size_t)D * v.NS;
+    rec.H = rec.G + cr_rec_capacity(nrec, D * D);
+    rec.Dinv = rec.H + cr_rec_capacity(nrec, D * D);
+    rec.y = rec.Dinv + cr_rec_capacity(nrec, D * D);
+    cr_top_load<D, RHS>(a, v, gm, threadIdx.x, blockDim.x);
+    __syncthreads();
+    LogDetAcc ld;
+    bool ok = cr_forward_levels<D, RHS>(v, rec, 0, gm, ld);
+    if (threadIdx.x == 0) ok = cr_top2<D, RHS, SELINV>(v, gm.T, ld) && ok;
+    __syncthreads();
+    cr_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
+    if (a.K == 0) cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, threadIdx.x, blockDim.x);
+    else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, threadIdx.x, blockDim.x);
+    const double s = cr_block_sum(ld.value(), red);
+    if (threadIdx.x == 0) a.ld[a.K] = s;
+    if (!ok) *a.notspd = 1;
 }
-template <int D>
-__global__ void k_bt_selinv(const BtLevel<D> lv, const double* cDr, const double* cOr, double* cD, double* cO) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < lv.K) bt_selinv_segment<D>(lv, k, cDr, cOr, cD, cO);
+
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    const int tile = blockIdx.x;
+    const int n0 = tile * a.T;
+    const int Tk = min(a.T, a.n - 1 - n0);
+    if (threadIdx.x == 0) cr_make_geom(gm, Tk);
+    __syncthreads();
+    const CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    cr_tile_seed<D, RHS, SELINV>(a, v, tile, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cr_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm);
+    const bool last = (tile == a.K - 1);
+    cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, threadIdx.x, blockDim.x);
 }
 
 // cell records for CostPlanarHinge from the column-major field

@@ -209,7 +209,7 @@ int gvib200_profile_end(gvib200_problem* prob, gvib200_profile* out);
 const char* gvib200_kernel_class_name(int kernel_class);
 
 typedef struct {
-    int num_states, dim_state, n_factors, n_gh_factors, n_linear_factors, chain_levels;
+    int num_states, dim_state, n_factors, n_gh_factors, n_linear_factors, chain_levels, chain_tiles, chain_tile_links;
     long long sigma_points_per_sweep; /* sum over GH factors of the nodes of their rule */
 } gvib200_info;
 int gvib200_problem_info(gvib200_problem* prob, gvib200_info* out);

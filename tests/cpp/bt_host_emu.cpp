@@ -79,3 +79,130 @@ extern "C" int emu_sqrt_invsqrt(int n, const double* Sigma, double* S, double* R
         default: return -1;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// second-generation engine (bt_cr.h): the three kernels of kernels.cuh replayed sequentially, "threads" of a CTA in
+// rounds of NT with both phases of a round separated exactly where the kernels place __syncthreads().
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../gaussianvi_b200/csrc/bt_cr_plan.h"
+
+namespace {
+constexpr int NT = 256;
+
+template <int D, bool RHS>
+bool emu_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, double& ldsum) {
+    bool ok = true;
+    std::vector<LogDetAcc> lds(NT);
+    for (int l = 0; l < gm.levels; ++l) {
+        const int cnt = cr_count(gm.T, l);
+        for (int base = 0; base < cnt; base += NT) {
+            std::vector<CrElim<D>> ctx(NT);
+            for (int tid = 0; tid < NT; ++tid)
+                if (base + tid < cnt) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, base + tid, ctx[tid], lds[tid]) && ok;
+            for (int tid = 0; tid < NT; ++tid)
+                if (base + tid < cnt) cr_fwd_B<D, RHS>(v, ctx[tid]);
+        }
+    }
+    for (auto& l : lds) ldsum += l.value();
+    return ok;
+}
+
+template <int D, bool RHS, bool SELINV>
+void emu_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm) {
+    for (int l = gm.levels - 1; l >= 0; --l) {
+        const int cnt = cr_count(gm.T, l);
+        for (int t = 0; t < cnt; ++t) {
+            if (SELINV) cr_bwd_selinv<D>(v, rec, rec_base, gm, l, t);
+            if (RHS) cr_bwd_solve<D>(v, rec, rec_base, gm, l, t);
+        }
+    }
+}
+
+template <int D, bool RHS, bool SELINV>
+int emu_cr_pass(int n, const double* D0, const double* O0, const double* rhs, double* x, double* cD, double* cO,
+                double* logdet, int force_T, size_t smem_bytes) {
+    CrPlan plan;
+    if (!cr_make_plan<D>(plan, n, 148, smem_bytes, force_T)) return -1;
+    std::vector<double> ws(plan.ws_doubles + 16, 0.0);
+    int notspd = 0;
+    CrArgs<D> a = cr_bind<D>(plan, ws.data(), D0, O0, rhs, x, cD, cO, &notspd);
+    bool ok = true;
+    // k_cr_tile_forward
+    for (int tile = 0; tile < a.K; ++tile) {
+        const int n0 = tile * a.T;
+        const int Tk = (a.T < a.n - 1 - n0) ? a.T : a.n - 1 - n0;
+        CrGeom gm;
+        cr_make_geom(gm, Tk);
+        std::vector<double> sm(cr_tile_doubles<D>(a.T), 0.0);
+        CrView<D> v = cr_make_view<D>(sm.data(), a.T + 1);
+        cr_tile_load<D, RHS>(a, v, gm, n0, 0, 1);
+        double ld = 0.0;
+        ok = emu_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld) && ok;
+        cr_tile_store_reduced<D, RHS>(a, v, gm, tile, n0, 0, 1);
+        a.ld[tile] = ld;
+    }
+    // k_cr_top
+    {
+        const int nt = (a.K == 0) ? a.n : a.K + 1;
+        CrGeom gm;
+        cr_make_geom(gm, nt - 1);
+        std::vector<double> sm(cr_top_doubles<D>(nt), 0.0);
+        CrView<D> v = cr_make_view<D>(sm.data(), nt);
+        const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
+        CrRec<D> rec;
+        rec.G = v.g + (size_t)D * v.NS;
+        rec.H = rec.G + cr_rec_capacity(nrec, D * D);
+        rec.Dinv = rec.H + cr_rec_capacity(nrec, D * D);
+        rec.y = rec.Dinv + cr_rec_capacity(nrec, D * D);
+        cr_top_load<D, RHS>(a, v, gm, 0, 1);
+        double ld = 0.0;
+        ok = emu_forward_levels<D, RHS>(v, rec, 0, gm, ld) && ok;
+        LogDetAcc l2;
+        ok = cr_top2<D, RHS, SELINV>(v, gm.T, l2) && ok;
+        ld += l2.value();
+        emu_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
+        if (a.K == 0) cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, 0, 1);
+        else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, 0, 1);
+        a.ld[a.K] = ld;
+    }
+    // k_cr_tile_backward
+    for (int tile = 0; tile < a.K; ++tile) {
+        const int n0 = tile * a.T;
+        const int Tk = (a.T < a.n - 1 - n0) ? a.T : a.n - 1 - n0;
+        CrGeom gm;
+        cr_make_geom(gm, Tk);
+        std::vector<double> sm(cr_tile_doubles<D>(a.T), 0.0);
+        CrView<D> v = cr_make_view<D>(sm.data(), a.T + 1);
+        cr_tile_seed<D, RHS, SELINV>(a, v, tile, 0, 1);
+        emu_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm);
+        const bool last = (tile == a.K - 1);
+        cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, 0, 1);
+    }
+    double ld = 0.0;
+    for (int i = 0; i < plan.ld_count; ++i) ld += a.ld[i];
+    if (logdet) *logdet = ld;
+    return (ok && !notspd) ? 0 : -4;
+}
+
+template <int D>
+int emu_cr(int n, const double* D0, const double* O0, const double* rhs, double* x, double* cD, double* cO, double* logdet,
+           int force_T, size_t smem_bytes) {
+    int rc = 0;
+    if (rhs) rc = emu_cr_pass<D, true, false>(n, D0, O0, rhs, x, nullptr, nullptr, logdet, force_T, smem_bytes);
+    if (rc == 0 && cD) rc = emu_cr_pass<D, false, true>(n, D0, O0, nullptr, nullptr, cD, cO, logdet, force_T, smem_bytes);
+    return rc;
+}
+}  // namespace
+
+// force_T: > 0 tile size, 0 automatic, < 0 top-only.  smem_bytes: the per-CTA shared-memory budget the plan assumes.
+extern "C" int emu_cr_blocktri(int n, int d, const double* D0, const double* O0, const double* rhs, double* x, double* cD,
+                               double* cO, double* logdet, int force_T, size_t smem_bytes) {
+    switch (d) {
+        case 1: return emu_cr<1>(n, D0, O0, rhs, x, cD, cO, logdet, force_T, smem_bytes);
+        case 2: return emu_cr<2>(n, D0, O0, rhs, x, cD, cO, logdet, force_T, smem_bytes);
+        case 3: return emu_cr<3>(n, D0, O0, rhs, x, cD, cO, logdet, force_T, smem_bytes);
+        case 4: return emu_cr<4>(n, D0, O0, rhs, x, cD, cO, logdet, force_T, smem_bytes);
+        case 6: return emu_cr<6>(n, D0, O0, rhs, x, cD, cO, logdet, force_T, smem_bytes);
+        default: return -1;
+    }
+}

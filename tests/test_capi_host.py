@@ -140,3 +140,53 @@ def test_jacobi_sqrt_matches_eigh(n):
         ref = o.sqrtm_psd(Sig)
         assert rel(S, ref) < 1e-12
         assert rel(R @ R, np.linalg.inv(Sig)) < 1e-9
+
+
+# ------------------------------------------------------------------ second-generation chain engine (bt_cr.h) on the host
+def emu_cr_run(S, d, D, O, rhs, force_T, smem=220 * 1024):
+    lib = _emu()
+    dp = C.POINTER(C.c_double)
+    Dc = np.ascontiguousarray(np.transpose(D, (0, 2, 1)))
+    Oc = np.ascontiguousarray(np.transpose(O, (0, 2, 1))) if S > 1 else np.zeros((1, d, d))
+    x = np.zeros(S * d)
+    cD = np.zeros((S, d, d))
+    cO = np.zeros((max(S - 1, 1), d, d))
+    ld = C.c_double()
+    p = lambda a: a.ctypes.data_as(dp)
+    rc = lib.emu_cr_blocktri(S, d, p(Dc), p(Oc), p(rhs), p(x), p(cD), p(cO), C.byref(ld), force_T, C.c_size_t(smem))
+    return rc, x, np.transpose(cD, (0, 2, 1)), np.transpose(cO[:S - 1], (0, 2, 1)), ld.value
+
+
+@pytest.mark.parametrize("S,d,force_T", [
+    (1, 4, -1), (2, 4, -1), (3, 4, -1), (4, 1, -1), (9, 4, -1), (100, 4, -1), (257, 3, -1), (40, 6, -1),   # top only
+    (3, 4, 2), (10, 4, 2), (10, 4, 3), (33, 2, 4), (100, 4, 7), (101, 4, 10), (1000, 4, 64), (1002, 4, 251),  # tiled
+    (1000, 4, 0), (5000, 4, 0), (700, 6, 0), (3000, 1, 0), (2500, 2, 37), (777, 3, 0),                       # automatic
+])
+def test_cr_engine_host_matches_oracle(S, d, force_T):
+    rng = np.random.default_rng(S * 10 + d)
+    D, O = rand_spd_chain(rng, S, d)
+    rhs = rng.standard_normal(S * d)
+    rc, x, cD, cO, ld = emu_cr_run(S, d, D, O, rhs, force_T)
+    assert rc == 0
+    bt = o.BlockTri(D, O)
+    ref = o.inverse_gbp(bt)
+    assert rel(x, o.block_solve(bt, rhs)) < 1e-11
+    assert rel(cD, ref.D) < 1e-11
+    if S > 1:
+        assert rel(cO, ref.O) < 1e-11
+    assert abs(ld - o.logdet(bt)) < 1e-10 * max(1.0, abs(ld))
+
+
+def test_cr_engine_reports_indefinite_and_too_long():
+    D = np.tile(np.eye(2), (50, 1, 1))
+    D[31] = -np.eye(2)
+    O = np.zeros((49, 2, 2))
+    rc, *_ = emu_cr_run(50, 2, D, O, np.zeros(100), 8)
+    assert rc == -4
+    rc, *_ = emu_cr_run(50, 2, D, O, np.zeros(100), -1)
+    assert rc == -4
+    # a chain that does not fit a two-level plan within the shared-memory budget is refused, not mangled
+    rng = np.random.default_rng(0)
+    Dl, Ol = rand_spd_chain(rng, 4000, 4)
+    rc, *_ = emu_cr_run(4000, 4, Dl, Ol, np.zeros(16000), 0, smem=16 * 1024)
+    assert rc == -1
