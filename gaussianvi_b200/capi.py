@@ -34,6 +34,7 @@ EXPORTS = [
     "gvib200_selected_inverse", "gvib200_blocktri_solve", "gvib200_time_stage", "gvib200_fp64_peak",
     "gvib200_launch_count", "gvib200_timer_start", "gvib200_timer_stop", "gvib200_profile_begin", "gvib200_profile_end",
     "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
+    "gvib200_problem_set_option",
 ]
 
 
@@ -368,6 +369,9 @@ class Problem:
         out = Info()
         _check(self.lib.gvib200_problem_info(self.h, C.byref(out)))
         return out
+
+    def set_option(self, name: str, value: int):
+        _check(self.lib.gvib200_problem_set_option(self.h, name.encode(), int(value)))
 
     def snapshot_save(self):
         _check(self.lib.gvib200_snapshot_save(self.h))

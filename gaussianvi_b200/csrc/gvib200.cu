@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "bt_cr_plan.h"
+#include "k1_sym.cuh"
 #include "kernels.cuh"
 #include "spgh_table.h"
 
@@ -49,7 +50,112 @@ struct Table {
     std::vector<double> nodes, w;  // host
     double ximax[12] = {};         // max |xi_c|
     double* d_rows = nullptr;      // device planes: NP x [n_pad] double2, then [n_pad] weights
+    bool sym_ok = false;           // the rule has the sign-group structure K1S needs (dim <= 4, fits the parameter)
+    SymTable sym;
 };
+
+// Sign-group view of a sparse-GH rule for K1S (k1_sym.cuh): every set of nodes sharing |xi| must be a full group of
+// 2^k sign combinations with one common weight.  Returns false when the rule does not have that structure.
+static bool build_sym_table(const Table& t, SymTable& st) {
+    const int dim = t.dim, n = t.n;
+    if (dim < 1 || dim > 4) return false;
+    std::memset(&st, 0, sizeof(st));
+    st.dim = dim;
+    st.n_nodes = n;
+    struct Grp {
+        std::vector<double> a;  // magnitudes of the non-zero coordinates
+        double w;
+        int count;
+        unsigned sign_seen;     // bitset over the 2^k sign patterns
+    };
+    std::map<std::vector<double>, Grp> groups;  // key: |xi| (all dim coordinates)
+    for (int i = 0; i < n; ++i) {
+        std::vector<double> key(dim);
+        int mask = 0, pat = 0, q = 0;
+        for (int c = 0; c < dim; ++c) {
+            const double v = t.nodes[(size_t)i * dim + c];
+            key[c] = std::fabs(v);
+            if (v != 0.0) {
+                mask |= 1 << c;
+                if (v < 0.0) pat |= 1 << q;
+                ++q;
+            }
+        }
+        if (mask == 0) {
+            if (st.w0 != 0.0) return false;  // two nodes at the origin
+            st.w0 = t.w[i];
+            continue;
+        }
+        auto it = groups.find(key);
+        if (it == groups.end()) {
+            Grp g;
+            for (int c = 0; c < dim; ++c)
+                if (key[c] != 0.0) g.a.push_back(key[c]);
+            g.w = t.w[i];
+            g.count = 0;
+            g.sign_seen = 0;
+            it = groups.emplace(key, g).first;
+        }
+        Grp& g = it->second;
+        if (g.w != t.w[i]) return false;           // weights must be bit-equal inside a group
+        if (g.sign_seen & (1u << pat)) return false;
+        g.sign_seen |= 1u << pat;
+        g.count++;
+    }
+    std::vector<std::vector<const Grp*>> by_mask(16);
+    for (auto& kv : groups) {
+        int mask = 0;
+        for (int c = 0; c < dim; ++c)
+            if (kv.first[c] != 0.0) mask |= 1 << c;
+        const int k = (int)kv.second.a.size();
+        if (kv.second.count != (1 << k)) return false;  // not a full sign group
+        by_mask[mask].push_back(&kv.second);
+    }
+    size_t off = 0, ngroups = 0;
+    for (int m = 1; m < 16; ++m) {
+        st.moff[m] = (int)off;
+        const int K = k1s_popc(m);
+        if (by_mask[m].size() > 1023) return false;
+        for (const Grp* g : by_mask[m]) {
+            if (off + (size_t)k1s_stride(K) > (size_t)K1S_MAX_DATA) return false;
+            double* e = st.data + off;
+            for (int i = 0; i < K; ++i) e[i] = g->a[i];
+            e[K] = g->w;
+            for (int i = 0; i < K; ++i) e[K + 1 + i] = g->w * g->a[i];
+            for (int i = 0; i < K; ++i) e[2 * K + 1 + i] = g->w * g->a[i] * g->a[i];
+            for (int i = 0; i < K; ++i)
+                for (int j = i + 1; j < K; ++j) e[3 * K + 1 + k1s_pair(K, i, j)] = g->w * g->a[i] * g->a[j];
+            off += k1s_stride(K);
+            ++ngroups;
+        }
+    }
+    if (ngroups > 1024) return false;
+    // parts: longest-processing-time assignment by node count, then mask order inside a part
+    struct Ref { int mask, g, nodes; };
+    std::vector<Ref> refs;
+    for (int m = 1; m < 16; ++m)
+        for (size_t g = 0; g < by_mask[m].size(); ++g) refs.push_back(Ref{m, (int)g, 1 << k1s_popc(m)});
+    std::stable_sort(refs.begin(), refs.end(), [](const Ref& x, const Ref& y) { return x.nodes > y.nodes; });
+    std::vector<std::vector<Ref>> parts(K1S_NPART);
+    std::vector<int> load(K1S_NPART, 0);
+    if (st.w0 != 0.0) load[0] = 1;
+    for (const Ref& r : refs) {
+        int best = 0;
+        for (int p = 1; p < K1S_NPART; ++p)
+            if (load[p] < load[best]) best = p;
+        parts[best].push_back(r);
+        load[best] += r.nodes;
+    }
+    int pos = 0;
+    for (int p = 0; p < K1S_NPART; ++p) {
+        st.pbeg[p] = pos;
+        std::stable_sort(parts[p].begin(), parts[p].end(),
+                         [](const Ref& x, const Ref& y) { return x.mask != y.mask ? x.mask < y.mask : x.g < y.g; });
+        for (const Ref& r : parts[p]) st.glist[pos++] = (unsigned short)((r.mask << 10) | r.g);
+    }
+    st.pbeg[K1S_NPART] = pos;
+    return true;
+}
 
 struct gvib200_ctx {
     int device = 0;
@@ -143,6 +249,7 @@ struct gvib200_problem {
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
     bool grads_valid = false;
+    bool force_generic_k1 = false;  // tests: run the generic node-loop kernel even where K1S applies
     // profiling: one CUDA event pair per launch while enabled
     bool profile = false;
     std::vector<ProfRec> prof;
@@ -234,6 +341,7 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
         }
         CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(t->d_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+        t->sym_ok = build_sym_table(*t, t->sym);
     }
     *out = t;
     return 0;
@@ -314,9 +422,39 @@ static int launch_prologue(gvib200_problem* p, const GhGroup& g, const double* c
     return 0;
 }
 
+// K1S (k1_sym.cuh): factors of dimension <= 4 on a rule with the sign-group structure
+template <int DIM, class Cost>
+static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
+                              double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+    SymArgs<Cost> a;
+    a.n = g.n;
+    a.state_dim = p->d;
+    a.start = g.d_start;
+    a.mu = mu;
+    a.SR = SR;
+    a.T = g.d_T;
+    a.fcost = fcost + g.first_id;
+    a.fVdmu = fVdmu + g.voff;
+    a.fVdd = fVdd + g.moff;
+    a.raw = raw;
+    for (int c = 0; c < 4; ++c) a.ximax[c] = g.table->ximax[c];
+    a.cost = cost;
+    const int grid = cdiv(g.n, 32);
+    if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
+    if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, 0, p->ls>>>(g.table->sym, a);
+    else k_moments_sym<DIM, Cost, false><<<grid, K1S_THREADS, 0, p->ls>>>(g.table->sym, a);
+    if (p->profile) prof_end(p);
+    p->ctx->launches++;
+    return check_launch("k_moments_sym");
+}
+
 template <int DIM, class Cost>
 static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
                           double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+    if constexpr (DIM <= 4) {
+        if (g.table->sym_ok && !p->force_generic_k1)
+            return launch_moments_sym<DIM, Cost>(p, g, cost, mu, SR, fcost, fVdmu, fVdd, raw, full);
+    }
     constexpr int XD = Cost::XD;
     constexpr int ROW = 2 * ((DIM + 1) / 2) + 1;  // doubles per node over all planes
     constexpr int THREADS = K1Cfg<DIM>::THREADS;
@@ -1534,6 +1672,16 @@ extern "C" int gvib200_profile_end(gvib200_problem* p, gvib200_profile* out) {
     }
     p->prof.clear();
     return 0;
+}
+
+extern "C" int gvib200_problem_set_option(gvib200_problem* p, const char* name, int value) {
+    if (!p || !name) return fail(GVIB200_EINVAL, "set_option: null");
+    if (std::strcmp(name, "generic_k1") == 0) {
+        p->force_generic_k1 = (value != 0);
+        p->sweep_valid = false;
+        return 0;
+    }
+    return fail(GVIB200_EINVAL, std::string("set_option: unknown option ") + name);
 }
 
 extern "C" const char* gvib200_kernel_class_name(int kc) { return (kc >= 0 && kc < KC_COUNT) ? KC_NAMES[kc] : ""; }

@@ -214,6 +214,10 @@ typedef struct {
 } gvib200_info;
 int gvib200_problem_info(gvib200_problem* prob, gvib200_info* out);
 
+/* tuning / test switches.  "generic_k1" = 1: run the generic node-loop moment kernel even where the sign-group kernel
+   (dimension <= 4) applies; both must give the same moments to rounding. */
+int gvib200_problem_set_option(gvib200_problem* prob, const char* name, int value);
+
 /* device-side snapshot / rewind of the optimizer state (mean, precision, covariance, factor marginals,
    iteration counter); no host traffic */
 int gvib200_snapshot_save(gvib200_problem* prob);

@@ -267,3 +267,32 @@ def test_cfg3_gradients_match_oracle(gpu_ctx):
     c, fc = p.cost()
     assert rel(fc, ref.factor_cost_vector()) < 1e-10
     assert abs(c - ref.cost_value()) < 1e-9 * abs(c)
+
+
+# ---------------------------------------------------------------- the two moment kernels agree (K1S vs generic K1)
+@pytest.mark.parametrize("dim,deg,kind", [(4, 6, "hinge"), (4, 4, "quad"), (3, 8, "quad"), (2, 10, "quad"), (1, 10, "stereo")])
+def test_sign_group_kernel_matches_generic_kernel(gpu_ctx, dim, deg, kind):
+    rng = np.random.default_rng(dim * 100 + deg)
+    if kind == "hinge":
+        spec = problems.make_factor_batch(N=999)
+    else:
+        N = 77
+        spec = problems.ProblemSpec(S=N, d=dim)
+        prm = np.array([2.5]) if kind == "quad" else capi.Stereo1DParams(20.0, 400.0, 0.1, 0.09, 9.0, -0.8)
+        k = capi.COST_QUADRATIC if kind == "quad" else capi.COST_STEREO_1D
+        spec.groups.append(problems.GhGroupSpec(k, dim, deg, np.arange(N, dtype=np.int32), prm, 1.0, 10.0))
+        spec.mu0 = (rng.standard_normal((N, dim)) + (20.0 if kind == "stereo" else 0.0)).reshape(-1)
+        A = rng.standard_normal((N, dim, dim))
+        spec.prec0_D = A @ np.transpose(A, (0, 2, 1)) + 0.5 * np.eye(dim)
+        spec.prec0_O = np.zeros((N - 1, dim, dim))
+    p = problems.build_device_problem(gpu_ctx, spec)
+    (a0, a1, a2), = p.moments()
+    ca, fa = p.cost()
+    p.set_option("generic_k1", 1)
+    (b0, b1, b2), = p.moments()
+    cb, fb = p.cost()
+    assert (a0 == 0).sum() == (b0 == 0).sum()
+    for f in range(len(a0)):
+        assert rel(a0[f], b0[f]) < 1e-11 and rel(a2[f], b2[f]) < 1e-11
+        assert np.abs(a1[f] - b1[f]).max() < 1e-11 * max(np.abs(b1[f]).max(), np.sqrt(np.abs(b2[f]).max() * abs(b0[f])), 1e-300)
+    assert rel(fa, fb) < 1e-11
