@@ -44,9 +44,11 @@ struct CostStereo1D {
 // CudaOperation_PlanarPR::cost_obstacle_planar (helpers/CudaOperation.h:491-508, n_balls = 1,
 // slope = 1) over PlanarSDF::getSignedDistance (:51-103, :123-125):
 //   psi(x) = sigma * max(0, eps + r - sd(x0, x1))^2,   sd = bilinear lookup, point clamped to the field.
-// The field is stored as one 32-byte record per cell {v(r,c), v(r+1,c), v(r,c+1), v(r+1,c+1)} (upper
-// indices clamped: the reference reads one past the edge with weight exactly 0 there), so a lookup is
-// a single sector instead of four scattered doubles.
+// The field is stored as one 32-byte record per cell (upper indices clamped: the reference reads one past the edge with
+// weight exactly 0 there), so a lookup is a single sector instead of four scattered doubles.  The record holds the
+// bilinear form already arranged for the hinge: with v00 = v(r,c), v10 = v(r+1,c), v01 = v(r,c+1), v11 = v(r+1,c+1)
+//   { thr - v00,  -(v10 - v00),  -(v01 - v00),  -((v11 - v01) - (v10 - v00)) }
+// so that  thr - sd = t0 + fr * n_dr + fc * (n_dc + fr * n_drc)  is three FMAs.
 struct CostPlanarHinge {
     static constexpr int XD = 2;
     const double4* __restrict__ rec;  // [cols][rows]
@@ -81,25 +83,26 @@ struct CostPlanarHinge {
         const double M = 6755399441055744.0;
         const double uc = __dadd_rd(col, M);
         const double ur = __dadd_rd(row, M);
-        const int lci = __double2loint(uc);
-        const int lri = __double2loint(ur);
+        const unsigned lci = (unsigned)__double2loint(uc);
+        const unsigned lri = (unsigned)__double2loint(ur);
         Pending p;
         p.fc = col - (uc - M);
         p.fr = row - (ur - M);
         // one 256-bit read-only load (SASS LDG.E.256.CONSTANT; records are 32-byte aligned)
         asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
                      : "=d"(p.v.x), "=d"(p.v.y), "=d"(p.v.z), "=d"(p.v.w)
-                     : "l"(rec + (size_t)lci * rows + lri));
+                     : "l"(rec + (lci * (unsigned)rows + lri)));  // 32-bit cell index: one IMAD + one IMAD.WIDE
         return p;
     }
     __device__ __forceinline__ double finish(const Pending& p) const {
-        const double a = fma(p.fr, p.v.y - p.v.x, p.v.x);
-        const double b = fma(p.fr, p.v.w - p.v.z, p.v.z);
-        const double sd = fma(p.fc, b - a, a);
-        const double h = fmax(thr - sd, 0.0);
-        return h * h;
+        // max(t, 0)^2 as (t + |t|)^2 / 4: t + |t| is exactly 2t or 0, so the square is exactly 4 max(t,0)^2 and the
+        // factor 1/4 (a power of two) folds into scale() without changing a bit; two FP64 instructions instead of a
+        // compare + select sequence.
+        const double t = fma(p.fc, fma(p.fr, p.v.w, p.v.z), fma(p.fr, p.v.y, p.v.x));  // thr - sd
+        const double u = t + fabs(t);
+        return u * u;
     }
-    __device__ __forceinline__ double scale() const { return sigma; }
+    __device__ __forceinline__ double scale() const { return 0.25 * sigma; }
 };
 
 // cost_linear_gp (gp/cost_functions.h:36-39 -> MinimumAccGP::cost gp/minimum_acc_prior.h:103-106,

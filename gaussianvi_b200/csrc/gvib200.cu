@@ -12,6 +12,8 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <type_traits>
+#include <cstdlib>
 #include <vector>
 
 #include "bt_cr_plan.h"
@@ -50,8 +52,10 @@ struct Table {
     std::vector<double> nodes, w;  // host
     double ximax[12] = {};         // max |xi_c|
     double* d_rows = nullptr;      // device planes: NP x [n_pad] double2, then [n_pad] weights
-    bool sym_ok = false;           // the rule has the sign-group structure K1S needs (dim <= 4, fits the parameter)
+    bool sym_ok = false;           // the rule has the sign-group structure K1S needs (dim <= 4, fits shared memory)
     SymTable sym;
+    std::vector<double> sym_data;  // host copy of sym.data
+    double* d_sym = nullptr;
 };
 
 // Sign-group view of a sparse-GH rule for K1S (k1_sym.cuh): every set of nodes sharing |xi| must be a full group of
@@ -68,6 +72,7 @@ static bool build_sym_table(const Table& t, SymTable& st) {
         int count;
         unsigned sign_seen;     // bitset over the 2^k sign patterns
     };
+    double w0 = 0.0;                            // weight of the node at the origin, if any
     std::map<std::vector<double>, Grp> groups;  // key: |xi| (all dim coordinates)
     for (int i = 0; i < n; ++i) {
         std::vector<double> key(dim);
@@ -82,8 +87,8 @@ static bool build_sym_table(const Table& t, SymTable& st) {
             }
         }
         if (mask == 0) {
-            if (st.w0 != 0.0) return false;  // two nodes at the origin
-            st.w0 = t.w[i];
+            if (w0 != 0.0) return false;  // two nodes at the origin
+            w0 = t.w[i];
             continue;
         }
         auto it = groups.find(key);
@@ -111,49 +116,35 @@ static bool build_sym_table(const Table& t, SymTable& st) {
         if (kv.second.count != (1 << k)) return false;  // not a full sign group
         by_mask[mask].push_back(&kv.second);
     }
-    size_t off = 0, ngroups = 0;
+    // device layout: mask 0 = the origin node ([part]: w0 for part 0); mask m: [round][entry][part], group 8 r + p of the
+    // mask goes to part p in round r, the last round is padded with zero-weight groups at xi = 0
+    std::vector<double>& data = const_cast<Table&>(t).sym_data;
+    data.assign(K1S_NPART, 0.0);
+    data[0] = w0;
+    st.moff[0] = 0;
+    st.rounds[0] = 1;
     for (int m = 1; m < 16; ++m) {
-        st.moff[m] = (int)off;
-        const int K = k1s_popc(m);
-        if (by_mask[m].size() > 1023) return false;
-        for (const Grp* g : by_mask[m]) {
-            if (off + (size_t)k1s_stride(K) > (size_t)K1S_MAX_DATA) return false;
-            double* e = st.data + off;
-            for (int i = 0; i < K; ++i) e[i] = g->a[i];
-            e[K] = g->w;
-            for (int i = 0; i < K; ++i) e[K + 1 + i] = g->w * g->a[i];
-            for (int i = 0; i < K; ++i) e[2 * K + 1 + i] = g->w * g->a[i] * g->a[i];
+        st.moff[m] = (int)data.size();
+        const int K = k1s_popc(m), stride = k1s_stride(K);
+        const int G = (int)by_mask[m].size();
+        const int rounds = (G + K1S_NPART - 1) / K1S_NPART;
+        st.rounds[m] = rounds;
+        data.resize(data.size() + (size_t)rounds * stride * K1S_NPART, 0.0);
+        double* blk = data.data() + st.moff[m];
+        for (int gi = 0; gi < G; ++gi) {
+            const Grp* g = by_mask[m][gi];
+            const int r = gi / K1S_NPART, p = gi % K1S_NPART;
+            auto put = [&](int e, double v) { blk[((size_t)r * stride + e) * K1S_NPART + p] = v; };
+            for (int i = 0; i < K; ++i) put(i, g->a[i]);
+            put(K, g->w);
+            for (int i = 0; i < K; ++i) put(K + 1 + i, g->w * g->a[i]);
+            for (int i = 0; i < K; ++i) put(2 * K + 1 + i, g->w * g->a[i] * g->a[i]);
             for (int i = 0; i < K; ++i)
-                for (int j = i + 1; j < K; ++j) e[3 * K + 1 + k1s_pair(K, i, j)] = g->w * g->a[i] * g->a[j];
-            off += k1s_stride(K);
-            ++ngroups;
+                for (int j = i + 1; j < K; ++j) put(3 * K + 1 + k1s_pair(K, i, j), g->w * g->a[i] * g->a[j]);
         }
     }
-    if (ngroups > 1024) return false;
-    // parts: longest-processing-time assignment by node count, then mask order inside a part
-    struct Ref { int mask, g, nodes; };
-    std::vector<Ref> refs;
-    for (int m = 1; m < 16; ++m)
-        for (size_t g = 0; g < by_mask[m].size(); ++g) refs.push_back(Ref{m, (int)g, 1 << k1s_popc(m)});
-    std::stable_sort(refs.begin(), refs.end(), [](const Ref& x, const Ref& y) { return x.nodes > y.nodes; });
-    std::vector<std::vector<Ref>> parts(K1S_NPART);
-    std::vector<int> load(K1S_NPART, 0);
-    if (st.w0 != 0.0) load[0] = 1;
-    for (const Ref& r : refs) {
-        int best = 0;
-        for (int p = 1; p < K1S_NPART; ++p)
-            if (load[p] < load[best]) best = p;
-        parts[best].push_back(r);
-        load[best] += r.nodes;
-    }
-    int pos = 0;
-    for (int p = 0; p < K1S_NPART; ++p) {
-        st.pbeg[p] = pos;
-        std::stable_sort(parts[p].begin(), parts[p].end(),
-                         [](const Ref& x, const Ref& y) { return x.mask != y.mask ? x.mask < y.mask : x.g < y.g; });
-        for (const Ref& r : parts[p]) st.glist[pos++] = (unsigned short)((r.mask << 10) | r.g);
-    }
-    st.pbeg[K1S_NPART] = pos;
+    if (data.size() > (size_t)K1S_MAX_DATA) return false;
+    st.ndata = (int)data.size();
     return true;
 }
 
@@ -219,7 +210,10 @@ struct gvib200_problem {
     int n_factors = 0;
     size_t nV = 0, nM = 0;  // sizes of fVdmu / fVdd
     // SDF
-    double4* d_sdf_rec = nullptr;
+    double4* d_sdf_rec = nullptr;   // hinge records, built for the threshold sdf_thr (epsilon + radius)
+    double* d_sdf_data = nullptr;   // the raw field (column-major), kept to rebuild the records
+    double sdf_thr = 0.0;
+    bool sdf_rec_valid = false;
     int sdf_rows = 0, sdf_cols = 0;
     double sdf_ox = 0, sdf_oy = 0, sdf_cell = 0;
     // state, double buffered (cur / candidate)
@@ -342,6 +336,11 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
         CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(t->d_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
         t->sym_ok = build_sym_table(*t, t->sym);
+        if (t->sym_ok) {
+            CUDA_TRY(cudaMalloc((void**)&t->d_sym, t->sym_data.size() * sizeof(double)));
+            CUDA_TRY(cudaMemcpy(t->d_sym, t->sym_data.data(), t->sym_data.size() * sizeof(double), cudaMemcpyHostToDevice));
+            t->sym.data = t->d_sym;
+        }
     }
     *out = t;
     return 0;
@@ -440,9 +439,18 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     for (int c = 0; c < 4; ++c) a.ximax[c] = g.table->ximax[c];
     a.cost = cost;
     const int grid = cdiv(g.n, 32);
+    const size_t smem = (size_t)g.table->sym.ndata * sizeof(double);
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_moments_sym<DIM, Cost, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K1S_MAX_DATA * (int)sizeof(double)));
+        CUDA_TRY(cudaFuncSetAttribute(k_moments_sym<DIM, Cost, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K1S_MAX_DATA * (int)sizeof(double)));
+        configured = true;
+    }
     if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
-    if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, 0, p->ls>>>(g.table->sym, a);
-    else k_moments_sym<DIM, Cost, false><<<grid, K1S_THREADS, 0, p->ls>>>(g.table->sym, a);
+    if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
+    else k_moments_sym<DIM, Cost, false><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
     if (p->profile) prof_end(p);
     p->ctx->launches++;
     return check_launch("k_moments_sym");
@@ -535,6 +543,14 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
             if constexpr (DIM >= 2 && DIM <= 4) {
                 if (p->d_sdf_rec == nullptr) return fail(GVIB200_ESTATE, "planar hinge cost needs gvib200_set_planar_sdf");
                 const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
+                const double thr = hp->epsilon + hp->radius;
+                if (!p->sdf_rec_valid || p->sdf_thr != thr) {  // (re)build the records for this threshold
+                    const long long ncell = (long long)p->sdf_rows * p->sdf_cols;
+                    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv(ncell, 256), 256, 0, p->sdf_rows, p->sdf_cols, thr,
+                           p->d_sdf_data, p->d_sdf_rec);
+                    p->sdf_thr = thr;
+                    p->sdf_rec_valid = true;
+                }
                 CostPlanarHinge c;
                 c.rec = p->d_sdf_rec;
                 c.rows = p->sdf_rows;
@@ -714,6 +730,8 @@ extern "C" int gvib200_ctx_destroy(gvib200_ctx* ctx) {
     if (!ctx) return 0;
     for (auto& kv : ctx->tables)
         if (kv.second->d_rows) cudaFree(kv.second->d_rows);
+    for (auto& kv : ctx->tables)
+        if (kv.second->d_sym) cudaFree(kv.second->d_sym);
     delete ctx;
     return 0;
 }
@@ -761,6 +779,7 @@ extern "C" int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, cons
     auto key = std::make_pair(dim, deg);
     auto it = ctx->tables.find(key);
     if (it != ctx->tables.end() && it->second->d_rows) cudaFree(it->second->d_rows);
+    if (it != ctx->tables.end() && it->second->d_sym) cudaFree(it->second->d_sym);
     ctx->tables[key] = std::move(t);
     return 0;
 }
@@ -797,6 +816,7 @@ static void free_problem(gvib200_problem* p) {
         F(g.d_start); F(g.d_Lambda); F(g.d_psi); F(g.d_Kinv); F(g.d_A); F(g.d_C); F(g.d_T);
     }
     F(p->d_sdf_rec);
+    F(p->d_sdf_data);
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
@@ -830,20 +850,21 @@ extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, do
     if (!p || rows < 2 || cols < 2 || !(cell > 0) || !data) return fail(GVIB200_EINVAL, "set_planar_sdf: bad arguments");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
     if (p->d_sdf_rec) cudaFree(p->d_sdf_rec);
-    double* d_data = nullptr;
+    if (p->d_sdf_data) cudaFree(p->d_sdf_data);
+    p->d_sdf_rec = nullptr;
+    p->d_sdf_data = nullptr;
     const size_t n = (size_t)rows * cols;
-    CUDA_TRY(cudaMalloc((void**)&d_data, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&p->d_sdf_data, n * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&p->d_sdf_rec, n * sizeof(double4)));
-    CUDA_TRY(cudaMemcpyAsync(d_data, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv((long long)n, 256), 256, 0, rows, cols, d_data, p->d_sdf_rec);
+    CUDA_TRY(cudaMemcpyAsync(p->d_sdf_data, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    cudaFree(d_data);
+    p->sdf_rec_valid = false;
     p->sdf_rows = rows;
     p->sdf_cols = cols;
     p->sdf_ox = ox;
     p->sdf_oy = oy;
     p->sdf_cell = cell;
-    return check_launch("k_build_sdf_records");
+    return 0;
 }
 
 static size_t cost_param_record(int kind, int dim) {

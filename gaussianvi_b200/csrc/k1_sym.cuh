@@ -12,12 +12,14 @@
 // adds instead of XD*DIM FMAs; the sums are the same numbers as SparseGaussHermite::Integrate's
 // (quadrature/SparseGaussHermite.h:197-221), in a different summation order.
 //
-// Mapping: one THREAD per factor, one WARP per part of the group list (the groups are split into NPART parts of
-// equal node count; the 32 lanes of a warp work on 32 consecutive factors, so every table access is warp uniform and
-// comes from the kernel-parameter constant bank).  A CTA = NPART warps = 32 factors; the partial sums of the parts
-// meet in shared memory in a fixed order (reproducible), then the CTA runs the Vdmu / Vddmu epilogue
-// (ngd/NGDFactorizedBaseGH.h:61-73).  Groups with four non-zero coordinates are processed as two 8-node units with
-// the sign of the fourth coordinate fixed, which bounds the live psi values to 8.
+// Mapping: 8 lanes ("parts") per factor, 4 factors per warp, 32 factors per CTA.  For every coordinate mask the groups
+// are dealt round-robin to the 8 parts (the last round is padded with zero-weight groups), so all lanes of a warp run
+// the same code on a group of the same shape while the 8 lanes of one factor gather neighbouring cells of the distance
+// field (a warp-wide gather touches ~10 sectors instead of 32).  The table (per mask: [round][entry][part]) is staged
+// once per CTA into shared memory with a TMA bulk copy.  The partial sums of the 8 parts meet in a fixed xor-butterfly
+// (reproducible), then the CTA runs the Vdmu / Vddmu epilogue (ngd/NGDFactorizedBaseGH.h:61-73).  Groups with four
+// non-zero coordinates are processed as two 8-node units with the sign of the fourth coordinate fixed, which bounds
+// the live psi values to 8.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,9 +28,9 @@
 
 namespace gvib200 {
 
-constexpr int K1S_NPART = 8;
-constexpr int K1S_THREADS = 32 * K1S_NPART;
-constexpr int K1S_MAX_DATA = 3400;  // doubles; the whole table travels as a kernel parameter (< 32 KB)
+constexpr int K1S_NPART = 8;          // lanes per factor
+constexpr int K1S_THREADS = 256;      // 8 warps x 4 factors = 32 factors per CTA
+constexpr int K1S_MAX_DATA = 6144;    // doubles of the staged table (48 KB of shared memory)
 
 // entries of one group with K non-zero coordinates c_0 < ... < c_{K-1}:
 //   a[K], w, (w a_i)[K], (w a_i^2)[K], (w a_i a_j)[pairs i < j in lexicographic order]
@@ -37,6 +39,11 @@ __host__ __device__ constexpr int k1s_popc(int m) { return (m & 1) + ((m >> 1) &
 __host__ __device__ constexpr int k1s_pair(int K, int i, int j) {  // index of pair (i < j)
     return i * K - i * (i + 1) / 2 + (j - i - 1);
 }
+
+// tuning (measured on B200 at the headline shape): 4 pending gathers per batch and 2 resident CTAs per SM (128
+// registers); 3 CTAs at 80 registers spill and run 25-35 % slower, 8 pending gathers change nothing
+__host__ __device__ constexpr int k1s_nb(int) { return 4; }
+__host__ __device__ constexpr int k1s_minb(int) { return 2; }
 
 // i-th set bit of mask m
 __host__ __device__ constexpr int k1s_coord(int m, int i) {
@@ -51,12 +58,11 @@ __host__ __device__ constexpr int k1s_coord(int m, int i) {
 
 struct SymTable {
     int dim;
-    int n_nodes;                 // nodes of the rule (for bookkeeping)
-    double w0;                   // weight of the node at the origin (0 when the rule has none); handled by part 0
-    int moff[16];                // first double of mask m's group list in data
-    int pbeg[K1S_NPART + 1];     // part p works on glist[pbeg[p] .. pbeg[p+1])
-    unsigned short glist[1024];  // (mask << 10) | group index within the mask; parts balanced by node count
-    double data[K1S_MAX_DATA];
+    int n_nodes;      // nodes of the rule (bookkeeping)
+    int ndata;        // doubles in data (multiple of 2)
+    int moff[16];     // first double of mask m's block in data; mask 0 = the node at the origin (one pseudo entry: w)
+    int rounds[16];   // rounds of mask m: round r hands group 8 r + p to part p
+    const double* data;  // device: per mask [round][entry][part]
 };
 
 template <class Cost>
@@ -102,7 +108,7 @@ __device__ __forceinline__ void k1s_wht(double (&v)[1 << KF]) {
 
 // psi at the 2^KF sign patterns of one unit.  Pattern bit i set = coordinate c_i negative.  cidx: the unit's
 // coordinates (warp uniform), sS: this thread's S rows in shared memory, sS[(r * DIM + c) * K1S_THREADS].
-template <int DIM, class Cost, bool FAST, int KF, bool HASFIX>
+template <int DIM, class Cost, bool FAST, int KF, bool HASFIX, int VAR>
 __device__ __forceinline__ void k1s_eval_unit(double (&psi)[1 << KF], const double* __restrict__ t, const int (&cidx)[4],
                                               double sfix, const double* __restrict__ sS, const double (&mu)[Cost::XD],
                                               const Cost& cost, int f) {
@@ -112,13 +118,13 @@ __device__ __forceinline__ void k1s_eval_unit(double (&psi)[1 << KF], const doub
 #pragma unroll
     for (int r = 0; r < XD; ++r) x[r] = mu[r];
     if (HASFIX) {
-        const double af = sfix * t[KF];  // the fixed coordinate is the last one of the group
+        const double af = sfix * t[KF * K1S_NPART];  // the fixed coordinate is the last one of the group
 #pragma unroll
         for (int r = 0; r < XD; ++r) x[r] = fma(sS[(r * DIM + cidx[KF]) * K1S_THREADS], af, x[r]);
     }
 #pragma unroll
     for (int i = 0; i < KF; ++i) {
-        const double a = t[i];
+        const double a = t[i * K1S_NPART];
 #pragma unroll
         for (int r = 0; r < XD; ++r) {
             const double d = sS[(r * DIM + cidx[i]) * K1S_THREADS] * a;
@@ -127,7 +133,7 @@ __device__ __forceinline__ void k1s_eval_unit(double (&psi)[1 << KF], const doub
         }
     }
     // Gray-code walk over the patterns, evaluated in batches so that a few gathers are in flight
-    constexpr int NB = (NP < 4) ? NP : 4;
+    constexpr int NB = (NP < k1s_nb(VAR)) ? NP : k1s_nb(VAR);
     int p = 0;
 #pragma unroll
     for (int s0 = 0; s0 < NP; s0 += NB) {
@@ -163,24 +169,24 @@ __device__ __forceinline__ void k1s_acc_mask(SymAcc<DIM>& acc, const double* __r
     constexpr int KF = HASFIX ? K - 1 : K;
     constexpr int c[4] = {k1s_coord(M, 0), k1s_coord(M, 1), k1s_coord(M, 2), k1s_coord(M, 3)};
     const double A0 = A[0];
-    acc.e0 = fma(t[K], A0, acc.e0);
+    acc.e0 = fma(t[K * K1S_NPART], A0, acc.e0);
 #pragma unroll
     for (int i = 0; i < KF; ++i) {
-        acc.e1[c[i]] = fma(t[K + 1 + i], A[1 << i], acc.e1[c[i]]);
-        acc.e2[k1s_e2<DIM>(c[i], c[i])] = fma(t[2 * K + 1 + i], A0, acc.e2[k1s_e2<DIM>(c[i], c[i])]);
+        acc.e1[c[i]] = fma(t[(K + 1 + i) * K1S_NPART], A[1 << i], acc.e1[c[i]]);
+        acc.e2[k1s_e2<DIM>(c[i], c[i])] = fma(t[(2 * K + 1 + i) * K1S_NPART], A0, acc.e2[k1s_e2<DIM>(c[i], c[i])]);
 #pragma unroll
         for (int j = i + 1; j < KF; ++j)
             acc.e2[k1s_e2<DIM>(c[i], c[j])] =
-                fma(t[3 * K + 1 + k1s_pair(K, i, j)], A[(1 << i) | (1 << j)], acc.e2[k1s_e2<DIM>(c[i], c[j])]);
+                fma(t[(3 * K + 1 + k1s_pair(K, i, j)) * K1S_NPART], A[(1 << i) | (1 << j)], acc.e2[k1s_e2<DIM>(c[i], c[j])]);
     }
     if (HASFIX) {
         constexpr int jf = K - 1;
-        acc.e1[c[jf]] = fma(sfix * t[K + 1 + jf], A0, acc.e1[c[jf]]);
-        acc.e2[k1s_e2<DIM>(c[jf], c[jf])] = fma(t[2 * K + 1 + jf], A0, acc.e2[k1s_e2<DIM>(c[jf], c[jf])]);
+        acc.e1[c[jf]] = fma(sfix * t[(K + 1 + jf) * K1S_NPART], A0, acc.e1[c[jf]]);
+        acc.e2[k1s_e2<DIM>(c[jf], c[jf])] = fma(t[(2 * K + 1 + jf) * K1S_NPART], A0, acc.e2[k1s_e2<DIM>(c[jf], c[jf])]);
 #pragma unroll
         for (int i = 0; i < KF; ++i)
             acc.e2[k1s_e2<DIM>(c[i], c[jf])] =
-                fma(sfix * t[3 * K + 1 + k1s_pair(K, i, jf)], A[1 << i], acc.e2[k1s_e2<DIM>(c[i], c[jf])]);
+                fma(sfix * t[(3 * K + 1 + k1s_pair(K, i, jf)) * K1S_NPART], A[1 << i], acc.e2[k1s_e2<DIM>(c[i], c[jf])]);
     }
 }
 
@@ -200,9 +206,9 @@ __device__ __forceinline__ void k1s_acc_switch(SymAcc<DIM>& acc, int mask, const
     }
 }
 
-// all groups [gb, ge) of one mask with K non-zero coordinates
-template <int DIM, class Cost, bool FULL, bool FAST, int K>
-__device__ __forceinline__ void k1s_run_mask(SymAcc<DIM>& acc, const SymTable& tab, int mask, int gb, int ge,
+// all rounds of one mask with K non-zero coordinates; tm: this lane's column of the mask's block in shared memory
+template <int DIM, class Cost, bool FULL, bool FAST, int K, int VAR>
+__device__ __forceinline__ void k1s_run_mask(SymAcc<DIM>& acc, const double* __restrict__ tm, int rounds, int mask,
                                              const double* __restrict__ sS, const double (&mu)[Cost::XD], const Cost& cost,
                                              int f) {
     constexpr bool HASFIX = (K == 4);
@@ -214,13 +220,14 @@ __device__ __forceinline__ void k1s_run_mask(SymAcc<DIM>& acc, const SymTable& t
         for (int b = 0; b < 4; ++b)
             if (mask & (1 << b)) cidx[q++] = b;
     }
-    for (int g = gb; g < ge; ++g) {
-        const double* t = tab.data + tab.moff[mask] + g * k1s_stride(K);
+#pragma unroll 1
+    for (int r = 0; r < rounds; ++r) {
+        const double* t = tm + r * (k1s_stride(K) * K1S_NPART);
 #pragma unroll 1
         for (int half = 0; half < (HASFIX ? 2 : 1); ++half) {
             const double sfix = half ? -1.0 : 1.0;
             double psi[1 << KF];
-            k1s_eval_unit<DIM, Cost, FAST, KF, HASFIX>(psi, t, cidx, sfix, sS, mu, cost, f);
+            k1s_eval_unit<DIM, Cost, FAST, KF, HASFIX, VAR>(psi, t, cidx, sfix, sS, mu, cost, f);
             if (FULL) {
                 k1s_wht<KF>(psi);
                 k1s_acc_switch<DIM, HASFIX>(acc, mask, t, psi, sfix);
@@ -228,51 +235,67 @@ __device__ __forceinline__ void k1s_run_mask(SymAcc<DIM>& acc, const SymTable& t
                 double s = psi[0];
 #pragma unroll
                 for (int q = 1; q < (1 << KF); ++q) s += psi[q];
-                acc.e0 = fma(t[K], s, acc.e0);
+                acc.e0 = fma(t[K * K1S_NPART], s, acc.e0);
             }
         }
     }
 }
 
-template <int DIM, class Cost, bool FULL, bool FAST>
-__device__ __forceinline__ void k1s_run_part(SymAcc<DIM>& acc, const SymTable& tab, int part, const double* __restrict__ sS,
-                                             const double (&mu)[Cost::XD], const Cost& cost, int f) {
-    if (part == 0 && tab.w0 != 0.0) {  // the node at the origin
+template <int DIM, class Cost, bool FULL, bool FAST, int VAR>
+__device__ __forceinline__ void k1s_run_part(SymAcc<DIM>& acc, const SymTable& tab, const double* __restrict__ stab, int part,
+                                             const double* __restrict__ sS, const double (&mu)[Cost::XD], const Cost& cost,
+                                             int f) {
+    {  // the node at the origin: weight w0 for part 0, zero for the other parts
         typename Cost::Pending pd = cost.template begin<FAST>(mu, f);
-        acc.e0 = fma(tab.w0, cost.finish(pd), acc.e0);
+        acc.e0 = fma(stab[tab.moff[0] + part], cost.finish(pd), acc.e0);
     }
 #pragma unroll 1
-    for (int idx = tab.pbeg[part]; idx < tab.pbeg[part + 1]; ++idx) {
-        const int ent = tab.glist[idx];
-        const int mask = ent >> 10, gb = ent & 1023;
+    for (int mask = 1; mask < (1 << DIM); ++mask) {
+        const int rounds = tab.rounds[mask];
+        if (rounds == 0) continue;
+        const double* tm = stab + tab.moff[mask] + part;
         const int K = __popc(mask);
-        if (K == 1) k1s_run_mask<DIM, Cost, FULL, FAST, 1>(acc, tab, mask, gb, gb + 1, sS, mu, cost, f);
+        if (K == 1) k1s_run_mask<DIM, Cost, FULL, FAST, 1, VAR>(acc, tm, rounds, mask, sS, mu, cost, f);
         if constexpr (DIM >= 2)
-            if (K == 2) k1s_run_mask<DIM, Cost, FULL, FAST, 2>(acc, tab, mask, gb, gb + 1, sS, mu, cost, f);
+            if (K == 2) k1s_run_mask<DIM, Cost, FULL, FAST, 2, VAR>(acc, tm, rounds, mask, sS, mu, cost, f);
         if constexpr (DIM >= 3)
-            if (K == 3) k1s_run_mask<DIM, Cost, FULL, FAST, 3>(acc, tab, mask, gb, gb + 1, sS, mu, cost, f);
+            if (K == 3) k1s_run_mask<DIM, Cost, FULL, FAST, 3, VAR>(acc, tm, rounds, mask, sS, mu, cost, f);
         if constexpr (DIM >= 4)
-            if (K == 4) k1s_run_mask<DIM, Cost, FULL, FAST, 4>(acc, tab, mask, gb, gb + 1, sS, mu, cost, f);
+            if (K == 4) k1s_run_mask<DIM, Cost, FULL, FAST, 4, VAR>(acc, tm, rounds, mask, sS, mu, cost, f);
     }
 }
 
-template <int DIM, class Cost, bool FULL>
-__global__ void __launch_bounds__(K1S_THREADS, 2)
+// TMA bulk copy helpers (cp.async.bulk + mbarrier), as in kernels.cuh
+__device__ __forceinline__ uint32_t k1s_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int DIM, class Cost, bool FULL, int VAR = 0>
+__global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     k_moments_sym(const __grid_constant__ SymTable tab, const __grid_constant__ SymArgs<Cost> a) {
     constexpr int XD = Cost::XD;
     constexpr int NE2 = DIM * (DIM + 1) / 2;
     constexpr int NACC = 1 + DIM + NE2;
     constexpr int NOUT = 1 + DIM + DIM * DIM;
-    // S rows [(r*DIM + c)][thread] during the node loop, afterwards the partial sums of the parts [part][e][lane]
-    constexpr int NBUF = (XD * DIM * K1S_THREADS > K1S_NPART * NACC * 32) ? XD * DIM * K1S_THREADS : K1S_NPART * NACC * 32;
-    __shared__ double buf[NBUF];
+    extern __shared__ __align__(16) double stab[];          // the staged table, tab.ndata doubles
+    __shared__ double sSall[XD * DIM * K1S_THREADS];        // S rows, [(r*DIM + c)][thread]
     __shared__ double tot[NOUT][33];                        // totals per factor: e0, e1, e2 (full, mirrored)
-    double* sSall = buf;
-    double (*red)[NACC][32] = reinterpret_cast<double (*)[NACC][32]>(buf);
+    __shared__ __align__(8) uint64_t mbar;
     const int lane = threadIdx.x & 31;
-    const int part = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int part = lane & (K1S_NPART - 1);
+    const int fl = warp * 4 + (lane >> 3);  // factor of this lane within the CTA, 0..31
     const int f0 = blockIdx.x * 32;
-    const int f = min(f0 + lane, a.n - 1);  // tail lanes recompute the last factor and do not store
+    const int f = min(f0 + fl, a.n - 1);    // tail lanes recompute the last factor and do not store
+    // ---- stage the table: one TMA bulk copy, completion on an mbarrier ----
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k1s_smem_u32(&mbar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)tab.ndata * sizeof(double);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k1s_smem_u32(&mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         k1s_smem_u32(stab)),
+                     "l"(tab.data), "r"(bytes), "r"(k1s_smem_u32(&mbar))
+                     : "memory");
+    }
     double mu[XD];
     const double* sS = sSall + threadIdx.x;
     bool fast;
@@ -295,43 +318,53 @@ __global__ void __launch_bounds__(K1S_THREADS, 2)
         }
         fast = __all_sync(0xffffffffu, a.cost.fast_ok(lo, hi));
     }
+    __syncthreads();  // mbarrier initialised (and visible) before anybody waits on it
+    {
+        uint32_t ok;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(k1s_smem_u32(&mbar)), "r"(0)
+                : "memory");
+        } while (!ok);
+    }
     SymAcc<DIM> acc;
     acc.e0 = 0.0;
 #pragma unroll
     for (int c = 0; c < DIM; ++c) acc.e1[c] = 0.0;
 #pragma unroll
     for (int c = 0; c < NE2; ++c) acc.e2[c] = 0.0;
-    if (fast) k1s_run_part<DIM, Cost, FULL, true>(acc, tab, part, sS, mu, a.cost, f);
-    else k1s_run_part<DIM, Cost, FULL, false>(acc, tab, part, sS, mu, a.cost, f);
+    if (fast) k1s_run_part<DIM, Cost, FULL, true, VAR>(acc, tab, stab, part, sS, mu, a.cost, f);
+    else k1s_run_part<DIM, Cost, FULL, false, VAR>(acc, tab, stab, part, sS, mu, a.cost, f);
 
-    // ---- parts meet in shared memory, summed in part order ----
-    __syncthreads();  // every warp is done with its S rows: the buffer is reused
-    red[part][0][lane] = acc.e0;
-    if (FULL) {
+    // ---- the 8 parts of a factor meet in a fixed xor-butterfly over lane bits 0..2 ----
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) red[part][1 + c][lane] = acc.e1[c];
+    for (int o = 1; o < K1S_NPART; o <<= 1) {
+        acc.e0 += __shfl_xor_sync(0xffffffffu, acc.e0, o);
+        if (FULL) {
 #pragma unroll
-        for (int c = 0; c < NE2; ++c) red[part][1 + DIM + c][lane] = acc.e2[c];
+            for (int c = 0; c < DIM; ++c) acc.e1[c] += __shfl_xor_sync(0xffffffffu, acc.e1[c], o);
+#pragma unroll
+            for (int c = 0; c < NE2; ++c) acc.e2[c] += __shfl_xor_sync(0xffffffffu, acc.e2[c], o);
+        }
     }
-    __syncthreads();
     const double sc = a.cost.scale();
-    for (int idx = threadIdx.x; idx < (FULL ? NACC : 1) * 32; idx += K1S_THREADS) {
-        const int e = idx >> 5, l = idx & 31;
-        double s = red[0][e][l];
+    if (part == 0) {
+        tot[0][fl] = acc.e0 * sc;
+        if (FULL) {
 #pragma unroll
-        for (int p = 1; p < K1S_NPART; ++p) s += red[p][e][l];
-        s *= sc;
-        if (e <= DIM) {
-            tot[e][l] = s;
-        } else {  // unpack the upper triangle into the full symmetric matrix
-            int q = e - 1 - DIM, ra = 0;
-            while (q >= DIM - ra) {
-                q -= DIM - ra;
-                ++ra;
-            }
-            const int rb = ra + q;
-            tot[1 + DIM + ra + rb * DIM][l] = s;
-            tot[1 + DIM + rb + ra * DIM][l] = s;
+            for (int c = 0; c < DIM; ++c) tot[1 + c][fl] = acc.e1[c] * sc;
+#pragma unroll
+            for (int ra = 0; ra < DIM; ++ra)
+#pragma unroll
+                for (int rb = ra; rb < DIM; ++rb) {
+                    const double v = acc.e2[k1s_e2<DIM>(ra, rb)] * sc;
+                    tot[1 + DIM + ra + rb * DIM][fl] = v;
+                    tot[1 + DIM + rb + ra * DIM][fl] = v;
+                }
         }
     }
     __syncthreads();

@@ -710,17 +710,19 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
     cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, threadIdx.x, blockDim.x);
 }
 
-// cell records for CostPlanarHinge from the column-major field
-__global__ void k_build_sdf_records(int rows, int cols, const double* __restrict__ data, double4* __restrict__ rec) {
+// cell records for CostPlanarHinge from the column-major field (layout: cost_functors.cuh)
+__global__ void k_build_sdf_records(int rows, int cols, double thr, const double* __restrict__ data, double4* __restrict__ rec) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cols) return;
     const int r = idx % rows, c = idx / rows;
     const int hr = min(r + 1, rows - 1), hc = min(c + 1, cols - 1);
+    const double v00 = data[r + (size_t)c * rows], v10 = data[hr + (size_t)c * rows];
+    const double v01 = data[r + (size_t)hc * rows], v11 = data[hr + (size_t)hc * rows];
     double4 v;
-    v.x = data[r + (size_t)c * rows];
-    v.y = data[hr + (size_t)c * rows];
-    v.z = data[r + (size_t)hc * rows];
-    v.w = data[hr + (size_t)hc * rows];
+    v.x = thr - v00;
+    v.y = -(v10 - v00);
+    v.z = -(v01 - v00);
+    v.w = -((v11 - v01) - (v10 - v00));
     rec[idx] = v;
 }
 
