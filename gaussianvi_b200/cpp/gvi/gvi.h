@@ -1,0 +1,745 @@
+// gvi.h -- header-only C++ facade that keeps the reference's operator API (namespace gvi) on top of the gvib200 C-ABI.
+//
+// A user of hzyu17/GaussianVI builds factors and an optimizer exactly as before:
+//     gvi::NGDFactorizedBaseGH<CostClass>(dimension, state_dim, gh_degree, function, cost_class, num_states, start_index,
+//                                         temperature, high_temperature)            ngd/NGDFactorizedBaseGH.h:37-41
+//     gvi::NGDFactorizedLinear<Factor>(dimension, dim_state, function, linear_factor, num_states, start_indx,
+//                                      temperature, high_temperature)               ngd/NGDFactorizedLinear.h:28-35
+//     gvi::NGDGH<F>(vec_factors, dim_state, num_states, niters, T, T_high)          ngd/NGD-GH.h:40-53
+//     set_initial_values / set_mu / set_precision / set_step_size_base / set_max_iter_backtrack /
+//     set_niter_low_temperature / optimize() / mean() / covariance() / precision() / cost_value() /
+//     factor_cost_vector() / E_Phis() ...                                          gvibase/GVI-GH-GBP.h:149-378
+//     gvi::MinimumAccGP / FixedPriorGP / LTV_GP and the aliases FixedGpPrior / LinearGpPrior
+//                                                                                   gp/*.h, gp/factorized_opts_linear.h:9-14
+// and the whole iteration runs on the GPU.  The `function` argument stays in the signatures for source compatibility
+// but is never called: the device path dispatches on CostClass through DeviceCostTraits<CostClass>; a cost class without
+// a specialisation is a compile-time error (there is no CPU fallback).
+//
+// Host code only: matrices are Eigen's when <Eigen/Dense> is found, else the stand-in of gvi/matrix.h.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/gvib200.h"
+#include "matrix.h"
+
+namespace gvi {
+
+struct NoneType {};
+
+inline void gvib200_check(int rc, const char* what) {
+    if (rc < 0) throw std::runtime_error(std::string(what) + ": gvib200 error " + std::to_string(rc) + ": " + gvib200_last_error());
+}
+
+// one context per process and device (the reference has no notion of a device; GVIB200_DEVICE selects it)
+inline gvib200_ctx* default_context() {
+    static gvib200_ctx* ctx = nullptr;
+    if (!ctx) {
+        const char* dev = std::getenv("GVIB200_DEVICE");
+        gvib200_check(gvib200_ctx_create(dev ? std::atoi(dev) : 0, &ctx), "gvib200_ctx_create");
+    }
+    return ctx;
+}
+
+// ------------------------------------------------------------------------------------------------ cost classes
+// 1-D stereo-camera cost of src/1d_example.cpp:25-35
+struct Stereo1DCost {
+    double mu_p = 20, f = 400, b = 0.1, sig_r_sq = 0.09, sig_p_sq = 9, y_offset = -0.8;
+};
+// PlanarSDF(origin, cell_size, data), helpers/CudaOperation.h:27-128
+struct PlanarSDF {
+    double origin_x = 0, origin_y = 0, cell_size = 1;
+    MatrixXd data;  // rows x cols signed distances
+};
+// cost_obstacle_planar of CudaOperation_PlanarPR, helpers/CudaOperation.h:491-508 (defaults :456)
+struct PlanarHingeCost {
+    std::shared_ptr<PlanarSDF> sdf;
+    double sigma = 15.5, epsilon = 0.5, radius = 1.0;
+};
+// x^T (c I) x, the integrand of tests/test_gh_spgh.cpp:21-25
+struct QuadraticCost {
+    double c = 1.0;
+};
+
+struct DeviceCostSpec {
+    int kind = 0;
+    std::vector<unsigned char> params;        // one struct (shared by the group)
+    std::shared_ptr<PlanarSDF> sdf;           // planar hinge only
+    bool operator<(const DeviceCostSpec& o) const {
+        if (kind != o.kind) return kind < o.kind;
+        if (sdf.get() != o.sdf.get()) return sdf.get() < o.sdf.get();
+        return params < o.params;
+    }
+};
+template <class P>
+inline std::vector<unsigned char> pod_bytes(const P& p) {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&p);
+    return std::vector<unsigned char>(b, b + sizeof(P));
+}
+
+template <class CostClass>
+struct DeviceCostTraits;  // no definition: an unspecialised cost class cannot run (compile-time error)
+template <>
+struct DeviceCostTraits<Stereo1DCost> {
+    static DeviceCostSpec spec(const Stereo1DCost& c) {
+        gvib200_stereo1d_params p{c.mu_p, c.f, c.b, c.sig_r_sq, c.sig_p_sq, c.y_offset};
+        return DeviceCostSpec{GVIB200_COST_STEREO_1D, pod_bytes(p), nullptr};
+    }
+};
+template <>
+struct DeviceCostTraits<PlanarHingeCost> {
+    static DeviceCostSpec spec(const PlanarHingeCost& c) {
+        gvib200_hinge_params p{c.sigma, c.epsilon, c.radius};
+        return DeviceCostSpec{GVIB200_COST_PLANAR_HINGE, pod_bytes(p), c.sdf};
+    }
+};
+template <>
+struct DeviceCostTraits<QuadraticCost> {
+    static DeviceCostSpec spec(const QuadraticCost& c) { return DeviceCostSpec{GVIB200_COST_QUADRATIC, pod_bytes(c.c), nullptr}; }
+};
+
+// ------------------------------------------------------------------------------------------------ linear priors
+// gp/linear_factor.h:18-31
+class LinearFactor {
+public:
+    virtual ~LinearFactor() {}
+    virtual VectorXd get_mu() const = 0;
+    virtual MatrixXd get_covariance() const = 0;
+    virtual MatrixXd get_precision() const = 0;
+    virtual MatrixXd get_Lambda() const = 0;
+    virtual MatrixXd get_Psi() const = 0;
+    virtual double get_Constant() const = 0;
+};
+
+// gp/fixed_prior.h:19-50
+class FixedPriorGP : public LinearFactor {
+public:
+    FixedPriorGP() {}
+    FixedPriorGP(const MatrixXd& Covariance, const VectorXd& mu) : _K(Covariance), _invK(Covariance.inverse()), _dim((int)mu.size()), _mu(mu) {}
+    VectorXd get_mu() const override { return _mu; }
+    MatrixXd get_precision() const override { return _invK; }
+    MatrixXd get_covariance() const override { return _K; }
+    MatrixXd get_Lambda() const override { return MatrixXd::Identity(_dim, _dim); }
+    MatrixXd get_Psi() const override { return MatrixXd::Identity(_dim, _dim); }
+    double get_Constant() const override { return 1.0; }
+
+private:
+    MatrixXd _K, _invK;
+    int _dim = 0;
+    VectorXd _mu;
+};
+
+namespace detail {
+inline MatrixXd lambda_from_phi(const MatrixXd& Phi) {  // [-Phi, I]
+    const long n = Phi.rows();
+    MatrixXd L = MatrixXd::Zero(n, 2 * n);
+    for (long j = 0; j < n; ++j)
+        for (long i = 0; i < n; ++i) L(i, j) = -Phi(i, j);
+    for (long i = 0; i < n; ++i) L(i, n + i) = 1.0;
+    return L;
+}
+// exp of a small square matrix: scaling and squaring with a Taylor series
+inline MatrixXd expm(const MatrixXd& X) {
+    const long n = X.rows();
+    double nrm = 0.0;
+    for (long i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (long j = 0; j < n; ++j) s += std::fabs(X(i, j));
+        nrm = nrm > s ? nrm : s;
+    }
+    int sq = 0;
+    while (nrm > 0.25) {
+        nrm *= 0.5;
+        ++sq;
+    }
+    MatrixXd Y = X * (1.0 / std::pow(2.0, sq));
+    MatrixXd E = MatrixXd::Identity(n, n), term = MatrixXd::Identity(n, n);
+    for (int k = 1; k < 19; ++k) {
+        term = (term * Y) * (1.0 / k);
+        E = E + term;
+    }
+    for (int s = 0; s < sq; ++s) E = E * E;
+    return E;
+}
+}  // namespace detail
+
+// gp/minimum_acc_prior.h:26-130
+class MinimumAccGP : public LinearFactor {
+public:
+    MinimumAccGP() {}
+    MinimumAccGP(const MatrixXd& Qc, double start_index, const double& delta_t, const VectorXd& mu_0)
+        : _dim((int)Qc.cols()), _dim_state(2 * (int)Qc.cols()), _delta_t(delta_t), _Qc(Qc) {
+        (void)start_index;
+        (void)mu_0;
+        const int n = _dim, ns = _dim_state;
+        _Phi = MatrixXd::Identity(ns, ns);
+        for (int i = 0; i < n; ++i) _Phi(i, n + i) = delta_t;
+        const MatrixXd iq = Qc.inverse();
+        _invQ = MatrixXd::Zero(ns, ns);
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                _invQ(i, j) = 12 * iq(i, j) / std::pow(delta_t, 3);
+                _invQ(i, n + j) = -6 * iq(i, j) / std::pow(delta_t, 2);
+                _invQ(n + i, j) = -6 * iq(i, j) / std::pow(delta_t, 2);
+                _invQ(n + i, n + j) = 4 * iq(i, j) / delta_t;
+            }
+        _Lambda = detail::lambda_from_phi(_Phi);
+        _Psi = MatrixXd::Zero(ns, 2 * ns);  // a(t) = 0: eliminated (:76-79)
+        _target_mu = VectorXd::Zero(2 * ns);
+    }
+    MatrixXd Phi() const { return _Phi; }
+    MatrixXd Qc() const { return _Qc; }
+    int dim_posvel() const { return 2 * _dim; }
+    VectorXd get_mu() const override { return _target_mu; }
+    MatrixXd get_precision() const override { return _invQ; }
+    MatrixXd get_covariance() const override { return _invQ.inverse(); }
+    MatrixXd get_Lambda() const override { return _Lambda; }
+    MatrixXd get_Psi() const override { return _Psi; }
+    double get_Constant() const override { return 0.5; }
+
+private:
+    int _dim = 0, _dim_state = 0;
+    double _delta_t = 0;
+    MatrixXd _Qc, _invQ, _Phi, _Lambda, _Psi;
+    VectorXd _target_mu;
+};
+
+// gp/LTV_prior.h:28-247.  Phi' = A Phi, Q' = A Q + Q A^T + B B^T with A, B piece-wise constant on the four quarter
+// intervals (:187-197); the reference integrates with GSL rkf45 at tolerance 1e-12, here each quarter is integrated
+// exactly with Van Loan's block exponential.
+class LTV_GP : public LinearFactor {
+public:
+    LTV_GP() {}
+    LTV_GP(const MatrixXd& Qc, int start_index, const double& delta_t, const VectorXd& mu_0, int n_states,
+           const std::vector<MatrixXd>& hA, const std::vector<MatrixXd>& hB, const std::vector<VectorXd>& target_mean)
+        : _dim((int)Qc.cols()), _dim_state(2 * (int)Qc.cols()) {
+        (void)mu_0;
+        (void)n_states;
+        const int ns = _dim_state;
+        const double h = delta_t / 4.0;
+        MatrixXd Phi = MatrixXd::Identity(ns, ns), Q = MatrixXd::Zero(ns, ns);
+        for (int k = 0; k < 4; ++k) {
+            const MatrixXd& A = hA[4 * start_index + k];
+            const MatrixXd& B = hB[4 * start_index + k];
+            const MatrixXd BBt = B * B.transpose();
+            MatrixXd M = MatrixXd::Zero(2 * ns, 2 * ns);
+            for (int j = 0; j < ns; ++j)
+                for (int i = 0; i < ns; ++i) {
+                    M(i, j) = -A(i, j) * h;
+                    M(i, ns + j) = BBt(i, j) * h;
+                    M(ns + i, ns + j) = A(j, i) * h;
+                }
+            const MatrixXd E = detail::expm(M);
+            MatrixXd Phik(ns, ns), E12(ns, ns);
+            for (int j = 0; j < ns; ++j)
+                for (int i = 0; i < ns; ++i) {
+                    Phik(i, j) = E(ns + j, ns + i);
+                    E12(i, j) = E(i, ns + j);
+                }
+            MatrixXd Qk = Phik * E12;
+            Qk = 0.5 * (Qk + Qk.transpose());
+            Q = Phik * Q * Phik.transpose() + Qk;
+            Phi = Phik * Phi;
+        }
+        _Phi = Phi;
+        _Q = 0.5 * (Q + Q.transpose());
+        MatrixXd iq = _Q.inverse();
+        _invQ = 0.5 * (iq + iq.transpose());
+        _Lambda = detail::lambda_from_phi(_Phi);
+        _Psi = -1.0 * _Lambda;  // [Phi, -I] (:91-94; note the sign quirk: the prior is centred on -target_mean)
+        _target_mu = VectorXd::Zero(2 * ns);
+        for (int i = 0; i < ns; ++i) {
+            _target_mu(i) = target_mean[start_index](i);
+            _target_mu(ns + i) = target_mean[start_index + 1](i);
+        }
+    }
+    MatrixXd Phi() const { return _Phi; }
+    MatrixXd Q() const { return _Q; }
+    VectorXd get_mu() const override { return _target_mu; }
+    MatrixXd get_precision() const override { return _invQ; }
+    MatrixXd get_covariance() const override { return _Q; }
+    MatrixXd get_Lambda() const override { return _Lambda; }
+    MatrixXd get_Psi() const override { return _Psi; }
+    double get_Constant() const override { return 0.5; }
+
+private:
+    int _dim = 0, _dim_state = 0;
+    MatrixXd _Phi, _Q, _invQ, _Lambda, _Psi;
+    VectorXd _target_mu;
+};
+
+// ------------------------------------------------------------------------------------------------ factors
+// GVIFactorizedBase (gvibase/GVIFactorizedBase.h:49-71): what the joint optimizer needs to know about one factor
+class GVIFactorizedBase {
+public:
+    virtual ~GVIFactorizedBase() {}
+    GVIFactorizedBase(int dimension, int state_dimension, int num_states, int start_index, double temperature,
+                      double high_temperature)
+        : _dim(dimension), _state_dim(state_dimension), _num_states(num_states), _start_index(start_index),
+          _temperature(temperature), _high_temperature(high_temperature) {}
+    int dimension() const { return _dim; }
+    int start_index() const { return _start_index; }
+    double temperature() const { return _temperature; }
+    double high_temperature() const { return _high_temperature; }
+    virtual bool is_linear() const = 0;
+    // what the joint optimizer needs to batch the factor onto the device (type-erased)
+    virtual const DeviceCostSpec* cost_spec() const { return nullptr; }
+    virtual int gh_degree() const { return 0; }
+    virtual const MatrixXd* lin_Lambda() const { return nullptr; }
+    virtual const MatrixXd* lin_Psi() const { return nullptr; }
+    virtual const MatrixXd* lin_Kinv() const { return nullptr; }
+    virtual const VectorXd* lin_mu() const { return nullptr; }
+    virtual double lin_constant() const { return 0.0; }
+
+    int _dim, _state_dim, _num_states, _start_index;
+    double _temperature, _high_temperature;
+};
+
+// ngd/NGDFactorizedBaseGH.h:37-129
+template <class CostClass>
+class NGDFactorizedBaseGH : public GVIFactorizedBase {
+public:
+    using GHFunction = std::function<double(const VectorXd&, const CostClass&)>;
+    NGDFactorizedBaseGH(int dimension, int state_dim, int gh_degree, const GHFunction& function, const CostClass& cost_class,
+                        int num_states, int start_index, double temperature = 1.0, double high_temperature = 10.0)
+        : GVIFactorizedBase(dimension, state_dim, num_states, start_index, temperature, high_temperature),
+          _gh_degree(gh_degree), _cost(DeviceCostTraits<CostClass>::spec(cost_class)) {
+        (void)function;  // kept for source compatibility; the device functor is selected by CostClass
+    }
+    bool is_linear() const override { return false; }
+    const DeviceCostSpec* cost_spec() const override { return &_cost; }
+    int gh_degree() const override { return _gh_degree; }
+    int _gh_degree;
+    DeviceCostSpec _cost;
+};
+// NGDFactorizedSimpleGH = NGDFactorizedBaseGH<NoneType> in the reference (an arbitrary host function): it has no device
+// functor, so instantiating it fails to compile -- use a cost class with DeviceCostTraits instead.
+using NGDFactorizedSimpleGH = NGDFactorizedBaseGH<NoneType>;
+
+// ngd/NGDFactorizedLinear.h:28-129
+template <class Factor>
+class NGDFactorizedLinear : public GVIFactorizedBase {
+public:
+    using CostFunction = std::function<double(const VectorXd&, const Factor&)>;
+    NGDFactorizedLinear(const int& dimension, int dim_state, const CostFunction& function, const Factor& linear_factor,
+                        int num_states, int start_indx, double temperature = 1.0, double high_temperature = 10.0)
+        : GVIFactorizedBase(dimension, dim_state, num_states, start_indx, temperature, high_temperature),
+          _target_mean(linear_factor.get_mu()), _target_precision(linear_factor.get_precision()),
+          _Lambda(linear_factor.get_Lambda()), _Psi(linear_factor.get_Psi()), _constant(linear_factor.get_Constant()) {
+        (void)function;
+    }
+    bool is_linear() const override { return true; }
+    const MatrixXd* lin_Lambda() const override { return &_Lambda; }
+    const MatrixXd* lin_Psi() const override { return &_Psi; }
+    const MatrixXd* lin_Kinv() const override { return &_target_precision; }
+    const VectorXd* lin_mu() const override { return &_target_mean; }
+    double lin_constant() const override { return _constant; }
+    VectorXd _target_mean;
+    MatrixXd _target_precision, _Lambda, _Psi;
+    double _constant;
+};
+using FixedGpPrior = NGDFactorizedLinear<FixedPriorGP>;    // gp/factorized_opts_linear.h:9-10
+using LinearGpPrior = NGDFactorizedLinear<MinimumAccGP>;
+using LTVGpPrior = NGDFactorizedLinear<LTV_GP>;            // gp/factorized_opts_LTV.h
+
+// cost_fixed_gp / cost_linear_gp (gp/cost_functions.h:25-39): signature placeholders for source compatibility
+inline double cost_fixed_gp(const VectorXd&, const FixedPriorGP&) { return 0.0; }
+inline double cost_linear_gp(const VectorXd&, const MinimumAccGP&) { return 0.0; }
+
+// block-tridiagonal result (GVIGH::covariance() / precision() return exactly this pattern as an SpMat in the reference)
+struct BlockTridiagonal {
+    int num_states = 0, dim_state = 0;
+    std::vector<double> diag, off;  // [S][d*d], [S-1][d*d] (block (i, i+1)), column-major blocks
+    double operator()(long r, long c) const {
+        const int d = dim_state;
+        const long bi = r / d, bj = c / d, i = r % d, j = c % d;
+        if (bi == bj) return diag[(size_t)bi * d * d + i + j * d];
+        if (bj == bi + 1) return off[(size_t)bi * d * d + i + j * d];
+        if (bi == bj + 1) return off[(size_t)bj * d * d + j + i * d];
+        return 0.0;
+    }
+    MatrixXd toDense() const {
+        const long n = (long)num_states * dim_state;
+        MatrixXd M = MatrixXd::Zero(n, n);
+        for (long c = 0; c < n; ++c)
+            for (long r = (c >= dim_state ? c - 2 * dim_state + 1 : 0); r < n && r < c + 2 * dim_state; ++r)
+                if (r >= 0) M(r, c) = (*this)(r, c);
+        return M;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ joint optimizer
+// GVIGH (gvibase/GVI-GH-GBP.h:28-433) -- the control skeleton stays on the host, the state lives on the device
+template <class FactorizedOptimizer>
+class GVIGH {
+public:
+    GVIGH(const std::vector<std::shared_ptr<FactorizedOptimizer>>& vec_fact_optimizers, int dim_state, int num_states,
+          int niterations = 5, double temperature = 1.0, double high_temperature = 100.0)
+        : _dim_state(dim_state), _num_states(num_states), _dim(dim_state * num_states), _niters(niterations),
+          _temperature(temperature), _high_temperature(high_temperature) {
+        for (auto& f : vec_fact_optimizers) _factors.push_back(f);
+        gvib200_default_opts(&_opts);
+    }
+    virtual ~GVIGH() {
+        if (_prob) gvib200_problem_destroy(_prob);
+    }
+    GVIGH(const GVIGH&) = delete;
+    GVIGH& operator=(const GVIGH&) = delete;
+
+    // factors of other concrete types can be appended before the first use (a joint problem mixes factor types)
+    void add_factor(const std::shared_ptr<GVIFactorizedBase>& f) {
+        if (_prob) throw std::logic_error("add_factor after the problem was built");
+        _factors.push_back(f);
+    }
+
+    // ---- knobs (gvibase/GVI-GH-GBP.h:168-248) ----
+    void set_step_size_base(double v) { _opts.step_size_base = v; }
+    void set_max_iter_backtrack(int v) { _opts.max_backtrack = v; }
+    void set_niter_low_temperature(int v) { _opts.niters_lowtemp = v; }
+    void set_niterations(int v) { _niters = v; }
+    void set_reuse_accepted_sweep(bool v) { _opts.reuse_accepted_sweep = v ? 1 : 0; }
+
+    void set_mu(const VectorXd& mean) {
+        _mu0.assign(mean.data(), mean.data() + mean.size());
+        if (_prob && _has_state) gvib200_check(gvib200_set_state(_prob, _mu0.data(), nullptr, nullptr), "set_mu");
+    }
+    // precision given as its block-tridiagonal part: any matrix type with operator()(row, col)
+    template <class Mat>
+    void set_precision(const Mat& P) {
+        const int d = _dim_state, S = _num_states;
+        _pd.assign((size_t)S * d * d, 0.0);
+        _po.assign((size_t)(S > 1 ? S - 1 : 1) * d * d, 0.0);
+        for (int s = 0; s < S; ++s)
+            for (int j = 0; j < d; ++j)
+                for (int i = 0; i < d; ++i) {
+                    _pd[(size_t)s * d * d + i + j * d] = P(s * d + i, s * d + j);
+                    if (s + 1 < S) _po[(size_t)s * d * d + i + j * d] = P(s * d + i, (s + 1) * d + j);
+                }
+        push_state();
+    }
+    template <class Mat>
+    void set_initial_values(const VectorXd& mean, const Mat& P) {
+        _mu0.assign(mean.data(), mean.data() + mean.size());
+        set_precision(P);
+    }
+    void initilize_precision_matrix(double initial_precision_factor) {  // (sic) gvibase/GVI-GH.h:201-204
+        const int d = _dim_state, S = _num_states;
+        _pd.assign((size_t)S * d * d, 0.0);
+        _po.assign((size_t)(S > 1 ? S - 1 : 1) * d * d, 0.0);
+        for (int s = 0; s < S; ++s)
+            for (int i = 0; i < d; ++i) _pd[(size_t)s * d * d + i + i * d] = initial_precision_factor;
+        push_state();
+    }
+
+    // ---- the loop (gvibase/GVI-GH-GBP-impl.h:33-130) ----
+    void optimize(std::optional<bool> verbose = std::nullopt) {
+        build();
+        _stats.assign((size_t)_niters, gvib200_iter_stats());
+        int done = 0;
+        gvib200_check(gvib200_optimize(_prob, &_opts, _niters, _stats.data(), &done, nullptr, nullptr), "optimize");
+        _stats.resize((size_t)done);
+        if (verbose.value_or(false))
+            for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, _stats[(size_t)i].cost);
+    }
+    const std::vector<gvib200_iter_stats>& iteration_stats() const { return _stats; }
+
+    // ---- results (gvibase/GVI-GH-GBP.h:163-167) ----
+    VectorXd mean() {
+        build();
+        VectorXd m = VectorXd::Zero(_dim);
+        gvib200_check(gvib200_get_mean(_prob, m.data()), "mean");
+        return m;
+    }
+    BlockTridiagonal covariance() { return blocks(true); }
+    BlockTridiagonal precision() { return blocks(false); }
+
+    double cost_value() {
+        build();
+        double c = 0.0;
+        gvib200_check(gvib200_cost(_prob, nullptr, nullptr, nullptr, &c, nullptr), "cost_value");
+        return c;
+    }
+    template <class Mat>
+    double cost_value(const VectorXd& mean, const Mat& P) {
+        build();
+        std::vector<double> pd, po;
+        pack_precision(P, pd, po);
+        double c = 0.0;
+        gvib200_check(gvib200_cost(_prob, mean.data(), pd.data(), _num_states > 1 ? po.data() : nullptr, &c, nullptr), "cost_value");
+        return c;
+    }
+    // factor costs in the order the factors were handed to the constructor
+    VectorXd factor_cost_vector() {
+        build();
+        std::vector<double> fc(_factors.size());
+        double c = 0.0;
+        gvib200_check(gvib200_cost(_prob, nullptr, nullptr, nullptr, &c, fc.data()), "factor_cost_vector");
+        VectorXd out = VectorXd::Zero((long)_factors.size());
+        for (size_t i = 0; i < _factors.size(); ++i) out(i) = fc[(size_t)_id_of_factor[i]];
+        return out;
+    }
+    gvib200_problem* handle() {
+        build();
+        return _prob;
+    }
+
+protected:
+    template <class Mat>
+    void pack_precision(const Mat& P, std::vector<double>& pd, std::vector<double>& po) const {
+        const int d = _dim_state, S = _num_states;
+        pd.assign((size_t)S * d * d, 0.0);
+        po.assign((size_t)(S > 1 ? S - 1 : 1) * d * d, 0.0);
+        for (int s = 0; s < S; ++s)
+            for (int j = 0; j < d; ++j)
+                for (int i = 0; i < d; ++i) {
+                    pd[(size_t)s * d * d + i + j * d] = P(s * d + i, s * d + j);
+                    if (s + 1 < S) po[(size_t)s * d * d + i + j * d] = P(s * d + i, (s + 1) * d + j);
+                }
+    }
+    BlockTridiagonal blocks(bool cov) {
+        build();
+        BlockTridiagonal b;
+        b.num_states = _num_states;
+        b.dim_state = _dim_state;
+        const size_t dd = (size_t)_dim_state * _dim_state;
+        b.diag.assign((size_t)_num_states * dd, 0.0);
+        b.off.assign((size_t)(_num_states > 1 ? _num_states - 1 : 1) * dd, 0.0);
+        gvib200_check((cov ? gvib200_get_cov_blocks : gvib200_get_prec_blocks)(_prob, b.diag.data(), b.off.data()), "blocks");
+        if (_num_states == 1) b.off.clear();
+        return b;
+    }
+    void push_state() {
+        if (!_prob) return;  // applied when the problem is built
+        if (_mu0.empty()) _mu0.assign((size_t)_dim, 0.0);
+        gvib200_check(gvib200_set_state(_prob, _mu0.data(), _pd.data(), _num_states > 1 ? _po.data() : nullptr), "set_state");
+        _has_state = true;
+    }
+
+    // Bucket the factors by (type, shape, cost parameters): every bucket becomes ONE batched group of the C-ABI, whatever
+    // order the caller interleaved them in; _id_of_factor maps the caller's order to the library's factor ids.
+    void build() {
+        if (_prob) return;
+        gvib200_ctx* ctx = default_context();
+        gvib200_check(gvib200_problem_create(ctx, _num_states, _dim_state, &_prob), "problem_create");
+        struct GhKey {
+            DeviceCostSpec cost;
+            int dim, deg;
+            bool operator<(const GhKey& o) const {
+                if (dim != o.dim) return dim < o.dim;
+                if (deg != o.deg) return deg < o.deg;
+                return cost < o.cost;
+            }
+        };
+        struct LinKey {
+            int dim, m, kdim;
+            bool operator<(const LinKey& o) const {
+                if (dim != o.dim) return dim < o.dim;
+                if (m != o.m) return m < o.m;
+                return kdim < o.kdim;
+            }
+        };
+        std::map<GhKey, std::vector<size_t>> gh;
+        std::map<LinKey, std::vector<size_t>> lin;
+        for (size_t i = 0; i < _factors.size(); ++i) {
+            GVIFactorizedBase* f = _factors[i].get();
+            if (!f->is_linear()) {
+                gh[GhKey{*f->cost_spec(), f->_dim, f->gh_degree()}].push_back(i);
+            } else {
+                lin[LinKey{f->_dim, (int)f->lin_Lambda()->rows(), (int)f->lin_Psi()->cols()}].push_back(i);
+            }
+        }
+        _id_of_factor.assign(_factors.size(), -1);
+        for (auto& kv : gh) {
+            const auto& idx = kv.second;
+            const int n = (int)idx.size();
+            std::vector<int32_t> start((size_t)n);
+            std::vector<double> T((size_t)n), Th((size_t)n);
+            for (int k = 0; k < n; ++k) {
+                GVIFactorizedBase* f = _factors[idx[(size_t)k]].get();
+                start[(size_t)k] = f->_start_index;
+                T[(size_t)k] = f->_temperature;
+                Th[(size_t)k] = f->_high_temperature;
+            }
+            const DeviceCostSpec& c = kv.first.cost;
+            if (c.sdf) {
+                const PlanarSDF& s = *c.sdf;
+                gvib200_check(gvib200_set_planar_sdf(_prob, (int)s.data.rows(), (int)s.data.cols(), s.origin_x, s.origin_y,
+                                                     s.cell_size, s.data.data()), "set_planar_sdf");
+            }
+            int first = 0;
+            gvib200_check(gvib200_add_gh_factors(_prob, c.kind, kv.first.dim, kv.first.deg, n, start.data(), T.data(), Th.data(),
+                                                 c.params.data(), c.params.size(), &first), "add_gh_factors");
+            for (int k = 0; k < n; ++k) _id_of_factor[idx[(size_t)k]] = first + k;
+        }
+        for (auto& kv : lin) {
+            const auto& idx = kv.second;
+            const int n = (int)idx.size(), dim = kv.first.dim, m = kv.first.m, kdim = kv.first.kdim;
+            std::vector<int32_t> start((size_t)n);
+            std::vector<double> L((size_t)n * m * dim), P((size_t)n * m * kdim), mt((size_t)n * kdim), K((size_t)n * m * m),
+                C((size_t)n), T((size_t)n), Th((size_t)n);
+            for (int k = 0; k < n; ++k) {
+                GVIFactorizedBase* f = _factors[idx[(size_t)k]].get();
+                const MatrixXd &La = *f->lin_Lambda(), &Ps = *f->lin_Psi(), &Ki = *f->lin_Kinv();
+                const VectorXd& mu = *f->lin_mu();
+                start[(size_t)k] = f->_start_index;
+                T[(size_t)k] = f->_temperature;
+                Th[(size_t)k] = f->_high_temperature;
+                C[(size_t)k] = f->lin_constant();
+                for (int j = 0; j < dim; ++j)
+                    for (int i = 0; i < m; ++i) L[((size_t)k * dim + j) * m + i] = La(i, j);
+                for (int j = 0; j < kdim; ++j)
+                    for (int i = 0; i < m; ++i) P[((size_t)k * kdim + j) * m + i] = Ps(i, j);
+                for (int j = 0; j < kdim; ++j) mt[(size_t)k * kdim + j] = mu(j);
+                for (int j = 0; j < m; ++j)
+                    for (int i = 0; i < m; ++i) K[((size_t)k * m + j) * m + i] = Ki(i, j);
+            }
+            int first = 0;
+            gvib200_check(gvib200_add_linear_factors(_prob, dim, m, kdim, n, start.data(), L.data(), P.data(), mt.data(), K.data(),
+                                                     C.data(), T.data(), Th.data(), &first), "add_linear_factors");
+            for (int k = 0; k < n; ++k) _id_of_factor[idx[(size_t)k]] = first + k;
+        }
+        gvib200_check(gvib200_problem_finalize(_prob), "finalize");
+        if (!_pd.empty()) push_state();
+    }
+
+    int _dim_state, _num_states, _dim, _niters;
+    double _temperature, _high_temperature;
+    std::vector<std::shared_ptr<GVIFactorizedBase>> _factors;
+    std::vector<int> _id_of_factor;
+    gvib200_opts _opts;
+    gvib200_problem* _prob = nullptr;
+    bool _has_state = false;
+    std::vector<double> _mu0, _pd, _po;
+    std::vector<gvib200_iter_stats> _stats;
+};
+
+// NGDGH (ngd/NGD-GH.h:28-110)
+template <class FactorizedOptimizer>
+class NGDGH : public GVIGH<FactorizedOptimizer> {
+    using Base = GVIGH<FactorizedOptimizer>;
+
+public:
+    NGDGH(const std::vector<std::shared_ptr<FactorizedOptimizer>>& vec_fact_optimizers, int dim_state, int num_states,
+          int niterations = 5, double temperature = 1.0, double high_temperature = 100.0)
+        : Base(vec_fact_optimizers, dim_state, num_states, niterations, temperature, high_temperature) {}
+
+    // compute_gradients (ngd/NGD-GH-impl.h:20-63): (dmu, dprecision)
+    std::pair<VectorXd, BlockTridiagonal> compute_gradients() {
+        Base::build();
+        VectorXd dmu = VectorXd::Zero(Base::_dim);
+        BlockTridiagonal dp;
+        dp.num_states = Base::_num_states;
+        dp.dim_state = Base::_dim_state;
+        const size_t dd = (size_t)Base::_dim_state * Base::_dim_state;
+        dp.diag.assign((size_t)Base::_num_states * dd, 0.0);
+        dp.off.assign((size_t)(Base::_num_states > 1 ? Base::_num_states - 1 : 1) * dd, 0.0);
+        gvib200_check(gvib200_gradients(Base::_prob, dmu.data(), dp.diag.data(), dp.off.data()), "compute_gradients");
+        return {dmu, dp};
+    }
+    VectorXd Vdmu() {  // ngd/NGD-GH.h:90
+        VectorXd v = VectorXd::Zero(Base::_dim);
+        gvib200_check(gvib200_get_V(Base::_prob, v.data(), nullptr, nullptr), "Vdmu");
+        return v;
+    }
+    BlockTridiagonal Vddmu() {  // ngd/NGD-GH.h:92
+        BlockTridiagonal b;
+        b.num_states = Base::_num_states;
+        b.dim_state = Base::_dim_state;
+        const size_t dd = (size_t)Base::_dim_state * Base::_dim_state;
+        b.diag.assign((size_t)Base::_num_states * dd, 0.0);
+        b.off.assign((size_t)(Base::_num_states > 1 ? Base::_num_states - 1 : 1) * dd, 0.0);
+        gvib200_check(gvib200_get_V(Base::_prob, nullptr, b.diag.data(), b.off.data()), "Vddmu");
+        return b;
+    }
+};
+
+// SparseGaussHermite (quadrature/SparseGaussHermite.h:38-277) for a DEVICE cost class: the three integrals the factor
+// optimizers take -- E[phi], E[(x-mu) phi], E[(x-mu)(x-mu)^T phi] -- evaluated by the fused moment kernel.
+template <class CostClass>
+class SparseGaussHermite {
+public:
+    SparseGaussHermite(int deg, int dim, const VectorXd& mean, const MatrixXd& P, const CostClass& cost_class)
+        : _deg(deg), _dim(dim), _mean(mean), _P(P), _cost(DeviceCostTraits<CostClass>::spec(cost_class)) {}
+    ~SparseGaussHermite() {
+        if (_prob) gvib200_problem_destroy(_prob);
+    }
+    void update_mean(const VectorXd& mean) { _mean = mean; _dirty = true; }
+    void update_P(const MatrixXd& P) { _P = P; _dirty = true; }
+    void set_polynomial_deg(int deg) { _deg = deg; reset(); }
+    VectorXd mean() const { return _mean; }
+    // nodes of the rule (zero-mean sigma points) and weights, straight from the table generator
+    MatrixXd zeromeanpts() const {
+        const int n = gvib200_table_size(_dim, _deg);
+        gvib200_check(n, "table_size");
+        std::vector<double> nodes((size_t)n * _dim), w((size_t)n);
+        gvib200_check(gvib200_table_generate(_dim, _deg, nodes.data(), w.data(), n), "table_generate");
+        MatrixXd Z = MatrixXd::Zero(n, _dim);
+        for (int i = 0; i < n; ++i)
+            for (int c = 0; c < _dim; ++c) Z(i, c) = nodes[(size_t)i * _dim + c];
+        return Z;
+    }
+    VectorXd weights() const {
+        const int n = gvib200_table_size(_dim, _deg);
+        gvib200_check(n, "table_size");
+        std::vector<double> nodes((size_t)n * _dim), w((size_t)n);
+        gvib200_check(gvib200_table_generate(_dim, _deg, nodes.data(), w.data(), n), "table_generate");
+        VectorXd out = VectorXd::Zero(n);
+        for (int i = 0; i < n; ++i) out(i) = w[(size_t)i];
+        return out;
+    }
+    struct Moments {
+        double E_phi;
+        VectorXd E_xmu_phi;
+        MatrixXd E_xmuxmuT_phi;
+    };
+    // Integrate (quadrature/SparseGaussHermite.h:197-221) of phi, (x-mu) phi and (x-mu)(x-mu)^T phi at (mean, P)
+    Moments Integrate() {
+        ensure();
+        Moments m;
+        m.E_xmu_phi = VectorXd::Zero(_dim);
+        m.E_xmuxmuT_phi = MatrixXd::Zero(_dim, _dim);
+        gvib200_check(gvib200_moments(_prob, &m.E_phi, m.E_xmu_phi.data(), m.E_xmuxmuT_phi.data()), "Integrate");
+        return m;
+    }
+
+private:
+    void reset() {
+        if (_prob) gvib200_problem_destroy(_prob);
+        _prob = nullptr;
+        _dirty = true;
+    }
+    void ensure() {
+        if (!_prob) {
+            gvib200_check(gvib200_problem_create(default_context(), 1, _dim, &_prob), "problem_create");
+            if (_cost.sdf) {
+                const PlanarSDF& s = *_cost.sdf;
+                gvib200_check(gvib200_set_planar_sdf(_prob, (int)s.data.rows(), (int)s.data.cols(), s.origin_x, s.origin_y,
+                                                     s.cell_size, s.data.data()), "set_planar_sdf");
+            }
+            const int32_t start = 0;
+            gvib200_check(gvib200_add_gh_factors(_prob, _cost.kind, _dim, _deg, 1, &start, nullptr, nullptr, _cost.params.data(),
+                                                 _cost.params.size(), nullptr), "add_gh_factors");
+            gvib200_check(gvib200_problem_finalize(_prob), "finalize");
+        }
+        if (_dirty) {
+            const MatrixXd prec = _P.inverse();  // the library state is a precision; P is the covariance (:231-233)
+            gvib200_check(gvib200_set_state(_prob, _mean.data(), prec.data(), nullptr), "set_state");
+            _dirty = false;
+        }
+    }
+    int _deg, _dim;
+    VectorXd _mean;
+    MatrixXd _P;
+    DeviceCostSpec _cost;
+    gvib200_problem* _prob = nullptr;
+    bool _dirty = true;
+};
+
+}  // namespace gvi

@@ -79,51 +79,6 @@ def rand_spd_chain(rng, S, d):
     return D, O
 
 
-def emu_run(S, d, D, O, rhs, seg, nserial):
-    lib = _emu()
-    dp = C.POINTER(C.c_double)
-    Dc = np.ascontiguousarray(np.transpose(D, (0, 2, 1)))
-    Oc = np.ascontiguousarray(np.transpose(O, (0, 2, 1))) if S > 1 else np.zeros((1, d, d))
-    x = np.zeros(S * d)
-    cD = np.zeros((S, d, d))
-    cO = np.zeros((max(S - 1, 1), d, d))
-    ld = C.c_double()
-    p = lambda a: a.ctypes.data_as(dp)
-    rc = lib.emu_blocktri(S, d, p(Dc), p(Oc), p(rhs), p(x), None, None, C.byref(ld), seg, nserial)
-    assert rc == 0
-    rc = lib.emu_blocktri(S, d, p(Dc), p(Oc), None, None, p(cD), p(cO), C.byref(ld), seg, nserial)
-    assert rc == 0
-    return x, np.transpose(cD, (0, 2, 1)), np.transpose(cO[:S - 1], (0, 2, 1)), ld.value
-
-
-@pytest.mark.parametrize("S,d,seg,nserial", [(1, 4, 4, 8), (2, 4, 4, 8), (9, 4, 4, 8), (10, 4, 4, 2), (33, 2, 4, 8), (100, 4, 4, 8),
-                                             (257, 3, 8, 4), (1000, 4, 16, 8), (1002, 4, 32, 16), (40, 6, 4, 8), (77, 1, 5, 3)])
-def test_chain_engine_host_matches_oracle(S, d, seg, nserial):
-    rng = np.random.default_rng(S * 10 + d)
-    D, O = rand_spd_chain(rng, S, d)
-    rhs = rng.standard_normal(S * d)
-    x, cD, cO, ld = emu_run(S, d, D, O, rhs, seg, nserial)
-    bt = o.BlockTri(D, O)
-    ref = o.inverse_gbp(bt)
-    assert rel(x, o.block_solve(bt, rhs)) < 1e-11
-    assert rel(cD, ref.D) < 1e-11
-    if S > 1:
-        assert rel(cO, ref.O) < 1e-11
-    assert abs(ld - o.logdet(bt)) < 1e-10 * max(1.0, abs(ld))
-
-
-def test_chain_engine_reports_indefinite():
-    lib = _emu()
-    dp = C.POINTER(C.c_double)
-    D = np.tile(np.eye(2), (5, 1, 1))
-    D[3] = -np.eye(2)
-    O = np.zeros((4, 2, 2))
-    cD, cO = np.zeros_like(D), np.zeros_like(O)
-    ld = C.c_double()
-    p = lambda a: a.ctypes.data_as(dp)
-    assert lib.emu_blocktri(5, 2, p(D), p(O), None, None, p(cD), p(cO), C.byref(ld), 4, 2) == -4
-
-
 @pytest.mark.parametrize("n", [1, 2, 4, 8, 12])
 def test_jacobi_sqrt_matches_eigh(n):
     """The device prologue's symmetric PSD root (quadrature/SparseGaussHermite.h:231-233) vs numpy eigh."""
@@ -142,7 +97,7 @@ def test_jacobi_sqrt_matches_eigh(n):
         assert rel(R @ R, np.linalg.inv(Sig)) < 1e-9
 
 
-# ------------------------------------------------------------------ second-generation chain engine (bt_cr.h) on the host
+# ------------------------------------------------------------------ chain engine (bt_cr.h) on the host
 def emu_cr_run(S, d, D, O, rhs, force_T, smem=220 * 1024):
     lib = _emu()
     dp = C.POINTER(C.c_double)

@@ -1,0 +1,86 @@
+"""C++ facade (gaussianvi_b200/cpp/gvi): the reference's class names on top of the C-ABI.
+CPU: the examples compile (with and without the Eigen stand-in there is only the stand-in in this image).
+GPU: examples/1d_example.cpp reproduces the reference's golden trace data/1d/*.csv; examples/planar_chain.cpp (factors
+interleaved the way a planner creates them) matches the same problem driven through the ctypes mirror and the oracle."""
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_bridge as ob
+from gaussianvi_b200 import capi, problems
+
+ROOT = ob.ROOT
+GOLDEN = ROOT / "tests" / "golden"
+BUILD = ROOT / "tests" / "cpp" / "_build"
+
+
+def compile_example(name):
+    BUILD.mkdir(exist_ok=True)
+    out = BUILD / name
+    src = ROOT / "examples" / f"{name}.cpp"
+    lib = ROOT / "gaussianvi_b200"
+    if not out.exists() or out.stat().st_mtime < max(src.stat().st_mtime, (lib / "cpp" / "gvi" / "gvi.h").stat().st_mtime):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(lib / "cpp"), str(src), "-L", str(lib), "-lgvib200",
+                        f"-Wl,-rpath,{lib}", "-o", str(out)], check=True)
+    return out
+
+
+@pytest.mark.parametrize("name", ["1d_example", "planar_chain"])
+def test_facade_examples_compile(name):
+    assert compile_example(name).exists()
+
+
+def test_unspecialised_cost_class_does_not_compile(tmp_path):
+    """NGDFactorizedSimpleGH (an arbitrary host function, NoneType) has no device functor: a compile-time error, not a
+    CPU fallback."""
+    src = tmp_path / "bad.cpp"
+    src.write_text('#include "ngd/NGDFactorizedSimpleGH.h"\n'
+                   'double f(const gvi::VectorXd&, const gvi::NoneType&) { return 0; }\n'
+                   'int main() { gvi::NGDFactorizedSimpleGH x(1, 1, 10, f, gvi::NoneType(), 1, 0, 1.0, 10.0); return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", str(ROOT / "gaussianvi_b200" / "cpp"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "DeviceCostTraits" in r.stderr
+
+
+@pytest.mark.gpu
+def test_facade_1d_example_golden_trace():
+    exe = compile_example("1d_example")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    rows = np.array([[float(x) for x in line.split()] for line in out.strip().splitlines()])
+    assert rows.shape == (10, 5)
+    g = lambda n: np.loadtxt(GOLDEN / "ref_1d" / f"{n}.csv", delimiter=",").reshape(-1)
+    for col, name in ((1, "mean"), (2, "cov"), (3, "precision"), (4, "cost")):
+        ref = g(name)
+        assert np.abs(rows[:, col] - ref).max() / np.abs(ref).max() < 1e-10, name
+
+
+@pytest.mark.gpu
+def test_facade_planar_chain_matches_ctypes_mirror_and_oracle(gpu_ctx):
+    S, niters = 40, 6
+    exe = compile_example("planar_chain")
+    out = subprocess.run([str(exe), str(S), str(niters)], capture_output=True, text=True, check=True).stdout
+    costs = np.array([float(l.split()[2]) for l in out.splitlines() if l.startswith("cost")])
+    mean = np.array([float(l.split()[2]) for l in out.splitlines() if l.startswith("mean")])
+    sumfc = float([l for l in out.splitlines() if l.startswith("sumfc")][0].split()[1])
+    # the same problem through the neutral spec
+    spec = problems.make_cfg2(S=S)
+    rows, cols, cell, origin = 120, 160, 0.25, (-20.0, -10.0)
+    xs = origin[0] + cell * np.arange(cols)
+    ys = origin[1] + cell * np.arange(rows)
+    X, Y = np.meshgrid(xs, ys)
+    spec.sdf = (np.hypot(X - 0.0, Y - 4.0) - 2.5, origin, cell)
+    spec.groups.append(problems.GhGroupSpec(capi.COST_PLANAR_HINGE, 4, 6, np.arange(1, S - 1, dtype=np.int32),
+                                            capi.HingeParams(0.1, 0.5, 1.0), 1.0, 10.0))
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    stats = p.optimize(niters, opts)
+    assert len(stats) == len(costs)
+    assert np.abs(costs - np.array([s.cost for s in stats])).max() < 1e-9 * np.abs(costs).max()
+    assert np.abs(mean - p.mean()).max() < 1e-9 * np.abs(mean).max()
+    c, fc = p.cost()
+    assert abs(sumfc - fc.sum()) < 1e-9 * abs(sumfc)
+    ref = ob.build_oracle(spec, niters=niters)
+    ref.optimize()
+    assert np.abs(mean - ref.mean()).max() < 1e-7 * np.abs(mean).max()
