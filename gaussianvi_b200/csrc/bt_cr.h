@@ -328,7 +328,36 @@ struct CrArgs {
     double *x, *cD, *cO;   // outputs: solution [n][D]; selected inverse diag [n][DD], off [n-1][DD]
     double* ld;            // [K + 1] partial log determinants (tiles, then the top)
     int* notspd;
+    // optional fusions of the line-search candidate (NGDGH::onestep_linesearch, ngd/NGD-GH-impl.h:129-148):
+    //   Dg2 != null: the system is Dg + alpha (Dg2 - Dg) (same for the off-diagonal blocks) and is also written to
+    //                Dout / Oout while it is loaded            (Lambda' = Lambda + a (Vddmu - Lambda))
+    //   xout != null: xout = xbase + xalpha * x is written next to the solution   (mu' = mu + a dmu)
+    const double *Dg2, *Og2;
+    double alpha;
+    double *Dout, *Oout;
+    const double* xbase;
+    double xalpha;
+    double* xout;
 };
+
+template <int D>
+GVI_HD double cr_sys_diag(const CrArgs<D>& a, size_t idx) {
+    double v = a.Dg[idx];
+    if (a.Dg2 != nullptr) {
+        v = v + a.alpha * (a.Dg2[idx] - v);
+        a.Dout[idx] = v;
+    }
+    return v;
+}
+template <int D>
+GVI_HD double cr_sys_off(const CrArgs<D>& a, size_t idx) {
+    double v = a.Og[idx];
+    if (a.Og2 != nullptr) {
+        v = v + a.alpha * (a.Og2[idx] - v);
+        a.Oout[idx] = v;
+    }
+    return v;
+}
 
 GVI_HD int cr_pad_slots(int nodes) { return nodes | 1; }  // odd stride: conflict-free transposing copies
 
@@ -352,20 +381,75 @@ GVI_HD CrView<D> cr_make_view(double* sm, int nodes) {
 }
 
 // tile -> working arrays.  Separator slots start from zero: they only collect this tile's Schur contributions.
+// The copies are unrolled CR_UNROLL deep (loads first, then the scattered shared-memory stores) so that every thread
+// keeps several global loads in flight: a tile CTA is alone on its SM and would otherwise pay one DRAM latency per
+// element.
+constexpr int CR_UNROLL = 8;
+
 template <int D, bool RHS>
 GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int n0, int tid, int nthreads) {
     constexpr int DD = D * D;
     const int Tk = gm.T;
-    for (int idx = tid; idx < (Tk + 1) * DD; idx += nthreads) {
-        const int node = idx / DD, e = idx - node * DD;
-        const int s = cr_slot(gm, node);
-        v.Dn[(size_t)e * v.NS + s] = (node == 0 || node == Tk) ? 0.0 : a.Dg[(size_t)(n0 + node) * DD + e];
-        if (node < Tk) v.P[(size_t)e * v.NS + s] = a.Og[(size_t)(n0 + node) * DD + e];
+    const int N = (Tk + 1) * DD;
+    const bool fused = (a.Dg2 != nullptr);
+    const size_t g0 = (size_t)n0 * DD;
+    for (int base = tid; base < N; base += nthreads * CR_UNROLL) {
+        // all loads first (the candidate stores below may alias them as far as the compiler knows)
+        double dv[CR_UNROLL], ov[CR_UNROLL], d2[CR_UNROLL], o2[CR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            const int idx = base + u * nthreads;
+            dv[u] = ov[u] = d2[u] = o2[u] = 0.0;
+            if (idx < N) {
+                const int node = idx / DD;
+                if (node != 0 && node != Tk) {
+                    dv[u] = a.Dg[g0 + idx];
+                    if (fused) d2[u] = a.Dg2[g0 + idx];
+                }
+                if (node < Tk) {
+                    ov[u] = a.Og[g0 + idx];
+                    if (fused) o2[u] = a.Og2[g0 + idx];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CR_UNROLL; ++u) {
+            const int idx = base + u * nthreads;
+            if (idx < N) {
+                const int node = idx / DD, e = idx - node * DD;
+                const int s = cr_slot(gm, node);
+                if (fused) {
+                    dv[u] = dv[u] + a.alpha * (d2[u] - dv[u]);
+                    ov[u] = ov[u] + a.alpha * (o2[u] - ov[u]);
+                    if (node != 0 && node != Tk) a.Dout[g0 + idx] = dv[u];
+                    if (node < Tk) a.Oout[g0 + idx] = ov[u];
+                }
+                v.Dn[(size_t)e * v.NS + s] = (node == 0 || node == Tk) ? 0.0 : dv[u];
+                if (node < Tk) v.P[(size_t)e * v.NS + s] = ov[u];
+            }
+        }
     }
     if (RHS) {
-        for (int idx = tid; idx < (Tk + 1) * D; idx += nthreads) {
-            const int node = idx / D, e = idx - node * D;
-            v.g[(size_t)e * v.NS + cr_slot(gm, node)] = (node == 0 || node == Tk) ? 0.0 : a.g[(size_t)(n0 + node) * D + e];
+        const int NV = (Tk + 1) * D;
+        for (int base = tid; base < NV; base += nthreads * CR_UNROLL) {
+            double gv[CR_UNROLL];
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                const int idx = base + u * nthreads;
+                gv[u] = 0.0;
+                if (idx < NV) {
+                    const int node = idx / D;
+                    if (node != 0 && node != Tk) gv[u] = a.g[(size_t)n0 * D + idx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                const int idx = base + u * nthreads;
+                if (idx < NV) {
+                    const int node = idx / D, e = idx - node * D;
+                    v.g[(size_t)e * v.NS + cr_slot(gm, node)] = gv[u];
+                }
+            }
         }
     }
 }
@@ -377,8 +461,8 @@ GVI_HD void cr_tile_store_reduced(const CrArgs<D>& a, const CrView<D>& v, const 
     constexpr int DD = D * D;
     const bool last = (tile == a.K - 1);
     for (int e = tid; e < DD; e += nthreads) {
-        a.rDn[(size_t)tile * DD + e] = a.Dg[(size_t)n0 * DD + e];
-        if (last) a.rDn[(size_t)a.K * DD + e] = a.Dg[(size_t)(a.n - 1) * DD + e];
+        a.rDn[(size_t)tile * DD + e] = cr_sys_diag<D>(a, (size_t)n0 * DD + e);
+        if (last) a.rDn[(size_t)a.K * DD + e] = cr_sys_diag<D>(a, (size_t)(a.n - 1) * DD + e);
         a.rCL[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 0];
         a.rCR[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 1];
         a.rO[(size_t)tile * DD + e] = v.P[(size_t)e * v.NS + 0];
@@ -403,8 +487,8 @@ GVI_HD void cr_top_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm
         const int s = cr_slot(gm, node);
         double dv;
         if (a.K == 0) {
-            dv = a.Dg[(size_t)node * DD + e];
-            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = a.Og[(size_t)node * DD + e];
+            dv = cr_sys_diag<D>(a, (size_t)node * DD + e);
+            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = cr_sys_off<D>(a, (size_t)node * DD + e);
         } else {
             dv = a.rDn[(size_t)node * DD + e];
             if (node < a.K) dv += a.rCL[(size_t)node * DD + e];
@@ -432,20 +516,36 @@ GVI_HD void cr_top_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm
 // working arrays -> AoS results for nodes [0, count) (diag / solution) and couplings [0, ncoup), written at node offset n0
 template <int D, bool RHS, bool SELINV>
 GVI_HD void cr_store_results(const CrView<D>& v, const CrGeom& gm, int count, int ncoup, double* x, double* cD, double* cO,
-                             size_t n0, int tid, int nthreads) {
+                             size_t n0, int tid, int nthreads, const double* xbase = nullptr, double xalpha = 0.0,
+                             double* xout = nullptr) {
     constexpr int DD = D * D;
     if (SELINV) {
         for (int idx = tid; idx < count * DD; idx += nthreads) {
             const int node = idx / DD, e = idx - node * DD;
             const int s = cr_slot(gm, node);
-            cD[(n0 + node) * DD + e] = v.Dn[(size_t)e * v.NS + s];
-            if (node < ncoup) cO[(n0 + node) * DD + e] = v.P[(size_t)e * v.NS + s];
+            cD[n0 * DD + idx] = v.Dn[(size_t)e * v.NS + s];
+            if (node < ncoup) cO[n0 * DD + idx] = v.P[(size_t)e * v.NS + s];
         }
     }
     if (RHS) {
-        for (int idx = tid; idx < count * D; idx += nthreads) {
-            const int node = idx / D, e = idx - node * D;
-            x[(n0 + node) * D + e] = v.g[(size_t)e * v.NS + cr_slot(gm, node)];
+        const int NV = count * D;
+        for (int base = tid; base < NV; base += nthreads * CR_UNROLL) {
+            double bv[CR_UNROLL];
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                const int idx = base + u * nthreads;
+                bv[u] = (xout != nullptr && idx < NV) ? xbase[n0 * D + idx] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                const int idx = base + u * nthreads;
+                if (idx < NV) {
+                    const int node = idx / D, e = idx - node * D;
+                    const double xv = v.g[(size_t)e * v.NS + cr_slot(gm, node)];
+                    x[n0 * D + idx] = xv;
+                    if (xout != nullptr) xout[n0 * D + idx] = bv[u] + xalpha * xv;
+                }
+            }
         }
     }
 }

@@ -130,6 +130,14 @@ inline CrArgs<D> cr_bind(const CrPlan& p, double* ws, const double* Dg, const do
     a.cO = cO;
     a.ld = ws + p.ld;
     a.notspd = notspd;
+    a.Dg2 = nullptr;
+    a.Og2 = nullptr;
+    a.alpha = 0.0;
+    a.Dout = nullptr;
+    a.Oout = nullptr;
+    a.xbase = nullptr;
+    a.xalpha = 0.0;
+    a.xout = nullptr;
     return a;
 }
 

@@ -355,11 +355,31 @@ static int cr_allow_smem(K kern, size_t bytes) {
     return 0;
 }
 
+// optional candidate fusions of a chain pass (see CrArgs)
+struct ChainFuse {
+    const double *Dg2 = nullptr, *Og2 = nullptr;
+    double alpha = 0.0;
+    double *Dout = nullptr, *Oout = nullptr;
+    const double* xbase = nullptr;
+    double xalpha = 0.0;
+    double* xout = nullptr;
+};
+
 template <int D, bool RHS, bool SELINV>
 static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const double* Og, const double* rhs, double* x,
-                      double* cD, double* cO, double* d_logdet, int* d_flag) {
+                      double* cD, double* cO, double* d_logdet, int* d_flag, const ChainFuse* fuse = nullptr) {
     const CrPlan& pl = p->plan;
     CrArgs<D> a = cr_bind<D>(pl, p->ws[slot], Dg, Og, rhs, x, cD, cO, d_flag);
+    if (fuse) {
+        a.Dg2 = fuse->Dg2;
+        a.Og2 = fuse->Og2;
+        a.alpha = fuse->alpha;
+        a.Dout = fuse->Dout;
+        a.Oout = fuse->Oout;
+        a.xbase = fuse->xbase;
+        a.xalpha = fuse->xalpha;
+        a.xout = fuse->xout;
+    }
     static bool configured = false;  // per instantiation
     if (!configured) {
         TRY(cr_allow_smem(k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 4096));
@@ -377,14 +397,14 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
 // selected inverse + log det of the block-tridiagonal (Dg, Og) -> (cD, cO), logdet scalar (device)
 template <int D>
 static int chain_selinv(gvib200_problem* p, int slot, const double* Dg, const double* Og, double* cD, double* cO,
-                        double* d_logdet, int* d_flag) {
-    return chain_pass<D, false, true>(p, slot, Dg, Og, nullptr, nullptr, cD, cO, d_logdet, d_flag);
+                        double* d_logdet, int* d_flag, const ChainFuse* fuse = nullptr) {
+    return chain_pass<D, false, true>(p, slot, Dg, Og, nullptr, nullptr, cD, cO, d_logdet, d_flag, fuse);
 }
 
 template <int D>
 static int chain_solve(gvib200_problem* p, int slot, const double* Dg, const double* Og, const double* rhs, double* x,
-                       double* d_logdet, int* d_flag) {
-    return chain_pass<D, true, false>(p, slot, Dg, Og, rhs, x, nullptr, nullptr, d_logdet, d_flag);
+                       double* d_logdet, int* d_flag, const ChainFuse* fuse = nullptr) {
+    return chain_pass<D, true, false>(p, slot, Dg, Og, rhs, x, nullptr, nullptr, d_logdet, d_flag, fuse);
 }
 
 #define DISPATCH_D(d, CALL)                                                              \
@@ -399,15 +419,15 @@ static int chain_solve(gvib200_problem* p, int slot, const double* Dg, const dou
 
 // slot: which workspace (0: main stream, 1: side stream); the not-SPD flag of slot s is d_flag[s]
 static int do_selinv(gvib200_problem* p, const double* Dg, const double* Og, double* cD, double* cO, double* d_logdet,
-                     int slot = 0) {
+                     int slot = 0, const ChainFuse* fuse = nullptr) {
     int rc = 0;
-    DISPATCH_D(p->d, rc = chain_selinv<D_>(p, slot, Dg, Og, cD, cO, d_logdet, p->d_flag + slot));
+    DISPATCH_D(p->d, rc = chain_selinv<D_>(p, slot, Dg, Og, cD, cO, d_logdet, p->d_flag + slot, fuse));
     return rc;
 }
 static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, const double* rhs, double* x, double* d_logdet,
-                    int slot = 0) {
+                    int slot = 0, const ChainFuse* fuse = nullptr) {
     int rc = 0;
-    DISPATCH_D(p->d, rc = chain_solve<D_>(p, slot, Dg, Og, rhs, x, d_logdet, p->d_flag + slot));
+    DISPATCH_D(p->d, rc = chain_solve<D_>(p, slot, Dg, Og, rhs, x, d_logdet, p->d_flag + slot, fuse));
     return rc;
 }
 
@@ -639,7 +659,12 @@ static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
         a.covO = t.cO;
         a.fcost = p->fcost[t.which] + g.first_id;
         a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
-        LAUNCH(p, KC_LINEAR, k_linear, cdiv(g.n, 128), 128, 0, a);
+        const int sd = p->d;
+        if (g.dim == 8 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<8, 4, 4>), cdiv(g.n, 128), 128, 0, a);
+        else if (g.dim == 4 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<4, 4, 4>), cdiv(g.n, 128), 128, 0, a);
+        else if (g.dim == 12 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<12, 6, 6>), cdiv(g.n, 128), 128, 0, a);
+        else if (g.dim == 6 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<6, 6, 6>), cdiv(g.n, 128), 128, 0, a);
+        else LAUNCH(p, KC_LINEAR, (k_linear<0, 0, 0>), cdiv(g.n, 128), 128, 0, a);
     }
     return check_launch("k_linear");
 }
@@ -1083,10 +1108,23 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     }
     for (auto& g : p->lin) {
         TRY(dev_upload(&g.d_start, g.start, p->stream));
-        TRY(dev_upload(&g.d_Lambda, g.Lambda, p->stream));
-        TRY(dev_upload(&g.d_psi, g.psi, p->stream));
-        TRY(dev_upload(&g.d_Kinv, g.Kinv, p->stream));
-        TRY(dev_upload(&g.d_A, g.A, p->stream));
+        // element-major device copies (see LinearArgs); A as its packed upper triangle
+        auto soa = [&](const std::vector<double>& aos, int ne) {
+            std::vector<double> out(aos.size());
+            for (int f = 0; f < g.n; ++f)
+                for (int e = 0; e < ne; ++e) out[(size_t)e * g.n + f] = aos[(size_t)f * ne + e];
+            return out;
+        };
+        std::vector<double> Apk((size_t)g.n * (g.dim * (g.dim + 1) / 2));
+        for (int f = 0; f < g.n; ++f) {
+            int e = 0;
+            for (int i = 0; i < g.dim; ++i)
+                for (int j = i; j < g.dim; ++j) Apk[(size_t)(e++) * g.n + f] = g.A[(size_t)f * g.dim * g.dim + i + (size_t)j * g.dim];
+        }
+        TRY(dev_upload(&g.d_Lambda, soa(g.Lambda, g.m * g.dim), p->stream));
+        TRY(dev_upload(&g.d_psi, soa(g.psi, g.m), p->stream));
+        TRY(dev_upload(&g.d_Kinv, soa(g.Kinv, g.m * g.m), p->stream));
+        TRY(dev_upload(&g.d_A, Apk, p->stream));
         TRY(dev_upload(&g.d_C, g.C, p->stream));
         TRY(dev_upload(&g.d_T, g.T, p->stream));
     }
@@ -1427,15 +1465,25 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         if (cnt == 0) {
             CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
+            // the candidate precision Lambda + a (Vddmu - Lambda) is formed while the selected inverse loads its tiles,
+            // the candidate mean mu + a dmu while the solve stores dmu: no separate candidate kernel on this path
             p->ls = p->stream2;
-            int rc = launch_candidate(p, step, 2);
-            if (rc == 0) rc = do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1);
+            ChainFuse fi;
+            fi.Dg2 = p->VD;
+            fi.Og2 = p->VO;
+            fi.alpha = step;
+            fi.Dout = p->LD[w];
+            fi.Oout = p->LO[w];
+            int rc = do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[w], p->CO[w], p->scal + w, 1, &fi);
             p->ls = p->stream;
             if (rc != 0) return rc;
             CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
-            TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0));
+            ChainFuse fs;
+            fs.xbase = p->mu[p->cur];
+            fs.xalpha = step;
+            fs.xout = p->mu[w];
+            TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &fs));
             p->grads_valid = true;
-            TRY(launch_candidate(p, step, 1));
             CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         } else {
             TRY(launch_candidate(p, step, 3));

@@ -423,13 +423,15 @@ __global__ void k_raw_to_x(int n, const double* __restrict__ raw, const double* 
 // algebraically the same, :107-119) and is pre-assembled once into the constant block-tridiagonal Klin.
 // ------------------------------------------------------------------------------------------
 constexpr int LIN_MAX_DIM = 12;
+// per-factor arrays are element-major ("structure of arrays": element e of factor f at [e * n + f]) so that the
+// thread-per-factor kernel reads consecutive addresses across a warp
 struct LinearArgs {
     int n, dim, m, state_dim;
     const int* start;
-    const double* Lambda;  // [n][m*dim]
-    const double* psi;     // [n][m] = Psi mu_t
-    const double* Kinv;    // [n][m*m]
-    const double* A;       // [n][dim*dim]
+    const double* Lambda;  // [m*dim][n]   (column-major element order within a factor)
+    const double* psi;     // [m][n] = Psi mu_t
+    const double* Kinv;    // [m*m][n]
+    const double* A;       // [dim*(dim+1)/2][n]: upper triangle of Lambda^T Kinv Lambda, packed row by row
     const double* C;       // [n]
     const double* T;       // [n]
     const double* mu;      // joint mean
@@ -439,51 +441,69 @@ struct LinearArgs {
     double* fVdmu;   // [n][dim] or null (cost only)
 };
 
-__global__ void k_linear(const LinearArgs a) {
+// DIM_, M_, SD_ > 0: compile-time shapes (fully unrolled); 0: taken from the arguments
+template <int DIM_, int M_, int SD_>
+__global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.n) return;
-    const int dim = a.dim, m = a.m, sd = a.state_dim;
+    const int dim = DIM_ ? DIM_ : a.dim, m = M_ ? M_ : a.m, sd = SD_ ? SD_ : a.state_dim;
+    constexpr int MAXD = DIM_ ? DIM_ : LIN_MAX_DIM, MAXM = M_ ? M_ : LIN_MAX_DIM;
+    const size_t n = (size_t)a.n;
     const int s = a.start[f];
-    const double* L = a.Lambda + (size_t)f * m * dim;
-    const double* Ki = a.Kinv + (size_t)f * m * m;
-    const double* mu = a.mu + (size_t)s * sd;
-    double r[LIN_MAX_DIM], kr[LIN_MAX_DIM];
-    for (int i = 0; i < m; ++i) {
-        double v = -a.psi[(size_t)f * m + i];
-        for (int k = 0; k < dim; ++k) v = fma(L[i + k * m], mu[k], v);
-        r[i] = v;
-    }
+    const double* L = a.Lambda + f;
+    const double* Ki = a.Kinv + f;
+    double mu[MAXD], r[MAXM], kr[MAXM];
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k)
+        if (k < dim) mu[k] = a.mu[(size_t)s * sd + k];
+#pragma unroll
+    for (int i = 0; i < MAXM; ++i)
+        if (i < m) {
+            double v = -a.psi[(size_t)i * n + f];
+#pragma unroll
+            for (int k = 0; k < MAXD; ++k)
+                if (k < dim) v = fma(L[(size_t)(i + k * m) * n], mu[k], v);
+            r[i] = v;
+        }
     double q = 0.0;
-    for (int i = 0; i < m; ++i) {
-        double v = 0.0;
-        for (int k = 0; k < m; ++k) v = fma(Ki[i + k * m], r[k], v);
-        kr[i] = v;
-        q = fma(v, r[i], q);
-    }
+#pragma unroll
+    for (int i = 0; i < MAXM; ++i)
+        if (i < m) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < MAXM; ++k)
+                if (k < m) v = fma(Ki[(size_t)(i + k * m) * n], r[k], v);
+            kr[i] = v;
+            q = fma(v, r[i], q);
+        }
     const double c_over_t = a.C[f] / a.T[f];
     if (a.fVdmu != nullptr) {
-        for (int k = 0; k < dim; ++k) {
-            double v = 0.0;
-            for (int i = 0; i < m; ++i) v = fma(L[i + k * m], kr[i], v);
-            a.fVdmu[(size_t)f * dim + k] = 2.0 * v * c_over_t;
-        }
+#pragma unroll
+        for (int k = 0; k < MAXD; ++k)
+            if (k < dim) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < MAXM; ++i)
+                    if (i < m) v = fma(L[(size_t)(i + k * m) * n], kr[i], v);
+                a.fVdmu[(size_t)f * dim + k] = 2.0 * v * c_over_t;
+            }
     }
-    // tr(A Sigma_k): Sigma_k assembled from the covariance blocks
-    const double* A = a.A + (size_t)f * dim * dim;
-    const int ns = dim / sd;
+    // tr(A Sigma_k) = sum_i A_ii S_ii + 2 sum_{i<j} A_ij S_ij, Sigma_k assembled from the covariance blocks
+    const double* A = a.A + f;
     double tr = 0.0;
-    for (int j = 0; j < dim; ++j) {
-        const int bj = j / sd, jj = j % sd;
-        for (int i = 0; i < dim; ++i) {
-            const int bi = i / sd, ii = i % sd;
-            double sij;
-            if (bi == bj) sij = a.covD[(size_t)(s + bi) * sd * sd + ii + jj * sd];
-            else if (bi < bj) sij = a.covO[(size_t)s * sd * sd + ii + jj * sd];
-            else sij = a.covO[(size_t)s * sd * sd + jj + ii * sd];
-            tr = fma(A[j + i * dim], sij, tr);  // A symmetric: sum_ij A_ji Sigma_ij
-        }
-    }
-    (void)ns;
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+#pragma unroll
+        for (int j = i; j < MAXD; ++j)
+            if (i < dim && j < dim) {
+                const int bi = i / sd, ii = i % sd, bj = j / sd, jj = j % sd;
+                const double sij = (bi == bj) ? a.covD[(size_t)(s + bi) * sd * sd + ii + jj * sd]
+                                              : a.covO[(size_t)s * sd * sd + ii + jj * sd];  // bi < bj: block (s, s+1)
+                const double av = A[(size_t)e * n];
+                tr = fma(i == j ? av : 2.0 * av, sij, tr);
+                ++e;
+            }
     a.fcost[f] = (tr + q) * c_over_t;
 }
 
@@ -686,7 +706,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
     if (threadIdx.x == 0) ok = cr_top2<D, RHS, SELINV>(v, gm.T, ld) && ok;
     __syncthreads();
     cr_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
-    if (a.K == 0) cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, threadIdx.x, blockDim.x);
+    if (a.K == 0)
+        cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, threadIdx.x, blockDim.x, a.xbase, a.xalpha, a.xout);
     else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, threadIdx.x, blockDim.x);
     const double s = cr_block_sum(ld.value(), red);
     if (threadIdx.x == 0) a.ld[a.K] = s;
@@ -707,7 +728,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
     __syncthreads();
     cr_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm);
     const bool last = (tile == a.K - 1);
-    cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, threadIdx.x, blockDim.x);
+    cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, threadIdx.x, blockDim.x,
+                                     a.xbase, a.xalpha, a.xout);
 }
 
 // cell records for CostPlanarHinge from the column-major field (layout: cost_functors.cuh)
