@@ -570,3 +570,106 @@ GVI_HD void cr_tile_seed(const CrArgs<D>& a, const CrView<D>& v, int tile, int t
 }
 
 }  // namespace gvib200
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU: the chain is cut along the time axis, rank r owns the links [r m, (r+1) m) and both of its end nodes (the
+// end nodes are shared with the neighbouring ranks; each rank holds only ITS share of a shared diagonal block / rhs).
+// Per pass every rank reduces its segment to its two end nodes with the same tile kernels applied twice (tiles ->
+// separator chain -> one "tile" over the separator chain), the P boundary records meet in ONE all-gather, every rank
+// solves the (P+1)-node chain of rank boundaries redundantly and walks back down.  Boundary record of a rank:
+//   [ Dfirst | Dlast | CL | CR | O | gfirst | glast | gl | gr ]  = 5 d^2 + 4 d doubles.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gvib200 {
+
+template <int D>
+GVI_HD constexpr int cr_boundary_doubles() { return 5 * D * D + 4 * D; }
+
+// level-1 separator system (three-term) -> plain arrays D1[K+1], O1[K], g1[K+1]
+template <int D, bool RHS>
+GVI_HD void cr_sum_level(const CrArgs<D>& a, double* D1, double* O1, double* g1, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    const int nt = a.K + 1;
+    for (int idx = tid; idx < nt * DD; idx += nthreads) {
+        const int node = idx / DD;
+        double dv = a.rDn[idx];
+        if (node < a.K) {
+            dv += a.rCL[idx];
+            O1[idx] = a.rO[idx];
+        }
+        if (node > 0) dv += a.rCR[idx - DD];
+        D1[idx] = dv;
+    }
+    if (RHS) {
+        for (int idx = tid; idx < nt * D; idx += nthreads) {
+            const int node = idx / D;
+            double gv = a.rg[idx];
+            if (node < a.K) gv += a.rgl[idx];
+            if (node > 0) gv += a.rgr[idx - D];
+            g1[idx] = gv;
+        }
+    }
+}
+
+// reduced arrays of the single mid tile -> this rank's boundary record
+template <int D, bool RHS>
+GVI_HD void cr_pack_boundary(const CrArgs<D>& mid, double* rec, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    for (int e = tid; e < DD; e += nthreads) {
+        rec[e] = mid.rDn[e];
+        rec[DD + e] = mid.rDn[DD + e];
+        rec[2 * DD + e] = mid.rCL[e];
+        rec[3 * DD + e] = mid.rCR[e];
+        rec[4 * DD + e] = mid.rO[e];
+    }
+    for (int e = tid; e < D; e += nthreads) {
+        double* gv = rec + 5 * DD;
+        gv[e] = RHS ? mid.rg[e] : 0.0;
+        gv[D + e] = RHS ? mid.rg[D + e] : 0.0;
+        gv[2 * D + e] = RHS ? mid.rgl[e] : 0.0;
+        gv[3 * D + e] = RHS ? mid.rgr[e] : 0.0;
+    }
+}
+
+// all boundary records -> the chain of rank boundaries (P + 1 nodes)
+template <int D>
+GVI_HD void cr_build_global(int P, const double* recs, double* Dt, double* Ot, double* gt, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    constexpr int NB = 5 * D * D + 4 * D;
+    for (int idx = tid; idx < (P + 1) * DD; idx += nthreads) {
+        const int node = idx / DD, e = idx - node * DD;
+        double dv = 0.0;
+        if (node > 0) dv += recs[(size_t)(node - 1) * NB + DD + e] + recs[(size_t)(node - 1) * NB + 3 * DD + e];  // Dlast + CR
+        if (node < P) {
+            dv += recs[(size_t)node * NB + e] + recs[(size_t)node * NB + 2 * DD + e];  // Dfirst + CL
+            Ot[idx] = recs[(size_t)node * NB + 4 * DD + e];
+        }
+        Dt[idx] = dv;
+    }
+    for (int idx = tid; idx < (P + 1) * D; idx += nthreads) {
+        const int node = idx / D, e = idx - node * D;
+        double gv = 0.0;
+        if (node > 0) gv += recs[(size_t)(node - 1) * NB + 5 * DD + D + e] + recs[(size_t)(node - 1) * NB + 5 * DD + 3 * D + e];
+        if (node < P) gv += recs[(size_t)node * NB + 5 * DD + e] + recs[(size_t)node * NB + 5 * DD + 2 * D + e];
+        gt[idx] = gv;
+    }
+}
+
+// results on the rank boundaries -> seeds of this rank's mid tile
+template <int D, bool RHS, bool SELINV>
+GVI_HD void cr_seed_mid(const CrArgs<D>& mid, int rank, const double* xt, const double* cDt, const double* cOt, int tid,
+                        int nthreads) {
+    constexpr int DD = D * D;
+    if (SELINV)
+        for (int e = tid; e < DD; e += nthreads) {
+            mid.tD[e] = cDt[(size_t)rank * DD + e];
+            mid.tD[DD + e] = cDt[(size_t)(rank + 1) * DD + e];
+            mid.tO[e] = cOt[(size_t)rank * DD + e];
+        }
+    if (RHS)
+        for (int e = tid; e < D; e += nthreads) {
+            mid.tx[e] = xt[(size_t)rank * D + e];
+            mid.tx[D + e] = xt[(size_t)(rank + 1) * D + e];
+        }
+}
+
+}  // namespace gvib200

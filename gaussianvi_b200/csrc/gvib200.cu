@@ -704,7 +704,7 @@ static void run_total(gvib200_problem* p, int which) {
 
 template <int D>
 static void launch_assemble(gvib200_problem* p, int which) {
-    LAUNCH(p, KC_ASSEMBLE, (k_assemble<D>), cdiv(p->S, 128), 128, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
+    LAUNCH(p, KC_ASSEMBLE, (k_assemble<D>), cdiv((long long)p->S * D * D, 256), 256, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
            p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, p->Vdmu, p->VD, p->VO, p->rhs);
 }
 
@@ -1475,6 +1475,7 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             fi.Dout = p->LD[w];
             fi.Oout = p->LO[w];
             int rc = do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[w], p->CO[w], p->scal + w, 1, &fi);
+            if (rc == 0) rc = run_prologue_only(p, w);  // factor marginals of the candidate, still on the side stream
             p->ls = p->stream;
             if (rc != 0) return rc;
             CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
@@ -1489,7 +1490,7 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             TRY(launch_candidate(p, step, 3));
             TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1));
         }
-        TRY(run_sweep(p, w, true, o.reuse_accepted_sweep != 0, false));
+        TRY(run_sweep(p, w, cnt != 0, o.reuse_accepted_sweep != 0, false));
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
         run_total(p, w);

@@ -509,53 +509,37 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
 
 // ------------------------------------------------------------------------------------------
 // K3: assembly (local2joint_* + the sums of NGDGH::compute_gradients, ngd/NGD-GH-impl.h:36-57).
-// One thread per state gathers, in a fixed order, the factor blocks that touch it:
+// Every output element gathers, in a fixed order, the factor blocks that touch its state:
 //   Vdmu[s]   = sum of fVdmu pieces;   VD[s] = KlinD[s] + sum of diag pieces;   VO[s] = KlinO[s] + off pieces
 // ------------------------------------------------------------------------------------------
+// One thread per (state, block element): consecutive threads read consecutive doubles of a factor's block, so the
+// gather is coalesced.  Threads e < D of a state also gather Vdmu.
 template <int D>
-__global__ void k_assemble(int S, const int* __restrict__ vptr, const int* __restrict__ voff,
+__global__ void __launch_bounds__(256) k_assemble(int S, const int* __restrict__ vptr, const int* __restrict__ voff,
                            const int* __restrict__ dptr, const int* __restrict__ doff, const int* __restrict__ dld,
                            const int* __restrict__ optr, const int* __restrict__ ooff, const int* __restrict__ old,
                            const double* __restrict__ fVdmu, const double* __restrict__ fVdd,
                            const double* __restrict__ KlinD, const double* __restrict__ KlinO,
                            double* __restrict__ Vdmu, double* __restrict__ VD, double* __restrict__ VO,
                            double* __restrict__ rhs) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int DD = D * D;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(gid / DD), e = (int)(gid % DD);
     if (s >= S) return;
-    Vec<D> v;
-    vec_zero<D>(v);
-    for (int e = vptr[s]; e < vptr[s + 1]; ++e) {
-        const double* p = fVdmu + voff[e];
-#pragma unroll
-        for (int i = 0; i < D; ++i) v.a[i] += p[i];
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        Vdmu[(size_t)s * D + i] = v.a[i];
-        rhs[(size_t)s * D + i] = -v.a[i];
-    }
-    Mat<D> M;
-    mat_load<D>(M, KlinD + (size_t)s * D * D);
-    for (int e = dptr[s]; e < dptr[s + 1]; ++e) {
-        const double* p = fVdd + doff[e];
-        const int ld = dld[e];
-#pragma unroll
-        for (int j = 0; j < D; ++j)
-#pragma unroll
-            for (int i = 0; i < D; ++i) M(i, j) += p[i + j * ld];
-    }
-    mat_store<D>(VD + (size_t)s * D * D, M);
+    const int i = e % D, j = e / D;
+    double m = KlinD[gid];
+    for (int q = dptr[s]; q < dptr[s + 1]; ++q) m += fVdd[doff[q] + i + j * dld[q]];
+    VD[gid] = m;
     if (s < S - 1) {
-        mat_load<D>(M, KlinO + (size_t)s * D * D);
-        for (int e = optr[s]; e < optr[s + 1]; ++e) {
-            const double* p = fVdd + ooff[e];
-            const int ld = old[e];
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-#pragma unroll
-                for (int i = 0; i < D; ++i) M(i, j) += p[i + j * ld];
-        }
-        mat_store<D>(VO + (size_t)s * D * D, M);
+        double o = KlinO[gid];
+        for (int q = optr[s]; q < optr[s + 1]; ++q) o += fVdd[ooff[q] + i + j * old[q]];
+        VO[gid] = o;
+    }
+    if (e < D) {
+        double v = 0.0;
+        for (int q = vptr[s]; q < vptr[s + 1]; ++q) v += fVdmu[voff[q] + e];
+        Vdmu[(size_t)s * D + e] = v;
+        rhs[(size_t)s * D + e] = -v;
     }
 }
 

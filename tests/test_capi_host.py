@@ -145,3 +145,52 @@ def test_cr_engine_reports_indefinite_and_too_long():
     Dl, Ol = rand_spd_chain(rng, 4000, 4)
     rc, *_ = emu_cr_run(4000, 4, Dl, Ol, np.zeros(16000), 0, smem=16 * 1024)
     assert rc == -1
+
+
+# ------------------------------------------------------------------ multi-GPU chain pass replayed on the host
+@pytest.mark.parametrize("P,m,d,T", [(2, 5, 4, 2), (2, 64, 4, 16), (3, 100, 2, 7), (4, 333, 4, 50), (8, 40, 4, 40),
+                                     (8, 257, 1, 32), (2, 90, 6, 30), (5, 1, 4, 2)])
+def test_distributed_chain_pass_matches_oracle(P, m, d, T):
+    """P ranks, each owning m links and its share of the end blocks; one boundary all-gather per pass.  The result must
+    equal the single-process solve / selected inverse of the global chain of P m + 1 nodes."""
+    rng = np.random.default_rng(P * 1000 + m + d)
+    S = P * m + 1
+    D, O = rand_spd_chain(rng, S, d)
+    rhs = rng.standard_normal(S * d).reshape(S, d)
+    n = m + 1
+    Dloc = np.zeros((P, n, d, d))
+    gloc = np.zeros((P, n, d))
+    Oloc = np.zeros((P, m, d, d))
+    for r in range(P):
+        Dloc[r] = D[r * m:r * m + n]
+        gloc[r] = rhs[r * m:r * m + n]
+        Oloc[r] = O[r * m:(r + 1) * m]
+    # shared end blocks: split the diagonal block and the rhs between the two neighbours (any split must work)
+    for r in range(1, P):
+        share = rng.uniform(0.2, 0.8)
+        Dloc[r - 1, m] = share * D[r * m]
+        Dloc[r, 0] = D[r * m] - Dloc[r - 1, m]
+        gloc[r - 1, m] = share * rhs[r * m]
+        gloc[r, 0] = rhs[r * m] - gloc[r - 1, m]
+    lib = _emu()
+    dp = C.POINTER(C.c_double)
+    p = lambda a: a.ctypes.data_as(dp)
+    Dc = np.ascontiguousarray(np.transpose(Dloc, (0, 1, 3, 2)))
+    Oc = np.ascontiguousarray(np.transpose(Oloc, (0, 1, 3, 2)))
+    gc = np.ascontiguousarray(gloc)
+    x = np.zeros((P, n, d))
+    cD = np.zeros((P, n, d, d))
+    cO = np.zeros((P, m, d, d))
+    ld = C.c_double()
+    rc = lib.emu_cr_distributed(P, m, d, p(Dc), p(Oc), p(gc), p(x), p(cD), p(cO), C.byref(ld), T)
+    assert rc == 0
+    bt = o.BlockTri(D, O)
+    ref = o.inverse_gbp(bt)
+    xe = o.block_solve(bt, rhs.reshape(-1)).reshape(S, d)
+    cD = np.transpose(cD, (0, 1, 3, 2))
+    cO = np.transpose(cO, (0, 1, 3, 2))
+    for r in range(P):
+        assert rel(x[r], xe[r * m:r * m + n]) < 1e-10
+        assert rel(cD[r], ref.D[r * m:r * m + n]) < 1e-10
+        assert rel(cO[r], ref.O[r * m:(r + 1) * m]) < 1e-10
+    assert abs(ld.value - o.logdet(bt)) < 1e-9 * max(1.0, abs(ld.value))
