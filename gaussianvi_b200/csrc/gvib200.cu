@@ -4,6 +4,7 @@
 #include "../../include/gvib200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -153,7 +154,11 @@ struct gvib200_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     std::map<std::pair<int, int>, std::unique_ptr<Table>> tables;
+    // multi-GPU: NCCL entry points resolved at run time from the library the caller initialised the communicator with
     void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
+    int (*ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int rank = 0, world = 1;
     long long launches = 0;  // kernels launched through this ctx
 };
@@ -235,6 +240,13 @@ struct gvib200_problem {
     CrPlan plan;
     double* ws[2] = {nullptr, nullptr};
     double* ldsum[2] = {nullptr, nullptr};
+    // multi-GPU (ctx->world > 1): the mid level (one "tile" over this rank's separator chain), the boundary exchange
+    // buffers and the redundantly solved chain of rank boundaries -- one set per workspace slot
+    CrPlan plan_mid, plan_top;
+    double* ws_mid[2] = {nullptr, nullptr};
+    double* ws_top[2] = {nullptr, nullptr};
+    double* dist_buf[2] = {nullptr, nullptr};  // D1 | O1 | g1 | send | recv | Dt | Ot | gt | xt | cDt | cOt
+    double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -243,6 +255,7 @@ struct gvib200_problem {
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
     bool grads_valid = false;
+    bool flags_synced = false;      // multi-GPU: the not-SPD flags were all-reduced since the last chain pass
     bool force_generic_k1 = false;  // tests: run the generic node-loop kernel even where K1S applies
     // profiling: one CUDA event pair per launch while enabled
     bool profile = false;
@@ -355,6 +368,68 @@ static int cr_allow_smem(K kern, size_t bytes) {
     return 0;
 }
 
+// layout of dist_buf (doubles) for P ranks, K local tiles
+struct DistLayout {
+    size_t D1, O1, g1, send, recv, Dt, Ot, gt, xt, cDt, cOt, total;
+};
+static DistLayout dist_layout(int D, int K, int P) {
+    const size_t DD = (size_t)D * D, NB = 5 * DD + 4 * D;
+    DistLayout L;
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off += (n + 1) & ~size_t(1);
+        return o;
+    };
+    L.D1 = take((size_t)(K + 1) * DD);
+    L.O1 = take((size_t)(K + 1) * DD);
+    L.g1 = take((size_t)(K + 1) * D);
+    L.send = take(NB);
+    L.recv = take((size_t)P * NB);
+    L.Dt = take((size_t)(P + 1) * DD);
+    L.Ot = take((size_t)(P + 1) * DD);
+    L.gt = take((size_t)(P + 1) * D);
+    L.xt = take((size_t)(P + 1) * D);
+    L.cDt = take((size_t)(P + 1) * DD);
+    L.cOt = take((size_t)(P + 1) * DD);
+    L.total = off;
+    return L;
+}
+
+// Multi-GPU chain pass (bt_cr.h, "Multi-GPU"): tiles -> separator chain -> mid tile -> ONE all-gather of the boundary
+// records -> chain of rank boundaries solved redundantly on every rank -> back down.  Everything on p->ls.
+template <int D, bool RHS, bool SELINV>
+static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, double* d_logdet) {
+    gvib200_ctx* ctx = p->ctx;
+    const CrPlan& pl = p->plan;
+    const int P = ctx->world;
+    const DistLayout L = dist_layout(D, pl.K, P);
+    double* buf = p->dist_buf[slot];
+    constexpr int NB = cr_boundary_doubles<D>();
+    // the mid tile works on the summed separator chain and writes its results into the seeds of the real tiles
+    CrArgs<D> mid = cr_bind<D>(p->plan_mid, p->ws_mid[slot], buf + L.D1, buf + L.O1, RHS ? buf + L.g1 : nullptr, a.tx, a.tD,
+                               a.tO, a.notspd);
+    CrArgs<D> top = cr_bind<D>(p->plan_top, p->ws_top[slot], buf + L.Dt, buf + L.Ot, RHS ? buf + L.gt : nullptr, buf + L.xt,
+                               buf + L.cDt, buf + L.cOt, a.notspd);
+    p->flags_synced = false;
+    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), 1, 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
+    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
+    LAUNCH(p, KC_OTHER, (k_cr_pack_boundary<D, RHS>), 1, 64, 0, mid, buf + L.send);
+    if (ctx->ncclAllGather(buf + L.send, buf + L.recv, (size_t)NB, /*ncclFloat64*/ 8, ctx->nccl_comm, p->ls) != 0)
+        return fail(GVIB200_ENCCL, "chain pass: ncclAllGather failed");
+    LAUNCH(p, KC_OTHER, (k_cr_build_global<D>), 1, 256, 0, P, buf + L.recv, buf + L.Dt, buf + L.Ot, buf + L.gt);
+    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, p->plan_top.top_smem_bytes, top);
+    LAUNCH(p, KC_OTHER, (k_cr_seed_mid<D, RHS, SELINV>), 1, 64, 0, mid, ctx->rank, buf + L.xt, buf + L.cDt, buf + L.cOt);
+    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
+    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    if (d_logdet) {
+        // this rank's share of log det: its tiles + its mid tile; the chain of rank boundaries is counted by rank 0 only
+        LAUNCH(p, KC_SUM, k_sum3, 1, 256, 0, (size_t)pl.K, a.ld, mid.ld, ctx->rank == 0 ? top.ld : nullptr, d_logdet);
+    }
+    return check_launch("chain_pass_dist");
+}
+
 // optional candidate fusions of a chain pass (see CrArgs)
 struct ChainFuse {
     const double *Dg2 = nullptr, *Og2 = nullptr;
@@ -387,6 +462,7 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
         TRY(cr_allow_smem(k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 4096));
         configured = true;
     }
+    if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
     if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
@@ -690,6 +766,18 @@ static int run_prologue_only(gvib200_problem* p, int which) {
     return 0;
 }
 
+// multi-GPU: sum the cost of buffer `which` over the ranks and make the not-SPD flags global (one small all-reduce)
+static int dist_reduce(gvib200_problem* p, double* d_cost) {
+    gvib200_ctx* ctx = p->ctx;
+    if (ctx->world <= 1) return 0;
+    LAUNCH(p, KC_OTHER, k_red_pack, 1, 1, 0, d_cost, p->d_flag, p->red_buf);
+    if (ctx->ncclAllReduce(p->red_buf, p->red_buf, 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, p->ls) != 0)
+        return fail(GVIB200_ENCCL, "ncclAllReduce failed");
+    LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, d_cost, p->d_flag);
+    p->flags_synced = true;
+    return check_launch("dist_reduce");
+}
+
 // total cost of buffer `which`: sum of factor costs + logdet/2 (GVI-GH-GBP-impl.h:217-239) -> scal[2 + which]
 static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
@@ -700,6 +788,7 @@ static void run_total(gvib200_problem* p, int which) {
     } else {
         LAUNCH(p, KC_SUM, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
     }
+    dist_reduce(p, p->scal + 2 + which);
 }
 
 template <int D>
@@ -709,7 +798,9 @@ static void launch_assemble(gvib200_problem* p, int which) {
 }
 
 // d_flag[0] / d_flag[1]: not-SPD flags of the chain passes run in workspace slot 0 / 1
+static int dist_reduce(gvib200_problem* p, double* d_cost);
 static int read_flags(gvib200_problem* p, int* flag0, int* flag1) {
+    if (p->ctx->world > 1 && !p->flags_synced) TRY(dist_reduce(p, p->scal + 7));  // scal[7]: scratch
     CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     *flag0 = p->h_flag[0];
@@ -761,8 +852,18 @@ extern "C" int gvib200_ctx_destroy(gvib200_ctx* ctx) {
     return 0;
 }
 
-extern "C" int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world) {
+extern "C" int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world, const char* libnccl_path) {
     if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(GVIB200_EINVAL, "ctx_set_comm: bad arguments");
+    if (world > 1) {
+        if (!nccl_comm) return fail(GVIB200_EINVAL, "ctx_set_comm: null communicator");
+        const char* path = (libnccl_path && libnccl_path[0]) ? libnccl_path : "libnccl.so.2";
+        void* lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return fail(GVIB200_ENCCL, std::string("ctx_set_comm: dlopen(") + path + "): " + dlerror());
+        ctx->nccl_lib = lib;
+        ctx->ncclAllGather = reinterpret_cast<decltype(ctx->ncclAllGather)>(dlsym(lib, "ncclAllGather"));
+        ctx->ncclAllReduce = reinterpret_cast<decltype(ctx->ncclAllReduce)>(dlsym(lib, "ncclAllReduce"));
+        if (!ctx->ncclAllGather || !ctx->ncclAllReduce) return fail(GVIB200_ENCCL, "ctx_set_comm: NCCL symbols not found");
+    }
     ctx->nccl_comm = nccl_comm;
     ctx->rank = rank;
     ctx->world = world;
@@ -847,6 +948,10 @@ static void free_problem(gvib200_problem* p) {
     }
     F(p->scal); F(p->partial); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
     F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
+    for (int i = 0; i < 2; ++i) {
+        F(p->ws_mid[i]); F(p->ws_top[i]); F(p->dist_buf[i]);
+    }
+    F(p->red_buf);
     F(p->snap);
     for (auto& r : p->prof) {
         cudaEventDestroy(r.a);
@@ -1160,20 +1265,42 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     {
         // dynamic shared memory left for the chain kernels next to their static arrays
         const size_t smem = p->ctx->smem_optin - 4096;
+        const int P = p->ctx->world;
         bool ok = false;
+#define PLAN_CASE(D_)                                                                                          \
+    case D_: {                                                                                                 \
+        int force_T = 0;                                                                                       \
+        if (P > 1) { /* multi-GPU: always tiled, the separator chain goes through the mid level */            \
+            int K = std::min(p->ctx->sm_count, cr_max_top_nodes<D_>(smem) - 1);                                \
+            K = std::max(1, std::min(K, S - 1));                                                               \
+            force_T = std::max(2, std::min((S - 1 + K - 1) / K, cr_max_tile_links<D_>(smem)));                 \
+        }                                                                                                      \
+        ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, force_T);                                    \
+        if (ok && P > 1)                                                                                       \
+            ok = cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, 1, smem, std::max(p->plan.K, 2)) &&              \
+                 cr_make_plan<D_>(p->plan_top, P + 1, 1, smem, -1);                                            \
+    } break;
         switch (d) {
-            case 1: ok = cr_make_plan<1>(p->plan, S, p->ctx->sm_count, smem); break;
-            case 2: ok = cr_make_plan<2>(p->plan, S, p->ctx->sm_count, smem); break;
-            case 3: ok = cr_make_plan<3>(p->plan, S, p->ctx->sm_count, smem); break;
-            case 4: ok = cr_make_plan<4>(p->plan, S, p->ctx->sm_count, smem); break;
-            case 6: ok = cr_make_plan<6>(p->plan, S, p->ctx->sm_count, smem); break;
+            PLAN_CASE(1) PLAN_CASE(2) PLAN_CASE(3) PLAN_CASE(4) PLAN_CASE(6)
         }
+#undef PLAN_CASE
+        if (P > 1 && S < 2) return fail(GVIB200_EINVAL, "finalize: a multi-GPU segment needs at least two states");
         if (!ok) return fail(GVIB200_EINVAL, "finalize: the chain is too long for the two-level block-tridiagonal plan");
     }
     for (int i = 0; i < 2; ++i) {
         TRY(dev_alloc(&p->ws[i], p->plan.ws_doubles + 16));
         CUDA_TRY(cudaMemsetAsync(p->ws[i], 0, (p->plan.ws_doubles + 16) * sizeof(double), p->stream));
+        if (p->ctx->world > 1) {
+            const DistLayout L = dist_layout(d, p->plan.K, p->ctx->world);
+            TRY(dev_alloc(&p->ws_mid[i], p->plan_mid.ws_doubles + 16));
+            TRY(dev_alloc(&p->ws_top[i], p->plan_top.ws_doubles + 16));
+            TRY(dev_alloc(&p->dist_buf[i], L.total + 16));
+            CUDA_TRY(cudaMemsetAsync(p->ws_mid[i], 0, (p->plan_mid.ws_doubles + 16) * sizeof(double), p->stream));
+            CUDA_TRY(cudaMemsetAsync(p->ws_top[i], 0, (p->plan_top.ws_doubles + 16) * sizeof(double), p->stream));
+            CUDA_TRY(cudaMemsetAsync(p->dist_buf[i], 0, (L.total + 16) * sizeof(double), p->stream));
+        }
     }
+    if (p->ctx->world > 1) TRY(dev_alloc(&p->red_buf, 8));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->finalized = true;
     return 0;
@@ -1462,7 +1589,23 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     while (true) {
         step *= o.backtrack_ratio;
         const int w = 1 - p->cur;
-        if (cnt == 0) {
+        const bool fork = (p->ctx->world == 1);  // one communicator: collectives stay in issue order on one stream
+        if (cnt == 0 && !fork) {
+            ChainFuse fi;
+            fi.Dg2 = p->VD;
+            fi.Og2 = p->VO;
+            fi.alpha = step;
+            fi.Dout = p->LD[w];
+            fi.Oout = p->LO[w];
+            TRY(do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[w], p->CO[w], p->scal + w, 1, &fi));
+            TRY(run_prologue_only(p, w));
+            ChainFuse fs;
+            fs.xbase = p->mu[p->cur];
+            fs.xalpha = step;
+            fs.xout = p->mu[w];
+            TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &fs));
+            p->grads_valid = true;
+        } else if (cnt == 0) {
             CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
             // the candidate precision Lambda + a (Vddmu - Lambda) is formed while the selected inverse loads its tiles,

@@ -716,6 +716,50 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
                                      a.xbase, a.xalpha, a.xout);
 }
 
+// multi-GPU glue kernels (single small CTAs; the arithmetic is in bt_cr.h)
+template <int D, bool RHS>
+__global__ void k_cr_sum_level(const CrArgs<D> a, double* D1, double* O1, double* g1) {
+    cr_sum_level<D, RHS>(a, D1, O1, g1, threadIdx.x, blockDim.x);
+}
+template <int D, bool RHS>
+__global__ void k_cr_pack_boundary(const CrArgs<D> mid, double* rec) {
+    cr_pack_boundary<D, RHS>(mid, rec, threadIdx.x, blockDim.x);
+}
+template <int D>
+__global__ void k_cr_build_global(int P, const double* recs, double* Dt, double* Ot, double* gt) {
+    cr_build_global<D>(P, recs, Dt, Ot, gt, threadIdx.x, blockDim.x);
+}
+template <int D, bool RHS, bool SELINV>
+__global__ void k_cr_seed_mid(const CrArgs<D> mid, int rank, const double* xt, const double* cDt, const double* cOt) {
+    cr_seed_mid<D, RHS, SELINV>(mid, rank, xt, cDt, cOt, threadIdx.x, blockDim.x);
+}
+// out[0] = sum(v[0..n)) + a[0] + (b ? b[0] : 0), fixed order
+__global__ void k_sum3(size_t n, const double* __restrict__ v, const double* __restrict__ a, const double* __restrict__ b,
+                       double* __restrict__ out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0] + a[0] + (b ? b[0] : 0.0);
+}
+// staging of the cost / flag all-reduce: buf = {cost, flag0, flag1, 0}; afterwards cost and flags are written back
+__global__ void k_red_pack(const double* cost, const int* flags, double* buf) {
+    buf[0] = cost[0];
+    buf[1] = (double)flags[0];
+    buf[2] = (double)flags[1];
+    buf[3] = 0.0;
+}
+__global__ void k_red_unpack(const double* buf, double* cost, int* flags) {
+    cost[0] = buf[0];
+    flags[0] = buf[1] > 0.0 ? 1 : 0;
+    flags[1] = buf[2] > 0.0 ? 1 : 0;
+}
+
 // cell records for CostPlanarHinge from the column-major field (layout: cost_functors.cuh)
 __global__ void k_build_sdf_records(int rows, int cols, double thr, const double* __restrict__ data, double4* __restrict__ rec) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -307,3 +307,106 @@ def make_factor_batch(N: int = 100_000, deg: int = 6, sigma: float = 0.1, seed: 
     spec.prec0_O = np.zeros((N - 1, d, d))
     spec.meta = dict(name="factor_batch", Sigma=Sigma)
     return spec
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-GPU: the cfg3 chain cut along the time axis; rank r owns the links [r m, (r+1) m), m = N + 1
+# ----------------------------------------------------------------------------------------------
+def make_cfg3_segment(rank: int, world: int, N: int = 100_000, delta_t: float = 0.2, deg: int = 6, sigma: float = 0.1,
+                      prec0: float = 100.0, seed: int = 3, clearance: Optional[float] = 0.6) -> ProblemSpec:
+    """Rank `rank`'s time segment of ONE cfg3 chain of world * (N + 1) + 1 states: N + 2 local states (the first / last
+    are shared with the neighbouring ranks), the LTV links it owns, the hinge factors of the states it owns (a shared
+    state's factor belongs to the right-hand rank) and its share of the initial precision (a shared diagonal block goes
+    entirely to the right-hand rank: only the sums matter).  merge_segments() of all ranks' segments is the single-GPU
+    problem."""
+    d = 4
+    m = N + 1
+    S = world * m + 1
+    g0 = rank * m
+    nominal = lissajous_nominal(S, delta_t, clearance, disc_layout())
+    loc = nominal[g0:g0 + m + 1]
+    spec = ProblemSpec(S=m + 1, d=d)
+    spec.sdf = disc_sdf()
+    ends, ends_mu = [], []
+    if rank == 0:
+        ends.append(0)
+        ends_mu.append(nominal[0])
+    if rank == world - 1:
+        ends.append(m)
+        ends_mu.append(nominal[-1])
+    if ends:
+        spec.groups.append(fixed_prior_group(ends, np.stack(ends_mu), 1e-4 * np.eye(d), d))
+    # LTV links: one global random stream (so that the merged problem does not depend on the partition), own slice
+    n_links = S - 1
+    rng = np.random.default_rng(seed)
+    nq = 4 * n_links + 1
+    w = rng.uniform(1.0, 2.0, nq)
+    c = rng.uniform(1.0, 2.0, nq)
+    q0 = 4 * g0
+    wq, cq = w[q0:q0 + 4 * m + 1], c[q0:q0 + 4 * m + 1]
+    dim, ds = 2, 4
+    hA = np.zeros((4 * m + 1, ds, ds))
+    hA[:, :dim, dim:] = np.eye(dim)
+    hA[:, dim:, :dim] = -(wq ** 2)[:, None, None] * np.eye(dim)
+    hA[:, dim:, dim:] = -cq[:, None, None] * np.eye(dim)
+    hB = np.zeros((4 * m + 1, ds, dim))
+    hB[:, dim:, :] = np.eye(dim)
+    idx = 4 * np.arange(m)[:, None] + np.arange(4)[None, :]
+    Phi, Q = ltv_transition_batch(hA[idx], hB[idx], delta_t)
+    Kinv = np.linalg.inv(Q)
+    Kinv = 0.5 * (Kinv + np.transpose(Kinv, (0, 2, 1)))
+    Lam = np.concatenate([-Phi, np.broadcast_to(np.eye(ds), (m, ds, ds))], axis=2)
+    target = -loc
+    spec.groups.append(LinGroupSpec(start=np.arange(m, dtype=np.int32), Lambda=Lam, Psi=-Lam,
+                                    mu_t=np.concatenate([target[:-1], target[1:]], axis=1), Kinv=Kinv, C=np.full(m, 0.5)))
+    first = 1 if rank == 0 else 0
+    spec.groups.append(GhGroupSpec(capi.COST_PLANAR_HINGE, d, deg, np.arange(first, m, dtype=np.int32),
+                                   capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
+    spec.mu0 = loc.reshape(-1).copy()
+    spec.prec0_D = np.tile(prec0 * np.eye(d), (m + 1, 1, 1))
+    if rank < world - 1:
+        spec.prec0_D[m] = 0.0  # the shared block belongs to the right-hand neighbour
+    spec.prec0_O = np.zeros((m, d, d))
+    spec.meta = dict(name="cfg3_segment", rank=rank, world=world, links=m, step_size_base=0.55, niters_lowtemp=10)
+    return spec
+
+
+def merge_segments(segs: List[ProblemSpec]) -> ProblemSpec:
+    """The single-GPU problem equivalent to a list of time segments (tests)."""
+    d = segs[0].d
+    m = segs[0].S - 1
+    world = len(segs)
+    S = world * m + 1
+    out = ProblemSpec(S=S, d=d)
+    out.sdf = segs[0].sdf
+    out.mu0 = np.concatenate([s.mu0.reshape(-1, d)[:m] for s in segs] + [segs[-1].mu0.reshape(-1, d)[m:]]).reshape(-1)
+    out.prec0_D = np.zeros((S, d, d))
+    out.prec0_O = np.zeros((S - 1, d, d))
+    for r, s in enumerate(segs):
+        out.prec0_D[r * m:r * m + m + 1] += s.prec0_D
+        out.prec0_O[r * m:(r + 1) * m] = s.prec0_O
+    # concatenate groups position-wise by kind: fixed priors, LTV links, hinge factors
+    def cat(groups, r_of):
+        g0 = groups[0]
+        if isinstance(g0, GhGroupSpec):
+            return GhGroupSpec(g0.kind, g0.dim, g0.deg, np.concatenate([g.start + r * m for g, r in zip(groups, r_of)]).astype(np.int32),
+                               g0.params, g0.T, g0.T_high)
+        return LinGroupSpec(start=np.concatenate([g.start + r * m for g, r in zip(groups, r_of)]).astype(np.int32),
+                            Lambda=np.concatenate([g.Lambda for g in groups]), Psi=np.concatenate([g.Psi for g in groups]),
+                            mu_t=np.concatenate([g.mu_t for g in groups]), Kinv=np.concatenate([g.Kinv for g in groups]),
+                            C=np.concatenate([np.broadcast_to(np.asarray(g.C, float), (len(g.start),)) for g in groups]),
+                            T=g0.T, T_high=g0.T_high)
+    fixed, ltv, hinge = [], [], []
+    for r, s in enumerate(segs):
+        for g in s.groups:
+            if isinstance(g, GhGroupSpec):
+                hinge.append((g, r))
+            elif g.Lambda.shape[2] == d:
+                fixed.append((g, r))
+            else:
+                ltv.append((g, r))
+    for lst in (fixed, ltv, hinge):
+        if lst:
+            out.groups.append(cat([g for g, _ in lst], [r for _, r in lst]))
+    out.meta = dict(segs[0].meta, name="cfg3_merged")
+    return out

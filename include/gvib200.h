@@ -70,10 +70,16 @@ const char* gvib200_last_error(void);
 /* library build identification: "gvib200 <version> sm_100a" */
 const char* gvib200_version(void);
 
-/* Multi-GPU (one process per GPU): attach an already-initialised NCCL communicator
-   (ncclComm_t passed as void*) plus this rank's index / world size.  The chain of every problem
-   created afterwards on this ctx is partitioned along the time axis.           */
-int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world);
+/* Multi-GPU (one process per GPU): attach an initialised NCCL communicator (ncclComm_t passed as void*),
+   this rank's index and the world size, and the path of the libnccl the communicator was created with (the library
+   resolves ncclAllGather / ncclAllReduce from it at run time; NULL = "libnccl.so.2").  Every problem created afterwards
+   on this ctx is ONE TIME SEGMENT of a chain that is cut along the time axis: rank r owns the links [r m, (r+1) m) and
+   both of its end states, i.e. num_states = m + 1 local states of which the first / last are shared with the
+   neighbouring ranks.  A shared state's precision diagonal block and its factors are split between the two ranks (each
+   passes ITS share; only the sums matter), its mean is passed identically to both.  Per block-tridiagonal pass the ranks
+   exchange 5 d^2 + 4 d doubles in one all-gather; per cost evaluation 4 doubles in one all-reduce.  All ranks must make
+   the same sequence of calls. */
+int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world, const char* libnccl_path);
 
 /* ---- sparse Gauss-Hermite tables (replaces the cereal map consumed at
         quadrature/SparseGaussHermite.h:138-166 and its MATLAB generator

@@ -1,0 +1,121 @@
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): each process builds ITS time segment
+(problems.make_cfg3_segment), assembles its share of Vddmu / Vdmu with the oracle's factor arithmetic, reduces its
+segment to the boundary record [Dfirst | Dlast | CL | CR | O | gfirst | glast | gl | gr] of gaussianvi_b200/csrc/bt_cr.h,
+all-gathers the records, solves the chain of rank boundaries and back-substitutes.  The result must equal the oracle's
+dmu on the merged single-process problem -- this pins segment ownership, the splitting of shared blocks and the
+boundary-record algebra the CUDA path uses (the kernels themselves are replayed in tests/test_capi_host.py)."""
+import os
+import sys
+import pathlib
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def _local_system(seg):
+    """This rank's share of (Vddmu, -Vdmu) as dense local arrays, from the oracle's per-factor arithmetic."""
+    sys.path[:0] = [str(ROOT), str(ROOT / "tests"), str(ROOT / "oracle")]
+    import oracle_bridge as ob
+    factors = ob.build_factors(seg)
+    # shares of the precision are not SPD on their own: take the covariance from the MERGED problem (passed in meta)
+    cov = seg.meta["cov_blocks"]
+    mu = np.asarray(seg.mu0, float).reshape(-1)
+    for f in factors:
+        f.update_mu_from_joint(mu)
+        f.update_precision_from_joint(cov.block(f.start_index, f.dim // seg.d))
+    S, d = seg.S, seg.d
+    Vdmu = np.zeros(S * d)
+    import gvi_oracle as o
+    V = o.BlockTri.identity(S, d, 0.0)
+    for f in factors:
+        f.calculate_partial_V()
+        Vdmu[f.offset:f.offset + f.dim] += f.Vdmu
+        V.add_block(f.start_index, f.dim // d, f.Vddmu)
+    return V, -Vdmu
+
+
+def _worker(rank, world, port, N, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [str(ROOT), str(ROOT / "tests"), str(ROOT / "oracle")]
+    import torch
+    import torch.distributed as dist
+    import gvi_oracle as o
+    import oracle_bridge as ob
+    from gaussianvi_b200 import problems
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    segs = [problems.make_cfg3_segment(r, world, N=N) for r in range(world)]
+    merged = problems.merge_segments(segs)
+    ref = ob.build_oracle(merged, niters=1)
+    seg = segs[rank]
+    m, d = seg.S - 1, seg.d
+    # local slice of the merged covariance (both neighbours hold the same blocks at a shared state)
+    seg.meta["cov_blocks"] = o.BlockTri(ref.cov.D[rank * m:rank * m + m + 1].copy(), ref.cov.O[rank * m:(rank + 1) * m].copy())
+    V, g = _local_system(seg)
+    A = V.dense()
+    n = (m + 1) * d
+    I = np.arange(d, n - d)                     # interior
+    B = np.r_[np.arange(d), np.arange(n - d, n)]  # first, last
+    Aii, Aib, Abb = A[np.ix_(I, I)], A[np.ix_(I, B)], A[np.ix_(B, B)]
+    sol = np.linalg.solve(Aii, np.c_[Aib, g[I]])
+    Sb = Abb - Aib.T @ sol[:, :2 * d]           # [[Dfirst + CL, O], [O^T, Dlast + CR]]
+    gb = g[B] - Aib.T @ sol[:, 2 * d]
+    rec = np.r_[Sb[:d, :d].ravel(), Sb[d:, d:].ravel(), Sb[:d, d:].ravel(), gb]
+    gathered = [torch.zeros(len(rec), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(rec))
+    # chain of rank boundaries, solved redundantly
+    P = world
+    Dt = np.zeros((P + 1, d, d))
+    Ot = np.zeros((P, d, d))
+    gt = np.zeros((P + 1, d))
+    for r, t in enumerate(gathered):
+        t = t.numpy()
+        Dt[r] += t[:d * d].reshape(d, d)
+        Dt[r + 1] += t[d * d:2 * d * d].reshape(d, d)
+        Ot[r] = t[2 * d * d:3 * d * d].reshape(d, d)
+        gt[r] += t[3 * d * d:3 * d * d + d]
+        gt[r + 1] += t[3 * d * d + d:]
+    xt = o.block_solve(o.BlockTri(Dt, Ot), gt.reshape(-1)).reshape(P + 1, d)
+    xb = np.r_[xt[rank], xt[rank + 1]]
+    xi = sol[:, 2 * d] - sol[:, :2 * d] @ xb
+    x = np.zeros(n)
+    x[B] = xb
+    x[I] = xi
+    dmu_ref, _ = ref.compute_gradients()
+    err = np.abs(x - dmu_ref[rank * m * d:rank * m * d + n]).max() / np.abs(dmu_ref).max()
+    out.put((rank, float(err)))
+    dist.destroy_process_group()
+
+
+def test_time_partition_two_processes_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 14, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-9, (rank, err)
+
+
+def test_bench_reference_arm_under_two_ranks():
+    """bench.py --impl reference under torchrun semantics: rank 0 prints the line, the other rank exits 0 silently."""
+    import json
+    import subprocess
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    outs = []
+    for rank in (0, 1):
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                           env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    line = json.loads(outs[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert outs[1] == ""
