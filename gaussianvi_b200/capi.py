@@ -34,7 +34,7 @@ EXPORTS = [
     "gvib200_selected_inverse", "gvib200_blocktri_solve", "gvib200_time_stage", "gvib200_fp64_peak",
     "gvib200_launch_count", "gvib200_timer_start", "gvib200_timer_stop", "gvib200_profile_begin", "gvib200_profile_end",
     "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
-    "gvib200_problem_set_option",
+    "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
 ]
 
 
@@ -343,6 +343,11 @@ class Problem:
         if want_traces:
             return out, fc[:done.value, :self.n_factors], mt[:done.value]
         return out
+
+    def prox_iterate(self, opts: Optional[Opts] = None) -> IterStats:
+        st = IterStats()
+        _check(self.lib.gvib200_prox_iterate(self.h, C.byref(opts) if opts is not None else None, C.byref(st)))
+        return st
 
     def reset_schedule(self):
         _check(self.lib.gvib200_reset_schedule(self.h))

@@ -528,6 +528,7 @@ protected:
         if (_prob) return;
         gvib200_ctx* ctx = default_context();
         gvib200_check(gvib200_problem_create(ctx, _num_states, _dim_state, &_prob), "problem_create");
+        if (_prox) gvib200_check(gvib200_problem_set_option(_prob, "prox", 1), "set_option prox");
         struct GhKey {
             DeviceCostSpec cost;
             int dim, deg;
@@ -616,6 +617,7 @@ protected:
     gvib200_opts _opts;
     gvib200_problem* _prob = nullptr;
     bool _has_state = false;
+    bool _prox = false;  // set by ProxGVIGH before the problem is built
     std::vector<double> _mu0, _pd, _po;
     std::vector<gvib200_iter_stats> _stats;
 };
@@ -657,6 +659,36 @@ public:
         b.off.assign((size_t)(Base::_num_states > 1 ? Base::_num_states - 1 : 1) * dd, 0.0);
         gvib200_check(gvib200_get_V(Base::_prob, nullptr, b.diag.data(), b.off.data()), "Vddmu");
         return b;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ Prox-GVI
+// proxgd/ProxGVIFactorizedBaseGH.h, ProxGVIFactorizedLinear.h: the factor classes carry the same data as their NGD
+// counterparts; the Bures-Wasserstein JKO step (BW_JKO) runs on the device.
+template <class CostClass>
+using ProxGVIFactorizedBaseGH = NGDFactorizedBaseGH<CostClass>;
+template <class Factor>
+using ProxGVIFactorizedLinear = NGDFactorizedLinear<Factor>;
+
+// ProxGVIGH (proxgd/ProxGVI-GH.h, -impl.h:124-205)
+template <class FactorizedOptimizer>
+class ProxGVIGH : public GVIGH<FactorizedOptimizer> {
+    using Base = GVIGH<FactorizedOptimizer>;
+
+public:
+    ProxGVIGH(const std::vector<std::shared_ptr<FactorizedOptimizer>>& vec_fact_optimizers, int dim_state, int num_states,
+              int niterations = 5, double temperature = 1.0, double high_temperature = 100.0)
+        : Base(vec_fact_optimizers, dim_state, num_states, niterations, temperature, high_temperature) {
+        Base::_prox = true;
+    }
+    void optimize(std::optional<bool> verbose = std::nullopt) {
+        Base::build();
+        Base::_stats.assign((size_t)Base::_niters, gvib200_iter_stats());
+        int done = 0;
+        gvib200_check(gvib200_prox_optimize(Base::_prob, &(this->_opts), Base::_niters, Base::_stats.data(), &done), "prox optimize");
+        Base::_stats.resize((size_t)done);
+        if (verbose.value_or(false))
+            for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, Base::_stats[(size_t)i].cost);
     }
 };
 

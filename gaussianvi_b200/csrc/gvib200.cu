@@ -180,7 +180,7 @@ struct GhGroup {
 
 struct LinGroup {
     int dim = 0, m = 0, kdim = 0, n = 0, first_id = 0;
-    size_t voff = 0;
+    size_t voff = 0, moff = 0;  // moff: offset of the Vddmu blocks in fVdd (Prox mode only)
     std::vector<int> start;
     std::vector<double> Lambda, psi, Kinv, A, C, T, Thigh;
     int* d_start = nullptr;
@@ -255,6 +255,8 @@ struct gvib200_problem {
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
     bool grads_valid = false;
+    bool prox = false;              // Prox-GVI problem (option "prox" before finalize): linear factors get per-iteration
+                                    // Vddmu blocks, no constant Klin, GH costs are not divided by a temperature
     bool flags_synced = false;      // multi-GPU: the not-SPD flags were all-reduced since the last chain pass
     bool force_generic_k1 = false;  // tests: run the generic node-loop kernel even where K1S applies
     // profiling: one CUDA event pair per launch while enabled
@@ -716,6 +718,27 @@ static void launch_raw_to_x(gvib200_problem* p, const GhGroup& g, const double* 
     LAUNCH(p, KC_OTHER, (k_raw_to_x<DIM>), cdiv(g.n, 128), 128, 0, g.n, g.d_raw, SR, E0, E1, E2);
 }
 
+static LinearArgs linear_args(gvib200_problem* p, const LinGroup& g, const SweepTarget& t, bool full) {
+    LinearArgs a;
+    a.n = g.n;
+    a.dim = g.dim;
+    a.m = g.m;
+    a.state_dim = p->d;
+    a.start = g.d_start;
+    a.Lambda = g.d_Lambda;
+    a.psi = g.d_psi;
+    a.Kinv = g.d_Kinv;
+    a.A = g.d_A;
+    a.C = g.d_C;
+    a.T = g.d_T;
+    a.mu = t.mu;
+    a.covD = t.cD;
+    a.covO = t.cO;
+    a.fcost = p->fcost[t.which] + g.first_id;
+    a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
+    return a;
+}
+
 static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
     for (auto& g : p->lin) {
         LinearArgs a;
@@ -1112,6 +1135,7 @@ static int upload_klin(gvib200_problem* p) {
     const size_t dd = (size_t)d * d;
     std::vector<double> KD((size_t)S * dd, 0.0), KO((size_t)std::max(S - 1, 1) * dd, 0.0);
     for (auto& g : p->lin) {
+        if (p->prox) break;  // Prox-GVI: the linear factors' Vddmu depends on the state (BW_JKO), nothing is constant
         for (int f = 0; f < g.n; ++f) {
             const double sc = 2.0 * g.C[f] / g.T[f];
             const double* A = g.A.data() + (size_t)f * g.dim * g.dim;
@@ -1150,7 +1174,16 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     for (auto& g : p->lin) {
         g.voff = nV;
         nV += (size_t)g.n * g.dim;
+        if (p->prox) {
+            g.moff = nM;
+            nM += (size_t)g.n * g.dim * g.dim;
+        }
     }
+    if (p->prox)  // ProxGVIFactorizedBaseGH::fact_cost_value does not divide by the temperature
+        for (auto& g : p->gh) {
+            g.T.assign(g.T.size(), 1.0);
+            g.Thigh.assign(g.Thigh.size(), 1.0);
+        }
     p->nV = nV;
     p->nM = nM;
     // adjacency (id order within each state => fixed summation order)
@@ -1174,6 +1207,17 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             const int s = g.start[fr.index], nst = g.dim / d;
             const size_t vo = g.voff + (size_t)fr.index * g.dim;
             for (int b = 0; b < nst; ++b) vl[s + b].push_back((int)(vo + (size_t)b * d));
+            if (p->prox) {
+                const size_t mo = g.moff + (size_t)fr.index * g.dim * g.dim;
+                for (int b = 0; b < nst; ++b) {
+                    dl[s + b].push_back((int)(mo + (size_t)b * d + (size_t)b * d * g.dim));
+                    dll[s + b].push_back(g.dim);
+                }
+                if (nst == 2) {
+                    ol[s].push_back((int)(mo + (size_t)d * g.dim));
+                    oll[s].push_back(g.dim);
+                }
+            }
         }
     }
     if (nV > 0x7fffffffULL || nM > 0x7fffffffULL) return fail(GVIB200_EINVAL, "finalize: problem too large for int32 offsets");
@@ -1711,6 +1755,142 @@ extern "C" int gvib200_optimize(gvib200_problem* p, const gvib200_opts* opts, in
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: Prox-GVI (proxgd/ProxGVI-GH-impl.h:45-86,124-205)
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+static void launch_prox_gh(gvib200_problem* p, const GhGroup& g, double eta, int which) {
+    LAUNCH(p, KC_OTHER, (k_prox_gh<DIM>), cdiv(g.n, 64), 64, 0, g.n, eta, g.d_raw, g.d_SR[which],
+           p->fcost[which] + g.first_id, p->fVdmu[which] + g.voff, p->fVdd[which] + g.moff);
+}
+
+// ProxGVIGH::compute_gradients(step): per-factor BW gradients + JKO step, scattered into dmu / dprecision (Vdmu, VD, VO)
+static int prox_gradients(gvib200_problem* p, double eta) {
+    const int c = p->cur;
+    SweepTarget t{p->mu[c], p->CD[c], p->CO[c], c};
+    TRY(run_sweep(p, c, false, true, true));  // full moments with the xi-space sums kept in `raw`
+    for (auto& g : p->gh) {
+        switch (g.dim) {
+            case 1: launch_prox_gh<1>(p, g, eta, c); break;
+            case 2: launch_prox_gh<2>(p, g, eta, c); break;
+            case 3: launch_prox_gh<3>(p, g, eta, c); break;
+            case 4: launch_prox_gh<4>(p, g, eta, c); break;
+            case 6: launch_prox_gh<6>(p, g, eta, c); break;
+            case 8: launch_prox_gh<8>(p, g, eta, c); break;
+            case 12: launch_prox_gh<12>(p, g, eta, c); break;
+            default: return fail(GVIB200_EINVAL, "prox: unsupported GH factor dim");
+        }
+    }
+    for (auto& g : p->lin) {
+        LinearArgs a = linear_args(p, g, t, true);
+        double* fm = p->fVdd[c] + g.moff;
+        const int sd = p->d;
+#define PROX_LIN(DIM_, M_, SD_)                                                                            \
+    if (g.dim == DIM_ && g.m == M_ && sd == SD_) {                                                         \
+        LAUNCH(p, KC_LINEAR, (k_prox_linear<DIM_, M_, SD_>), cdiv(g.n, 64), 64, 0, a, eta, fm);            \
+        continue;                                                                                          \
+    }
+        PROX_LIN(1, 1, 1) PROX_LIN(2, 2, 2) PROX_LIN(2, 1, 1) PROX_LIN(4, 4, 4) PROX_LIN(8, 4, 4) PROX_LIN(6, 6, 6) PROX_LIN(12, 6, 6)
+#undef PROX_LIN
+        return fail(GVIB200_EINVAL, "prox: unsupported linear factor shape");
+    }
+    run_total(p, c);
+    p->sweep_valid = false;  // the NGD outputs of the sweep were overwritten
+    TRY(dispatch_assemble(p, c));
+    return check_launch("prox_gradients");
+}
+
+extern "C" int gvib200_prox_iterate(gvib200_problem* p, const gvib200_opts* opts_in, gvib200_iter_stats* st) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "prox_iterate: no state");
+    if (!p->prox) return fail(GVIB200_ESTATE, "prox_iterate: the problem was not created with option \"prox\"");
+    if (p->ctx->world > 1) return fail(GVIB200_EINVAL, "prox_iterate: single-GPU only");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    gvib200_opts o;
+    if (opts_in) o = *opts_in;
+    else gvib200_default_opts(&o);
+    gvib200_iter_stats s;
+    std::memset(&s, 0, sizeof(s));
+    if (p->iter == o.niters_lowtemp && p->is_lowtemp) {  // ProxGVI-GH-impl.h:130-133
+        TRY(switch_to_high_temperature(p));
+        p->is_lowtemp = false;
+        s.switched_high_T = 1;
+    }
+    TRY(clear_flag(p));
+    const int S = p->S, d = p->d;
+    const size_t dd = (size_t)d * d;
+    const size_t nmu = (size_t)S * d, nD = S * dd, nO = (S - 1) * dd;
+    // cost_iter and the gradients at eta = base (:136-154)
+    TRY(prox_gradients(p, o.step_size_base));
+    s.n_moment_sweeps++;
+    CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    int flag = 0;
+    TRY(read_flag(p, &flag));
+    const double cost_iter = p->h_scal[2 + p->cur];
+    s.cost = cost_iter;
+    int cnt = 0, B = 1;
+    while (true) {
+        const double step = std::pow(o.step_size_base, B);  // :163
+        const int c = p->cur, w = 1 - p->cur;
+        LAUNCH(p, KC_CANDIDATE, k_candidate_add, cdiv(nD, 256), 256, 0, nmu, nD, nO, step, p->mu[c], p->Vdmu, p->LD[c], p->LO[c],
+               p->VD, p->VO, p->mu[w], p->LD[w], p->LO[w]);
+        TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w));
+        TRY(run_sweep(p, w, true, false, false));
+        s.n_cost_sweeps++;
+        run_total(p, w);
+        CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        TRY(read_flag(p, &flag));
+        const double new_cost = p->h_scal[2 + w];
+        s.new_cost = new_cost;
+        s.step = step;
+        const bool ok = (flag == 0) && (new_cost < cost_iter);
+        if (ok) {
+            p->cur = w;
+            s.accepted = 1;
+            s.n_backtrack = cnt;
+            break;
+        }
+        B += 1;
+        cnt += 1;
+        if (cnt > o.max_backtrack) {  // :192-199: the last candidate is taken anyway -- unless it is not even SPD
+            s.n_backtrack = cnt;
+            if (flag) {
+                s.status = GVIB200_ENOTSPD;
+                TRY(clear_flag(p));
+                if (st) *st = s;
+                p->iter++;
+                return fail(GVIB200_ENOTSPD, "prox_iterate: back-tracking exhausted on a candidate precision that is not SPD");
+            }
+            p->cur = w;
+            break;
+        }
+        if (flag) TRY(clear_flag(p));
+    }
+    p->sweep_valid = false;
+    p->grads_valid = false;
+    p->iter++;
+    if (st) *st = s;
+    return 0;
+}
+
+extern "C" int gvib200_prox_optimize(gvib200_problem* p, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats,
+                                     int* n_done) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "prox_optimize: no state");
+    int done = 0;
+    for (int it = 0; it < n_iters; ++it) {
+        gvib200_iter_stats s;
+        const int rc = gvib200_prox_iterate(p, opts, &s);
+        if (stats) stats[it] = s;
+        if (rc != 0) {
+            if (n_done) *n_done = done;
+            return rc;
+        }
+        done++;
+    }
+    if (n_done) *n_done = done;
+    return 0;
+}
+
 extern "C" int gvib200_reset_schedule(gvib200_problem* p) {
     if (!p) return fail(GVIB200_EINVAL, "reset_schedule: null");
     p->iter = 0;
@@ -1889,6 +2069,11 @@ extern "C" int gvib200_profile_end(gvib200_problem* p, gvib200_profile* out) {
 
 extern "C" int gvib200_problem_set_option(gvib200_problem* p, const char* name, int value) {
     if (!p || !name) return fail(GVIB200_EINVAL, "set_option: null");
+    if (std::strcmp(name, "prox") == 0) {
+        if (p->finalized) return fail(GVIB200_ESTATE, "set_option: \"prox\" must be set before finalize");
+        p->prox = (value != 0);
+        return 0;
+    }
     if (std::strcmp(name, "generic_k1") == 0) {
         p->force_generic_k1 = (value != 0);
         p->sweep_valid = false;

@@ -508,6 +508,119 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Prox-GVI (proxgd/): per-factor Bures-Wasserstein JKO epilogues.  One thread per factor.
+//   GH factors   (ProxGVIFactorizedBaseGH.h:153-161): b_k = P E1 = R e1,  S_k = P E2 P - P E0 = R (e2 - e0 I) R
+//                from the xi-space moments K1 left in `raw`; cost = E0 (not divided by the temperature, :250-257)
+//   linear       (ProxGVIFactorizedLinear.h:95-104): b_k = Lambda^T Kinv (Lambda mu - Psi mu_t), S_k = Lambda^T Kinv Lambda
+//   both:        Vdmu = -b_k,  Vddmu = (inv(Sigma+) - P)/eta  (bw_jko, smallmat.h)
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(64) k_prox_gh(int n, double eta, const double* __restrict__ raw, const double* __restrict__ SR,
+                                                double* __restrict__ fcost, double* __restrict__ fVdmu,
+                                                double* __restrict__ fVdd) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    constexpr int NOUT = 1 + DIM + DIM * DIM;
+    const double* r = raw + (size_t)f * NOUT;
+    Mat<DIM> S, R, E, Sig, P, Sk, T, Vdd;
+    mat_load<DIM>(S, SR + (size_t)f * 2 * DIM * DIM);
+    mat_load<DIM>(R, SR + (size_t)f * 2 * DIM * DIM + DIM * DIM);
+    const double e0 = r[0];
+#pragma unroll
+    for (int j = 0; j < DIM; ++j)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) E(i, j) = r[1 + DIM + i + j * DIM] - (i == j ? e0 : 0.0);
+    mm<DIM>(T, R, E);
+    mm<DIM>(Sk, T, R);
+    symmetrize<DIM>(Sk);
+    mm<DIM>(Sig, S, S);
+    mm<DIM>(P, R, R);
+    bw_jko<DIM>(Vdd, Sig, P, Sk, eta);
+    mat_store<DIM>(fVdd + (size_t)f * DIM * DIM, Vdd);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+        double b = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) b = fma(R(i, k), r[1 + k], b);
+        fVdmu[(size_t)f * DIM + i] = -b;
+    }
+    fcost[f] = e0;
+}
+
+template <int DIM, int M, int SD>
+__global__ void __launch_bounds__(64) k_prox_linear(const LinearArgs a, double eta, double* __restrict__ fVdd) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n) return;
+    const size_t n = (size_t)a.n;
+    const int s = a.start[f];
+    const double* L = a.Lambda + f;
+    const double* Ki = a.Kinv + f;
+    double mu[DIM], r[M], kr[M];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) mu[k] = a.mu[(size_t)s * SD + k];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double v = -a.psi[(size_t)i * n + f];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) v = fma(L[(size_t)(i + k * M) * n], mu[k], v);
+        r[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) v = fma(Ki[(size_t)(i + k * M) * n], r[k], v);
+        kr[i] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) v = fma(L[(size_t)(i + k * M) * n], kr[i], v);
+        a.fVdmu[(size_t)f * DIM + k] = -v;  // Vdmu = -b_k
+    }
+    Mat<DIM> Sk, Sig, P, Vdd;
+    {
+        const double* A = a.A + f;
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = i; j < DIM; ++j) {
+                const double av = A[(size_t)e * n];
+                Sk(i, j) = av;
+                Sk(j, i) = av;
+                ++e;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < DIM; ++j)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            const int bi = i / SD, ii = i % SD, bj = j / SD, jj = j % SD;
+            Sig(i, j) = (bi == bj)  ? a.covD[(size_t)(s + bi) * SD * SD + ii + jj * SD]
+                        : (bi < bj) ? a.covO[(size_t)s * SD * SD + ii + jj * SD]
+                                    : a.covO[(size_t)s * SD * SD + jj + ii * SD];
+        }
+    symmetrize<DIM>(Sig);
+    LogDetAcc ld;
+    spd_inverse<DIM>(P, Sig, ld);
+    bw_jko<DIM>(Vdd, Sig, P, Sk, eta);
+    mat_store<DIM>(fVdd + (size_t)f * DIM * DIM, Vdd);
+}
+
+// Prox candidate (ProxGVIGH::onestep_linesearch, proxgd/ProxGVI-GH-impl.h:24-43): mu' = mu + a dmu, Lambda' = Lambda + a dLambda
+__global__ void k_candidate_add(size_t nmu, size_t nD, size_t nO, double alpha, const double* __restrict__ mu,
+                                const double* __restrict__ dmu, const double* __restrict__ LD, const double* __restrict__ LO,
+                                const double* __restrict__ dD, const double* __restrict__ dO, double* __restrict__ mu_c,
+                                double* __restrict__ LD_c, double* __restrict__ LO_c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nmu) mu_c[i] = mu[i] + alpha * dmu[i];
+    if (i < nD) LD_c[i] = LD[i] + alpha * dD[i];
+    if (i < nO) LO_c[i] = LO[i] + alpha * dO[i];
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: assembly (local2joint_* + the sums of NGDGH::compute_gradients, ngd/NGD-GH-impl.h:36-57).
 // Every output element gathers, in a fixed order, the factor blocks that touch its state:
 //   Vdmu[s]   = sum of fVdmu pieces;   VD[s] = KlinD[s] + sum of diag pieces;   VO[s] = KlinO[s] + off pieces

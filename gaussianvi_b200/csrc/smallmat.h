@@ -343,4 +343,40 @@ GVI_HD void sqrt_and_invsqrt(Mat<N>& S, Mat<N>& R, const Mat<N>& Sigma) {
         }
 }
 
+// Bures-Wasserstein JKO step of one factor (BW_JKO, proxgd/ProxGVIFactorizedBaseGH.h:64-113 and
+// proxgd/ProxGVIFactorizedLinear.h:118-157):
+//   M = I - eta S_k;  H = M Sigma M^T;  Sigma+ = H/2 + eta I + sqrtm(H (H + 4 eta I))/2;  Vddmu = (inv(Sigma+) - P)/eta.
+// H (H + 4 eta I) is a polynomial in the symmetric H, so with H = V diag(lam) V^T everything is diagonal in V:
+//   inv(Sigma+) = V diag(1 / (lam/2 + eta + sqrt(lam^2 + 4 eta lam)/2)) V^T     (one Jacobi decomposition, no Schur form).
+template <int N>
+GVI_HD void bw_jko(Mat<N>& Vdd, const Mat<N>& Sigma, const Mat<N>& P, const Mat<N>& Sk, double eta) {
+    Mat<N> M, T, H, V;
+    Vec<N> lam;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) M(i, j) = (i == j ? 1.0 : 0.0) - eta * Sk(i, j);
+    mm<N>(T, M, Sigma);
+    mmt<N>(H, T, M);
+    symmetrize<N>(H);
+    jacobi_eig<N>(H, V, lam);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double l = lam(k);
+        const double disc = fma(l, l, 4.0 * eta * l);
+        lam(k) = 1.0 / (0.5 * l + eta + 0.5 * sqrt(disc > 0.0 ? disc : 0.0));
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j; i < N; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) v = fma(V(i, k) * V(j, k), lam(k), v);
+            const double r = (v - 0.5 * (P(i, j) + P(j, i))) / eta;
+            Vdd(i, j) = r;
+            Vdd(j, i) = r;
+        }
+}
+
 }  // namespace gvib200

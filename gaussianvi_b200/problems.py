@@ -56,8 +56,10 @@ class ProblemSpec:
         return sum(len(g.start) for g in self.groups)
 
 
-def build_device_problem(ctx: "capi.Context", spec: ProblemSpec, set_state: bool = True) -> "capi.Problem":
+def build_device_problem(ctx: "capi.Context", spec: ProblemSpec, set_state: bool = True, prox: bool = False) -> "capi.Problem":
     p = capi.Problem(ctx, spec.S, spec.d)
+    if prox:
+        p.set_option("prox", 1)
     if spec.sdf is not None:
         data, origin, cell = spec.sdf
         p.set_planar_sdf(data, origin, cell)
@@ -410,3 +412,32 @@ def merge_segments(segs: List[ProblemSpec]) -> ProblemSpec:
             out.groups.append(cat([g for g, _ in lst], [r for _, r in lst]))
     out.meta = dict(segs[0].meta, name="cfg3_merged")
     return out
+
+
+def make_cfg4(S: int = 10_001, delta_t: float = 1.0, deg: int = 4, closed_form: bool = False) -> ProblemSpec:
+    """Prox-GVI shape of BASELINE.json configs[3]: 3-D point robot, state 6 (position + velocity), S states, S - 1
+    two-state factors of dim 12 evaluated by sparse GH degree `deg` (2649 nodes at deg 4) with psi = cost_linear_gp
+    (exactly integrable: closed_form=True builds the same problem from ProxFactorizedLinear factors -- a built-in KAT),
+    fixed priors at both ends.  Delta t = 1, Lambda_0 = 50 I and eta base 0.1 put the reference's factor-wise JKO
+    iteration in a regime where every iteration accepts a trial and the cost decreases (with the demo's base 0.75 it
+    exhausts its back-tracking every iteration; probed with the oracle)."""
+    d, dim = 6, 3
+    start = np.array([-2.0, -1.0, 0.5, 0.0, 0.0, 0.0])
+    goal = np.array([2.0, 1.5, 1.0, 0.0, 0.0, 0.0])
+    tt = np.linspace(0.0, 1.0, S)[:, None]
+    mu0 = start[None, :] * (1 - tt) + goal[None, :] * tt
+    mu0[:, 3:] = (goal[:3] - start[:3]) / (max(S - 1, 1) * delta_t)
+    spec = ProblemSpec(S=S, d=d)
+    spec.groups.append(fixed_prior_group([0, S - 1], np.stack([start, goal]), 0.5 * np.eye(d), d))
+    lin = minacc_group(S, 0.8 * np.eye(dim), delta_t)
+    if closed_form:
+        spec.groups.append(lin)
+    else:
+        Phi = -lin.Lambda[0][:, :d]
+        rec = np.concatenate([np.tile(Phi.T.reshape(-1), (S - 1, 1)), np.tile(lin.Kinv[0].T.reshape(-1), (S - 1, 1))], axis=1)
+        spec.groups.append(GhGroupSpec(capi.COST_LINEAR_GP, 2 * d, deg, lin.start, rec, 1.0, 10.0))
+    spec.mu0 = mu0.reshape(-1)
+    spec.prec0_D = np.tile(50.0 * np.eye(d), (S, 1, 1))
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(name="cfg4", step_size_base=0.1, niters=5, niters_lowtemp=1 << 30)
+    return spec

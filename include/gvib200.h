@@ -180,6 +180,12 @@ int gvib200_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iter
                      int* n_done, double* fac_costs_trace, double* mean_trace);
 /* one iteration (same code path; iteration index is kept inside the problem for the temperature switch) */
 int gvib200_ngd_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats);
+/* Prox-GVI (proxgd/ProxGVI-GH-impl.h:124-205 over ProxGVIFactorizedBaseGH / ProxFactorizedLinear): per-factor
+   Bures-Wasserstein JKO steps instead of natural gradients, no linear solve, step eta = step_size_base^B, the last
+   candidate is accepted when back-tracking is exhausted.  The problem must have been given
+   gvib200_problem_set_option(prob, "prox", 1) BEFORE finalize.  Single GPU. */
+int gvib200_prox_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats);
+int gvib200_prox_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats, int* n_done);
 /* reset the iteration counter / temperature phase (keeps the state) */
 int gvib200_reset_schedule(gvib200_problem* prob);
 
@@ -220,7 +226,7 @@ typedef struct {
 } gvib200_info;
 int gvib200_problem_info(gvib200_problem* prob, gvib200_info* out);
 
-/* tuning / test switches.  "generic_k1" = 1: run the generic node-loop moment kernel even where the sign-group kernel
+/* switches.  "prox" = 1 (before finalize): a Prox-GVI problem.  "generic_k1" = 1: run the generic node-loop moment kernel even where the sign-group kernel
    (dimension <= 4) applies; both must give the same moments to rounding. */
 int gvib200_problem_set_option(gvib200_problem* prob, const char* name, int value);
 

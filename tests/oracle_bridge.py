@@ -72,3 +72,25 @@ def build_oracle(spec, fast=True, faithful_linear=False, solver="direct", niters
     if spec.mu0 is not None:
         opt.set_initial_values(spec.mu0, o.BlockTri(np.array(spec.prec0_D, float), np.array(spec.prec0_O, float).reshape(max(spec.S - 1, 0), spec.d, spec.d)))
     return opt
+
+
+def build_oracle_prox(spec, fast=True, niters=None):
+    """Prox-GVI twin (oracle ProxGVIGH over ProxGHFactor / ProxLinearFactor) of a ProblemSpec."""
+    factors = []
+    for g in spec.groups:
+        if isinstance(g, problems.GhGroupSpec):
+            shared = psi_for_group(spec, g, 0) if g.kind in (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC) else None
+            for i, s in enumerate(g.start):
+                psi = shared if shared is not None else psi_for_group(spec, g, i)
+                factors.append(o.ProxGHFactor(g.dim, spec.d, g.deg, psi, int(s), g.T, g.T_high, fast=fast))
+        else:
+            n = len(g.start)
+            Cv = np.broadcast_to(np.asarray(g.C, float), (n,))
+            for i, s in enumerate(g.start):
+                m = o.LinearModel(g.Lambda[i], g.Psi[i], g.mu_t[i], g.Kinv[i], float(Cv[i]))
+                factors.append(o.ProxLinearFactor(g.Lambda.shape[2], spec.d, m, int(s), g.T, g.T_high, faithful=False))
+    opt = o.ProxGVIGH(factors, spec.d, spec.S, niters or spec.meta.get("niters", 5))
+    opt.set_step_size_base(spec.meta.get("step_size_base", 0.55))
+    opt.set_niter_low_temperature(spec.meta.get("niters_lowtemp", 10))
+    opt.set_initial_values(spec.mu0, o.BlockTri(np.array(spec.prec0_D, float), np.array(spec.prec0_O, float).reshape(max(spec.S - 1, 0), spec.d, spec.d)))
+    return opt

@@ -27,7 +27,7 @@ def compile_example(name):
     return out
 
 
-@pytest.mark.parametrize("name", ["1d_example", "planar_chain"])
+@pytest.mark.parametrize("name", ["1d_example", "planar_chain", "1d_example_proxGVI"])
 def test_facade_examples_compile(name):
     assert compile_example(name).exists()
 
@@ -51,6 +51,18 @@ def test_facade_1d_example_golden_trace():
     rows = np.array([[float(x) for x in line.split()] for line in out.strip().splitlines()])
     assert rows.shape == (10, 5)
     g = lambda n: np.loadtxt(GOLDEN / "ref_1d" / f"{n}.csv", delimiter=",").reshape(-1)
+    for col, name in ((1, "mean"), (2, "cov"), (3, "precision"), (4, "cost")):
+        ref = g(name)
+        assert np.abs(rows[:, col] - ref).max() / np.abs(ref).max() < 1e-10, name
+
+
+@pytest.mark.gpu
+def test_facade_1d_prox_example_golden_trace():
+    exe = compile_example("1d_example_proxGVI")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    rows = np.array([[float(x) for x in line.split()] for line in out.strip().splitlines()])
+    assert rows.shape == (10, 5)
+    g = lambda n: np.loadtxt(GOLDEN / "ref_1d_proxgvi" / f"{n}.csv", delimiter=",").reshape(-1)
     for col, name in ((1, "mean"), (2, "cov"), (3, "precision"), (4, "cost")):
         ref = g(name)
         assert np.abs(rows[:, col] - ref).max() / np.abs(ref).max() < 1e-10, name

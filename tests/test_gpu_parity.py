@@ -296,3 +296,61 @@ def test_sign_group_kernel_matches_generic_kernel(gpu_ctx, dim, deg, kind):
         assert rel(a0[f], b0[f]) < 1e-11 and rel(a2[f], b2[f]) < 1e-11
         assert np.abs(a1[f] - b1[f]).max() < 1e-11 * max(np.abs(b1[f]).max(), np.sqrt(np.abs(b2[f]).max() * abs(b0[f])), 1e-300)
     assert rel(fa, fb) < 1e-11
+
+
+# ---------------------------------------------------------------- Prox-GVI (a15)
+def test_prox_1d_golden_trace(gpu_ctx):
+    """src/1d_example_proxGVI.cpp against the reference's committed outputs data/1d_proxgvi/*.csv (10 iterations)."""
+    spec = problems.make_cfg1()
+    p = problems.build_device_problem(gpu_ctx, spec, prox=True)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = 0.75
+    opts.niters_lowtemp = 10
+    g = lambda n: np.loadtxt(GOLDEN / "ref_1d_proxgvi" / f"{n}.csv", delimiter=",").reshape(-1)
+    means, covs, precs, costs = [], [], [], []
+    for it in range(10):
+        means.append(p.mean()[0])
+        covs.append(p.covariance()[0][0, 0, 0])
+        precs.append(p.precision()[0][0, 0, 0])
+        st = p.prox_iterate(opts)
+        costs.append(st.cost)
+    assert rel(means, g("mean")) < 1e-10
+    assert rel(covs, g("cov")) < 1e-10
+    assert rel(precs, g("precision")) < 1e-10
+    assert rel(costs, g("cost")) < 1e-10
+
+
+@pytest.mark.parametrize("closed_form", [False, True])
+def test_prox_cfg4_small_matches_oracle(gpu_ctx, closed_form):
+    """cfg4 generator at a size the oracle reaches: dim-12 two-state factors, sparse GH degree 4 (2649 nodes)."""
+    spec = problems.make_cfg4(S=7, closed_form=closed_form)
+    p = problems.build_device_problem(gpu_ctx, spec, prox=True)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = spec.meta["step_size_base"]
+    opts.niters_lowtemp = spec.meta["niters_lowtemp"]
+    ref = ob.build_oracle_prox(spec, niters=4)
+    recs = ref.optimize()
+    stats = [p.prox_iterate(opts) for _ in range(4)]
+    for s, r in zip(stats, recs):
+        assert s.n_backtrack == r.n_backtrack and bool(s.accepted) == r.accepted
+        assert abs(s.cost - r.cost) < 1e-8 * max(1.0, abs(r.cost))
+    cD, cO = p.covariance()
+    e_mu = rel(p.mean(), ref.mean())
+    e_cov = rel(np.concatenate([cD.reshape(-1), cO.reshape(-1)]), np.concatenate([ref.cov.D.reshape(-1), ref.cov.O.reshape(-1)]))
+    print("prox cfg4 S=7 closed_form", closed_form, "rel err mu", e_mu, "cov", e_cov)
+    assert e_mu < FINAL_TOL and e_cov < FINAL_TOL
+
+
+def test_prox_quadrature_equals_closed_form(gpu_ctx):
+    """cost_linear_gp is exactly integrable: the GH factors and ProxFactorizedLinear give the same iteration."""
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = 0.1
+    opts.niters_lowtemp = 1 << 30
+    out = []
+    for closed_form in (False, True):
+        spec = problems.make_cfg4(S=12, closed_form=closed_form)
+        p = problems.build_device_problem(gpu_ctx, spec, prox=True)
+        st = [p.prox_iterate(opts) for _ in range(3)]
+        out.append((p.mean(), [s.cost for s in st]))
+    assert rel(out[0][0], out[1][0]) < 1e-9
+    assert rel(out[0][1], out[1][1]) < 1e-9

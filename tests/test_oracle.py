@@ -202,3 +202,27 @@ def test_cfg3_small_is_spd_and_accepts_first_trial():
     assert all(r.accepted and r.n_backtrack == 0 for r in recs)
     assert np.linalg.eigvalsh(opt.Vddmu.dense()).min() > 0
     assert all(recs[i + 1].cost < recs[i].cost for i in range(len(recs) - 1))
+
+
+# ------------------------------------------------------------------ Prox-GVI (a15)
+def test_prox_1d_golden_trace():
+    """src/1d_example_proxGVI.cpp against data/1d_proxgvi/*.csv: 10 Prox-GVI iterations, all printed digits."""
+    f = o.ProxGHFactor(1, 1, 10, o.cost_1d_stereo, 0, 1.0, 10.0, fast=False)
+    opt = o.ProxGVIGH([f], 1, 1, 10)
+    opt.set_step_size_base(0.75)
+    opt.set_niter_low_temperature(10)
+    opt.set_initial_values(np.array([20.0]), o.BlockTri(np.array([[[1.0 / 9.0]]]), np.zeros((0, 1, 1))))
+    recs = opt.optimize()
+    g = lambda n: np.loadtxt(GOLDEN / "ref_1d_proxgvi" / f"{n}.csv", delimiter=",").reshape(-1)
+    assert rel([r.mean[0] for r in recs], g("mean")) < 1e-11
+    assert rel([r.cov.D[0, 0, 0] for r in recs], g("cov")) < 1e-11
+    assert rel([r.prec.D[0, 0, 0] for r in recs], g("precision")) < 1e-11
+    assert rel([r.cost for r in recs], g("cost")) < 1e-11
+    assert rel([r.factor_costs[0] for r in recs], g("factor_costs")) < 1e-11
+
+
+def test_prox_cfg4_regime_decreases_cost():
+    spec = problems.make_cfg4(S=6, closed_form=True)
+    recs = ob.build_oracle_prox(spec, niters=5).optimize()
+    assert all(r.accepted for r in recs)
+    assert all(recs[i + 1].cost < recs[i].cost for i in range(len(recs) - 1))
