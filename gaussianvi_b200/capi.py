@@ -263,6 +263,17 @@ class Problem:
         Oc = None if (prec_O is None or self.S == 1) else _blocks_to_c(prec_O)
         _check(self.lib.gvib200_set_state(self.h, _dp(mu_c), _dp(Dc), _dp(Oc)))
 
+    # ---- raw variants: caller-owned buffers already in the C-ABI layout (column-major blocks), no marshalling; with
+    # pinned buffers the library's cudaMemcpyAsync is a single DMA ----
+    def set_state_raw(self, mu: np.ndarray, prec_diag: np.ndarray, prec_off: Optional[np.ndarray]):
+        _check(self.lib.gvib200_set_state(self.h, _dp(mu), _dp(prec_diag), _dp(prec_off) if self.S > 1 else None))
+
+    def get_mean_into(self, mu: np.ndarray):
+        _check(self.lib.gvib200_get_mean(self.h, _dp(mu)))
+
+    def get_cov_blocks_into(self, diag: np.ndarray, off: np.ndarray):
+        _check(self.lib.gvib200_get_cov_blocks(self.h, _dp(diag), _dp(off)))
+
     def mean(self) -> np.ndarray:
         mu = np.zeros(self.S * self.d)
         _check(self.lib.gvib200_get_mean(self.h, _dp(mu)))

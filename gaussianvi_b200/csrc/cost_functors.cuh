@@ -15,6 +15,7 @@ namespace gvib200 {
 
 // functors without long-latency loads evaluate everything in begin()
 #define GVIB200_SIMPLE_FUNCTOR_INTERFACE()                                                        \
+    static constexpr bool PREMAP = false;                                                         \
     struct Pending {                                                                              \
         double psi;                                                                               \
     };                                                                                            \
@@ -65,18 +66,27 @@ struct CostPlanarHinge {
         const double cell = 1.0 / inv_cell;
         return lo[0] >= ox + cell && hi[0] <= xmax - cell && lo[1] >= oy + cell && hi[1] <= ymax - cell;
     }
+    // PREMAP: the sign-group kernel applies the affine map x -> cell coordinates once per factor (to mu and to the
+    // columns of S) instead of once per sigma point, and hands cell coordinates to begin_mapped()
+    static constexpr bool PREMAP = true;
+    __device__ __forceinline__ double pre_mu(int r, double v) const { return fma(v, inv_cell, r == 0 ? cx0 : cy0); }
+    __device__ __forceinline__ double pre_scale(int) const { return inv_cell; }
     template <bool FAST>
-    __device__ __forceinline__ Pending begin(const double* x, int) const {
+    __device__ __forceinline__ Pending begin(const double* x, int f) const {
         double xin = x[0], yin = x[1];
         if (!FAST) {
             xin = fmin(fmax(xin, ox), xmax);
             yin = fmin(fmax(yin, oy), ymax);
         }
-        double col = fma(xin, inv_cell, cx0);
-        double row = fma(yin, inv_cell, cy0);
-        if (!FAST) {  // x == origin may round to -tiny: keep floor() at cell 0
-            col = fmax(col, 0.0);
-            row = fmax(row, 0.0);
+        const double cr[2] = {fma(xin, inv_cell, cx0), fma(yin, inv_cell, cy0)};
+        return begin_mapped<FAST>(cr, f);
+    }
+    template <bool FAST>
+    __device__ __forceinline__ Pending begin_mapped(const double* cr, int) const {
+        double col = cr[0], row = cr[1];
+        if (!FAST) {  // clamp to the field (convertPoint2toCell, helpers/CudaOperation.h:61-81) in cell coordinates
+            col = fmin(fmax(col, 0.0), (double)(cols - 1));
+            row = fmin(fmax(row, 0.0), (double)(rows - 1));
         }
         // floor() by adding 1.5*2^52 with round-toward-minus-infinity (one DADD.RM); the low word of the
         // sum is the integer cell index, the difference back is floor(col) as a double.

@@ -536,7 +536,7 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     a.raw = raw;
     for (int c = 0; c < 4; ++c) a.ximax[c] = g.table->ximax[c];
     a.cost = cost;
-    const int grid = cdiv(g.n, 32);
+    const int grid = cdiv(g.n, K1S_FPC);
     const size_t smem = (size_t)g.table->sym.ndata * sizeof(double);
     static bool configured = false;  // per instantiation
     if (!configured) {

@@ -29,7 +29,8 @@
 namespace gvib200 {
 
 constexpr int K1S_NPART = 8;          // lanes per factor
-constexpr int K1S_THREADS = 256;      // 8 warps x 4 factors = 32 factors per CTA
+constexpr int K1S_THREADS = 256;      // 8 warps x 4 factors per CTA (10 x 2 and 6 x 3 CTAs per SM spill and run ~10 % slower)
+constexpr int K1S_FPC = K1S_THREADS / K1S_NPART;  // factors per CTA
 constexpr int K1S_MAX_DATA = 6144;    // doubles of the staged table (48 KB of shared memory)
 
 // entries of one group with K non-zero coordinates c_0 < ... < c_{K-1}:
@@ -155,7 +156,8 @@ __device__ __forceinline__ void k1s_eval_unit(double (&psi)[1 << KF], const doub
                 }
             }
             pat[q] = p;
-            pend[q] = cost.template begin<FAST>(x, f);
+            if constexpr (Cost::PREMAP) pend[q] = cost.template begin_mapped<FAST>(x, f);
+            else pend[q] = cost.template begin<FAST>(x, f);
         }
 #pragma unroll
         for (int q = 0; q < NB; ++q) psi[pat[q]] = cost.finish(pend[q]);
@@ -246,7 +248,9 @@ __device__ __forceinline__ void k1s_run_part(SymAcc<DIM>& acc, const SymTable& t
                                              const double* __restrict__ sS, const double (&mu)[Cost::XD], const Cost& cost,
                                              int f) {
     {  // the node at the origin: weight w0 for part 0, zero for the other parts
-        typename Cost::Pending pd = cost.template begin<FAST>(mu, f);
+        typename Cost::Pending pd;
+        if constexpr (Cost::PREMAP) pd = cost.template begin_mapped<FAST>(mu, f);
+        else pd = cost.template begin<FAST>(mu, f);
         acc.e0 = fma(stab[tab.moff[0] + part], cost.finish(pd), acc.e0);
     }
 #pragma unroll 1
@@ -277,13 +281,13 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     constexpr int NOUT = 1 + DIM + DIM * DIM;
     extern __shared__ __align__(16) double stab[];          // the staged table, tab.ndata doubles
     __shared__ double sSall[XD * DIM * K1S_THREADS];        // S rows, [(r*DIM + c)][thread]
-    __shared__ double tot[NOUT][33];                        // totals per factor: e0, e1, e2 (full, mirrored)
+    __shared__ double tot[NOUT][K1S_FPC + 1];                        // totals per factor: e0, e1, e2 (full, mirrored)
     __shared__ __align__(8) uint64_t mbar;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int part = lane & (K1S_NPART - 1);
     const int fl = warp * 4 + (lane >> 3);  // factor of this lane within the CTA, 0..31
-    const int f0 = blockIdx.x * 32;
+    const int f0 = blockIdx.x * K1S_FPC;
     const int f = min(f0 + fl, a.n - 1);    // tail lanes recompute the last factor and do not store
     // ---- stage the table: one TMA bulk copy, completion on an mbarrier ----
     if (threadIdx.x == 0) {
@@ -317,6 +321,14 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
             hi[r] = mu[r] + rad;
         }
         fast = __all_sync(0xffffffffu, a.cost.fast_ok(lo, hi));
+        if constexpr (Cost::PREMAP) {  // from here on mu and S live in the functor's mapped coordinates
+#pragma unroll
+            for (int r = 0; r < XD; ++r) {
+                mu[r] = a.cost.pre_mu(r, mu[r]);
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) sSall[(r * DIM + c) * K1S_THREADS + threadIdx.x] *= a.cost.pre_scale(r);
+            }
+        }
     }
     __syncthreads();  // mbarrier initialised (and visible) before anybody waits on it
     {
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     }
     __syncthreads();
     // ---- epilogue: Vdmu = R e1 / T, Vddmu = R (e2 - e0 I) R / T (upper triangle mirrored), cost = e0 / T ----
-    const int nf = min(32, a.n - f0);
+    const int nf = min(K1S_FPC, a.n - f0);
     if (!FULL) {
         if (threadIdx.x < nf) a.fcost[f0 + threadIdx.x] = tot[0][threadIdx.x] / __ldg(a.T + f0 + threadIdx.x);
         return;

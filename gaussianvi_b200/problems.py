@@ -441,3 +441,33 @@ def make_cfg4(S: int = 10_001, delta_t: float = 1.0, deg: int = 4, closed_form: 
     spec.prec0_O = np.zeros((S - 1, d, d))
     spec.meta = dict(name="cfg4", step_size_base=0.1, niters=5, niters_lowtemp=1 << 30)
     return spec
+
+
+def make_cfg5(n_problems: int = 64, N: int = 1000, first_seed: int = 1000, **kw) -> ProblemSpec:
+    """BASELINE.json configs[4]: independent copies of the cfg3 generator (seeds first_seed, first_seed + 1, ...) batched
+    as ONE block-diagonal chain: problem b occupies the states [b (N+2), (b+1)(N+2)) and nothing couples consecutive
+    problems (the off-diagonal block between them stays zero), so the chain engine, the sweeps and the assembly run over
+    the whole batch in single launches.  The line search is shared by the batch (one step size, the summed cost); as long
+    as every problem would accept the same trial this is exactly the independent iteration."""
+    subs = [make_cfg3(N=N, seed=first_seed + b, **kw) for b in range(n_problems)]
+    Sb = subs[0].S
+    d = subs[0].d
+    out = ProblemSpec(S=Sb * n_problems, d=d)
+    out.sdf = subs[0].sdf
+    out.mu0 = np.concatenate([s.mu0 for s in subs])
+    out.prec0_D = np.concatenate([s.prec0_D for s in subs])
+    out.prec0_O = np.zeros((out.S - 1, d, d))
+    for b, s in enumerate(subs):
+        out.prec0_O[b * Sb:b * Sb + Sb - 1] = s.prec0_O
+    for gi in range(len(subs[0].groups)):
+        g0 = subs[0].groups[gi]
+        starts = np.concatenate([s.groups[gi].start + b * Sb for b, s in enumerate(subs)]).astype(np.int32)
+        if isinstance(g0, GhGroupSpec):
+            out.groups.append(GhGroupSpec(g0.kind, g0.dim, g0.deg, starts, g0.params, g0.T, g0.T_high))
+        else:
+            cat = lambda name: np.concatenate([getattr(s.groups[gi], name) for s in subs])
+            out.groups.append(LinGroupSpec(start=starts, Lambda=cat("Lambda"), Psi=cat("Psi"), mu_t=cat("mu_t"), Kinv=cat("Kinv"),
+                                           C=np.concatenate([np.broadcast_to(np.asarray(s.groups[gi].C, float), (len(s.groups[gi].start),)) for s in subs]),
+                                           T=g0.T, T_high=g0.T_high))
+    out.meta = dict(subs[0].meta, name="cfg5", n_problems=n_problems, states_per_problem=Sb)
+    return out

@@ -354,3 +354,26 @@ def test_prox_quadrature_equals_closed_form(gpu_ctx):
         out.append((p.mean(), [s.cost for s in st]))
     assert rel(out[0][0], out[1][0]) < 1e-9
     assert rel(out[0][1], out[1][1]) < 1e-9
+
+
+# ---------------------------------------------------------------- cfg5: independent problems batched as one chain
+def test_cfg5_batch_matches_independent_oracle_runs(gpu_ctx):
+    nb, N, niters = 5, 40, 6
+    spec = problems.make_cfg5(n_problems=nb, N=N)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    stats = p.optimize(niters, opts)
+    assert all(s.accepted and s.n_backtrack == 0 for s in stats)
+    mu = p.mean().reshape(nb, -1)
+    cD, _ = p.covariance()
+    Sb = spec.meta["states_per_problem"]
+    total_cost = 0.0
+    for b in range(nb):
+        sub = problems.make_cfg3(N=N, seed=1000 + b)
+        ref = ob.build_oracle(sub, niters=niters)
+        recs = ref.optimize()
+        assert all(r.accepted and r.n_backtrack == 0 for r in recs)
+        total_cost += recs[-1].cost
+        assert rel(mu[b], ref.mean()) < FINAL_TOL
+        assert rel(cD[b * Sb:(b + 1) * Sb], ref.cov.D) < FINAL_TOL
+    assert abs(stats[-1].cost - total_cost) < 1e-8 * abs(total_cost)
