@@ -42,8 +42,9 @@ inline int cr_max_tile_links(size_t smem_bytes) {
 // tiles_hint: how many tile CTAs the device runs at once (SM count); smem_bytes: dynamic shared memory per CTA.
 // force_T > 0 fixes the tile size (tests); force_T < 0 forces the top-only path.  Returns false when the chain is too
 // long for a two-level plan on this device.
+// allow_mid: the separator chain may exceed what the top kernel holds (the caller runs a mid level over it).
 template <int D>
-inline bool cr_make_plan(CrPlan& p, int n, int tiles_hint, size_t smem_bytes, int force_T = 0) {
+inline bool cr_make_plan(CrPlan& p, int n, int tiles_hint, size_t smem_bytes, int force_T = 0, bool allow_mid = false) {
     constexpr size_t DD = (size_t)D * D;
     p = CrPlan();
     p.n = n;
@@ -64,12 +65,13 @@ inline bool cr_make_plan(CrPlan& p, int n, int tiles_hint, size_t smem_bytes, in
             T = (n - 1 + K - 1) / K;
             if (T < 32) T = 32;
             if (T > t_max) T = t_max;
+            if (allow_mid && (n - 1 + T - 1) / T + 1 > top_max) T = t_max;  // long chain: the largest tiles that fit
         }
         if (T < 2) T = 2;
         if (T > t_max) return false;
         p.T = T;
         p.K = (n - 1 + T - 1) / T;
-        if (p.K + 1 > top_max) return false;
+        if (p.K + 1 > top_max && !allow_mid) return false;
     }
     size_t off = 0;
     auto take = [&](size_t cnt) {
@@ -97,7 +99,7 @@ inline bool cr_make_plan(CrPlan& p, int n, int tiles_hint, size_t smem_bytes, in
     p.ld_count = p.K + 1;
     p.ws_doubles = off;
     p.tile_smem_bytes = p.K > 0 ? cr_tile_doubles<D>(p.T) * sizeof(double) : 0;
-    p.top_smem_bytes = cr_top_doubles<D>(p.K > 0 ? p.K + 1 : n) * sizeof(double);
+    p.top_smem_bytes = (p.K + 1 > top_max) ? 0 : cr_top_doubles<D>(p.K > 0 ? p.K + 1 : n) * sizeof(double);
     return true;
 }
 

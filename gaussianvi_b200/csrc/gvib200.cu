@@ -243,6 +243,7 @@ struct gvib200_problem {
     // multi-GPU (ctx->world > 1): the mid level (one "tile" over this rank's separator chain), the boundary exchange
     // buffers and the redundantly solved chain of rank boundaries -- one set per workspace slot
     CrPlan plan_mid, plan_top;
+    bool three_level = false;                  // single GPU, very long chain: plan_mid tiles the separator chain
     double* ws_mid[2] = {nullptr, nullptr};
     double* ws_top[2] = {nullptr, nullptr};
     double* dist_buf[2] = {nullptr, nullptr};  // D1 | O1 | g1 | send | recv | Dt | Ot | gt | xt | cDt | cOt
@@ -432,6 +433,27 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     return check_launch("chain_pass_dist");
 }
 
+// Single GPU, chains too long for two levels: the separator chain (K + 1 nodes) is itself tiled (plan_mid), its top
+// results seed the tiles of the first level.
+template <int D, bool RHS, bool SELINV>
+static int chain_pass_3level(gvib200_problem* p, int slot, const CrArgs<D>& a, double* d_logdet) {
+    const CrPlan &pl = p->plan, &pm = p->plan_mid;
+    const DistLayout L = dist_layout(D, pl.K, 1);
+    double* buf = p->dist_buf[slot];
+    CrArgs<D> mid = cr_bind<D>(pm, p->ws_mid[slot], buf + L.D1, buf + L.O1, RHS ? buf + L.g1 : nullptr, a.tx, a.tD, a.tO, a.notspd);
+    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), std::min(64, cdiv(pl.K + 1, 16)), 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
+    if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
+    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pm.top_smem_bytes, mid);
+    if (pm.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
+    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    if (d_logdet) {
+        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)pm.ld_count, mid.ld, nullptr, 0.0, p->scal + 6);
+        LAUNCH(p, KC_SUM, k_sum3, 1, 256, 0, (size_t)pl.K, a.ld, p->scal + 6, nullptr, d_logdet);
+    }
+    return check_launch("chain_pass_3level");
+}
+
 // optional candidate fusions of a chain pass (see CrArgs)
 struct ChainFuse {
     const double *Dg2 = nullptr, *Og2 = nullptr;
@@ -465,6 +487,7 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
         configured = true;
     }
     if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
+    if (p->three_level) return chain_pass_3level<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
     if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
@@ -1320,6 +1343,11 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             force_T = std::max(2, std::min((S - 1 + K - 1) / K, cr_max_tile_links<D_>(smem)));                 \
         }                                                                                                      \
         ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, force_T);                                    \
+        if (!ok && P == 1) { /* long chain: three levels (tiles -> tiles over the separator chain -> top) */   \
+            ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, 0, true) &&                              \
+                 cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, p->ctx->sm_count, smem);                         \
+            p->three_level = ok;                                                                               \
+        }                                                                                                      \
         if (ok && P > 1)                                                                                       \
             ok = cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, 1, smem, std::max(p->plan.K, 2)) &&              \
                  cr_make_plan<D_>(p->plan_top, P + 1, 1, smem, -1);                                            \
@@ -1334,6 +1362,13 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     for (int i = 0; i < 2; ++i) {
         TRY(dev_alloc(&p->ws[i], p->plan.ws_doubles + 16));
         CUDA_TRY(cudaMemsetAsync(p->ws[i], 0, (p->plan.ws_doubles + 16) * sizeof(double), p->stream));
+        if (p->three_level) {
+            const DistLayout L = dist_layout(d, p->plan.K, 1);
+            TRY(dev_alloc(&p->ws_mid[i], p->plan_mid.ws_doubles + 16));
+            TRY(dev_alloc(&p->dist_buf[i], L.total + 16));
+            CUDA_TRY(cudaMemsetAsync(p->ws_mid[i], 0, (p->plan_mid.ws_doubles + 16) * sizeof(double), p->stream));
+            CUDA_TRY(cudaMemsetAsync(p->dist_buf[i], 0, (L.total + 16) * sizeof(double), p->stream));
+        }
         if (p->ctx->world > 1) {
             const DistLayout L = dist_layout(d, p->plan.K, p->ctx->world);
             TRY(dev_alloc(&p->ws_mid[i], p->plan_mid.ws_doubles + 16));

@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
 // multi-GPU glue kernels (single small CTAs; the arithmetic is in bt_cr.h)
 template <int D, bool RHS>
 __global__ void k_cr_sum_level(const CrArgs<D> a, double* D1, double* O1, double* g1) {
-    cr_sum_level<D, RHS>(a, D1, O1, g1, threadIdx.x, blockDim.x);
+    cr_sum_level<D, RHS>(a, D1, O1, g1, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 template <int D, bool RHS>
 __global__ void k_cr_pack_boundary(const CrArgs<D> mid, double* rec) {

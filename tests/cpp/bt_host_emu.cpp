@@ -65,68 +65,69 @@ void emu_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_bas
     }
 }
 
+template <int D, bool RHS>
+void emu_tile_forward(const CrArgs<D>& a, bool& ok);
+template <int D, bool RHS, bool SELINV>
+void emu_tile_backward(const CrArgs<D>& a);
+
+// k_cr_top replayed: a.K == 0 works on the chain itself, else on the separator system of `a`
+template <int D, bool RHS, bool SELINV>
+void emu_top(const CrArgs<D>& a, bool& ok) {
+    const int nt = (a.K == 0) ? a.n : a.K + 1;
+    CrGeom gm;
+    cr_make_geom(gm, nt - 1);
+    std::vector<double> sm(cr_top_doubles<D>(nt), 0.0);
+    CrView<D> v = cr_make_view<D>(sm.data(), nt);
+    const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
+    CrRec<D> rec;
+    rec.G = v.g + (size_t)D * v.NS;
+    rec.H = rec.G + cr_rec_capacity(nrec, D * D);
+    rec.Dinv = rec.H + cr_rec_capacity(nrec, D * D);
+    rec.y = rec.Dinv + cr_rec_capacity(nrec, D * D);
+    cr_top_load<D, RHS>(a, v, gm, 0, 1);
+    double ld = 0.0;
+    ok = emu_forward_levels<D, RHS>(v, rec, 0, gm, ld) && ok;
+    LogDetAcc l2;
+    ok = cr_top2<D, RHS, SELINV>(v, gm.T, l2) && ok;
+    ld += l2.value();
+    emu_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
+    if (a.K == 0) cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, 0, 1);
+    else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, 0, 1);
+    a.ld[a.K] = ld;
+}
+
 template <int D, bool RHS, bool SELINV>
 int emu_cr_pass(int n, const double* D0, const double* O0, const double* rhs, double* x, double* cD, double* cO,
                 double* logdet, int force_T, size_t smem_bytes) {
-    CrPlan plan;
-    if (!cr_make_plan<D>(plan, n, 148, smem_bytes, force_T)) return -1;
+    constexpr int DD = D * D;
+    CrPlan plan, pmid;
+    bool three = false;
+    if (!cr_make_plan<D>(plan, n, 148, smem_bytes, force_T)) {  // same fallback as gvib200_problem_finalize
+        if (force_T != 0) return -1;
+        if (!cr_make_plan<D>(plan, n, 148, smem_bytes, 0, true) || !cr_make_plan<D>(pmid, plan.K + 1, 148, smem_bytes)) return -1;
+        three = true;
+    }
     std::vector<double> ws(plan.ws_doubles + 16, 0.0);
     int notspd = 0;
     CrArgs<D> a = cr_bind<D>(plan, ws.data(), D0, O0, rhs, x, cD, cO, &notspd);
     bool ok = true;
-    // k_cr_tile_forward
-    for (int tile = 0; tile < a.K; ++tile) {
-        const int n0 = tile * a.T;
-        const int Tk = (a.T < a.n - 1 - n0) ? a.T : a.n - 1 - n0;
-        CrGeom gm;
-        cr_make_geom(gm, Tk);
-        std::vector<double> sm(cr_tile_doubles<D>(a.T), 0.0);
-        CrView<D> v = cr_make_view<D>(sm.data(), a.T + 1);
-        cr_tile_load<D, RHS>(a, v, gm, n0, 0, 1);
-        double ld = 0.0;
-        ok = emu_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld) && ok;
-        cr_tile_store_reduced<D, RHS>(a, v, gm, tile, n0, 0, 1);
-        a.ld[tile] = ld;
-    }
-    // k_cr_top
-    {
-        const int nt = (a.K == 0) ? a.n : a.K + 1;
-        CrGeom gm;
-        cr_make_geom(gm, nt - 1);
-        std::vector<double> sm(cr_top_doubles<D>(nt), 0.0);
-        CrView<D> v = cr_make_view<D>(sm.data(), nt);
-        const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
-        CrRec<D> rec;
-        rec.G = v.g + (size_t)D * v.NS;
-        rec.H = rec.G + cr_rec_capacity(nrec, D * D);
-        rec.Dinv = rec.H + cr_rec_capacity(nrec, D * D);
-        rec.y = rec.Dinv + cr_rec_capacity(nrec, D * D);
-        cr_top_load<D, RHS>(a, v, gm, 0, 1);
-        double ld = 0.0;
-        ok = emu_forward_levels<D, RHS>(v, rec, 0, gm, ld) && ok;
-        LogDetAcc l2;
-        ok = cr_top2<D, RHS, SELINV>(v, gm.T, l2) && ok;
-        ld += l2.value();
-        emu_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
-        if (a.K == 0) cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.x, a.cD, a.cO, 0, 0, 1);
-        else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, 0, 1);
-        a.ld[a.K] = ld;
-    }
-    // k_cr_tile_backward
-    for (int tile = 0; tile < a.K; ++tile) {
-        const int n0 = tile * a.T;
-        const int Tk = (a.T < a.n - 1 - n0) ? a.T : a.n - 1 - n0;
-        CrGeom gm;
-        cr_make_geom(gm, Tk);
-        std::vector<double> sm(cr_tile_doubles<D>(a.T), 0.0);
-        CrView<D> v = cr_make_view<D>(sm.data(), a.T + 1);
-        cr_tile_seed<D, RHS, SELINV>(a, v, tile, 0, 1);
-        emu_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm);
-        const bool last = (tile == a.K - 1);
-        cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, 0, 1);
-    }
     double ld = 0.0;
-    for (int i = 0; i < plan.ld_count; ++i) ld += a.ld[i];
+    emu_tile_forward<D, RHS>(a, ok);
+    if (three) {
+        std::vector<double> wsm(pmid.ws_doubles + 16, 0.0), D1((size_t)(plan.K + 1) * DD), O1((size_t)(plan.K + 1) * DD),
+            g1((size_t)(plan.K + 1) * D);
+        cr_sum_level<D, RHS>(a, D1.data(), O1.data(), g1.data(), 0, 1);
+        CrArgs<D> mid = cr_bind<D>(pmid, wsm.data(), D1.data(), O1.data(), RHS ? g1.data() : nullptr, a.tx, a.tD, a.tO, &notspd);
+        emu_tile_forward<D, RHS>(mid, ok);
+        emu_top<D, RHS, SELINV>(mid, ok);
+        emu_tile_backward<D, RHS, SELINV>(mid);
+        for (int i = 0; i < pmid.ld_count; ++i) ld += mid.ld[i];
+        for (int i = 0; i < plan.K; ++i) ld += a.ld[i];
+    } else {
+        emu_top<D, RHS, SELINV>(a, ok);
+        for (int i = 0; i < plan.ld_count; ++i) ld += a.ld[i];
+    }
+    emu_tile_backward<D, RHS, SELINV>(a);
     if (logdet) *logdet = ld;
     return (ok && !notspd) ? 0 : -4;
 }

@@ -140,11 +140,26 @@ def test_cr_engine_reports_indefinite_and_too_long():
     assert rc == -4
     rc, *_ = emu_cr_run(50, 2, D, O, np.zeros(100), -1)
     assert rc == -4
-    # a chain that does not fit a two-level plan within the shared-memory budget is refused, not mangled
+    # a forced tile size whose separator chain does not fit the top is refused, not mangled
     rng = np.random.default_rng(0)
     Dl, Ol = rand_spd_chain(rng, 4000, 4)
-    rc, *_ = emu_cr_run(4000, 4, Dl, Ol, np.zeros(16000), 0, smem=16 * 1024)
+    rc, *_ = emu_cr_run(4000, 4, Dl, Ol, np.zeros(16000), 2, smem=16 * 1024)
     assert rc == -1
+
+
+@pytest.mark.parametrize("S,d,smem", [(4000, 4, 16 * 1024), (20000, 2, 8 * 1024), (3000, 6, 48 * 1024)])
+def test_cr_engine_three_levels(S, d, smem):
+    """Chains too long for two levels (here: a tiny shared-memory budget) go through a tiled separator chain."""
+    rng = np.random.default_rng(S + d)
+    D, O = rand_spd_chain(rng, S, d)
+    rhs = rng.standard_normal(S * d)
+    rc, x, cD, cO, ld = emu_cr_run(S, d, D, O, rhs, 0, smem=smem)
+    assert rc == 0
+    bt = o.BlockTri(D, O)
+    ref = o.inverse_gbp(bt)
+    assert rel(x, o.block_solve(bt, rhs)) < 1e-10
+    assert rel(cD, ref.D) < 1e-10 and rel(cO, ref.O) < 1e-10
+    assert abs(ld - o.logdet(bt)) < 1e-9 * max(1.0, abs(ld))
 
 
 # ------------------------------------------------------------------ multi-GPU chain pass replayed on the host

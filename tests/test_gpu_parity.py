@@ -377,3 +377,32 @@ def test_cfg5_batch_matches_independent_oracle_runs(gpu_ctx):
         assert rel(mu[b], ref.mean()) < FINAL_TOL
         assert rel(cD[b * Sb:(b + 1) * Sb], ref.cov.D) < FINAL_TOL
     assert abs(stats[-1].cost - total_cost) < 1e-8 * abs(total_cost)
+
+
+# ---------------------------------------------------------------- very long chains: three-level engine
+def test_three_level_chain_engine_long_chain(gpu_ctx):
+    """S = 700k states (beyond the two-level plan): selected inverse vs the C oracle's inverse_GBP, solve by residual."""
+    import ctypes as C
+    import gvi_oracle_c as oc
+    rng = np.random.default_rng(9)
+    S, d = 700_000, 4
+    A = rng.standard_normal((S, d, d))
+    D = 0.1 * A @ np.transpose(A, (0, 2, 1)) + 3.0 * np.eye(d)
+    O = 0.3 * rng.standard_normal((S - 1, d, d))
+    rhs = rng.standard_normal(S * d)
+    cD, cO, ld = gpu_ctx.selected_inverse(D, O)
+    x, _ = gpu_ctx.blocktri_solve(D, O, rhs)
+    # residual of the solve: block-tridiagonal matvec
+    xs = x.reshape(S, d)
+    r = np.einsum("sij,sj->si", D, xs)
+    r[:-1] += np.einsum("sij,sj->si", O, xs[1:])
+    r[1:] += np.einsum("sji,sj->si", O, xs[:-1])
+    assert np.abs(r.reshape(-1) - rhs).max() < 1e-9 * np.abs(rhs).max()
+    # selected inverse against the C restatement of inverse_GBP
+    Dc = np.ascontiguousarray(np.transpose(D, (0, 2, 1)))
+    Oc = np.ascontiguousarray(np.transpose(O, (0, 2, 1)))
+    rD, rO = np.zeros_like(Dc), np.zeros((S, d, d))
+    dp = C.POINTER(C.c_double)
+    assert oc.lib().orc_inverse_gbp(S, d, Dc.ctypes.data_as(dp), Oc.ctypes.data_as(dp), rD.ctypes.data_as(dp), rO.ctypes.data_as(dp)) == 0
+    assert rel(cD, np.transpose(rD, (0, 2, 1))) < 1e-11
+    assert rel(cO, np.transpose(rO[:S - 1], (0, 2, 1))) < 1e-11
