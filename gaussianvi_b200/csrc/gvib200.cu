@@ -1342,7 +1342,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             K = std::max(1, std::min(K, S - 1));                                                               \
             force_T = std::max(2, std::min((S - 1 + K - 1) / K, cr_max_tile_links<D_>(smem)));                 \
         }                                                                                                      \
-        ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, force_T);                                    \
+        /* two SMs are left free of tile CTAs: the single-CTA top kernels of the two concurrent passes run there */ \
+        ok = cr_make_plan<D_>(p->plan, S, std::max(1, p->ctx->sm_count - 2), smem, force_T);                   \
         if (!ok && P == 1) { /* long chain: three levels (tiles -> tiles over the separator chain -> top) */   \
             ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, 0, true) &&                              \
                  cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, p->ctx->sm_count, smem);                         \
@@ -1668,7 +1669,8 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     while (true) {
         step *= o.backtrack_ratio;
         const int w = 1 - p->cur;
-        const bool fork = (p->ctx->world == 1);  // one communicator: collectives stay in issue order on one stream
+        static const bool no_fork_env = getenv("GVIB200_NO_FORK") != nullptr;  // development switch
+        const bool fork = (p->ctx->world == 1) && !no_fork_env;  // one communicator: collectives stay in issue order on one stream
         if (cnt == 0 && !fork) {
             ChainFuse fi;
             fi.Dg2 = p->VD;

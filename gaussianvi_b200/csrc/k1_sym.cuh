@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     extern __shared__ __align__(16) double stab[];          // the staged table, tab.ndata doubles
     __shared__ double sSall[XD * DIM * K1S_THREADS];        // S rows, [(r*DIM + c)][thread]
     __shared__ double tot[NOUT][K1S_FPC + 1];                        // totals per factor: e0, e1, e2 (full, mirrored)
+    __shared__ double sR[DIM * DIM + 1][K1S_FPC + 1];                // R = Sigma^-1/2 and 1/T of the CTA's factors, fetched up
+                                                                     // front so that the epilogue does not wait on HBM
     __shared__ __align__(8) uint64_t mbar;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -305,6 +307,10 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     bool fast;
     {
         const double* Sp = a.SR + (size_t)f * 2 * DIM * DIM;
+        if (FULL) {  // the 8 lanes of a factor share the loads of R (and 1/T)
+            for (int e = part; e < DIM * DIM; e += K1S_NPART) sR[e][fl] = __ldg(Sp + DIM * DIM + e);
+        }
+        if (part == 0) sR[DIM * DIM][fl] = 1.0 / __ldg(a.T + f);
         const double* mp = a.mu + (size_t)a.start[f] * a.state_dim;
         double lo[XD], hi[XD];
 #pragma unroll
@@ -383,15 +389,14 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     // ---- epilogue: Vdmu = R e1 / T, Vddmu = R (e2 - e0 I) R / T (upper triangle mirrored), cost = e0 / T ----
     const int nf = min(K1S_FPC, a.n - f0);
     if (!FULL) {
-        if (threadIdx.x < nf) a.fcost[f0 + threadIdx.x] = tot[0][threadIdx.x] / __ldg(a.T + f0 + threadIdx.x);
+        if (threadIdx.x < nf) a.fcost[f0 + threadIdx.x] = tot[0][threadIdx.x] * sR[DIM * DIM][threadIdx.x];
         return;
     }
     constexpr int NEP = DIM * DIM + DIM + 1;
     for (int idx = threadIdx.x; idx < nf * NEP; idx += K1S_THREADS) {
         const int l = idx / NEP, e = idx - l * NEP;
         const int ff = f0 + l;
-        const double invT = 1.0 / __ldg(a.T + ff);
-        const double* R = a.SR + (size_t)ff * 2 * DIM * DIM + DIM * DIM;
+        const double invT = sR[DIM * DIM][l];
         const double e0 = tot[0][l];
         if (e < DIM * DIM) {
             int i = e % DIM, j = e / DIM;
@@ -405,15 +410,15 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
                 double t = 0.0;
                 for (int aa = 0; aa < DIM; ++aa) {
                     const double m = tot[1 + DIM + aa + b * DIM][l] - (aa == b ? e0 : 0.0);
-                    t = fma(__ldg(R + aa + i * DIM), m, t);
+                    t = fma(sR[aa + i * DIM][l], m, t);
                 }
-                v = fma(t, __ldg(R + b + j * DIM), v);
+                v = fma(t, sR[b + j * DIM][l], v);
             }
             a.fVdd[(size_t)ff * DIM * DIM + e] = v * invT;
         } else if (e < DIM * DIM + DIM) {
             const int i = e - DIM * DIM;
             double v = 0.0;
-            for (int aa = 0; aa < DIM; ++aa) v = fma(__ldg(R + i + aa * DIM), tot[1 + aa][l], v);
+            for (int aa = 0; aa < DIM; ++aa) v = fma(sR[i + aa * DIM][l], tot[1 + aa][l], v);
             a.fVdmu[(size_t)ff * DIM + i] = v * invT;
         } else {
             a.fcost[ff] = e0 * invT;
