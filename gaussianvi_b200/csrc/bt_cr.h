@@ -327,6 +327,7 @@ struct CrArgs {
     double *tD, *tO, *tx;  // results of the top on the separators: [K+1][DD], [K][DD], [K+1][D]
     double *x, *cD, *cO;   // outputs: solution [n][D]; selected inverse diag [n][DD], off [n-1][DD]
     double* ld;            // [K + 1] partial log determinants (tiles, then the top)
+    double* ldout;         // optional: the top kernel also writes the total log determinant (sum of ld[0..K]) here
     int* notspd;
     // optional fusions of the line-search candidate (NGDGH::onestep_linesearch, ngd/NGD-GH-impl.h:129-148):
     //   Dg2 != null: the system is Dg + alpha (Dg2 - Dg) (same for the off-diagonal blocks) and is also written to

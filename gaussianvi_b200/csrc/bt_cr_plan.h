@@ -131,6 +131,7 @@ inline CrArgs<D> cr_bind(const CrPlan& p, double* ws, const double* Dg, const do
     a.cD = cD;
     a.cO = cO;
     a.ld = ws + p.ld;
+    a.ldout = nullptr;
     a.notspd = notspd;
     a.Dg2 = nullptr;
     a.Og2 = nullptr;

@@ -196,6 +196,7 @@ static const char* const KC_NAMES[KC_COUNT] = {"k_moments<full>", "k_moments<cos
 struct ProfRec {
     int kc;
     cudaEvent_t a, b;
+    bool side;  // launched on the side stream
 };
 
 struct FactorRef {
@@ -229,6 +230,7 @@ struct gvib200_problem {
     double* scal = nullptr;    // device scalars: [0..1] logdet cur/cand slots, [2..3] cost slots, [4] tmp
     double* h_scal = nullptr;  // pinned mirror
     int* d_flag = nullptr;     // not-SPD flag
+    unsigned* d_counter = nullptr;  // arrival counter of k_total (zero between launches)
     int* h_flag = nullptr;
     double *Vdmu = nullptr, *VD = nullptr, *VO = nullptr, *rhs = nullptr, *dmu = nullptr;
     double *KlinD = nullptr, *KlinO = nullptr;
@@ -250,7 +252,7 @@ struct gvib200_problem {
     double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr;
     // schedule (GVIGH::optimize locals)
     int iter = 0;
     bool is_lowtemp = true, converged = false;
@@ -306,6 +308,7 @@ static inline void prof_begin(gvib200_problem* p, int kc) {
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, p->ls);
+    r.side = (p->ls != p->stream);
     p->prof.push_back(r);
 }
 static inline void prof_end(gvib200_problem* p) { cudaEventRecord(p->prof.back().b, p->ls); }
@@ -488,10 +491,10 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
     }
     if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (p->three_level) return chain_pass_3level<D, RHS, SELINV>(p, slot, a, d_logdet);
+    a.ldout = d_logdet;  // the top kernel adds up the partial log determinants itself
     if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
     if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
-    if (d_logdet) LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)pl.ld_count, a.ld, nullptr, 0.0, d_logdet);
     return check_launch("chain_pass");
 }
 
@@ -792,7 +795,7 @@ static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
 }
 
 // prologue + sweep over every factor at (mu, cov) of buffer `which`
-static int run_sweep(gvib200_problem* p, int which, bool prologue, bool full, bool want_raw) {
+static int run_sweep(gvib200_problem* p, int which, bool prologue, bool full, bool want_raw, bool with_linear = true) {
     SweepTarget t{p->mu[which], p->CD[which], p->CO[which], which};
     for (auto& g : p->gh) {
         double* raw = nullptr;
@@ -802,7 +805,7 @@ static int run_sweep(gvib200_problem* p, int which, bool prologue, bool full, bo
         }
         TRY(gh_group_dispatch(p, g, t, prologue, true, full, raw));
     }
-    TRY(run_linear(p, t, full));
+    if (with_linear) TRY(run_linear(p, t, full));
     return 0;
 }
 
@@ -829,8 +832,8 @@ static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
-        LAUNCH(p, KC_SUM, k_partial_sum, nb, 256, 0, n, p->fcost[which], p->partial);
-        LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)nb, p->partial, p->scal + which, 0.5, p->scal + 2 + which);
+        LAUNCH(p, KC_SUM, k_total, nb, 256, 0, n, p->fcost[which], p->partial, p->d_counter, p->scal + which, 0.5,
+               p->scal + 2 + which);
     } else {
         LAUNCH(p, KC_SUM, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
     }
@@ -969,9 +972,15 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     p->S = num_states;
     p->d = dim_state;
     CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&p->stream2, cudaStreamNonBlocking, prio_hi));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
     p->ls = p->stream;
     *out = p.release();
     return 0;
@@ -992,7 +1001,7 @@ static void free_problem(gvib200_problem* p) {
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
-    F(p->scal); F(p->partial); F(p->d_flag); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
+    F(p->scal); F(p->partial); F(p->d_flag); F(p->d_counter); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
     F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
     for (int i = 0; i < 2; ++i) {
         F(p->ws_mid[i]); F(p->ws_top[i]); F(p->dist_buf[i]);
@@ -1009,6 +1018,8 @@ static void free_problem(gvib200_problem* p) {
     if (p->h_flag) cudaFreeHost(p->h_flag);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->ev_pro) cudaEventDestroy(p->ev_pro);
+    if (p->ev_mu) cudaEventDestroy(p->ev_mu);
     if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream) cudaStreamDestroy(p->stream);
 }
@@ -1319,6 +1330,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     CUDA_TRY(cudaMallocHost((void**)&p->h_scal, 8 * sizeof(double)));
     TRY(dev_alloc(&p->d_flag, 2));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), p->stream));
+    TRY(dev_alloc(&p->d_counter, 1));
+    CUDA_TRY(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), p->stream));
     CUDA_TRY(cudaMallocHost((void**)&p->h_flag, 2 * sizeof(int)));
     TRY(dev_alloc(&p->Vdmu, (size_t)S * d));
     TRY(dev_alloc(&p->rhs, (size_t)S * d));
@@ -1334,6 +1347,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
         const size_t smem = p->ctx->smem_optin - 4096;
         const int P = p->ctx->world;
         bool ok = false;
+        int tiles_per_sm = 1;
+        if (const char* e = getenv("GVIB200_TILES_PER_SM")) tiles_per_sm = std::max(1, atoi(e));
 #define PLAN_CASE(D_)                                                                                          \
     case D_: {                                                                                                 \
         int force_T = 0;                                                                                       \
@@ -1343,7 +1358,7 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             force_T = std::max(2, std::min((S - 1 + K - 1) / K, cr_max_tile_links<D_>(smem)));                 \
         }                                                                                                      \
         /* two SMs are left free of tile CTAs: the single-CTA top kernels of the two concurrent passes run there */ \
-        ok = cr_make_plan<D_>(p->plan, S, std::max(1, p->ctx->sm_count - 2), smem, force_T);                   \
+        ok = cr_make_plan<D_>(p->plan, S, tiles_per_sm * std::max(1, p->ctx->sm_count - 2), smem, force_T);    \
         if (!ok && P == 1) { /* long chain: three levels (tiles -> tiles over the separator chain -> top) */   \
             ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, 0, true) &&                              \
                  cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, p->ctx->sm_count, smem);                         \
@@ -1669,6 +1684,7 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     while (true) {
         step *= o.backtrack_ratio;
         const int w = 1 - p->cur;
+        bool linear_forked = false;
         static const bool no_fork_env = getenv("GVIB200_NO_FORK") != nullptr;  // development switch
         const bool fork = (p->ctx->world == 1) && !no_fork_env;  // one communicator: collectives stay in issue order on one stream
         if (cnt == 0 && !fork) {
@@ -1687,34 +1703,50 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &fs));
             p->grads_valid = true;
         } else if (cnt == 0) {
+            // Critical path on the main stream: selected inverse of the candidate precision -> factor marginals ->
+            // quadrature sweep.  The candidate precision Lambda + a (Vddmu - Lambda) is formed while the selected
+            // inverse loads its tiles, the candidate mean mu + a dmu while the solve stores dmu: no separate candidate
+            // kernel.  The side stream (higher priority, so that its CTAs are placed as soon as SMs free up) carries what
+            // is off the critical path: the dmu solve and the closed-form linear factors of the candidate (HBM bound),
+            // which run underneath the FP64-bound quadrature sweep.
             CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
-            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
-            // the candidate precision Lambda + a (Vddmu - Lambda) is formed while the selected inverse loads its tiles,
-            // the candidate mean mu + a dmu while the solve stores dmu: no separate candidate kernel on this path
-            p->ls = p->stream2;
             ChainFuse fi;
             fi.Dg2 = p->VD;
             fi.Og2 = p->VO;
             fi.alpha = step;
             fi.Dout = p->LD[w];
             fi.Oout = p->LO[w];
-            int rc = do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[w], p->CO[w], p->scal + w, 1, &fi);
-            if (rc == 0) rc = run_prologue_only(p, w);  // factor marginals of the candidate, still on the side stream
-            p->ls = p->stream;
-            if (rc != 0) return rc;
-            CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
+            TRY(do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[w], p->CO[w], p->scal + w, 1, &fi));
+            CUDA_TRY(cudaEventRecord(p->ev_pro, p->stream));  // candidate covariance blocks are complete
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
+            p->ls = p->stream2;
             ChainFuse fs;
             fs.xbase = p->mu[p->cur];
             fs.xalpha = step;
             fs.xout = p->mu[w];
-            TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &fs));
+            int rc = do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &fs);
+            p->ls = p->stream;
+            if (rc != 0) return rc;
             p->grads_valid = true;
-            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+            CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));  // candidate mean is complete
+            TRY(run_prologue_only(p, w));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
+            p->ls = p->stream2;
+            {
+                SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
+                rc = run_linear(p, t, o.reuse_accepted_sweep != 0);
+            }
+            p->ls = p->stream;
+            if (rc != 0) return rc;
+            CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_mu, 0));
+            linear_forked = true;
         } else {
             TRY(launch_candidate(p, step, 3));
             TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1));
         }
-        TRY(run_sweep(p, w, cnt != 0, o.reuse_accepted_sweep != 0, false));
+        TRY(run_sweep(p, w, cnt != 0, o.reuse_accepted_sweep != 0, false, !linear_forked));
+        if (linear_forked) CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
         run_total(p, w);
@@ -2092,14 +2124,26 @@ extern "C" int gvib200_profile_end(gvib200_problem* p, gvib200_profile* out) {
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     std::memset(out, 0, sizeof(*out));
     out->n_classes = KC_COUNT;
+    // development aid: GVIB200_TIMELINE=<file> writes one line per launch (class, stream, start and end in ms since
+    // the first launch of the profiled region)
+    FILE* tl = nullptr;
+    if (const char* tlp = getenv("GVIB200_TIMELINE")) tl = fopen(tlp, "w");
     for (auto& r : p->prof) {
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (tl) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, p->prof.front().a, r.a);
+            fprintf(tl, "%s %d %.4f %.4f\n", KC_NAMES[r.kc], r.side ? 1 : 0, t0, t0 + ms);
+        }
         out->count[r.kc]++;
         out->ms[r.kc] += ms;
+    }
+    for (auto& r : p->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
+    if (tl) fclose(tl);
     p->prof.clear();
     return 0;
 }

@@ -692,6 +692,46 @@ __global__ void k_partial_sum(size_t n, const double* __restrict__ v, double* __
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// Deterministic one-launch total: block b reduces a fixed contiguous slice of v into partial[b]; the block that
+// finishes last (device counter) adds the partials in index order: out[0] = sum(v) + half * extra[0].
+__global__ void __launch_bounds__(256) k_total(size_t n, const double* __restrict__ v, double* __restrict__ partial,
+                                               unsigned* __restrict__ counter, const double* __restrict__ extra, double half,
+                                               double* __restrict__ out) {
+    __shared__ double sh[256];
+    __shared__ bool is_last;
+    const size_t per = (n + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per;
+    const size_t hi = (lo + per < n) ? lo + per : n;
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0];
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(partial + i);
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sh[0] + (extra ? half * extra[0] : 0.0);
+        *counter = 0u;  // ready for the next launch
+    }
+}
+
 // Deterministic single-block sum: out[0] = sum(v[0..n)) (+ half * extra[0] if extra != null)
 __global__ void k_sum(size_t n, const double* __restrict__ v, const double* __restrict__ extra, double half,
                       double* __restrict__ out) {
@@ -808,6 +848,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
     else cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, threadIdx.x, blockDim.x);
     const double s = cr_block_sum(ld.value(), red);
     if (threadIdx.x == 0) a.ld[a.K] = s;
+    if (a.ldout != nullptr) {  // total log determinant: the tiles' partial sums are complete (previous launch)
+        __syncthreads();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < a.K; i += blockDim.x) t += a.ld[i];
+        const double tot = cr_block_sum(t, red);
+        if (threadIdx.x == 0) a.ldout[0] = tot + s;
+    }
     if (!ok) *a.notspd = 1;
 }
 

@@ -249,6 +249,77 @@ GVI_HD bool spd_inverse(Mat<N>& Ainv, const Mat<N>& A, LogDetAcc& ld) {
 // columns.  Used for the symmetric PSD square root S = V sqrt(lam) V^T that the reference takes with
 // SelfAdjointEigenSolver::operatorSqrt() (quadrature/SparseGaussHermite.h:231-243) and for
 // P_k = Sigma_k^-1 (gvibase/GVIFactorizedBase.h:111-114).
+// Branch-free Jacobi rotation parameters for the pivot (app, aqq, apq): t = tan, c = cos, s = sin of the angle that
+// annihilates apq.  One square root, one division, one reciprocal square root:
+//   t = sign(d) b / (|d| + sqrt(d^2 + b^2)),  d = aqq - app, b = 2 apq   (the smaller root of t^2 + 2 theta t - 1 = 0)
+GVI_HD void jacobi_angle(double app, double aqq, double apq, double& t, double& c, double& s) {
+    const double d = aqq - app, b = 2.0 * apq;
+    const bool tiny = fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq));  // the rotation would not change app / aqq at all
+    const double den = fabs(d) + sqrt(fma(d, d, b * b));
+    t = (tiny || den == 0.0) ? 0.0 : (d >= 0.0 ? b : -b) / den;
+#ifdef __CUDA_ARCH__
+    c = rsqrt(fma(t, t, 1.0));
+#else
+    c = 1.0 / sqrt(fma(t, t, 1.0));
+#endif
+    s = t * c;
+}
+
+template <int N>
+GVI_HD void jacobi_rotate(Mat<N>& A, Mat<N>& V, int p, int q, double t, double c, double s) {
+    const double apq = A(p, q);
+    A(p, p) -= t * apq;
+    A(q, q) += t * apq;
+    A(p, q) = 0.0;
+    A(q, p) = 0.0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        if (r != p && r != q) {
+            const double arp = A(r, p), arq = A(r, q);
+            const double nrp = fma(c, arp, -s * arq);
+            const double nrq = fma(s, arp, c * arq);
+            A(r, p) = nrp;
+            A(p, r) = nrp;
+            A(r, q) = nrq;
+            A(q, r) = nrq;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const double vrp = V(r, p), vrq = V(r, q);
+        V(r, p) = fma(c, vrp, -s * vrq);
+        V(r, q) = fma(s, vrp, c * vrq);
+    }
+}
+
+// N = 4: tournament ordering {(0,1),(2,3)}, {(0,2),(1,3)}, {(0,3),(1,2)} -- the two pivots of a round touch disjoint
+// rows / columns, so their angles come from the same matrix and the two (long, division / square-root bound)
+// dependency chains overlap inside one thread.  Same fixed point and convergence as the cyclic sweep.
+GVI_HD void jacobi_eig4(Mat<4>& A, Mat<4>& V, Vec<4>& lam) {
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            diag += fabs(A(j, j));
+#pragma unroll
+            for (int i = 0; i < j; ++i) off += fabs(A(i, j));
+        }
+        if (off <= 1e-300 || off <= 1e-22 * diag) break;
+#pragma unroll
+        for (int round = 0; round < 3; ++round) {
+            const int p0 = 0, q0 = round + 1;
+            const int p1 = (round == 0) ? 2 : 1, q1 = (round == 2) ? 2 : 3;
+            double t0, c0, s0, t1, c1, s1;
+            jacobi_angle(A(p0, p0), A(q0, q0), A(p0, q0), t0, c0, s0);
+            jacobi_angle(A(p1, p1), A(q1, q1), A(p1, q1), t1, c1, s1);
+            jacobi_rotate<4>(A, V, p0, q0, t0, c0, s0);
+            jacobi_rotate<4>(A, V, p1, q1, t1, c1, s1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lam(j) = A(j, j);
+}
+
 template <int N>
 GVI_HD void jacobi_eig(Mat<N>& A, Mat<N>& V, Vec<N>& lam) {
 #pragma unroll
@@ -257,6 +328,10 @@ GVI_HD void jacobi_eig(Mat<N>& A, Mat<N>& V, Vec<N>& lam) {
         for (int i = 0; i < N; ++i) V(i, j) = (i == j) ? 1.0 : 0.0;
     if (N == 1) {
         lam(0) = A(0, 0);
+        return;
+    }
+    if constexpr (N == 4) {
+        jacobi_eig4(A, V, lam);
         return;
     }
     for (int sweep = 0; sweep < 30; ++sweep) {
