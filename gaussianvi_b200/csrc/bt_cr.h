@@ -50,10 +50,12 @@ GVI_HD void cr_make_geom(CrGeom& g, int T) {
     }
 }
 
-GVI_HD int cr_ctz(int j) {
-    int c = 0;
-    while (((j >> c) & 1) == 0) ++c;
-    return c;
+GVI_HD int cr_ctz(int j) {  // j > 0
+#ifdef __CUDA_ARCH__
+    return __ffs(j) - 1;
+#else
+    return __builtin_ctz((unsigned)j);
+#endif
 }
 
 GVI_HD int cr_slot(const CrGeom& g, int j) {
@@ -125,129 +127,203 @@ GVI_HD void cr_rec_stv(double* base, size_t r, const Vec<D>& v) {
     for (int e = 0; e < D; ++e) base[cr_rec(r, e, D)] = v.a[e];
 }
 
-// what one elimination keeps between its two phases
+// ------------------------------------------------------------------------------------------------------------------
+// Node arithmetic, D workers per node.  Worker c (0 <= c < D) of a node produces column c (forward) or row c (backward)
+// of every block the elimination writes; what it needs beyond that (pivot factor, the full neighbouring blocks) it
+// reads from shared memory or recomputes -- the D workers of a node never exchange values, so the only ordering the
+// caller has to provide are the two phase boundaries documented below.  Per worker this is ~1/D of the block products
+// of a one-thread-per-node elimination: the levels of the reduction are latency bound, so the depth per level is what
+// counts.
+// ------------------------------------------------------------------------------------------------------------------
+template <int D>
+GVI_HD void cr_ld_col(Vec<D>& x, const double* base, int NS, int s, int c) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) x.a[i] = base[(size_t)(i + c * D) * NS + s];
+}
+template <int D>
+GVI_HD void cr_ld_row(Vec<D>& x, const double* base, int NS, int s, int c) {
+#pragma unroll
+    for (int m = 0; m < D; ++m) x.a[m] = base[(size_t)(c + m * D) * NS + s];
+}
+
+// what worker c of an elimination keeps between its two phases
 template <int D>
 struct CrElim {
-    int si, sj, sk;
-    Mat<D> Pi, G, H;
-    Vec<D> y;
+    int si;
+    Mat<D> Pi;         // coupling (i, j)
+    Vec<D> Pirow;      // its row c
+    Vec<D> Gc, Hc, y;  // column c of G and H, all of y
 };
 
-// Forward elimination of node j = (2t+1) 2^l, phase A: pivot inverse, record, Schur update of the RIGHT neighbour
-// (every right neighbour is updated by exactly one elimination of the level, so phase A is race free).
+// Forward elimination of node j = (2t+1) 2^l, phase A: pivot factor, column c of the record, column c of the Schur
+// update of the RIGHT neighbour (every right neighbour is updated by exactly one elimination of the level and phase A
+// only reads blocks of j and the coupling of i, so phase A is race free).
 template <int D, bool RHS>
-GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t,
-                     CrElim<D>& c, LogDetAcc& ld) {
+GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t, int c,
+                     CrElim<D>& el, LogDetAcc& ld) {
     const int j = (2 * t + 1) << l;
     const int i = j - (1 << l);
     const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
-    c.sj = 2 + gm.off[l] + t;
-    c.si = cr_slot(gm, i);
-    c.sk = cr_slot(gm, k);
-    const size_t r = rec_base + (size_t)(c.sj - 2);
-    Mat<D> Dt, Pj, Dinv, Tm;
-    cr_ld<D>(Dt, v.Dn, v.NS, c.sj);
-    cr_ld<D>(c.Pi, v.P, v.NS, c.si);
-    cr_ld<D>(Pj, v.P, v.NS, c.sj);
+    const int sj = 2 + gm.off[l] + t;
+    const int sk = cr_slot(gm, k);
+    el.si = cr_slot(gm, i);
+    const size_t r = rec_base + (size_t)(sj - 2);
+    Mat<D> Dt, Pj, L;
+    Vec<D> Pjc, ec, Dic;
+    double rd[D];
+    cr_ld<D>(Dt, v.Dn, v.NS, sj);
+    cr_ld<D>(Pj, v.P, v.NS, sj);
+    cr_ld<D>(el.Pi, v.P, v.NS, el.si);
+    cr_ld_col<D>(Pjc, v.P, v.NS, sj, c);
+    cr_ld_row<D>(el.Pirow, v.P, v.NS, el.si, c);
     symmetrize<D>(Dt);
-    const bool ok = spd_inverse<D>(Dinv, Dt, ld);
-    mm<D>(c.G, Dinv, Pj);
-    mmt<D>(c.H, Dinv, c.Pi);  // Dinv * Pi^T
-    cr_rec_st<D>(rec.G, r, c.G);
-    cr_rec_st<D>(rec.H, r, c.H);
-    cr_rec_st<D>(rec.Dinv, r, Dinv);
+    LogDetAcc other;  // the pivots count once per node: worker 0 carries them
+    const bool ok = chol_factor<D>(L, rd, Dt, c == 0 ? ld : other);
+#pragma unroll
+    for (int m = 0; m < D; ++m) ec.a[m] = (m == c) ? 1.0 : 0.0;
+    chol_solve<D>(el.Gc, L, rd, Pjc);       // G = Dinv Pj
+    chol_solve<D>(el.Hc, L, rd, el.Pirow);  // H = Dinv Pi^T
+    chol_solve<D>(Dic, L, rd, ec);
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        rec.G[cr_rec(r, m + c * D, D * D)] = el.Gc.a[m];
+        rec.H[cr_rec(r, m + c * D, D * D)] = el.Hc.a[m];
+        rec.Dinv[cr_rec(r, m + c * D, D * D)] = Dic.a[m];
+    }
     // right neighbour: Dn[k] -= Pj^T G
-    mtm<D>(Tm, Pj, c.G);
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) v.Dn[(size_t)e * v.NS + c.sk] -= Tm.a[e];
+    for (int q = 0; q < D; ++q) {
+        double sum = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; ++m) sum = fma(Pj(m, q), el.Gc.a[m], sum);
+        v.Dn[(size_t)(q + c * D) * v.NS + sk] -= sum;
+    }
     if (RHS) {
-        Vec<D> gv, tv;
-        cr_ldv<D>(gv, v.g, v.NS, c.sj);
-        mv<D>(c.y, Dinv, gv);
-        cr_rec_stv<D>(rec.y, r, c.y);
-        mtv<D>(tv, Pj, c.y);
+        Vec<D> gv;
+        cr_ldv<D>(gv, v.g, v.NS, sj);
+        chol_solve<D>(el.y, L, rd, gv);
+        double yc = 0.0, sum = 0.0;
 #pragma unroll
-        for (int e = 0; e < D; ++e) v.g[(size_t)e * v.NS + c.sk] -= tv.a[e];
+        for (int m = 0; m < D; ++m) {
+            yc = (m == c) ? el.y.a[m] : yc;
+            sum = fma(Pjc.a[m], el.y.a[m], sum);
+        }
+        rec.y[cr_rec(r, c, D)] = yc;
+        v.g[(size_t)c * v.NS + sk] -= sum;
     }
     return ok;
 }
 
-// phase B: Schur update of the LEFT neighbour and its new coupling to k (again one writer per node)
+// phase B: column c of the Schur update of the LEFT neighbour and of its new coupling to k (again one writer per
+// element; the old coupling was read in phase A)
 template <int D, bool RHS>
-GVI_HD void cr_fwd_B(const CrView<D>& v, const CrElim<D>& c) {
-    Mat<D> Tm;
-    mm<D>(Tm, c.Pi, c.H);
+GVI_HD void cr_fwd_B(const CrView<D>& v, const CrElim<D>& el, int c) {
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) v.Dn[(size_t)e * v.NS + c.si] -= Tm.a[e];
-    mm<D>(Tm, c.Pi, c.G);
+    for (int q = 0; q < D; ++q) {
+        double sh = 0.0, sg = 0.0;
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) v.P[(size_t)e * v.NS + c.si] = -Tm.a[e];
+        for (int m = 0; m < D; ++m) {
+            sh = fma(el.Pi(q, m), el.Hc.a[m], sh);
+            sg = fma(el.Pi(q, m), el.Gc.a[m], sg);
+        }
+        v.Dn[(size_t)(q + c * D) * v.NS + el.si] -= sh;
+        v.P[(size_t)(q + c * D) * v.NS + el.si] = -sg;
+    }
     if (RHS) {
-        Vec<D> tv;
-        mv<D>(tv, c.Pi, c.y);
+        double sum = 0.0;
 #pragma unroll
-        for (int e = 0; e < D; ++e) v.g[(size_t)e * v.NS + c.si] -= tv.a[e];
+        for (int m = 0; m < D; ++m) sum = fma(el.Pirow.a[m], el.y.a[m], sum);
+        v.g[(size_t)c * v.NS + el.si] -= sum;
     }
 }
 
-// Back substitution of node j at level l: x_j = y_j - G x_k - H x_i (x lives in v.g)
+// Back substitution of node j at level l, component c: x_j = y_j - G x_k - H x_i (x lives in v.g)
 template <int D>
-GVI_HD void cr_bwd_solve(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t) {
+GVI_HD void cr_bwd_solve(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t, int c) {
     const int j = (2 * t + 1) << l;
     const int i = j - (1 << l);
     const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
     const int sj = 2 + gm.off[l] + t, si = cr_slot(gm, i), sk = cr_slot(gm, k);
     const size_t r = rec_base + (size_t)(sj - 2);
-    Mat<D> G, H;
-    Vec<D> xi, xk, y, t1, t2;
-    cr_rec_ld<D>(G, rec.G, r);
-    cr_rec_ld<D>(H, rec.H, r);
-    cr_rec_ldv<D>(y, rec.y, r);
+    Vec<D> xi, xk;
     cr_ldv<D>(xi, v.g, v.NS, si);
     cr_ldv<D>(xk, v.g, v.NS, sk);
-    mv<D>(t1, G, xk);
-    mv<D>(t2, H, xi);
+    double x = rec.y[cr_rec(r, c, D)];
 #pragma unroll
-    for (int e = 0; e < D; ++e) y.a[e] -= t1.a[e] + t2.a[e];
-    cr_stv<D>(v.g, v.NS, sj, y);
+    for (int m = 0; m < D; ++m) {
+        x = fma(-rec.G[cr_rec(r, c + m * D, D * D)], xk.a[m], x);
+        x = fma(-rec.H[cr_rec(r, c + m * D, D * D)], xi.a[m], x);
+    }
+    v.g[(size_t)c * v.NS + sj] = x;
 }
 
-// Takahashi recursion for node j at level l.  On entry v.Dn holds Sigma_ii, Sigma_kk and v.P[si] = Sigma_{i,k};
-// on exit v.Dn[sj] = Sigma_jj, v.P[si] = Sigma_{i,j}, v.P[sj] = Sigma_{j,k}.
+// Takahashi recursion for node j at level l, row c.  On entry v.Dn holds Sigma_ii, Sigma_kk and v.P[si] = Sigma_{i,k};
+// cr_bwd_selinv_compute only reads; after a barrier cr_bwd_selinv_store writes row c of v.Dn[sj] = Sigma_jj and of
+// v.P[sj] = Sigma_{j,k}, and column c of v.P[si] = Sigma_{i,j} (the coupling of i is overwritten: hence the barrier).
 template <int D>
-GVI_HD void cr_bwd_selinv(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t) {
+struct CrSel {
+    int si, sj;
+    Vec<D> jj, jk, ji;  // row c of Sigma_jj, Sigma_jk, Sigma_ji
+};
+
+template <int D>
+GVI_HD void cr_bwd_selinv_compute(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t,
+                                  int c, CrSel<D>& o) {
     const int j = (2 * t + 1) << l;
     const int i = j - (1 << l);
     const int k = (j + (1 << l) < gm.T) ? j + (1 << l) : gm.T;
-    const int sj = 2 + gm.off[l] + t, si = cr_slot(gm, i), sk = cr_slot(gm, k);
-    const size_t r = rec_base + (size_t)(sj - 2);
-    Mat<D> G, H, Dinv, Sii, Skk, Sik, Sjk, Sji, T1, T2;
+    const int sk = cr_slot(gm, k);
+    o.sj = 2 + gm.off[l] + t;
+    o.si = cr_slot(gm, i);
+    const size_t r = rec_base + (size_t)(o.sj - 2);
+    Mat<D> G, H, Sii, Skk, Sik;
+    Vec<D> Gr, Hr;
     cr_rec_ld<D>(G, rec.G, r);
     cr_rec_ld<D>(H, rec.H, r);
-    cr_rec_ld<D>(Dinv, rec.Dinv, r);
-    cr_ld<D>(Sii, v.Dn, v.NS, si);
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        Gr.a[m] = rec.G[cr_rec(r, c + m * D, D * D)];
+        Hr.a[m] = rec.H[cr_rec(r, c + m * D, D * D)];
+        o.jj.a[m] = rec.Dinv[cr_rec(r, c + m * D, D * D)];
+    }
+    cr_ld<D>(Sii, v.Dn, v.NS, o.si);
     cr_ld<D>(Skk, v.Dn, v.NS, sk);
-    cr_ld<D>(Sik, v.P, v.NS, si);
-    // Sigma_{j,k} = -(G Sigma_kk + H Sigma_ik)
-    mm<D>(T1, G, Skk);
-    mm<D>(T2, H, Sik);
+    cr_ld<D>(Sik, v.P, v.NS, o.si);
+    // Sigma_{j,k} = -(G Sigma_kk + H Sigma_ik);  Sigma_{j,i} = -(G Sigma_ik^T + H Sigma_ii)
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) Sjk.a[e] = -(T1.a[e] + T2.a[e]);
-    // Sigma_{j,i} = -(G Sigma_ki + H Sigma_ii),  Sigma_ki = Sigma_ik^T
-    mmt<D>(T1, G, Sik);
-    mm<D>(T2, H, Sii);
+    for (int q = 0; q < D; ++q) {
+        double a = 0.0, b = 0.0;
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) Sji.a[e] = -(T1.a[e] + T2.a[e]);
+        for (int m = 0; m < D; ++m) {
+            a = fma(Gr.a[m], Skk(m, q), a);
+            a = fma(Hr.a[m], Sik(m, q), a);
+            b = fma(Gr.a[m], Sik(q, m), b);
+            b = fma(Hr.a[m], Sii(m, q), b);
+        }
+        o.jk.a[q] = -a;
+        o.ji.a[q] = -b;
+    }
     // Sigma_jj = Dinv - Sigma_jk G^T - Sigma_ji H^T
-    mmt<D>(T1, Sjk, G);
-    mmt<D>(T2, Sji, H);
 #pragma unroll
-    for (int e = 0; e < D * D; ++e) Dinv.a[e] -= T1.a[e] + T2.a[e];
-    symmetrize<D>(Dinv);
-    cr_st<D>(v.Dn, v.NS, sj, Dinv);
-    cr_st<D>(v.P, v.NS, sj, Sjk);
-    mat_transpose<D>(T1, Sji);
-    cr_st<D>(v.P, v.NS, si, T1);
+    for (int q = 0; q < D; ++q) {
+        double a = o.jj.a[q];
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            a = fma(-o.jk.a[m], G(q, m), a);
+            a = fma(-o.ji.a[m], H(q, m), a);
+        }
+        o.jj.a[q] = a;
+    }
+}
+
+template <int D>
+GVI_HD void cr_bwd_selinv_store(const CrView<D>& v, const CrSel<D>& o, int c) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+        v.Dn[(size_t)(c + q * D) * v.NS + o.sj] = o.jj.a[q];
+        v.P[(size_t)(c + q * D) * v.NS + o.sj] = o.jk.a[q];
+        v.P[(size_t)(q + c * D) * v.NS + o.si] = o.ji.a[q];
+    }
 }
 
 // The system left after all levels: nodes 0 and T (slots 0, 1) coupled by P[slot 0]; T == 0: a single node.
@@ -524,7 +600,8 @@ GVI_HD void cr_store_results(const CrView<D>& v, const CrGeom& gm, int count, in
         for (int idx = tid; idx < count * DD; idx += nthreads) {
             const int node = idx / DD, e = idx - node * DD;
             const int s = cr_slot(gm, node);
-            cD[n0 * DD + idx] = v.Dn[(size_t)e * v.NS + s];
+            const int et = (e % D) * D + e / D;  // the rows of a diagonal block come from different workers: symmetrize
+            cD[n0 * DD + idx] = 0.5 * (v.Dn[(size_t)e * v.NS + s] + v.Dn[(size_t)et * v.NS + s]);
             if (node < ncoup) cO[n0 * DD + idx] = v.P[(size_t)e * v.NS + s];
         }
     }

@@ -229,10 +229,18 @@ struct gvib200_problem {
     double* partial = nullptr; // per-block partial sums of the factor costs
     double* scal = nullptr;    // device scalars: [0..1] logdet cur/cand slots, [2..3] cost slots, [4] tmp
     double* h_scal = nullptr;  // pinned mirror
+    double* zc = nullptr;      // mapped pinned memory written by k_total: [0..1] total cost of buffer 0 / 1, [2..3] flags
+    double* zc_dev = nullptr;  // its device address
+    bool zc_ok[2] = {false, false};  // zc[which] is the cost of buffer `which` as it stands on the device
     int* d_flag = nullptr;     // not-SPD flag
     unsigned* d_counter = nullptr;  // arrival counter of k_total (zero between launches)
     int* h_flag = nullptr;
     double *Vdmu = nullptr, *VD = nullptr, *VO = nullptr, *rhs = nullptr, *dmu = nullptr;
+    // second set of assembled gradients: the assembly of a trial's sweep is launched speculatively (before the host
+    // knows whether the trial is accepted) so that the host round trip hides underneath it; swapped in on acceptance
+    double *Vdmu2 = nullptr, *VD2 = nullptr, *VO2 = nullptr, *rhs2 = nullptr;
+    bool asm_valid = false;  // Vdmu / VD / VO / rhs hold the assembly of the sweep at the current state
+    cudaEvent_t ev_host = nullptr;
     double *KlinD = nullptr, *KlinO = nullptr;
     // adjacency
     int *vptr = nullptr, *voff = nullptr, *dptr = nullptr, *doff = nullptr, *dld = nullptr, *optr = nullptr,
@@ -240,6 +248,7 @@ struct gvib200_problem {
     // chain engine (bt_cr.h): one plan, two workspaces so that the dmu solve and the candidate's selected inverse
     // can run concurrently on the two streams
     CrPlan plan;
+    int tile_threads = CR_THREADS;  // threads of a tile CTA (two co-resident tile CTAs per SM run 256 each)
     double* ws[2] = {nullptr, nullptr};
     double* ldsum[2] = {nullptr, nullptr};
     // multi-GPU (ctx->world > 1): the mid level (one "tile" over this rank's separator chain), the boundary exchange
@@ -371,6 +380,7 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
 template <class K>
 static int cr_allow_smem(K kern, size_t bytes) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 
@@ -418,7 +428,7 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     CrArgs<D> top = cr_bind<D>(p->plan_top, p->ws_top[slot], buf + L.Dt, buf + L.Ot, RHS ? buf + L.gt : nullptr, buf + L.xt,
                                buf + L.cDt, buf + L.cOt, a.notspd);
     p->flags_synced = false;
-    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), 1, 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
     LAUNCH(p, KC_OTHER, (k_cr_pack_boundary<D, RHS>), 1, 64, 0, mid, buf + L.send);
@@ -428,7 +438,7 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, p->plan_top.top_smem_bytes, top);
     LAUNCH(p, KC_OTHER, (k_cr_seed_mid<D, RHS, SELINV>), 1, 64, 0, mid, ctx->rank, buf + L.xt, buf + L.cDt, buf + L.cOt);
     LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
-    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     if (d_logdet) {
         // this rank's share of log det: its tiles + its mid tile; the chain of rank boundaries is counted by rank 0 only
         LAUNCH(p, KC_SUM, k_sum3, 1, 256, 0, (size_t)pl.K, a.ld, mid.ld, ctx->rank == 0 ? top.ld : nullptr, d_logdet);
@@ -444,12 +454,12 @@ static int chain_pass_3level(gvib200_problem* p, int slot, const CrArgs<D>& a, d
     const DistLayout L = dist_layout(D, pl.K, 1);
     double* buf = p->dist_buf[slot];
     CrArgs<D> mid = cr_bind<D>(pm, p->ws_mid[slot], buf + L.D1, buf + L.O1, RHS ? buf + L.g1 : nullptr, a.tx, a.tD, a.tO, a.notspd);
-    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), std::min(64, cdiv(pl.K + 1, 16)), 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
     if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pm.top_smem_bytes, mid);
     if (pm.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
-    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     if (d_logdet) {
         LAUNCH(p, KC_SUM, k_sum, 1, 256, 0, (size_t)pm.ld_count, mid.ld, nullptr, 0.0, p->scal + 6);
         LAUNCH(p, KC_SUM, k_sum3, 1, 256, 0, (size_t)pl.K, a.ld, p->scal + 6, nullptr, d_logdet);
@@ -484,17 +494,17 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
     }
     static bool configured = false;  // per instantiation
     if (!configured) {
-        TRY(cr_allow_smem(k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 4096));
-        TRY(cr_allow_smem(k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 4096));
-        TRY(cr_allow_smem(k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 4096));
+        TRY(cr_allow_smem(k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 5120));
+        TRY(cr_allow_smem(k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
+        TRY(cr_allow_smem(k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
         configured = true;
     }
     if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (p->three_level) return chain_pass_3level<D, RHS, SELINV>(p, slot, a, d_logdet);
     a.ldout = d_logdet;  // the top kernel adds up the partial log determinants itself
-    if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
-    if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, CR_THREADS, pl.tile_smem_bytes, a);
+    if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     return check_launch("chain_pass");
 }
 
@@ -832,26 +842,42 @@ static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
+        const bool zc = (p->ctx->world == 1);
         LAUNCH(p, KC_SUM, k_total, nb, 256, 0, n, p->fcost[which], p->partial, p->d_counter, p->scal + which, 0.5,
-               p->scal + 2 + which);
+               p->scal + 2 + which, p->d_flag, zc ? p->zc_dev : nullptr, which);
+        p->zc_ok[which] = zc;
     } else {
         LAUNCH(p, KC_SUM, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
+        p->zc_ok[which] = false;
     }
     dist_reduce(p, p->scal + 2 + which);
 }
 
 template <int D>
-static void launch_assemble(gvib200_problem* p, int which) {
+static void launch_assemble(gvib200_problem* p, int which, bool alt) {
     LAUNCH(p, KC_ASSEMBLE, (k_assemble<D>), cdiv((long long)p->S * D * D, 256), 256, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
-           p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, p->Vdmu, p->VD, p->VO, p->rhs);
+           p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, alt ? p->Vdmu2 : p->Vdmu, alt ? p->VD2 : p->VD,
+           alt ? p->VO2 : p->VO, alt ? p->rhs2 : p->rhs);
 }
 
 // d_flag[0] / d_flag[1]: not-SPD flags of the chain passes run in workspace slot 0 / 1
 static int dist_reduce(gvib200_problem* p, double* d_cost);
-static int read_flags(gvib200_problem* p, int* flag0, int* flag1) {
+static int dispatch_assemble(gvib200_problem* p, int which, bool alt = false);
+// spec_which >= 0: the assembly of that buffer's sweep is enqueued behind the copies; the host waits for the copies only
+static int read_flags(gvib200_problem* p, int* flag0, int* flag1, int spec_which = -1, bool zc = false) {
     if (p->ctx->world > 1 && !p->flags_synced) TRY(dist_reduce(p, p->scal + 7));  // scal[7]: scratch
-    CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (!zc) CUDA_TRY(cudaMemcpyAsync(p->h_flag, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    if (spec_which >= 0) {
+        CUDA_TRY(cudaEventRecord(p->ev_host, p->stream));
+        TRY(dispatch_assemble(p, spec_which, true));
+        CUDA_TRY(cudaEventSynchronize(p->ev_host));
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
+    if (zc) {
+        p->h_flag[0] = p->zc[2] != 0.0;
+        p->h_flag[1] = p->zc[3] != 0.0;
+    }
     *flag0 = p->h_flag[0];
     *flag1 = p->h_flag[1];
     return 0;
@@ -980,6 +1006,7 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_host, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
     p->ls = p->stream;
     *out = p.release();
@@ -1001,7 +1028,7 @@ static void free_problem(gvib200_problem* p) {
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
-    F(p->scal); F(p->partial); F(p->d_flag); F(p->d_counter); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->dmu); F(p->KlinD); F(p->KlinO);
+    F(p->scal); F(p->partial); F(p->d_flag); F(p->d_counter); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->Vdmu2); F(p->VD2); F(p->VO2); F(p->rhs2); F(p->dmu); F(p->KlinD); F(p->KlinO);
     F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
     for (int i = 0; i < 2; ++i) {
         F(p->ws_mid[i]); F(p->ws_top[i]); F(p->dist_buf[i]);
@@ -1015,10 +1042,12 @@ static void free_problem(gvib200_problem* p) {
     if (p->t0) cudaEventDestroy(p->t0);
     if (p->t1) cudaEventDestroy(p->t1);
     if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->zc) cudaFreeHost(p->zc);
     if (p->h_flag) cudaFreeHost(p->h_flag);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_pro) cudaEventDestroy(p->ev_pro);
+    if (p->ev_host) cudaEventDestroy(p->ev_host);
     if (p->ev_mu) cudaEventDestroy(p->ev_mu);
     if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1328,6 +1357,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     TRY(dev_alloc(&p->partial, 1024));
     CUDA_TRY(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
     CUDA_TRY(cudaMallocHost((void**)&p->h_scal, 8 * sizeof(double)));
+    CUDA_TRY(cudaHostAlloc((void**)&p->zc, 8 * sizeof(double), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&p->zc_dev, p->zc, 0));
     TRY(dev_alloc(&p->d_flag, 2));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), p->stream));
     TRY(dev_alloc(&p->d_counter, 1));
@@ -1335,20 +1366,25 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     CUDA_TRY(cudaMallocHost((void**)&p->h_flag, 2 * sizeof(int)));
     TRY(dev_alloc(&p->Vdmu, (size_t)S * d));
     TRY(dev_alloc(&p->rhs, (size_t)S * d));
+    TRY(dev_alloc(&p->Vdmu2, (size_t)S * d));
+    TRY(dev_alloc(&p->rhs2, (size_t)S * d));
     TRY(dev_alloc(&p->dmu, (size_t)S * d));
     TRY(dev_alloc(&p->VD, (size_t)S * dd));
     TRY(dev_alloc(&p->VO, (size_t)S * dd));
+    TRY(dev_alloc(&p->VD2, (size_t)S * dd));
+    TRY(dev_alloc(&p->VO2, (size_t)S * dd));
     TRY(dev_alloc(&p->KlinD, (size_t)S * dd));
     TRY(dev_alloc(&p->KlinO, (size_t)S * dd));
     TRY(upload_klin(p));
     // chain plan
     {
         // dynamic shared memory left for the chain kernels next to their static arrays
-        const size_t smem = p->ctx->smem_optin - 4096;
+        const size_t smem = p->ctx->smem_optin - 5120;
         const int P = p->ctx->world;
         bool ok = false;
         int tiles_per_sm = 1;
         if (const char* e = getenv("GVIB200_TILES_PER_SM")) tiles_per_sm = std::max(1, atoi(e));
+        if (const char* e = getenv("GVIB200_TILE_THREADS")) p->tile_threads = std::max(32, std::min(CR_THREADS, atoi(e)));
 #define PLAN_CASE(D_)                                                                                          \
     case D_: {                                                                                                 \
         int force_T = 0;                                                                                       \
@@ -1428,6 +1464,7 @@ extern "C" int gvib200_set_state(gvib200_problem* p, const double* mu, const dou
         }
     }
     p->sweep_valid = false;
+    p->asm_valid = false;
     p->grads_valid = false;
     if (pd || !p->has_state) {
         if (!pd) return fail(GVIB200_ESTATE, "set_state: the first call must provide a precision");
@@ -1557,15 +1594,16 @@ extern "C" int gvib200_cost(gvib200_problem* p, const double* mu, const double* 
     return check_launch("cost");
 }
 
-static int dispatch_assemble(gvib200_problem* p, int which) {
+static int dispatch_assemble(gvib200_problem* p, int which, bool alt) {
     switch (p->d) {
-        case 1: launch_assemble<1>(p, which); break;
-        case 2: launch_assemble<2>(p, which); break;
-        case 3: launch_assemble<3>(p, which); break;
-        case 4: launch_assemble<4>(p, which); break;
-        case 6: launch_assemble<6>(p, which); break;
+        case 1: launch_assemble<1>(p, which, alt); break;
+        case 2: launch_assemble<2>(p, which, alt); break;
+        case 3: launch_assemble<3>(p, which, alt); break;
+        case 4: launch_assemble<4>(p, which, alt); break;
+        case 6: launch_assemble<6>(p, which, alt); break;
         default: return fail(GVIB200_EINVAL, "unsupported state dim");
     }
+    if (!alt) p->asm_valid = false;  // callers that assemble the current sweep set it themselves
     return 0;
 }
 
@@ -1636,6 +1674,7 @@ static int switch_to_high_temperature(gvib200_problem* p) {
     }
     TRY(upload_klin(p));
     p->sweep_valid = false;
+    p->asm_valid = false;
     p->grads_valid = false;
     return 0;
 }
@@ -1674,7 +1713,10 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     // cost_iter + factor costs + gradients from ONE full-moment sweep at the current state
     if (!p->sweep_valid) s.n_moment_sweeps++;
     TRY(ensure_sweep(p, false));
-    TRY(dispatch_assemble(p, p->cur));
+    if (!p->asm_valid) {
+        TRY(dispatch_assemble(p, p->cur));
+        p->asm_valid = true;
+    }
     // back-tracking (GVI-GH-GBP-impl.h:82-124).  The first trial's candidate precision Lambda + a (Vddmu - Lambda) does
     // not depend on dmu, so its selected inverse runs on the side stream while the main stream solves for dmu.
     int cnt = 0;
@@ -1750,8 +1792,17 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
         run_total(p, w);
-        CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-        TRY(read_flags(p, &flag_solve, &flag_inv));
+        // k_total hands the cost and the flags to the host through mapped memory; copies only where that is not valid
+        const bool zc = p->zc_ok[w] && p->zc_ok[p->cur];
+        if (!zc) CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        // speculation: if this trial is accepted its sweep is the next iteration's gradient sweep -- assemble it now,
+        // into the second set of buffers, so that the host round trip below costs no device time
+        const bool speculate = (o.reuse_accepted_sweep != 0);
+        TRY(read_flags(p, &flag_solve, &flag_inv, speculate ? w : -1, zc));
+        if (zc) {
+            p->h_scal[2] = p->zc[0];
+            p->h_scal[3] = p->zc[1];
+        }
         if (cnt == 0) {
             cost_iter = p->h_scal[2 + p->cur];
             s.cost = cost_iter;
@@ -1774,6 +1825,14 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             p->cur = w;
             p->sweep_valid = (o.reuse_accepted_sweep != 0);
             p->grads_valid = false;
+            p->asm_valid = false;
+            if (speculate) {
+                std::swap(p->Vdmu, p->Vdmu2);
+                std::swap(p->VD, p->VD2);
+                std::swap(p->VO, p->VO2);
+                std::swap(p->rhs, p->rhs2);
+                p->asm_valid = true;
+            }
             s.accepted = 1;
             s.step = step;
             s.n_backtrack = cnt;
@@ -1865,7 +1924,8 @@ static int prox_gradients(gvib200_problem* p, double eta) {
         return fail(GVIB200_EINVAL, "prox: unsupported linear factor shape");
     }
     run_total(p, c);
-    p->sweep_valid = false;  // the NGD outputs of the sweep were overwritten
+    p->sweep_valid = false;
+    p->asm_valid = false;  // the NGD outputs of the sweep were overwritten
     TRY(dispatch_assemble(p, c));
     return check_launch("prox_gradients");
 }
@@ -1936,6 +1996,7 @@ extern "C" int gvib200_prox_iterate(gvib200_problem* p, const gvib200_opts* opts
         if (flag) TRY(clear_flag(p));
     }
     p->sweep_valid = false;
+    p->asm_valid = false;
     p->grads_valid = false;
     p->iter++;
     if (st) *st = s;
@@ -2078,6 +2139,8 @@ extern "C" int gvib200_snapshot_restore(gvib200_problem* p) {
     p->iter = p->snap_iter;
     p->converged = false;
     p->sweep_valid = p->snap_sweep_valid;
+    p->asm_valid = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
     p->grads_valid = false;
     return 0;
 }
@@ -2106,7 +2169,34 @@ extern "C" int gvib200_timer_stop(gvib200_problem* p, float* ms) {
     return 0;
 }
 
+// development aid: GVIB200_CHAIN_CLOCKS=1 -> clock64() stamps of CTA 0 of the chain kernels (kernels.cuh, cr_stamp)
+static long long* g_clk_buf = nullptr;
+static void chain_clocks_enable() {
+    if (g_clk_buf || !getenv("GVIB200_CHAIN_CLOCKS")) return;
+    cudaMalloc((void**)&g_clk_buf, 128 * sizeof(long long));
+    cudaMemset(g_clk_buf, 0, 128 * sizeof(long long));
+    cudaMemcpyToSymbol(g_cr_clk, &g_clk_buf, sizeof(g_clk_buf));
+}
+static void chain_clocks_dump() {
+    if (!g_clk_buf) return;
+    long long h[128];
+    cudaMemcpy(h, g_clk_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[4] = {"forward<solve>", "forward<selinv>", "backward<solve>", "backward<selinv>"};
+    for (int k = 0; k < 4; ++k) {
+        const long long* c = h + 32 * k;
+        if (c[0] == 0) continue;
+        fprintf(stderr, "[chain clocks] %s: in %lld", names[k], c[1] - c[0]);
+        long long prev = c[1];
+        for (int l = 2; l < 20 && c[l] != 0; ++l) {
+            fprintf(stderr, " L%d %lld", l - 2, c[l] - prev);
+            prev = c[l];
+        }
+        fprintf(stderr, " out %lld total %lld\n", c[20] - prev, c[20] - c[0]);
+    }
+}
+
 extern "C" int gvib200_profile_begin(gvib200_problem* p) {
+    chain_clocks_enable();
     if (!p) return fail(GVIB200_EINVAL, "profile_begin: null");
     for (auto& r : p->prof) {
         cudaEventDestroy(r.a);
@@ -2144,6 +2234,7 @@ extern "C" int gvib200_profile_end(gvib200_problem* p, gvib200_profile* out) {
         cudaEventDestroy(r.b);
     }
     if (tl) fclose(tl);
+    chain_clocks_dump();
     p->prof.clear();
     return 0;
 }
@@ -2158,6 +2249,7 @@ extern "C" int gvib200_problem_set_option(gvib200_problem* p, const char* name, 
     if (std::strcmp(name, "generic_k1") == 0) {
         p->force_generic_k1 = (value != 0);
         p->sweep_valid = false;
+        p->asm_valid = false;
         return 0;
     }
     return fail(GVIB200_EINVAL, std::string("set_option: unknown option ") + name);
@@ -2238,6 +2330,7 @@ extern "C" int gvib200_time_stage(gvib200_problem* p, int stage, int reps, const
         // the sweep overwrote fcost[cur] consistently (same state), totals need refreshing
         run_total(p, c);
         p->sweep_valid = (stage == 0);
+        p->asm_valid = false;
     }
     return check_launch("time_stage");
 }

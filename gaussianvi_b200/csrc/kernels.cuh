@@ -696,7 +696,7 @@ __global__ void k_partial_sum(size_t n, const double* __restrict__ v, double* __
 // finishes last (device counter) adds the partials in index order: out[0] = sum(v) + half * extra[0].
 __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restrict__ v, double* __restrict__ partial,
                                                unsigned* __restrict__ counter, const double* __restrict__ extra, double half,
-                                               double* __restrict__ out) {
+                                               double* __restrict__ out, const int* __restrict__ dflag, double* zc, int which) {
     __shared__ double sh[256];
     __shared__ bool is_last;
     const size_t per = (n + gridDim.x - 1) / gridDim.x;
@@ -727,8 +727,15 @@ __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restric
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out[0] = sh[0] + (extra ? half * extra[0] : 0.0);
+        const double total = sh[0] + (extra ? half * extra[0] : 0.0);
+        out[0] = total;
         *counter = 0u;  // ready for the next launch
+        if (zc != nullptr) {  // mapped host memory: the host reads the cost and the not-SPD flags without a copy
+            zc[which] = total;
+            zc[2] = (double)dflag[0];
+            zc[3] = (double)dflag[1];
+            __threadfence_system();
+        }
     }
 }
 
@@ -755,7 +762,16 @@ __global__ void k_sum(size_t n, const double* __restrict__ v, const double* __re
 //                       solve, expansion back to every separator (or, K == 0, the whole chain at once)
 //   k_cr_tile_backward  one CTA per tile: back substitution and / or Takahashi selected inverse, level by level
 // ------------------------------------------------------------------------------------------
-constexpr int CR_THREADS = 256;
+constexpr int CR_THREADS = 512;
+
+// development aid (GVIB200_CHAIN_CLOCKS=1): CTA 0 of the chain kernels stamps clock64() at its phase boundaries
+// (compile with -DGVIB200_CHAIN_CLOCKS; the production build has no stamps)
+__device__ long long* g_cr_clk = nullptr;
+__device__ __forceinline__ void cr_stamp(int slot) {
+#ifdef GVIB200_CHAIN_CLOCKS
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_cr_clk != nullptr) g_cr_clk[slot] = clock64();
+#endif
+}
 
 // deterministic block sum of one double per thread (fixed tree), result valid in thread 0
 __device__ __forceinline__ double cr_block_sum(double v, double* red) {
@@ -768,34 +784,49 @@ __device__ __forceinline__ double cr_block_sum(double v, double* red) {
     return red[0];
 }
 
+// D workers per node (bt_cr.h): thread tid works on node tid / D of the round as worker tid % D
 template <int D, bool RHS>
 __device__ __forceinline__ bool cr_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm,
-                                                  LogDetAcc& ld) {
+                                                  LogDetAcc& ld, int clk0 = 0) {
     bool ok = true;
+    const int per_round = blockDim.x / D;
+    const int tn = threadIdx.x / D, c = threadIdx.x - tn * D;
     for (int l = 0; l < gm.levels; ++l) {
         const int cnt = cr_count(gm.T, l);
-        for (int base = 0; base < cnt; base += blockDim.x) {
-            const int t = base + threadIdx.x;
-            CrElim<D> c;
-            if (t < cnt) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, t, c, ld) && ok;
+        for (int base = 0; base < cnt; base += per_round) {
+            const int t = base + tn;
+            const bool on = (tn < per_round) && (t < cnt);
+            CrElim<D> el;
+            if (on) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, t, c, el, ld) && ok;
             __syncthreads();
-            if (t < cnt) cr_fwd_B<D, RHS>(v, c);
+            if (on) cr_fwd_B<D, RHS>(v, el, c);
             __syncthreads();
         }
+        cr_stamp(clk0 + 2 + l);
     }
     return ok;
 }
 
 template <int D, bool RHS, bool SELINV>
 __device__ __forceinline__ void cr_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base,
-                                                   const CrGeom& gm) {
+                                                   const CrGeom& gm, int clk0 = 0) {
+    const int per_round = blockDim.x / D;
+    const int tn = threadIdx.x / D, c = threadIdx.x - tn * D;
     for (int l = gm.levels - 1; l >= 0; --l) {
         const int cnt = cr_count(gm.T, l);
-        for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
-            if (SELINV) cr_bwd_selinv<D>(v, rec, rec_base, gm, l, t);
-            if (RHS) cr_bwd_solve<D>(v, rec, rec_base, gm, l, t);
+        for (int base = 0; base < cnt; base += per_round) {
+            const int t = base + tn;
+            const bool on = (tn < per_round) && (t < cnt);
+            if (SELINV) {
+                CrSel<D> o;
+                if (on) cr_bwd_selinv_compute<D>(v, rec, rec_base, gm, l, t, c, o);
+                __syncthreads();  // the coupling of the left neighbour is overwritten
+                if (on) cr_bwd_selinv_store<D>(v, o, c);
+            }
+            if (RHS && on) cr_bwd_solve<D>(v, rec, rec_base, gm, l, t, c);
         }
         __syncthreads();
+        cr_stamp(clk0 + 2 + (gm.levels - 1 - l));
     }
 }
 
@@ -810,14 +841,18 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
     __syncthreads();
     const CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    const int clk0 = RHS ? 0 : 32;
+    cr_stamp(clk0);
     cr_tile_load<D, RHS>(a, v, gm, n0, threadIdx.x, blockDim.x);
     __syncthreads();
+    cr_stamp(clk0 + 1);
     LogDetAcc ld;
-    const bool ok = cr_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld);
+    const bool ok = cr_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld, clk0);
     cr_tile_store_reduced<D, RHS>(a, v, gm, tile, n0, threadIdx.x, blockDim.x);
     const double s = cr_block_sum(ld.value(), red);
     if (threadIdx.x == 0) a.ld[tile] = s;
     if (!ok) *a.notspd = 1;
+    cr_stamp(clk0 + 20);
 }
 
 template <int D, bool RHS, bool SELINV>
@@ -868,12 +903,17 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
     __syncthreads();
     const CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    const int clk0 = RHS ? 64 : 96;
+    cr_stamp(clk0);
     cr_tile_seed<D, RHS, SELINV>(a, v, tile, threadIdx.x, blockDim.x);
     __syncthreads();
-    cr_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm);
+    cr_stamp(clk0 + 1);
+    cr_backward_levels<D, RHS, SELINV>(v, a.rec, (size_t)tile * (a.T - 1), gm, clk0);
     const bool last = (tile == a.K - 1);
     cr_store_results<D, RHS, SELINV>(v, gm, Tk + (last ? 1 : 0), Tk, a.x, a.cD, a.cO, (size_t)n0, threadIdx.x, blockDim.x,
                                      a.xbase, a.xalpha, a.xout);
+    __syncthreads();
+    cr_stamp(clk0 + 20);
 }
 
 // multi-GPU glue kernels (single small CTAs; the arithmetic is in bt_cr.h)

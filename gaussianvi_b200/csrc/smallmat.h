@@ -188,6 +188,53 @@ struct LogDetAcc {
     GVI_HD double value() const { return log(m) + (double)e * 0.69314718055994530942; }
 };
 
+// Cholesky factor A = L L^T of an SPD matrix (only the lower triangle of A is read) with rd[j] = 1 / L_jj (rsqrt of the
+// pivot: division free).  The pivots are multiplied into `ld`; returns false when a pivot is not strictly positive.
+template <int N>
+GVI_HD bool chol_factor(Mat<N>& L, double* rd, const Mat<N>& A, LogDetAcc& ld) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = A(j, j);
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L(j, k), L(j, k), s);
+        ok = ok && (s > 0.0);
+        ld.mul(s);
+        const double r = gvi_rsqrt(s);
+        rd[j] = r;
+        L(j, j) = s * r;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double t = A(i, j);
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L(i, k), L(j, k), t);
+            L(i, j) = t * r;
+        }
+    }
+    ld.normalize();
+    return ok;
+}
+
+// x = A^-1 b from the factor of chol_factor (forward then backward substitution)
+template <int N>
+GVI_HD void chol_solve(Vec<N>& x, const Mat<N>& L, const double* rd, const Vec<N>& b) {
+    Vec<N> z;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double t = b(i);
+#pragma unroll
+        for (int k = 0; k < i; ++k) t = fma(-L(i, k), z(k), t);
+        z(i) = t * rd[i];
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double t = z(i);
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) t = fma(-L(k, i), x(k), t);
+        x(i) = t * rd[i];
+    }
+}
+
 // Inverse of an SPD matrix through its Cholesky factor: A = L L^T, Ainv = L^-T L^-1.
 // The pivots are multiplied into `ld` (log det accumulator); returns false (and leaves Ainv
 // unspecified, possibly NaN) when a pivot is not strictly positive -- the caller raises
@@ -304,7 +351,8 @@ GVI_HD void jacobi_eig4(Mat<4>& A, Mat<4>& V, Vec<4>& lam) {
 #pragma unroll
             for (int i = 0; i < j; ++i) off += fabs(A(i, j));
         }
-        if (off <= 1e-300 || off <= 1e-22 * diag) break;
+        // convergence is quadratic: a sweep entered with off <= 1e-17 diag would only move the result below rounding
+        if (off <= 1e-300 || off <= 1e-17 * diag) break;
 #pragma unroll
         for (int round = 0; round < 3; ++round) {
             const int p0 = 0, q0 = round + 1;

@@ -34,20 +34,22 @@ extern "C" int emu_sqrt_invsqrt(int n, const double* Sigma, double* S, double* R
 // rounds of NT with both phases of a round separated exactly where the kernels place __syncthreads().
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr int NT = 256;
+constexpr int NT = 512;
 
 template <int D, bool RHS>
 bool emu_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, double& ldsum) {
     bool ok = true;
+    const int per_round = NT / D;
     std::vector<LogDetAcc> lds(NT);
     for (int l = 0; l < gm.levels; ++l) {
         const int cnt = cr_count(gm.T, l);
-        for (int base = 0; base < cnt; base += NT) {
+        for (int base = 0; base < cnt; base += per_round) {
             std::vector<CrElim<D>> ctx(NT);
-            for (int tid = 0; tid < NT; ++tid)
-                if (base + tid < cnt) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, base + tid, ctx[tid], lds[tid]) && ok;
-            for (int tid = 0; tid < NT; ++tid)
-                if (base + tid < cnt) cr_fwd_B<D, RHS>(v, ctx[tid]);
+            for (int tid = 0; tid < per_round * D; ++tid)
+                if (base + tid / D < cnt)
+                    ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, base + tid / D, tid % D, ctx[tid], lds[tid]) && ok;
+            for (int tid = 0; tid < per_round * D; ++tid)
+                if (base + tid / D < cnt) cr_fwd_B<D, RHS>(v, ctx[tid], tid % D);
         }
     }
     for (auto& l : lds) ldsum += l.value();
@@ -56,11 +58,20 @@ bool emu_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base
 
 template <int D, bool RHS, bool SELINV>
 void emu_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm) {
+    const int per_round = NT / D;
     for (int l = gm.levels - 1; l >= 0; --l) {
         const int cnt = cr_count(gm.T, l);
-        for (int t = 0; t < cnt; ++t) {
-            if (SELINV) cr_bwd_selinv<D>(v, rec, rec_base, gm, l, t);
-            if (RHS) cr_bwd_solve<D>(v, rec, rec_base, gm, l, t);
+        for (int base = 0; base < cnt; base += per_round) {
+            if (SELINV) {
+                std::vector<CrSel<D>> ctx(NT);
+                for (int tid = 0; tid < per_round * D; ++tid)
+                    if (base + tid / D < cnt) cr_bwd_selinv_compute<D>(v, rec, rec_base, gm, l, base + tid / D, tid % D, ctx[tid]);
+                for (int tid = 0; tid < per_round * D; ++tid)
+                    if (base + tid / D < cnt) cr_bwd_selinv_store<D>(v, ctx[tid], tid % D);
+            }
+            if (RHS)
+                for (int tid = 0; tid < per_round * D; ++tid)
+                    if (base + tid / D < cnt) cr_bwd_solve<D>(v, rec, rec_base, gm, l, base + tid / D, tid % D);
         }
     }
 }
