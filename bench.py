@@ -362,7 +362,18 @@ def run_gpu(args, rank, world, local_rank):
 
 
 def main():
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL prints its version banner on stdout otherwise; stdout carries ONE JSON line
+    # stdout carries ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are sent to
+    # stderr for the whole run; the JSON line goes to the saved descriptor
+    global print
+    real_out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001 -- only the final JSON line is printed through this
+        k.setdefault("file", real_out)
+        _print(*a, **k)
+        real_out.flush()
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

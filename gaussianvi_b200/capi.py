@@ -35,6 +35,7 @@ EXPORTS = [
     "gvib200_launch_count", "gvib200_timer_start", "gvib200_timer_stop", "gvib200_profile_begin", "gvib200_profile_end",
     "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
+    "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
 ]
 
 
@@ -133,6 +134,25 @@ def table_generate(dim: int, deg: int):
     return nodes, w
 
 
+def table_file_write(path: str, keys):
+    """Write the rules [(dim, deg), ...] in the reference's cereal table format (quadrature/saveSparseGHWeightMap.h)."""
+    lib = load_library()
+    dims = np.ascontiguousarray([k[0] for k in keys], dtype=np.int32)
+    degs = np.ascontiguousarray([k[1] for k in keys], dtype=np.int32)
+    _check(lib.gvib200_table_file_write(str(path).encode(), len(keys), dims.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        degs.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+def table_file_query(path: str):
+    """[(dim, deg, n_nodes), ...] of a table file, in file order."""
+    lib = load_library()
+    n = _check(lib.gvib200_table_file_query(str(path).encode(), 0, None, None, None))
+    dims, degs, sizes = (np.zeros(max(n, 1), dtype=np.int32) for _ in range(3))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    _check(lib.gvib200_table_file_query(str(path).encode(), n, ip(dims), ip(degs), ip(sizes)))
+    return [(int(dims[i]), int(degs[i]), int(sizes[i])) for i in range(n)]
+
+
 class Context:
     def __init__(self, device: int = 0):
         self.lib = load_library()
@@ -154,6 +174,18 @@ class Context:
         nodes = np.ascontiguousarray(nodes, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
         _check(self.lib.gvib200_table_set(self.h, dim, deg, len(w), _dp(nodes), _dp(w)))
+
+    def table_file_load(self, path: str) -> int:
+        n = C.c_int()
+        _check(self.lib.gvib200_table_file_load(self.h, str(path).encode(), C.byref(n)))
+        return n.value
+
+    def table_get(self, dim: int, deg: int):
+        n = _check(self.lib.gvib200_table_get(self.h, dim, deg, None, None, 0))
+        nodes = np.zeros((n, dim))
+        w = np.zeros(n)
+        _check(self.lib.gvib200_table_get(self.h, dim, deg, _dp(nodes), _dp(w), n))
+        return nodes, w
 
     def fp64_peak_tflops(self) -> float:
         v = C.c_double()

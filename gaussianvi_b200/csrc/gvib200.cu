@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <map>
 #include <memory>
 #include <string>
@@ -156,6 +157,7 @@ struct gvib200_ctx {
     std::map<std::pair<int, int>, std::unique_ptr<Table>> tables;
     // multi-GPU: NCCL entry points resolved at run time from the library the caller initialised the communicator with
     void* nccl_comm = nullptr;
+    void* nccl_comm2 = nullptr;  // split of nccl_comm for the side stream (the two chain passes of an iteration overlap)
     void* nccl_lib = nullptr;
     int (*ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
@@ -432,7 +434,8 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), 1, 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
     LAUNCH(p, KC_OTHER, (k_cr_pack_boundary<D, RHS>), 1, 64, 0, mid, buf + L.send);
-    if (ctx->ncclAllGather(buf + L.send, buf + L.recv, (size_t)NB, /*ncclFloat64*/ 8, ctx->nccl_comm, p->ls) != 0)
+    void* comm = (p->ls == p->stream2 && ctx->nccl_comm2) ? ctx->nccl_comm2 : ctx->nccl_comm;
+    if (ctx->ncclAllGather(buf + L.send, buf + L.recv, (size_t)NB, /*ncclFloat64*/ 8, comm, p->ls) != 0)
         return fail(GVIB200_ENCCL, "chain pass: ncclAllGather failed");
     LAUNCH(p, KC_OTHER, (k_cr_build_global<D>), 1, 256, 0, P, buf + L.recv, buf + L.Dt, buf + L.Ot, buf + L.gt);
     LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, p->plan_top.top_smem_bytes, top);
@@ -938,6 +941,15 @@ extern "C" int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank,
         ctx->ncclAllGather = reinterpret_cast<decltype(ctx->ncclAllGather)>(dlsym(lib, "ncclAllGather"));
         ctx->ncclAllReduce = reinterpret_cast<decltype(ctx->ncclAllReduce)>(dlsym(lib, "ncclAllReduce"));
         if (!ctx->ncclAllGather || !ctx->ncclAllReduce) return fail(GVIB200_ENCCL, "ctx_set_comm: NCCL symbols not found");
+        // a second communicator over the same ranks (collective call: every rank is inside ctx_set_comm) so that the dmu
+        // solve and the candidate's selected inverse can issue their boundary all-gathers from two streams
+        using split_fn = int (*)(void*, int, int, void**, void*);
+        split_fn split = reinterpret_cast<split_fn>(dlsym(lib, "ncclCommSplit"));
+        ctx->nccl_comm2 = nullptr;
+        if (split && !getenv("GVIB200_NO_FORK")) {
+            void* c2 = nullptr;
+            if (split(nccl_comm, 0, rank, &c2, nullptr) == 0) ctx->nccl_comm2 = c2;
+        }
     }
     ctx->nccl_comm = nccl_comm;
     ctx->rank = rank;
@@ -983,6 +995,77 @@ extern "C" int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, cons
     if (it != ctx->tables.end() && it->second->d_sym) cudaFree(it->second->d_sym);
     ctx->tables[key] = std::move(t);
     return 0;
+}
+
+extern "C" int gvib200_table_file_write(const char* path, int n_keys, const int32_t* dims, const int32_t* degs) {
+    if (!path || n_keys < 0 || (n_keys > 0 && (!dims || !degs))) return fail(GVIB200_EINVAL, "table_file_write: bad arguments");
+    try {
+        std::vector<SpghTableEntry> entries((size_t)n_keys);
+        for (int i = 0; i < n_keys; ++i) {
+            entries[i].dim = dims[i];
+            entries[i].deg = degs[i];
+            generate_spgh_table(dims[i], degs[i], entries[i].nodes_rowmajor, entries[i].weights);
+        }
+        write_spgh_table_file(path, entries);
+    } catch (const std::invalid_argument& e) {
+        return fail(GVIB200_ENOTABLE, e.what());
+    } catch (const std::exception& e) {
+        return fail(GVIB200_EINVAL, e.what());
+    }
+    return 0;
+}
+
+extern "C" int gvib200_table_file_load(gvib200_ctx* ctx, const char* path, int* n_loaded) {
+    if (!ctx || !path) return fail(GVIB200_EINVAL, "table_file_load: bad arguments");
+    std::vector<SpghTableEntry> entries;
+    try {
+        read_spgh_table_file(path, entries);
+    } catch (const std::exception& e) {
+        return fail(GVIB200_EINVAL, e.what());
+    }
+    for (auto& e : entries) {
+        if (e.weights.empty()) continue;
+        TRY(gvib200_table_set(ctx, e.dim, e.deg, (int)e.weights.size(), e.nodes_rowmajor.data(), e.weights.data()));
+    }
+    if (n_loaded) *n_loaded = (int)entries.size();
+    return 0;
+}
+
+extern "C" int gvib200_table_file_query(const char* path, int capacity, int32_t* dims, int32_t* degs, int32_t* sizes) {
+    if (!path) return fail(GVIB200_EINVAL, "table_file_query: null path");
+    std::vector<SpghTableEntry> entries;
+    try {
+        read_spgh_table_file(path, entries);
+    } catch (const std::exception& e) {
+        return fail(GVIB200_EINVAL, e.what());
+    }
+    for (int i = 0; i < (int)entries.size() && i < capacity; ++i) {
+        if (dims) dims[i] = entries[i].dim;
+        if (degs) degs[i] = entries[i].deg;
+        if (sizes) sizes[i] = (int32_t)entries[i].weights.size();
+    }
+    return (int)entries.size();
+}
+
+extern "C" int gvib200_table_get(gvib200_ctx* ctx, int dim, int deg, double* nodes_rowmajor, double* weights, int capacity) {
+    if (!ctx) return fail(GVIB200_EINVAL, "table_get: null context");
+    auto it = ctx->tables.find(std::make_pair(dim, deg));
+    std::vector<double> n, w;
+    if (it != ctx->tables.end()) {
+        n = it->second->nodes;
+        w = it->second->w;
+    } else {
+        try {
+            generate_spgh_table(dim, deg, n, w);
+        } catch (const std::exception& e) {
+            return fail(GVIB200_ENOTABLE, e.what());
+        }
+    }
+    if (!nodes_rowmajor && !weights) return (int)w.size();  // size query
+    if ((int)w.size() > capacity) return fail(GVIB200_EINVAL, "table_get: capacity too small");
+    if (nodes_rowmajor) std::memcpy(nodes_rowmajor, n.data(), n.size() * sizeof(double));
+    if (weights) std::memcpy(weights, w.data(), w.size() * sizeof(double));
+    return (int)w.size();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1728,7 +1811,8 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         const int w = 1 - p->cur;
         bool linear_forked = false;
         static const bool no_fork_env = getenv("GVIB200_NO_FORK") != nullptr;  // development switch
-        const bool fork = (p->ctx->world == 1) && !no_fork_env;  // one communicator: collectives stay in issue order on one stream
+        // multi-GPU: the side stream needs its own communicator (collectives of one communicator stay on one stream)
+        const bool fork = (p->ctx->world == 1 || p->ctx->nccl_comm2 != nullptr) && !no_fork_env;
         if (cnt == 0 && !fork) {
             ChainFuse fi;
             fi.Dg2 = p->VD;

@@ -91,6 +91,19 @@ int gvib200_table_generate(int dim, int deg, double* nodes_rowmajor, double* wei
 /* override the generated table of (dim, deg) with an externally loaded one (e.g. read from the
    reference's SparseGHQuadratureWeights_cereal.bin) */
 int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, const double* nodes_rowmajor, const double* weights);
+/* Table file in the reference's wire format: cereal BinaryOutputArchive of
+   unordered_map<tuple<double,double>, tuple<MatrixXd,VectorXd>> (quadrature/saveSparseGHWeightMap.h:43-51,
+   helpers/SerializeEigenMaps.h:195-224), the file SparseGaussHermite reads at construction
+   (quadrature/SparseGaussHermite.h:58-72).
+   _write: generate the n_keys rules (dims[i], degs[i]) and write them (replaces save_pointweightmaps()).
+   _load:  read a file and register every rule in the context (as gvib200_table_set does); *n_loaded = rules read.
+   _query: without a context: number of rules in the file; if dims/degs/sizes are non-null, up to `capacity` of them. */
+int gvib200_table_file_write(const char* path, int n_keys, const int32_t* dims, const int32_t* degs);
+int gvib200_table_file_load(gvib200_ctx* ctx, const char* path, int* n_loaded);
+int gvib200_table_file_query(const char* path, int capacity, int32_t* dims, int32_t* degs, int32_t* sizes);
+/* copy the rule (dim, deg) the context currently holds (generated or loaded) into caller buffers; returns the number of
+   nodes (both buffers null: size query only) */
+int gvib200_table_get(gvib200_ctx* ctx, int dim, int deg, double* nodes_rowmajor, double* weights, int capacity);
 
 /* ---- problem definition (replaces the construction of GVIGH<Factor>, gvibase/GVI-GH-GBP.h:41-64,
         from a vector of factor optimizers) --------------------------------------------------- */
