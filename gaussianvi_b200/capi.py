@@ -36,6 +36,7 @@ EXPORTS = [
     "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
+    "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save",
 ]
 
 
@@ -58,6 +59,12 @@ class IterStats(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("n_classes", C.c_int), ("count", C.c_longlong * 16), ("ms", C.c_double * 16)]
+
+
+class Trace(C.Structure):
+    _fields_ = [("capacity", C.c_int), ("n_recorded", C.c_int), ("mean", C.POINTER(C.c_double)),
+                ("cov_diag", C.POINTER(C.c_double)), ("prec_diag", C.POINTER(C.c_double)), ("cov_off", C.POINTER(C.c_double)),
+                ("prec_off", C.POINTER(C.c_double)), ("cost", C.POINTER(C.c_double)), ("fac_costs", C.POINTER(C.c_double))]
 
 
 class Info(C.Structure):
@@ -132,6 +139,40 @@ def table_generate(dim: int, deg: int):
     w = np.zeros(n)
     _check(lib.gvib200_table_generate(dim, deg, _dp(nodes), _dp(w), n))
     return nodes, w
+
+
+def csv_write(path, a: np.ndarray):
+    """MatrixIO::saveData (helpers/MatrixHelper.h:52-61): Eigen CSVFormat, 15 significant digits."""
+    a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+    f = np.asfortranarray(a)
+    _check(load_library().gvib200_csv_write(str(path).encode(), a.shape[0], a.shape[1], f.ctypes.data_as(_DP)))
+
+
+class ResultRecorder:
+    """Host buffers of gvib200_trace + save_data() (VIMPResults::save_data, helpers/DataRecorder.h:177-224)."""
+
+    def __init__(self, niters: int, dim_state: int, nstates: int, n_factors: int, joint: bool = False):
+        self.niters, self.d, self.S, self.n_factors = niters, dim_state, nstates, n_factors
+        d, S = dim_state, nstates
+        self.mean = np.zeros((niters, S * d))
+        self.cov = np.zeros((niters, S * d * d))
+        self.precision = np.zeros((niters, S * d * d))
+        self.cov_off = np.zeros((niters, max(S - 1, 1) * d * d)) if joint else None
+        self.prec_off = np.zeros((niters, max(S - 1, 1) * d * d)) if joint else None
+        self.cost = np.zeros(niters)
+        self.factor_costs = np.zeros((niters, max(n_factors, 1)))
+        self.joint = joint
+        p = lambda a: a.ctypes.data_as(_DP) if a is not None else None
+        self.trace = Trace(niters, 0, p(self.mean), p(self.cov), p(self.precision), p(self.cov_off), p(self.prec_off),
+                           p(self.cost), p(self.factor_costs))
+
+    @property
+    def n_recorded(self) -> int:
+        return self.trace.n_recorded
+
+    def save_data(self, prefix: str = "", afterfix: str = "", dense_limit: int = 64):
+        _check(load_library().gvib200_trace_save(C.byref(self.trace), self.S, self.d, self.n_factors, str(prefix).encode(),
+                                                 str(afterfix).encode(), dense_limit if self.joint else 0))
 
 
 def table_file_write(path: str, keys):
@@ -386,6 +427,16 @@ class Problem:
         if want_traces:
             return out, fc[:done.value, :self.n_factors], mt[:done.value]
         return out
+
+    def optimize_recorded(self, n_iters: int, opts: Optional[Opts] = None, prox: bool = False, joint: bool = False):
+        """Run n_iters iterations with the result recorder attached (VIMPResults, helpers/DataRecorder.h, in banded form).
+        Returns (stats, ResultRecorder); ResultRecorder.save_data(prefix, afterfix) writes the reference's CSV files."""
+        rec = ResultRecorder(n_iters, self.d, self.S, self.n_factors, joint=joint)
+        stats = (IterStats * n_iters)()
+        done = C.c_int()
+        _check(self.lib.gvib200_optimize_traced(self.h, C.byref(opts) if opts is not None else None, n_iters, 1 if prox else 0,
+                                                stats, C.byref(done), C.byref(rec.trace)))
+        return [stats[i] for i in range(done.value)], rec
 
     def prox_iterate(self, opts: Optional[Opts] = None) -> IterStats:
         st = IterStats()

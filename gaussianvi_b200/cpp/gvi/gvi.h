@@ -439,14 +439,22 @@ public:
     }
 
     // ---- the loop (gvibase/GVI-GH-GBP-impl.h:33-130) ----
-    void optimize(std::optional<bool> verbose = std::nullopt) {
-        build();
-        _stats.assign((size_t)_niters, gvib200_iter_stats());
-        int done = 0;
-        gvib200_check(gvib200_optimize(_prob, &_opts, _niters, _stats.data(), &done, nullptr, nullptr), "optimize");
-        _stats.resize((size_t)done);
-        if (verbose.value_or(false))
-            for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, _stats[(size_t)i].cost);
+    void optimize(std::optional<bool> verbose = std::nullopt) { run_loop(false, verbose.value_or(false)); }
+
+    // ---- result files (gvibase/GVI-GH.h:282-329, helpers/DataRecorder.h:154-224) ----
+    // Naming the files switches the recorder on: optimize() then records mean / marginal covariance / marginal precision /
+    // cost / factor costs at the start of every iteration and writes <prefix>{mean,cov,precision,cost,factor_costs,zk_sdf,
+    // Sk_sdf}[_afterfix].csv when it ends (the dense joint_cov / joint_precision files only for joint dimension <= 64).
+    void update_file_names(const std::string& prefix = "", const std::string& afterfix = "") {
+        _file_prefix = prefix;
+        _file_afterfix = afterfix;
+        _record = true;
+    }
+    void save_data(bool verbose = true) {
+        if (_trace.n_recorded < 1) return;
+        if (verbose) std::printf("Saving data to: %s*.csv\n", _file_prefix.c_str());
+        gvib200_check(gvib200_trace_save(&_trace, _num_states, _dim_state, (int)_factors.size(), _file_prefix.c_str(),
+                                         _file_afterfix.c_str(), 64), "save_data");
     }
     const std::vector<gvib200_iter_stats>& iteration_stats() const { return _stats; }
 
@@ -610,7 +618,39 @@ protected:
         if (!_pd.empty()) push_state();
     }
 
+    void run_loop(bool prox, bool verbose) {
+        build();
+        _stats.assign((size_t)_niters, gvib200_iter_stats());
+        int done = 0;
+        if (_record) {
+            const size_t dd = (size_t)_dim_state * _dim_state, n = (size_t)_niters;
+            _t_mean.assign(n * _dim, 0.0);
+            _t_cov.assign(n * _num_states * dd, 0.0);
+            _t_prec.assign(n * _num_states * dd, 0.0);
+            _t_cov_off.assign(n * (size_t)(_num_states > 1 ? _num_states - 1 : 1) * dd, 0.0);
+            _t_prec_off.assign(_t_cov_off.size(), 0.0);
+            _t_cost.assign(n, 0.0);
+            _t_fac.assign(n * _factors.size(), 0.0);
+            const bool joint = _dim <= 64;
+            _trace = gvib200_trace{_niters, 0, _t_mean.data(), _t_cov.data(), _t_prec.data(), joint ? _t_cov_off.data() : nullptr,
+                                   joint ? _t_prec_off.data() : nullptr, _t_cost.data(), _t_fac.data()};
+            gvib200_check(gvib200_optimize_traced(_prob, &_opts, _niters, prox ? 1 : 0, _stats.data(), &done, &_trace), "optimize");
+            save_data(verbose);
+        } else if (prox) {
+            gvib200_check(gvib200_prox_optimize(_prob, &_opts, _niters, _stats.data(), &done), "prox optimize");
+        } else {
+            gvib200_check(gvib200_optimize(_prob, &_opts, _niters, _stats.data(), &done, nullptr, nullptr), "optimize");
+        }
+        _stats.resize((size_t)done);
+        if (verbose)
+            for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, _stats[(size_t)i].cost);
+    }
+
     int _dim_state, _num_states, _dim, _niters;
+    bool _record = false;
+    std::string _file_prefix, _file_afterfix;
+    gvib200_trace _trace{};
+    std::vector<double> _t_mean, _t_cov, _t_prec, _t_cov_off, _t_prec_off, _t_cost, _t_fac;
     double _temperature, _high_temperature;
     std::vector<std::shared_ptr<GVIFactorizedBase>> _factors;
     std::vector<int> _id_of_factor;
@@ -681,15 +721,7 @@ public:
         : Base(vec_fact_optimizers, dim_state, num_states, niterations, temperature, high_temperature) {
         Base::_prox = true;
     }
-    void optimize(std::optional<bool> verbose = std::nullopt) {
-        Base::build();
-        Base::_stats.assign((size_t)Base::_niters, gvib200_iter_stats());
-        int done = 0;
-        gvib200_check(gvib200_prox_optimize(Base::_prob, &(this->_opts), Base::_niters, Base::_stats.data(), &done), "prox optimize");
-        Base::_stats.resize((size_t)done);
-        if (verbose.value_or(false))
-            for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, Base::_stats[(size_t)i].cost);
-    }
+    void optimize(std::optional<bool> verbose = std::nullopt) { Base::run_loop(true, verbose.value_or(false)); }
 };
 
 // SparseGaussHermite (quadrature/SparseGaussHermite.h:38-277) for a DEVICE cost class: the three integrals the factor

@@ -1969,6 +1969,112 @@ extern "C" int gvib200_optimize(gvib200_problem* p, const gvib200_opts* opts, in
 
 
 // ------------------------------------------------------------------------------------------------
+// C-ABI: result recorder (helpers/DataRecorder.h, banded)
+// ------------------------------------------------------------------------------------------------
+extern "C" int gvib200_optimize_traced(gvib200_problem* p, const gvib200_opts* opts, int n_iters, int prox,
+                                       gvib200_iter_stats* stats, int* n_done, gvib200_trace* tr) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "optimize_traced: no state");
+    if (!tr) return fail(GVIB200_EINVAL, "optimize_traced: null trace");
+    const size_t nmu = (size_t)p->S * p->d, nblk = (size_t)p->S * p->d * p->d, noff = (size_t)(p->S - 1) * p->d * p->d;
+    tr->n_recorded = 0;
+    int done = 0;
+    for (int it = 0; it < n_iters; ++it) {
+        if (p->converged) break;
+        const bool rec = it < tr->capacity;
+        // the state before the step (the covariance / precision blocks are resident on the device)
+        if (rec && tr->mean) TRY(gvib200_get_mean(p, tr->mean + (size_t)it * nmu));
+        if (rec && tr->cov_diag) {
+            TRY(download(p, tr->cov_diag + (size_t)it * nblk, p->CD[p->cur], nblk));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        if (rec && tr->prec_diag) {
+            TRY(download(p, tr->prec_diag + (size_t)it * nblk, p->LD[p->cur], nblk));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        if (rec && tr->cov_off && noff) {
+            TRY(download(p, tr->cov_off + (size_t)it * noff, p->CO[p->cur], noff));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        if (rec && tr->prec_off && noff) {
+            TRY(download(p, tr->prec_off + (size_t)it * noff, p->LO[p->cur], noff));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        gvib200_iter_stats s;
+        const int rc = prox ? gvib200_prox_iterate(p, opts, &s) : gvib200_ngd_iterate(p, opts, &s);
+        if (stats) stats[it] = s;
+        if (rc != 0) {
+            if (n_done) *n_done = done;
+            return rc;
+        }
+        if (rec && tr->cost) tr->cost[it] = s.cost;
+        if (rec && tr->fac_costs) {  // factor costs of the iteration's start state: still in the pre-flip buffer
+            const int src = s.accepted ? 1 - p->cur : p->cur;
+            TRY(download(p, tr->fac_costs + (size_t)it * p->n_factors, p->fcost[src], (size_t)p->n_factors));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        if (rec) tr->n_recorded = it + 1;
+        done++;
+    }
+    if (n_done) *n_done = done;
+    return 0;
+}
+
+extern "C" int gvib200_csv_write(const char* path, int rows, int cols, const double* a) {
+    if (!path || rows < 0 || cols < 0 || (!a && rows * cols > 0)) return fail(GVIB200_EINVAL, "csv_write: bad arguments");
+    FILE* f = std::fopen(path, "w");
+    if (!f) return fail(GVIB200_EINVAL, std::string("csv_write: cannot open ") + path);
+    for (int i = 0; i < rows; ++i) {
+        for (int j = 0; j < cols; ++j) std::fprintf(f, j ? ", %.15g" : "%.15g", a[(size_t)i + (size_t)j * rows]);
+        if (i + 1 < rows) std::fputc('\n', f);  // Eigen's IOFormat puts the row separator BETWEEN rows
+    }
+    const bool ok = std::fclose(f) == 0;
+    return ok ? 0 : fail(GVIB200_EINVAL, std::string("csv_write: write failed: ") + path);
+}
+
+extern "C" int gvib200_trace_save(const gvib200_trace* tr, int S, int d, int n_factors, const char* prefix, const char* afterfix,
+                                  int dense_limit) {
+    if (!tr || S < 1 || d < 1) return fail(GVIB200_EINVAL, "trace_save: bad arguments");
+    const int n = tr->n_recorded;  // "early ended": only the recorded iterations are written (DataRecorder.h:179-181)
+    if (n < 1) return fail(GVIB200_ESTATE, "trace_save: nothing recorded");
+    const std::string pre = prefix ? prefix : "", post = (afterfix && afterfix[0]) ? std::string("_") + afterfix : "";
+    auto name = [&](const char* base) { return pre + base + post + ".csv"; };
+    const int nmu = S * d, nblk = S * d * d;
+    if (tr->mean) TRY(gvib200_csv_write(name("mean").c_str(), nmu, n, tr->mean));
+    if (tr->cov_diag) TRY(gvib200_csv_write(name("cov").c_str(), nblk, n, tr->cov_diag));
+    if (tr->prec_diag) TRY(gvib200_csv_write(name("precision").c_str(), nblk, n, tr->prec_diag));
+    if (tr->cost) TRY(gvib200_csv_write(name("cost").c_str(), n, 1, tr->cost));
+    if (tr->fac_costs) TRY(gvib200_csv_write(name("factor_costs").c_str(), n_factors, n, tr->fac_costs));
+    // last iteration in the planner's layout: zk_sdf is d x S, Sk_sdf is d*d x S (DataRecorder.h:205-217)
+    if (tr->mean) TRY(gvib200_csv_write(name("zk_sdf").c_str(), d, S, tr->mean + (size_t)(n - 1) * nmu));
+    if (tr->cov_diag) TRY(gvib200_csv_write(name("Sk_sdf").c_str(), d * d, S, tr->cov_diag + (size_t)(n - 1) * nblk));
+    if (nmu <= dense_limit) {
+        // dense joint files from the recorded blocks (block tridiagonal)
+        const int noff = (S - 1) * d * d;
+        for (int which = 0; which < 2; ++which) {
+            const double* src = which ? tr->prec_diag : tr->cov_diag;
+            const double* off = which ? tr->prec_off : tr->cov_off;
+            if (!src || (S > 1 && !off)) continue;
+            std::vector<double> J((size_t)nmu * nmu * n, 0.0);
+            for (int it = 0; it < n; ++it) {
+                double* Jt = J.data() + (size_t)it * nmu * nmu;
+                for (int s = 0; s < S; ++s)
+                    for (int j = 0; j < d; ++j)
+                        for (int i = 0; i < d; ++i) {
+                            Jt[(size_t)(s * d + i) + (size_t)(s * d + j) * nmu] = src[(size_t)it * nblk + (size_t)s * d * d + i + j * d];
+                            if (s + 1 < S) {
+                                const double o = off[(size_t)it * noff + (size_t)s * d * d + i + j * d];  // block (s, s+1)
+                                Jt[(size_t)(s * d + i) + (size_t)((s + 1) * d + j) * nmu] = o;
+                                Jt[(size_t)((s + 1) * d + j) + (size_t)(s * d + i) * nmu] = o;
+                            }
+                        }
+            }
+            TRY(gvib200_csv_write(name(which ? "joint_precision" : "joint_cov").c_str(), nmu * nmu, n, J.data()));
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI: Prox-GVI (proxgd/ProxGVI-GH-impl.h:45-86,124-205)
 // ------------------------------------------------------------------------------------------------
 template <int DIM>

@@ -193,6 +193,36 @@ int gvib200_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iter
                      int* n_done, double* fac_costs_trace, double* mean_trace);
 /* one iteration (same code path; iteration index is kept inside the problem for the temperature switch) */
 int gvib200_ngd_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats);
+
+/* Result recorder (replaces VIMPResults::update_data / save_data, helpers/DataRecorder.h:96-118,177-224, and
+   GVIGH::update_file_names / save_data, gvibase/GVI-GH.h:282-329) in BANDED form: the joint covariance / precision are
+   recorded as their d x d diagonal blocks, exactly the blocks the reference's joint2marginals() extracts
+   (helpers/DataRecorder.h:124-131); the dense joint_cov / joint_precision files are written only when the joint
+   dimension is <= dense_limit (from the diagonal and first off-diagonal blocks: the precision is exactly block
+   tridiagonal and the reference's covariance() holds only the block-tridiagonal part of the inverse,
+   gvibase/GVI-GH-GBP-impl.h:245-305).  What is recorded at iteration i is the state BEFORE the step, its cost and its factor
+   costs (gvibase/GVI-GH-GBP-impl.h:61-72).  All buffers are caller-owned host memory; null members are skipped. */
+typedef struct gvib200_trace {
+    int capacity;        /* iterations the buffers hold */
+    int n_recorded;      /* out */
+    double* mean;        /* [capacity][S*d] */
+    double* cov_diag;    /* [capacity][S*d*d]  column-major d x d blocks */
+    double* prec_diag;   /* [capacity][S*d*d] */
+    double* cov_off;     /* [capacity][(S-1)*d*d]  blocks (i, i+1); only needed for the dense joint files */
+    double* prec_off;    /* [capacity][(S-1)*d*d] */
+    double* cost;        /* [capacity] */
+    double* fac_costs;   /* [capacity][n_factors] */
+} gvib200_trace;
+/* prox != 0 runs gvib200_prox_iterate instead of gvib200_ngd_iterate */
+int gvib200_optimize_traced(gvib200_problem* prob, const gvib200_opts* opts, int n_iters, int prox, gvib200_iter_stats* stats,
+                            int* n_done, gvib200_trace* trace);
+/* MatrixIO::saveData (helpers/MatrixHelper.h:52-61) with CSVFormat (helpers/CommonDefinitions.h:32): rows on lines,
+   ", " between coefficients, 15 significant digits.  data is column-major rows x cols. */
+int gvib200_csv_write(const char* path, int rows, int cols, const double* data_colmajor);
+/* writes <prefix>mean[_afterfix].csv, cov, precision, cost, factor_costs, zk_sdf, Sk_sdf (and joint_cov / joint_precision
+   when S*d <= dense_limit) with the reference's shapes: one column per iteration */
+int gvib200_trace_save(const gvib200_trace* trace, int num_states, int dim_state, int n_factors, const char* prefix,
+                       const char* afterfix, int dense_limit);
 /* Prox-GVI (proxgd/ProxGVI-GH-impl.h:124-205 over ProxGVIFactorizedBaseGH / ProxFactorizedLinear): per-factor
    Bures-Wasserstein JKO steps instead of natural gradients, no linear solve, step eta = step_size_base^B, the last
    candidate is accepted when back-tracking is exhausted.  The problem must have been given
