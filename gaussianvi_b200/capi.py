@@ -20,6 +20,8 @@ COST_PLANAR_HINGE = 2
 COST_LINEAR_GP = 3
 COST_FIXED_GP = 4
 COST_QUADRATIC = 5
+COST_HINGE_3D = 6
+COST_QUAD_HINGE = 7
 
 E_NOTSPD = -4
 
@@ -36,7 +38,7 @@ EXPORTS = [
     "gvib200_kernel_class_name", "gvib200_problem_info", "gvib200_snapshot_save", "gvib200_snapshot_restore",
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
-    "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save",
+    "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
 ]
 
 
@@ -284,6 +286,13 @@ class Problem:
         col_major = np.ascontiguousarray(np.asarray(data, dtype=np.float64).T)  # [cols, rows] == column-major rows x cols
         _check(self.lib.gvib200_set_planar_sdf(self.h, rows, cols, C.c_double(origin[0]), C.c_double(origin[1]),
                                                C.c_double(cell_size), _dp(col_major)))
+
+    def set_sdf3d(self, data: np.ndarray, origin, cell_size: float):
+        """data [nz, rows, cols] (SignedDistanceField, helpers/CudaOperation.h:133-160)."""
+        nz, rows, cols = data.shape
+        flat = np.ascontiguousarray(np.transpose(np.asarray(data, dtype=np.float64), (0, 2, 1)))  # [z][c][r] -> r + c*rows + z*rows*cols
+        _check(self.lib.gvib200_set_sdf3d(self.h, rows, cols, nz, C.c_double(origin[0]), C.c_double(origin[1]),
+                                          C.c_double(origin[2]), C.c_double(cell_size), _dp(flat)))
 
     def add_gh_factors(self, kind: int, dim: int, deg: int, start_index, params, T=None, T_high=None) -> int:
         start = np.ascontiguousarray(start_index, dtype=np.int32)

@@ -67,17 +67,52 @@ struct PlanarHingeCost {
 struct QuadraticCost {
     double c = 1.0;
 };
+// SignedDistanceField(origin, cell_size, data), helpers/CudaOperation.h:133-160: z slices of rows x cols matrices
+struct SignedDistanceField {
+    double origin_x = 0, origin_y = 0, origin_z = 0, cell_size = 1;
+    std::vector<MatrixXd> data;  // data[z] is rows x cols
+};
+// cost_obstacle_planar of CudaOperation_3dpR, helpers/CudaOperation.h:641-674 (3-D point robot, x(0:3) = position)
+struct Hinge3DCost {
+    std::shared_ptr<SignedDistanceField> sdf;
+    double sigma = 15.5, epsilon = 0.5, radius = 1.0;
+};
+// cost_obstacle_planar of CudaOperation_Quad, helpers/CudaOperation.h:565-605 (planar quadrotor, x = (x, z, phi, ...))
+struct QuadHingeCost {
+    std::shared_ptr<PlanarSDF> sdf;
+    double sigma = 15.5, epsilon = 0.5, radius = 1.0;
+};
 
 struct DeviceCostSpec {
     int kind = 0;
     std::vector<unsigned char> params;        // one struct (shared by the group)
-    std::shared_ptr<PlanarSDF> sdf;           // planar hinge only
+    std::shared_ptr<PlanarSDF> sdf;           // planar hinge / quadrotor hinge
+    std::shared_ptr<SignedDistanceField> sdf3d;  // 3-D hinge
     bool operator<(const DeviceCostSpec& o) const {
         if (kind != o.kind) return kind < o.kind;
         if (sdf.get() != o.sdf.get()) return sdf.get() < o.sdf.get();
+        if (sdf3d.get() != o.sdf3d.get()) return sdf3d.get() < o.sdf3d.get();
         return params < o.params;
     }
 };
+// hand the field(s) of a cost spec to a problem (before the factors that use them are added)
+inline void upload_cost_fields(gvib200_problem* prob, const DeviceCostSpec& c) {
+    if (c.sdf) {
+        const PlanarSDF& s = *c.sdf;
+        gvib200_check(gvib200_set_planar_sdf(prob, (int)s.data.rows(), (int)s.data.cols(), s.origin_x, s.origin_y, s.cell_size,
+                                             s.data.data()), "set_planar_sdf");
+    }
+    if (c.sdf3d && !c.sdf3d->data.empty()) {
+        const SignedDistanceField& s = *c.sdf3d;
+        const int rows = (int)s.data[0].rows(), cols = (int)s.data[0].cols(), nz = (int)s.data.size();
+        std::vector<double> flat((size_t)rows * cols * nz);  // data[r + c * rows + z * rows * cols], CudaOperation.h:299-301
+        for (int z = 0; z < nz; ++z)
+            for (int cc = 0; cc < cols; ++cc)
+                for (int r = 0; r < rows; ++r) flat[(size_t)r + (size_t)cc * rows + (size_t)z * rows * cols] = s.data[(size_t)z](r, cc);
+        gvib200_check(gvib200_set_sdf3d(prob, rows, cols, nz, s.origin_x, s.origin_y, s.origin_z, s.cell_size, flat.data()),
+                      "set_sdf3d");
+    }
+}
 template <class P>
 inline std::vector<unsigned char> pod_bytes(const P& p) {
     const unsigned char* b = reinterpret_cast<const unsigned char*>(&p);
@@ -90,19 +125,33 @@ template <>
 struct DeviceCostTraits<Stereo1DCost> {
     static DeviceCostSpec spec(const Stereo1DCost& c) {
         gvib200_stereo1d_params p{c.mu_p, c.f, c.b, c.sig_r_sq, c.sig_p_sq, c.y_offset};
-        return DeviceCostSpec{GVIB200_COST_STEREO_1D, pod_bytes(p), nullptr};
+        return DeviceCostSpec{GVIB200_COST_STEREO_1D, pod_bytes(p), nullptr, nullptr};
     }
 };
 template <>
 struct DeviceCostTraits<PlanarHingeCost> {
     static DeviceCostSpec spec(const PlanarHingeCost& c) {
         gvib200_hinge_params p{c.sigma, c.epsilon, c.radius};
-        return DeviceCostSpec{GVIB200_COST_PLANAR_HINGE, pod_bytes(p), c.sdf};
+        return DeviceCostSpec{GVIB200_COST_PLANAR_HINGE, pod_bytes(p), c.sdf, nullptr};
+    }
+};
+template <>
+struct DeviceCostTraits<Hinge3DCost> {
+    static DeviceCostSpec spec(const Hinge3DCost& c) {
+        gvib200_hinge_params p{c.sigma, c.epsilon, c.radius};
+        return DeviceCostSpec{GVIB200_COST_HINGE_3D, pod_bytes(p), nullptr, c.sdf};
+    }
+};
+template <>
+struct DeviceCostTraits<QuadHingeCost> {
+    static DeviceCostSpec spec(const QuadHingeCost& c) {
+        gvib200_hinge_params p{c.sigma, c.epsilon, c.radius};
+        return DeviceCostSpec{GVIB200_COST_QUAD_HINGE, pod_bytes(p), c.sdf, nullptr};
     }
 };
 template <>
 struct DeviceCostTraits<QuadraticCost> {
-    static DeviceCostSpec spec(const QuadraticCost& c) { return DeviceCostSpec{GVIB200_COST_QUADRATIC, pod_bytes(c.c), nullptr}; }
+    static DeviceCostSpec spec(const QuadraticCost& c) { return DeviceCostSpec{GVIB200_COST_QUADRATIC, pod_bytes(c.c), nullptr, nullptr}; }
 };
 
 // ------------------------------------------------------------------------------------------------ linear priors
@@ -577,11 +626,7 @@ protected:
                 Th[(size_t)k] = f->_high_temperature;
             }
             const DeviceCostSpec& c = kv.first.cost;
-            if (c.sdf) {
-                const PlanarSDF& s = *c.sdf;
-                gvib200_check(gvib200_set_planar_sdf(_prob, (int)s.data.rows(), (int)s.data.cols(), s.origin_x, s.origin_y,
-                                                     s.cell_size, s.data.data()), "set_planar_sdf");
-            }
+            upload_cost_fields(_prob, c);
             int first = 0;
             gvib200_check(gvib200_add_gh_factors(_prob, c.kind, kv.first.dim, kv.first.deg, n, start.data(), T.data(), Th.data(),
                                                  c.params.data(), c.params.size(), &first), "add_gh_factors");
@@ -782,11 +827,7 @@ private:
     void ensure() {
         if (!_prob) {
             gvib200_check(gvib200_problem_create(default_context(), 1, _dim, &_prob), "problem_create");
-            if (_cost.sdf) {
-                const PlanarSDF& s = *_cost.sdf;
-                gvib200_check(gvib200_set_planar_sdf(_prob, (int)s.data.rows(), (int)s.data.cols(), s.origin_x, s.origin_y,
-                                                     s.cell_size, s.data.data()), "set_planar_sdf");
-            }
+            upload_cost_fields(_prob, _cost);
             const int32_t start = 0;
             gvib200_check(gvib200_add_gh_factors(_prob, _cost.kind, _dim, _deg, 1, &start, nullptr, nullptr, _cost.params.data(),
                                                  _cost.params.size(), nullptr), "add_gh_factors");

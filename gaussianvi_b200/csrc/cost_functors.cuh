@@ -115,6 +115,101 @@ struct CostPlanarHinge {
     __device__ __forceinline__ double scale() const { return 0.25 * sigma; }
 };
 
+// CudaOperation_Quad::cost_obstacle_planar (helpers/CudaOperation.h:565-605): a planar quadrotor x = (pos_x, pos_z, phi, ...)
+// carries n_balls = 5 check points along its body axis (L = 5),
+//   l = pos - (L - 1.5 r) (cos phi, sin phi) / 2,   pt_i = l + L (cos phi, sin phi) i / 5,   i = 0..4,
+// each looked up in the PlanarSDF and hinged with slope 5:  psi = sigma * sum_i (5 max(0, eps + r - sd_i))^2.
+// Reuses the 32-byte hinge records of CostPlanarHinge (thr - sd in three FMAs); the five points are clamped to the field
+// one by one, as convertPoint2toCell does.
+struct CostQuadHinge {
+    static constexpr int XD = 3;
+    static constexpr bool PREMAP = false;
+    CostPlanarHinge h;  // field, threshold, sigma
+    double radius;
+    struct Pending {
+        CostPlanarHinge::Pending b[5];
+    };
+    __device__ __forceinline__ bool fast_ok(const double*, const double*) const { return false; }
+    template <bool FAST>
+    __device__ __forceinline__ Pending begin(const double* x, int f) const {
+        constexpr double L = 5.0;
+        double sn, cs;
+        sincos(x[2], &sn, &cs);
+        const double lx = x[0] - (L - radius * 1.5) * cs / 2.0;
+        const double lz = x[1] - (L - radius * 1.5) * sn / 2.0;
+        Pending p;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double pt[2] = {lx + L * cs / 5 * i, lz + L * sn / 5 * i};
+            p.b[i] = h.template begin<false>(pt, f);
+        }
+        return p;
+    }
+    __device__ __forceinline__ double finish(const Pending& p) const {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s += h.finish(p.b[i]);
+        return s;
+    }
+    __device__ __forceinline__ double scale() const { return 25.0 * h.scale(); }  // slope^2 = 25
+};
+
+// CudaOperation_3dpR::cost_obstacle_planar (helpers/CudaOperation.h:641-674, n_balls = 1, slope = 1) over the 3-D
+// SignedDistanceField (:133-236): psi(x) = sigma * max(0, eps + r - sd(x0, x1, x2))^2 with the trilinear lookup of
+// :219-236 on data[r + c * rows + z * rows * cols] (:299-301), the point clamped to the field (:176-205).
+// Upper indices are clamped (the reference reads one past the edge with weight exactly 0 there).
+struct CostHinge3D {
+    static constexpr int XD = 3;
+    static constexpr bool PREMAP = false;
+    const double* __restrict__ data;
+    int rows, cols, nz;
+    double ox, oy, oz, xmax, ymax, zmax, inv_cell, thr, sigma;
+    struct Pending {
+        double v[8];
+        double fr, fc, fz;
+    };
+    __device__ __forceinline__ bool fast_ok(const double* lo, const double* hi) const {
+        const double cell = 1.0 / inv_cell;
+        return lo[0] >= ox + cell && hi[0] <= xmax - cell && lo[1] >= oy + cell && hi[1] <= ymax - cell &&
+               lo[2] >= oz + cell && hi[2] <= zmax - cell;
+    }
+    template <bool FAST>
+    __device__ __forceinline__ Pending begin(const double* x, int) const {
+        double xin = x[0], yin = x[1], zin = x[2];
+        if (!FAST) {
+            xin = fmin(fmax(xin, ox), xmax);
+            yin = fmin(fmax(yin, oy), ymax);
+            zin = fmin(fmax(zin, oz), zmax);
+        }
+        const double col = (xin - ox) * inv_cell, row = (yin - oy) * inv_cell, zz = (zin - oz) * inv_cell;
+        const double lr = floor(row), lc = floor(col), lz = floor(zz);
+        const int lri = (int)lr, lci = (int)lc, lzi = (int)lz;
+        const int hri = min(lri + 1, rows - 1), hci = min(lci + 1, cols - 1), hzi = min(lzi + 1, nz - 1);
+        Pending p;
+        p.fr = row - lr;
+        p.fc = col - lc;
+        p.fz = zz - lz;
+        const size_t sl = (size_t)rows * cols;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = (k & 1) ? hri : lri, c = (k & 2) ? hci : lci, z = (k & 4) ? hzi : lzi;
+            p.v[k] = __ldg(data + r + (size_t)c * rows + (size_t)z * sl);
+        }
+        return p;
+    }
+    __device__ __forceinline__ double finish(const Pending& p) const {
+        // trilinear: along rows, then columns, then z
+        const double c00 = fma(p.fr, p.v[1] - p.v[0], p.v[0]), c10 = fma(p.fr, p.v[3] - p.v[2], p.v[2]);
+        const double c01 = fma(p.fr, p.v[5] - p.v[4], p.v[4]), c11 = fma(p.fr, p.v[7] - p.v[6], p.v[6]);
+        const double c0 = fma(p.fc, c10 - c00, c00), c1 = fma(p.fc, c11 - c01, c01);
+        const double sd = fma(p.fz, c1 - c0, c0);
+        const double t = thr - sd;
+        const double u = t + fabs(t);
+        return u * u;
+    }
+    __device__ __forceinline__ double scale() const { return 0.25 * sigma; }
+};
+
 // cost_linear_gp (gp/cost_functions.h:36-39 -> MinimumAccGP::cost gp/minimum_acc_prior.h:103-106,
 // LTV_GP::cost gp/LTV_prior.h:217-220): 1/2 (Phi th1 - th2)^T Qinv (Phi th1 - th2).
 // Per-factor parameters: Phi[DS*DS], Qinv[DS*DS] column-major.

@@ -224,6 +224,10 @@ struct gvib200_problem {
     bool sdf_rec_valid = false;
     int sdf_rows = 0, sdf_cols = 0;
     double sdf_ox = 0, sdf_oy = 0, sdf_cell = 0;
+    // 3-D SDF (GVIB200_COST_HINGE_3D)
+    double* d_sdf3 = nullptr;
+    int sdf3_rows = 0, sdf3_cols = 0, sdf3_nz = 0;
+    double sdf3_o[3] = {0, 0, 0}, sdf3_cell = 0;
     // state, double buffered (cur / candidate)
     int cur = 0;
     double *mu[2] = {}, *LD[2] = {}, *LO[2] = {}, *CD[2] = {}, *CO[2] = {};
@@ -705,6 +709,58 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
             }
             break;
         }
+        case GVIB200_COST_QUAD_HINGE: {
+            if constexpr (DIM == 6) {  // planar quadrotor state (x, z, phi, vx, vz, vphi)
+                if (p->d_sdf_rec == nullptr) return fail(GVIB200_ESTATE, "quadrotor hinge cost needs gvib200_set_planar_sdf");
+                const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
+                const double thr = hp->epsilon + hp->radius;
+                if (!p->sdf_rec_valid || p->sdf_thr != thr) {
+                    const long long ncell = (long long)p->sdf_rows * p->sdf_cols;
+                    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv(ncell, 256), 256, 0, p->sdf_rows, p->sdf_cols, thr,
+                           p->d_sdf_data, p->d_sdf_rec);
+                    p->sdf_thr = thr;
+                    p->sdf_rec_valid = true;
+                }
+                CostQuadHinge c;
+                c.h.rec = p->d_sdf_rec;
+                c.h.rows = p->sdf_rows;
+                c.h.cols = p->sdf_cols;
+                c.h.ox = p->sdf_ox;
+                c.h.oy = p->sdf_oy;
+                c.h.xmax = p->sdf_ox + (p->sdf_cols - 1.0) * p->sdf_cell;
+                c.h.ymax = p->sdf_oy + (p->sdf_rows - 1.0) * p->sdf_cell;
+                c.h.inv_cell = 1.0 / p->sdf_cell;
+                c.h.cx0 = -p->sdf_ox * c.h.inv_cell;
+                c.h.cy0 = -p->sdf_oy * c.h.inv_cell;
+                c.h.thr = thr;
+                c.h.sigma = hp->sigma;
+                c.radius = hp->radius;
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
+        case GVIB200_COST_HINGE_3D: {
+            if constexpr (DIM == 3 || DIM == 6) {
+                if (p->d_sdf3 == nullptr) return fail(GVIB200_ESTATE, "3-D hinge cost needs gvib200_set_sdf3d");
+                const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
+                CostHinge3D c;
+                c.data = p->d_sdf3;
+                c.rows = p->sdf3_rows;
+                c.cols = p->sdf3_cols;
+                c.nz = p->sdf3_nz;
+                c.ox = p->sdf3_o[0];
+                c.oy = p->sdf3_o[1];
+                c.oz = p->sdf3_o[2];
+                c.xmax = c.ox + (c.cols - 1.0) * p->sdf3_cell;
+                c.ymax = c.oy + (c.rows - 1.0) * p->sdf3_cell;
+                c.zmax = c.oz + (c.nz - 1.0) * p->sdf3_cell;
+                c.inv_cell = 1.0 / p->sdf3_cell;
+                c.thr = hp->epsilon + hp->radius;
+                c.sigma = hp->sigma;
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+            }
+            break;
+        }
         case GVIB200_COST_LINEAR_GP: {
             if constexpr (DIM % 2 == 0 && DIM == 2 * SD) {
                 CostLinearGP<DIM / 2> c;
@@ -1108,6 +1164,7 @@ static void free_problem(gvib200_problem* p) {
     }
     F(p->d_sdf_rec);
     F(p->d_sdf_data);
+    F(p->d_sdf3);
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
@@ -1166,6 +1223,28 @@ extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, do
     return 0;
 }
 
+extern "C" int gvib200_set_sdf3d(gvib200_problem* p, int rows, int cols, int nz, double ox, double oy, double oz, double cell,
+                                 const double* data) {
+    if (!p || rows < 2 || cols < 2 || nz < 2 || !(cell > 0) || !data) return fail(GVIB200_EINVAL, "set_sdf3d: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (p->d_sdf3) cudaFree(p->d_sdf3);
+    p->d_sdf3 = nullptr;
+    const size_t n = (size_t)rows * cols * nz;
+    CUDA_TRY(cudaMalloc((void**)&p->d_sdf3, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_sdf3, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->sdf3_rows = rows;
+    p->sdf3_cols = cols;
+    p->sdf3_nz = nz;
+    p->sdf3_o[0] = ox;
+    p->sdf3_o[1] = oy;
+    p->sdf3_o[2] = oz;
+    p->sdf3_cell = cell;
+    p->sweep_valid = false;
+    p->asm_valid = false;
+    return 0;
+}
+
 static size_t cost_param_record(int kind, int dim) {
     switch (kind) {
         case GVIB200_COST_LINEAR_GP: return (size_t)2 * (dim / 2) * (dim / 2) * sizeof(double);
@@ -1187,7 +1266,9 @@ extern "C" int gvib200_add_gh_factors(gvib200_problem* p, int kind, int dim, int
     size_t want = 0;
     switch (kind) {
         case GVIB200_COST_STEREO_1D: want = sizeof(gvib200_stereo1d_params); break;
-        case GVIB200_COST_PLANAR_HINGE: want = sizeof(gvib200_hinge_params); break;
+        case GVIB200_COST_PLANAR_HINGE:
+        case GVIB200_COST_HINGE_3D:
+        case GVIB200_COST_QUAD_HINGE: want = sizeof(gvib200_hinge_params); break;
         case GVIB200_COST_QUADRATIC: want = sizeof(double); break;
         case GVIB200_COST_LINEAR_GP:
         case GVIB200_COST_FIXED_GP: want = cost_param_record(kind, dim) * n; break;

@@ -42,6 +42,7 @@ class ProblemSpec:
     d: int
     groups: List[object] = field(default_factory=list)   # GhGroupSpec | LinGroupSpec, id order
     sdf: Optional[Tuple[np.ndarray, Tuple[float, float], float]] = None  # (data [rows, cols], origin, cell)
+    sdf3d: Optional[Tuple[np.ndarray, Tuple[float, float, float], float]] = None  # (data [nz, rows, cols], origin, cell)
     mu0: Optional[np.ndarray] = None
     prec0_D: Optional[np.ndarray] = None   # [S, d, d]
     prec0_O: Optional[np.ndarray] = None   # [S-1, d, d]
@@ -63,6 +64,9 @@ def build_device_problem(ctx: "capi.Context", spec: ProblemSpec, set_state: bool
     if spec.sdf is not None:
         data, origin, cell = spec.sdf
         p.set_planar_sdf(data, origin, cell)
+    if spec.sdf3d is not None:
+        data, origin, cell = spec.sdf3d
+        p.set_sdf3d(data, origin, cell)
     for g in spec.groups:
         if isinstance(g, GhGroupSpec):
             p.add_gh_factors(g.kind, g.dim, g.deg, g.start, g.params, g.T, g.T_high)
@@ -308,6 +312,66 @@ def make_factor_batch(N: int = 100_000, deg: int = 6, sigma: float = 0.1, seed: 
     spec.prec0_D = prec
     spec.prec0_O = np.zeros((N - 1, d, d))
     spec.meta = dict(name="factor_batch", Sigma=Sigma)
+    return spec
+
+
+def ball_sdf3d(nz: int = 40, rows: int = 60, cols: int = 80, origin=(-4.0, -3.0, -2.0), cell: float = 0.1, n_balls: int = 6,
+               seed: int = 7):
+    """Analytic 3-D signed distance to a few balls on a [nz, rows, cols] grid (x along columns, y along rows)."""
+    rng = np.random.default_rng(seed)
+    ext = np.array([(cols - 1) * cell, (rows - 1) * cell, (nz - 1) * cell])
+    c = np.asarray(origin) + rng.uniform(0.1, 0.9, (n_balls, 3)) * ext
+    r = rng.uniform(0.4, 1.0, n_balls)
+    x = origin[0] + cell * np.arange(cols)
+    y = origin[1] + cell * np.arange(rows)
+    z = origin[2] + cell * np.arange(nz)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    sd = np.full(X.shape, np.inf)
+    for k in range(n_balls):
+        sd = np.minimum(sd, np.sqrt((X - c[k, 0]) ** 2 + (Y - c[k, 1]) ** 2 + (Z - c[k, 2]) ** 2) - r[k])
+    return sd, tuple(origin), cell
+
+
+def _random_spd(rng, N, d, lo=1e-3, hi=1.0):
+    lam = np.exp(rng.uniform(np.log(lo), np.log(hi), (N, d)))
+    G = rng.standard_normal((N, d, d))
+    Qm, Rm = np.linalg.qr(G)
+    Qm = Qm * np.sign(np.diagonal(Rm, axis1=1, axis2=2))[:, None, :]
+    Sigma = (Qm * lam[:, None, :]) @ np.transpose(Qm, (0, 2, 1))
+    return 0.5 * (Sigma + np.transpose(Sigma, (0, 2, 1)))
+
+
+def make_factor_batch_functor(kind: int, N: int = 64, d: int = 6, deg: int = 3, sigma: float = 0.5, seed: int = 5) -> ProblemSpec:
+    """Factor-batch input for the moment parity of the robot cost functors beyond the planar point robot:
+    kind = COST_HINGE_3D (3-D point robot, x[0:3] position in a 3-D field) or COST_QUAD_HINGE (planar quadrotor
+    (x, z, phi, ...) in the planar field).  Means are spread over the field (some sigma points leave it: the clamp is
+    exercised), covariances random SPD."""
+    rng = np.random.default_rng(seed)
+    spec = ProblemSpec(S=N, d=d)
+    mu = rng.standard_normal((N, d))
+    if kind == capi.COST_HINGE_3D:
+        spec.sdf3d = ball_sdf3d()
+        data, origin, cell = spec.sdf3d
+        nz, rows, cols = data.shape
+        ext = np.array([(cols - 1) * cell, (rows - 1) * cell, (nz - 1) * cell])
+        mu[:, :3] = np.asarray(origin) + rng.uniform(-0.05, 1.05, (N, 3)) * ext
+    elif kind == capi.COST_QUAD_HINGE:
+        spec.sdf = disc_sdf()
+        data, origin, cell = spec.sdf
+        rows, cols = data.shape
+        mu[:, 0] = rng.uniform(origin[0] - 1.0, origin[0] + (cols - 1) * cell + 1.0, N)
+        mu[:, 1] = rng.uniform(origin[1] - 1.0, origin[1] + (rows - 1) * cell + 1.0, N)
+        mu[:, 2] = rng.uniform(-np.pi, np.pi, N)
+    else:
+        raise ValueError(kind)
+    Sigma = _random_spd(rng, N, d, 1e-3, 0.3)
+    prec = np.linalg.inv(Sigma)
+    prec = 0.5 * (prec + np.transpose(prec, (0, 2, 1)))
+    spec.groups.append(GhGroupSpec(kind, d, deg, np.arange(N, dtype=np.int32), capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
+    spec.mu0 = mu.reshape(-1)
+    spec.prec0_D = prec
+    spec.prec0_O = np.zeros((N - 1, d, d))
+    spec.meta = dict(name="factor_batch_functor", Sigma=Sigma)
     return spec
 
 

@@ -52,7 +52,13 @@ enum {
     /* cost_fixed_gp, gp/cost_functions.h:25-27: (x-mu)^T Kinv (x-mu); per-factor params: Kinv[dim*dim], mu[dim] */
     GVIB200_COST_FIXED_GP = 4,
     /* x^T (c I) x  -- the test integrand gx_1d of tests/test_gh_spgh.cpp:21-25 (params: one double c) */
-    GVIB200_COST_QUADRATIC = 5
+    GVIB200_COST_QUADRATIC = 5,
+    /* CudaOperation_3dpR::cost_obstacle_planar, helpers/CudaOperation.h:641-674 over the 3-D SignedDistanceField
+       :133-236 (trilinear lookup; params: gvib200_hinge_params; field set with gvib200_set_sdf3d); reads x[0:3] */
+    GVIB200_COST_HINGE_3D = 6,
+    /* CudaOperation_Quad::cost_obstacle_planar, helpers/CudaOperation.h:565-605: planar quadrotor (x, z, phi, ...), five
+       check points along the body axis (L = 5), slope 5, over the PlanarSDF (params: gvib200_hinge_params) */
+    GVIB200_COST_QUAD_HINGE = 7
 };
 
 typedef struct {
@@ -114,6 +120,11 @@ int gvib200_problem_destroy(gvib200_problem* prob);
    helpers/CudaOperation.h:40-45; data column-major rows x cols */
 int gvib200_set_planar_sdf(gvib200_problem* prob, int rows, int cols, double origin_x, double origin_y,
                            double cell_size, const double* data_colmajor);
+
+/* 3-D signed-distance field used by GVIB200_COST_HINGE_3D: SignedDistanceField(origin, cell_size, data)
+   helpers/CudaOperation.h:151-160; data[r + c * rows + z * rows * cols] (:299-301), x along columns, y along rows */
+int gvib200_set_sdf3d(gvib200_problem* prob, int rows, int cols, int nz, double origin_x, double origin_y, double origin_z,
+                      double cell_size, const double* data);
 
 /* n nonlinear factors NGDFactorizedBaseGH<CostClass>(dimension, state_dim, gh_degree, function, cost_class,
    num_states, start_index, temperature, high_temperature) -- ngd/NGDFactorizedBaseGH.h:37-41.

@@ -13,6 +13,9 @@ import gvi_oracle as o  # noqa: E402
 from gaussianvi_b200 import capi, problems  # noqa: E402
 
 
+SHARED_KINDS = (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC, capi.COST_HINGE_3D, capi.COST_QUAD_HINGE)
+
+
 def psi_for_group(spec, g, i):
     """Vectorised psi(X) of GH factor i of group g."""
     if g.kind == capi.COST_STEREO_1D:
@@ -26,6 +29,14 @@ def psi_for_group(spec, g, i):
         data, origin, cell = spec.sdf
         sdf = o.PlanarSDF(np.asarray(origin), cell, data)
         return o.make_hinge_cost(sdf, g.params.sigma, g.params.epsilon, g.params.radius)
+    if g.kind == capi.COST_QUAD_HINGE:
+        data, origin, cell = spec.sdf
+        sdf = o.PlanarSDF(np.asarray(origin), cell, data)
+        return o.make_quad_hinge_cost(sdf, g.params.sigma, g.params.epsilon, g.params.radius)
+    if g.kind == capi.COST_HINGE_3D:
+        data, origin, cell = spec.sdf3d
+        sdf = o.SignedDistanceField3D(np.asarray(origin), cell, data)
+        return o.make_hinge3d_cost(sdf, g.params.sigma, g.params.epsilon, g.params.radius)
     if g.kind == capi.COST_LINEAR_GP:
         ds = g.dim // 2
         rec = np.asarray(g.params).reshape(len(g.start), 2, ds, ds)
@@ -47,7 +58,7 @@ def build_factors(spec, fast=True, faithful_linear=False):
     factors = []
     for g in spec.groups:
         if isinstance(g, problems.GhGroupSpec):
-            shared = psi_for_group(spec, g, 0) if g.kind in (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC) else None
+            shared = psi_for_group(spec, g, 0) if g.kind in SHARED_KINDS else None
             for i, s in enumerate(g.start):
                 psi = shared if shared is not None else psi_for_group(spec, g, i)
                 factors.append(o.GHFactor(g.dim, spec.d, g.deg, psi, int(s), g.T, g.T_high, fast=fast))
@@ -79,7 +90,7 @@ def build_oracle_prox(spec, fast=True, niters=None):
     factors = []
     for g in spec.groups:
         if isinstance(g, problems.GhGroupSpec):
-            shared = psi_for_group(spec, g, 0) if g.kind in (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC) else None
+            shared = psi_for_group(spec, g, 0) if g.kind in SHARED_KINDS else None
             for i, s in enumerate(g.start):
                 psi = shared if shared is not None else psi_for_group(spec, g, i)
                 factors.append(o.ProxGHFactor(g.dim, spec.d, g.deg, psi, int(s), g.T, g.T_high, fast=fast))

@@ -96,3 +96,22 @@ def test_facade_planar_chain_matches_ctypes_mirror_and_oracle(gpu_ctx):
     ref = ob.build_oracle(spec, niters=niters)
     ref.optimize()
     assert np.abs(mean - ref.mean()).max() < 1e-7 * np.abs(mean).max()
+
+
+def test_robot_cost_classes_compile(tmp_path):
+    """Hinge3DCost / QuadHingeCost are device cost classes of the facade."""
+    src = tmp_path / "robots.cpp"
+    src.write_text('#include "ngd/NGDFactorizedBaseGH.h"\n#include "ngd/NGD-GH.h"\n'
+                   'using namespace gvi;\n'
+                   'double f3(const VectorXd&, const Hinge3DCost&) { return 0; }\n'
+                   'double fq(const VectorXd&, const QuadHingeCost&) { return 0; }\n'
+                   'int main() {\n'
+                   '  auto sdf = std::make_shared<SignedDistanceField>();\n'
+                   '  Hinge3DCost c3; c3.sdf = sdf;\n'
+                   '  QuadHingeCost cq; cq.sdf = std::make_shared<PlanarSDF>();\n'
+                   '  NGDFactorizedBaseGH<Hinge3DCost> a(6, 6, 3, f3, c3, 4, 1, 1.0, 10.0);\n'
+                   '  NGDFactorizedBaseGH<QuadHingeCost> b(6, 6, 3, fq, cq, 4, 1, 1.0, 10.0);\n'
+                   '  return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", str(ROOT / "gaussianvi_b200" / "cpp"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
