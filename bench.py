@@ -232,6 +232,7 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     stats = []
     barrier()
+    prob.evaluated_factors(reset=True)
     l0 = ctx.launch_count()
     sampler.start()
     t_wall = time.perf_counter()
@@ -250,7 +251,12 @@ def run_gpu(args, rank, world, local_rank):
         raise SystemExit("bench.py: a timed NGD iteration was not accepted")
     ms_per_step = ms / K
     value = world * (N / N_FACTORS) * 1e3 / ms_per_step
-    evals = sum_over_ranks(pts * (n_full + n_cost)) / (ms * 1e-3)
+    # free-space culling (library default, bit-identical results): only part of the factors is evaluated per sweep; every
+    # throughput / roofline figure below counts the sigma points that were actually evaluated
+    n_eval = prob.evaluated_factors(reset=True)                   # factor evaluations over the K timed steps
+    eval_frac = n_eval / float(info.n_gh_factors * (n_full + n_cost)) if (n_full + n_cost) else 1.0
+    evals_nominal = sum_over_ranks(pts * (n_full + n_cost)) / (ms * 1e-3)
+    evals = sum_over_ranks(n_eval * N_NODES) / (ms * 1e-3)
 
     # ---- per-launch profile of the same K steps (event pair per launch; separate pass, not the timed one)
     prob.snapshot_restore()
@@ -259,7 +265,26 @@ def run_gpu(args, rank, world, local_rank):
     prof = prob.profile_end()
     k1 = prof.get("k_moments<full>", (0, 0.0))
     k1_ms = k1[1] / max(k1[0], 1)
-    k1_tflops = pts * FLOPS_FULL / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+    n_eval_prof = prob.evaluated_factors(reset=True)
+    pts_launch = n_eval_prof * N_NODES / max(k1[0], 1)            # sigma points evaluated per launch of K1
+    k1_tflops = pts_launch * FLOPS_FULL / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+
+    # ---- the same K steps with the culling switched off (every sigma point of every factor evaluated)
+    prob.snapshot_restore()
+    prob.set_option("cull", 0)
+    for _ in range(3):
+        prob.iterate(opts)
+    prob.snapshot_restore()
+    barrier()
+    prob.timer_start()
+    run_steps(K)
+    ms_all = max_over_ranks(prob.timer_stop())
+    barrier()
+    value_all = world * (N / N_FACTORS) * 1e3 / (ms_all / K)
+    prob.set_option("cull", 1)
+    prob.snapshot_restore()
+    prob.iterate(opts)
+    prob.snapshot_restore()
     prof_total = sum(v[1] for v in prof.values())
     # chain engine: algorithmic HBM bytes per block-tridiagonal pass (~8*8*d^2 per state per inversion)
     S, d = info.num_states, info.dim_state
@@ -273,7 +298,7 @@ def run_gpu(args, rank, world, local_rank):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (6650 GB/s)"
-    flops_iter = pts * (FLOPS_FULL * n_full + FLOPS_COST * n_cost) / K
+    flops_iter = eval_frac * pts * (FLOPS_FULL * n_full + FLOPS_COST * n_cost) / K   # executed (culled factors cost nothing)
 
     # ---- end to end through the C-ABI with host buffers (pinned), every step: H2D state, iterate, D2H result
     # host buffers in the C-ABI layout (column-major d x d blocks), pinned
@@ -331,8 +356,13 @@ def run_gpu(args, rank, world, local_rank):
                        f"+ 1 cost all-reduce over NCCL, issued by the library on the problem's stream",
                        "l2": "working set per iteration (state, factor marginals, chain workspace, SDF: ~0.25 GB) exceeds the "
                              "126 MB L2; no flush",
-                       "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)"},
-            "sigma_pt_evals_per_s": evals,
+                       "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)",
+                       "culling": "library default: a hinge factor whose whole sigma-point box lies provably in free space (bound from "
+                                  "the distance field) is not evaluated -- its moments are exactly zero either way, results are "
+                                  "bit-identical (tests/test_gpu_parity.py::test_free_space_culling_is_bit_identical)"},
+            "culling": {"evaluated_factor_fraction": eval_frac, "value_all_factors_evaluated": value_all,
+                        "ms_per_step_all_factors_evaluated": ms_all / K},
+            "sigma_pt_evals_per_s": evals, "sigma_pt_evals_per_s_nominal": evals_nominal,
             "wall_ms_per_step": 1e3 * t_wall / K,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -343,7 +373,8 @@ def run_gpu(args, rank, world, local_rank):
                          "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure",
-                         "algorithmic_flops_per_launch": pts * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],
+                         "algorithmic_flops_per_launch": pts_launch * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],
+                         "sigma_points_evaluated_per_launch": pts_launch, "sigma_points_nominal_per_launch": pts,
                          "share_of_step": k1[1] / prof_total if prof_total else None,
                          "whole_iteration": {"flops": flops_iter, "achieved": flops_iter / (ms_per_step * 1e-3) / 1e12,
                                              "frac": flops_iter / (ms_per_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},

@@ -39,6 +39,7 @@ EXPORTS = [
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
+    "gvib200_evaluated_factors",
 ]
 
 
@@ -446,6 +447,11 @@ class Problem:
         _check(self.lib.gvib200_optimize_traced(self.h, C.byref(opts) if opts is not None else None, n_iters, 1 if prox else 0,
                                                 stats, C.byref(done), C.byref(rec.trace)))
         return [stats[i] for i in range(done.value)], rec
+
+    def evaluated_factors(self, reset: bool = True) -> int:
+        v = C.c_longlong()
+        _check(self.lib.gvib200_evaluated_factors(self.h, C.byref(v), 1 if reset else 0))
+        return v.value
 
     def prox_iterate(self, opts: Optional[Opts] = None) -> IterStats:
         st = IterStats()

@@ -7,6 +7,9 @@
 //   fast_ok(lo, hi)    per-factor, warp-uniform: may the FAST variant be used for sigma points whose
 //                      leading coordinates lie in the box [lo, hi]?  (FAST must give identical results)
 //   scale()            constant folded into the epilogue (e.g. the hinge weight sigma)
+//   all_zero(lo, hi)   per-factor: is psi PROVABLY zero at every point of the box [lo, hi]?  (conservative: false when
+//                      in doubt.)  A factor whose sigma-point box passes has moments that are exactly zero, so the
+//                      sign-group kernel does not evaluate it at all (free-space culling; results are bit-identical).
 // The split lets the kernel keep the gather of node i+32 in flight while it finishes node i.
 #pragma once
 #include <cuda_runtime.h>
@@ -16,6 +19,7 @@ namespace gvib200 {
 // functors without long-latency loads evaluate everything in begin()
 #define GVIB200_SIMPLE_FUNCTOR_INTERFACE()                                                        \
     static constexpr bool PREMAP = false;                                                         \
+    static constexpr bool CULL = false;                                                           \
     struct Pending {                                                                              \
         double psi;                                                                               \
     };                                                                                            \
@@ -26,7 +30,8 @@ namespace gvib200 {
         return p;                                                                                 \
     }                                                                                             \
     __device__ __forceinline__ double finish(const Pending& p) const { return p.psi; }            \
-    __device__ __forceinline__ bool fast_ok(const double*, const double*) const { return false; }
+    __device__ __forceinline__ bool fast_ok(const double*, const double*) const { return false; } \
+    __device__ __forceinline__ bool all_zero(const double*, const double*) const { return false; }
 
 // src/1d_example.cpp:25-35 (and tests/test_GH.cpp:21-34 with y_offset = +0.05)
 struct CostStereo1D {
@@ -52,6 +57,7 @@ struct CostStereo1D {
 // so that  thr - sd = t0 + fr * n_dr + fc * (n_dc + fr * n_drc)  is three FMAs.
 struct CostPlanarHinge {
     static constexpr int XD = 2;
+    static constexpr bool CULL = true;
     const double4* __restrict__ rec;  // [cols][rows]
     int rows, cols;
     double ox, oy, xmax, ymax, inv_cell, thr, sigma;
@@ -65,6 +71,27 @@ struct CostPlanarHinge {
         // one cell of margin keeps the cell coordinate safely positive / below the last node under rounding
         const double cell = 1.0 / inv_cell;
         return lo[0] >= ox + cell && hi[0] <= xmax - cell && lo[1] >= oy + cell && hi[1] <= ymax - cell;
+    }
+    // Free-space culling.  coarse[R + C * crows] = max over the 4 x 4 cells of block (R, C) of (thr - min of the cell's
+    // four corner distances): bilinear interpolation stays between its corners, so thr - sd <= that bound anywhere in
+    // the block.  A box whose blocks (one cell of slack on every side for rounding in the cell coordinates) are all
+    // below -1e-9 has psi = max(0, thr - sd)^2 == 0 at every point: the hinge is exactly zero there.
+    const double* __restrict__ coarse = nullptr;
+    int crows = 0;
+    __device__ __forceinline__ bool all_zero(const double* lo, const double* hi) const {
+        if (coarse == nullptr) return false;
+        const double c0 = fmin(fmax(fma(lo[0], inv_cell, cx0), 0.0), (double)(cols - 1));
+        const double c1 = fmin(fmax(fma(hi[0], inv_cell, cx0), 0.0), (double)(cols - 1));
+        const double r0 = fmin(fmax(fma(lo[1], inv_cell, cy0), 0.0), (double)(rows - 1));
+        const double r1 = fmin(fmax(fma(hi[1], inv_cell, cy0), 0.0), (double)(rows - 1));
+        if (!(c1 >= c0) || !(r1 >= r0)) return false;  // NaN / inverted box
+        const int C0 = max((int)c0 - 1, 0) >> 2, C1 = min((int)c1 + 1, cols - 1) >> 2;
+        const int R0 = max((int)r0 - 1, 0) >> 2, R1 = min((int)r1 + 1, rows - 1) >> 2;
+        if ((C1 - C0 + 1) * (R1 - R0 + 1) > 64) return false;  // a very wide factor: not worth the scan
+        double m = -1.0;
+        for (int C = C0; C <= C1; ++C)
+            for (int R = R0; R <= R1; ++R) m = fmax(m, __ldg(coarse + R + C * crows));
+        return m < -1e-9;
     }
     // PREMAP: the sign-group kernel applies the affine map x -> cell coordinates once per factor (to mu and to the
     // columns of S) instead of once per sigma point, and hands cell coordinates to begin_mapped()
@@ -124,12 +151,14 @@ struct CostPlanarHinge {
 struct CostQuadHinge {
     static constexpr int XD = 3;
     static constexpr bool PREMAP = false;
+    static constexpr bool CULL = false;
     CostPlanarHinge h;  // field, threshold, sigma
     double radius;
     struct Pending {
         CostPlanarHinge::Pending b[5];
     };
     __device__ __forceinline__ bool fast_ok(const double*, const double*) const { return false; }
+    __device__ __forceinline__ bool all_zero(const double*, const double*) const { return false; }
     template <bool FAST>
     __device__ __forceinline__ Pending begin(const double* x, int f) const {
         constexpr double L = 5.0;
@@ -161,6 +190,7 @@ struct CostQuadHinge {
 struct CostHinge3D {
     static constexpr int XD = 3;
     static constexpr bool PREMAP = false;
+    static constexpr bool CULL = false;
     const double* __restrict__ data;
     int rows, cols, nz;
     double ox, oy, oz, xmax, ymax, zmax, inv_cell, thr, sigma;
@@ -173,6 +203,7 @@ struct CostHinge3D {
         return lo[0] >= ox + cell && hi[0] <= xmax - cell && lo[1] >= oy + cell && hi[1] <= ymax - cell &&
                lo[2] >= oz + cell && hi[2] <= zmax - cell;
     }
+    __device__ __forceinline__ bool all_zero(const double*, const double*) const { return false; }
     template <bool FAST>
     __device__ __forceinline__ Pending begin(const double* x, int) const {
         double xin = x[0], yin = x[1], zin = x[2];

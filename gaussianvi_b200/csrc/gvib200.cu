@@ -53,6 +53,7 @@ struct Table {
     int dim = 0, deg = 0, n = 0, n_pad = 0;
     std::vector<double> nodes, w;  // host
     double ximax[12] = {};         // max |xi_c|
+    double xinorm = 0.0;           // max ||xi||_2 over the nodes
     double* d_rows = nullptr;      // device planes: NP x [n_pad] double2, then [n_pad] weights
     bool sym_ok = false;           // the rule has the sign-group structure K1S needs (dim <= 4, fits shared memory)
     SymTable sym;
@@ -178,6 +179,8 @@ struct GhGroup {
     void* d_params = nullptr;
     double* d_SR[2] = {nullptr, nullptr};
     double* d_raw = nullptr;
+    mutable int* d_active = nullptr;   // free-space culling: compacted list of the factors to evaluate
+    mutable int* d_nactive = nullptr;  // [2]: list length, finished-CTA counter
 };
 
 struct LinGroup {
@@ -191,10 +194,10 @@ struct LinGroup {
 
 // kernel classes for the per-launch profile (gvib200_profile_begin / _end)
 enum { KC_MOMENTS_FULL = 0, KC_MOMENTS_COST, KC_PROLOGUE, KC_LINEAR, KC_ASSEMBLE, KC_BT_FORWARD, KC_BT_TOP, KC_BT_BACK,
-       KC_SUM, KC_CANDIDATE, KC_OTHER, KC_COUNT };
+       KC_SUM, KC_CANDIDATE, KC_OTHER, KC_CULL, KC_COUNT };
 static const char* const KC_NAMES[KC_COUNT] = {"k_moments<full>", "k_moments<cost>", "k_prologue", "k_linear", "k_assemble",
                                                "k_bt_forward",   "k_bt_top",        "k_bt_back",  "k_sum",    "k_candidate",
-                                               "other"};
+                                               "other",          "k_cull"};
 struct ProfRec {
     int kc;
     cudaEvent_t a, b;
@@ -220,6 +223,9 @@ struct gvib200_problem {
     // SDF
     double4* d_sdf_rec = nullptr;   // hinge records, built for the threshold sdf_thr (epsilon + radius)
     double* d_sdf_data = nullptr;   // the raw field (column-major), kept to rebuild the records
+    double* d_sdf_coarse = nullptr; // free-space culling: per 8 x 8 cell block, max of thr - (min corner distance)
+    bool cull = true;               // option "cull"
+    unsigned long long* d_evaluated = nullptr;  // factors evaluated by the sign-group kernel (statistics)
     double sdf_thr = 0.0;
     bool sdf_rec_valid = false;
     int sdf_rows = 0, sdf_cols = 0;
@@ -267,7 +273,7 @@ struct gvib200_problem {
     double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_cull = nullptr;
     // schedule (GVIGH::optimize locals)
     int iter = 0;
     bool is_lowtemp = true, converged = false;
@@ -360,11 +366,14 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
         std::vector<double> rows((size_t)t->n_pad * (2 * NP + 1), 0.0);
         for (int c = 0; c < 12; ++c) t->ximax[c] = 0.0;
         for (int i = 0; i < t->n; ++i) {
+            double nrm2 = 0.0;
             for (int c = 0; c < dim; ++c) {
                 const double v = t->nodes[(size_t)i * dim + c];
                 rows[(size_t)(c / 2) * 2 * t->n_pad + (size_t)2 * i + (c & 1)] = v;
                 if (c < 12) t->ximax[c] = std::max(t->ximax[c], std::fabs(v));
+                nrm2 += v * v;
             }
+            t->xinorm = std::max(t->xinorm, std::sqrt(nrm2));
             rows[(size_t)2 * NP * t->n_pad + i] = t->w[i];
         }
         CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
@@ -565,7 +574,7 @@ static int launch_prologue(gvib200_problem* p, const GhGroup& g, const double* c
 // K1S (k1_sym.cuh): factors of dimension <= 4 on a rule with the sign-group structure
 template <int DIM, class Cost>
 static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
-                              double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+                              double* fcost, double* fVdmu, double* fVdd, double* raw, bool full, const double* covD) {
     SymArgs<Cost> a;
     a.n = g.n;
     a.state_dim = p->d;
@@ -577,6 +586,24 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     a.fVdmu = fVdmu + g.voff;
     a.fVdd = fVdd + g.moff;
     a.raw = raw;
+    a.evaluated = p->d_evaluated;
+    a.covD = covD;
+    a.xinorm = g.table->xinorm;
+    a.active = nullptr;
+    a.n_active = nullptr;
+    a.done = nullptr;
+    if constexpr (Cost::CULL) {
+        if (p->cull) {
+            if (g.d_active == nullptr) {
+                TRY(dev_alloc(&g.d_active, (size_t)g.n));
+                TRY(dev_alloc(&g.d_nactive, 2));  // [0] compacted count, [1] finished CTAs (both reset by the moment kernel)
+                CUDA_TRY(cudaMemsetAsync(g.d_nactive, 0, 2 * sizeof(int), p->ls));
+            }
+            a.active = g.d_active;
+            a.n_active = g.d_nactive;
+            a.done = reinterpret_cast<unsigned*>(g.d_nactive + 1);
+        }
+    }
     for (int c = 0; c < 4; ++c) a.ximax[c] = g.table->ximax[c];
     a.cost = cost;
     const int grid = cdiv(g.n, K1S_FPC);
@@ -589,6 +616,11 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
                                       K1S_MAX_DATA * (int)sizeof(double)));
         configured = true;
     }
+    if (a.active != nullptr) {
+        if (full) LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
+        else LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, false>), cdiv(g.n, 256), 256, 0, a);
+        CUDA_TRY(cudaEventRecord(p->ev_cull, p->ls));  // ngd_iterate starts the linear factors behind the culling pass
+    }
     if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
     if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
     else k_moments_sym<DIM, Cost, false><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
@@ -599,10 +631,10 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
 
 template <int DIM, class Cost>
 static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
-                          double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+                          double* fcost, double* fVdmu, double* fVdd, double* raw, bool full, const double* covD) {
     if constexpr (DIM <= 4) {
         if (g.table->sym_ok && !p->force_generic_k1)
-            return launch_moments_sym<DIM, Cost>(p, g, cost, mu, SR, fcost, fVdmu, fVdd, raw, full);
+            return launch_moments_sym<DIM, Cost>(p, g, cost, mu, SR, fcost, fVdmu, fVdd, raw, full, covD);
     }
     constexpr int XD = Cost::XD;
     constexpr int ROW = 2 * ((DIM + 1) / 2) + 1;  // doubles per node over all planes
@@ -650,6 +682,19 @@ static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost
     return check_launch("k_moments");
 }
 
+// hinge records + the coarse free-space bound for the threshold thr (rebuilt when the threshold changes)
+static int ensure_sdf_records(gvib200_problem* p, double thr) {
+    if (p->sdf_rec_valid && p->sdf_thr == thr) return 0;
+    const long long ncell = (long long)p->sdf_rows * p->sdf_cols;
+    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv(ncell, 256), 256, 0, p->sdf_rows, p->sdf_cols, thr, p->d_sdf_data, p->d_sdf_rec);
+    const int crows = (p->sdf_rows + 3) / 4, ccols = (p->sdf_cols + 3) / 4;
+    LAUNCH(p, KC_OTHER, k_build_sdf_coarse, cdiv((long long)crows * ccols, 128), 128, 0, p->sdf_rows, p->sdf_cols, thr, p->d_sdf_data,
+           p->d_sdf_coarse);
+    p->sdf_thr = thr;
+    p->sdf_rec_valid = true;
+    return check_launch("sdf records");
+}
+
 struct SweepTarget {
     const double* mu;
     const double* cD;
@@ -676,7 +721,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.sig_p_sq = hp->sig_p_sq;
                 c.sig_r_sq = hp->sig_r_sq;
                 c.y = hp->f * hp->b / hp->mu_p + hp->y_offset;
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -685,14 +730,10 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 if (p->d_sdf_rec == nullptr) return fail(GVIB200_ESTATE, "planar hinge cost needs gvib200_set_planar_sdf");
                 const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
                 const double thr = hp->epsilon + hp->radius;
-                if (!p->sdf_rec_valid || p->sdf_thr != thr) {  // (re)build the records for this threshold
-                    const long long ncell = (long long)p->sdf_rows * p->sdf_cols;
-                    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv(ncell, 256), 256, 0, p->sdf_rows, p->sdf_cols, thr,
-                           p->d_sdf_data, p->d_sdf_rec);
-                    p->sdf_thr = thr;
-                    p->sdf_rec_valid = true;
-                }
+                TRY(ensure_sdf_records(p, thr));
                 CostPlanarHinge c;
+                c.coarse = p->d_sdf_coarse;
+                c.crows = (p->sdf_rows + 3) / 4;
                 c.rec = p->d_sdf_rec;
                 c.rows = p->sdf_rows;
                 c.cols = p->sdf_cols;
@@ -705,7 +746,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.cy0 = -p->sdf_oy * c.inv_cell;
                 c.thr = hp->epsilon + hp->radius;
                 c.sigma = hp->sigma;
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -714,13 +755,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 if (p->d_sdf_rec == nullptr) return fail(GVIB200_ESTATE, "quadrotor hinge cost needs gvib200_set_planar_sdf");
                 const auto* hp = reinterpret_cast<const gvib200_hinge_params*>(g.params.data());
                 const double thr = hp->epsilon + hp->radius;
-                if (!p->sdf_rec_valid || p->sdf_thr != thr) {
-                    const long long ncell = (long long)p->sdf_rows * p->sdf_cols;
-                    LAUNCH(p, KC_OTHER, k_build_sdf_records, cdiv(ncell, 256), 256, 0, p->sdf_rows, p->sdf_cols, thr,
-                           p->d_sdf_data, p->d_sdf_rec);
-                    p->sdf_thr = thr;
-                    p->sdf_rec_valid = true;
-                }
+                TRY(ensure_sdf_records(p, thr));
                 CostQuadHinge c;
                 c.h.rec = p->d_sdf_rec;
                 c.h.rows = p->sdf_rows;
@@ -735,7 +770,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.h.thr = thr;
                 c.h.sigma = hp->sigma;
                 c.radius = hp->radius;
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -757,7 +792,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.inv_cell = 1.0 / p->sdf3_cell;
                 c.thr = hp->epsilon + hp->radius;
                 c.sigma = hp->sigma;
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -765,7 +800,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
             if constexpr (DIM % 2 == 0 && DIM == 2 * SD) {
                 CostLinearGP<DIM / 2> c;
                 c.params = reinterpret_cast<const double*>(g.d_params);
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -773,7 +808,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
             if constexpr (DIM == SD) {
                 CostFixedGP<DIM> c;
                 c.params = reinterpret_cast<const double*>(g.d_params);
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -781,7 +816,7 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
             if constexpr (DIM <= 4) {
                 CostQuadratic<DIM> c;
                 c.c = *reinterpret_cast<const double*>(g.params.data());
-                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full);
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
         }
@@ -1145,6 +1180,7 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_cull, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_host, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
     p->ls = p->stream;
@@ -1157,7 +1193,7 @@ static void free_problem(gvib200_problem* p) {
         if (q) cudaFree(q);
     };
     for (auto& g : p->gh) {
-        F(g.d_start); F(g.d_T); F(g.d_Thigh); F(g.d_params); F(g.d_SR[0]); F(g.d_SR[1]); F(g.d_raw);
+        F(g.d_start); F(g.d_T); F(g.d_Thigh); F(g.d_params); F(g.d_SR[0]); F(g.d_SR[1]); F(g.d_raw); F(g.d_active); F(g.d_nactive);
     }
     for (auto& g : p->lin) {
         F(g.d_start); F(g.d_Lambda); F(g.d_psi); F(g.d_Kinv); F(g.d_A); F(g.d_C); F(g.d_T);
@@ -1165,6 +1201,8 @@ static void free_problem(gvib200_problem* p) {
     F(p->d_sdf_rec);
     F(p->d_sdf_data);
     F(p->d_sdf3);
+    F(p->d_sdf_coarse);
+    F(p->d_evaluated);
     for (int i = 0; i < 2; ++i) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
@@ -1187,6 +1225,7 @@ static void free_problem(gvib200_problem* p) {
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_pro) cudaEventDestroy(p->ev_pro);
+    if (p->ev_cull) cudaEventDestroy(p->ev_cull);
     if (p->ev_host) cudaEventDestroy(p->ev_host);
     if (p->ev_mu) cudaEventDestroy(p->ev_mu);
     if (p->stream2) cudaStreamDestroy(p->stream2);
@@ -1212,6 +1251,9 @@ extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, do
     const size_t n = (size_t)rows * cols;
     CUDA_TRY(cudaMalloc((void**)&p->d_sdf_data, n * sizeof(double)));
     CUDA_TRY(cudaMalloc((void**)&p->d_sdf_rec, n * sizeof(double4)));
+    if (p->d_sdf_coarse) cudaFree(p->d_sdf_coarse);
+    p->d_sdf_coarse = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&p->d_sdf_coarse, (size_t)((rows + 3) / 4) * ((cols + 3) / 4) * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(p->d_sdf_data, data, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->sdf_rec_valid = false;
@@ -1525,6 +1567,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     CUDA_TRY(cudaHostGetDevicePointer((void**)&p->zc_dev, p->zc, 0));
     TRY(dev_alloc(&p->d_flag, 2));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), p->stream));
+    TRY(dev_alloc(&p->d_evaluated, 1));
+    CUDA_TRY(cudaMemsetAsync(p->d_evaluated, 0, sizeof(unsigned long long), p->stream));
     TRY(dev_alloc(&p->d_counter, 1));
     CUDA_TRY(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned), p->stream));
     CUDA_TRY(cudaMallocHost((void**)&p->h_flag, 2 * sizeof(int)));
@@ -1937,15 +1981,6 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             p->grads_valid = true;
             CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));  // candidate mean is complete
             TRY(run_prologue_only(p, w));
-            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
-            p->ls = p->stream2;
-            {
-                SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
-                rc = run_linear(p, t, o.reuse_accepted_sweep != 0);
-            }
-            p->ls = p->stream;
-            if (rc != 0) return rc;
-            CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
             CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_mu, 0));
             linear_forked = true;
         } else {
@@ -1953,7 +1988,19 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1));
         }
         TRY(run_sweep(p, w, cnt != 0, o.reuse_accepted_sweep != 0, false, !linear_forked));
-        if (linear_forked) CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+        if (linear_forked) {
+            // the linear factors start on the side stream once the candidate is complete and the (short, latency bound)
+            // culling pass of the quadrature sweep is through; they then run underneath the moment kernel
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_cull, 0));
+            p->ls = p->stream2;
+            SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
+            const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0);
+            p->ls = p->stream;
+            if (rc != 0) return rc;
+            CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+        }
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
         run_total(p, w);
@@ -2517,6 +2564,12 @@ extern "C" int gvib200_problem_set_option(gvib200_problem* p, const char* name, 
         p->prox = (value != 0);
         return 0;
     }
+    if (std::strcmp(name, "cull") == 0) {  // free-space culling of the sign-group kernel (default on; results are identical)
+        p->cull = (value != 0);
+        p->sweep_valid = false;
+        p->asm_valid = false;
+        return 0;
+    }
     if (std::strcmp(name, "generic_k1") == 0) {
         p->force_generic_k1 = (value != 0);
         p->sweep_valid = false;
@@ -2524,6 +2577,17 @@ extern "C" int gvib200_problem_set_option(gvib200_problem* p, const char* name, 
         return 0;
     }
     return fail(GVIB200_EINVAL, std::string("set_option: unknown option ") + name);
+}
+
+extern "C" int gvib200_evaluated_factors(gvib200_problem* p, long long* count, int reset) {
+    if (!p || !p->finalized || !count) return fail(GVIB200_EINVAL, "evaluated_factors: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    unsigned long long v = 0;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaMemcpy(&v, p->d_evaluated, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(p->d_evaluated, 0, sizeof(v)));
+    *count = (long long)v;
+    return 0;
 }
 
 extern "C" const char* gvib200_kernel_class_name(int kc) { return (kc >= 0 && kc < KC_COUNT) ? KC_NAMES[kc] : ""; }

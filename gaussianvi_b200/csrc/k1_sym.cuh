@@ -78,6 +78,13 @@ struct SymArgs {
     double* fVdmu;         // [n][DIM]
     double* fVdd;          // [n][DIM*DIM]
     double* raw;           // optional [n][1 + DIM + DIM*DIM]
+    unsigned long long* evaluated;  // optional counter: factors whose sigma points were evaluated (not culled)
+    const double* covD;    // marginal covariance blocks of the sweep's state (culling pass only)
+    double xinorm;         // max ||xi||_2 over the rule's nodes
+    // free-space culling (k_cull_sym): the factors to evaluate, compacted; null = all n factors in order
+    int* active;           // [n] factor indices
+    int* n_active;         // their number; reset (together with done) by the last CTA of the moment kernel
+    unsigned* done;        // CTAs of the moment kernel that have finished
     double ximax[4];
     Cost cost;
 };
@@ -272,6 +279,74 @@ __device__ __forceinline__ void k1s_run_part(SymAcc<DIM>& acc, const SymTable& t
 // TMA bulk copy helpers (cp.async.bulk + mbarrier), as in kernels.cuh
 __device__ __forceinline__ uint32_t k1s_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// last CTA out resets the compacted-list counters for the next sweep
+template <class Args>
+__device__ __forceinline__ void k1s_finish_cta(const Args& a) {
+    if (a.active == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
+            *a.n_active = 0;
+            *a.done = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// Free-space culling pass (one thread per factor, before the moment kernel).  Every sigma point x = mu + S xi has
+//   |x_r - mu_r| = |sum_c S_rc xi_c| <= ||S_r||_2 ||xi||_2 = sqrt(Sigma_rr) ||xi||_2      (S = Sigma^1/2 is symmetric),
+// so the box mu_r +- sqrt(Sigma_rr) max_i ||xi_i||_2 holds them all and needs only the diagonal of the factor's marginal
+// covariance.  A factor whose cost functor proves psi == 0 on that box gets its (exactly zero) outputs written here; the
+// others are appended to the compacted list the moment kernel works on (warp-aggregated append: the order of the list
+// varies from run to run, the per-factor arithmetic and therefore every result does not).
+template <int DIM, class Cost, bool FULL>
+__global__ void __launch_bounds__(256) k_cull_sym(const __grid_constant__ SymArgs<Cost> a) {
+    constexpr int XD = Cost::XD;
+    constexpr int NOUT = 1 + DIM + DIM * DIM;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (f < a.n) {
+        const int s = a.start[f], sd = a.state_dim;
+        const double* mp = a.mu + (size_t)s * sd;
+        double lo[XD], hi[XD];
+#pragma unroll
+        for (int r = 0; r < XD; ++r) {
+            const int blk = r / sd, q = r - blk * sd;  // coordinate r lives in state s + blk
+            const double var = __ldg(a.covD + (size_t)(s + blk) * sd * sd + q + q * sd);
+            const double m = __ldg(mp + r);
+            const double rad = sqrt(fmax(var, 0.0)) * a.xinorm * (1.0 + 1e-12);
+            lo[r] = m - rad;
+            hi[r] = m + rad;
+        }
+        keep = !a.cost.all_zero(lo, hi);
+        if (!keep) a.fcost[f] = 0.0;
+    }
+    const int lane_ = threadIdx.x & 31;
+    if (FULL) {
+        // the warp zeroes the outputs of its culled factors together: whole lines instead of 8-byte pieces
+        unsigned z = __ballot_sync(0xffffffffu, f < a.n && !keep);
+        const int fw = f - lane_;  // first factor of the warp
+        while (z != 0u) {
+            const int l = __ffs(z) - 1;
+            z &= z - 1u;
+            const size_t ff = (size_t)(fw + l);
+            for (int e = lane_; e < DIM * DIM; e += 32) a.fVdd[ff * DIM * DIM + e] = 0.0;
+            if (lane_ < DIM) a.fVdmu[ff * DIM + lane_] = 0.0;
+            if (a.raw != nullptr)
+                for (int e = lane_; e < NOUT; e += 32) a.raw[ff * NOUT + e] = 0.0;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m != 0u) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(a.n_active, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) a.active[base + __popc(m & ((1u << lane) - 1u))] = f;
+    }
+}
+
 template <int DIM, class Cost, bool FULL, int VAR = 0>
 __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     k_moments_sym(const __grid_constant__ SymTable tab, const __grid_constant__ SymArgs<Cost> a) {
@@ -290,7 +365,15 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     const int part = lane & (K1S_NPART - 1);
     const int fl = warp * 4 + (lane >> 3);  // factor of this lane within the CTA, 0..31
     const int f0 = blockIdx.x * K1S_FPC;
-    const int f = min(f0 + fl, a.n - 1);    // tail lanes recompute the last factor and do not store
+    // with culling the CTA works on the compacted list; CTAs beyond it leave at once
+    const int nwork = (a.active != nullptr) ? *a.n_active : a.n;
+    if (f0 >= nwork) {
+        k1s_finish_cta(a);
+        return;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && a.evaluated != nullptr) atomicAdd(a.evaluated, (unsigned long long)nwork);
+    const int slot = min(f0 + fl, nwork - 1);  // tail lanes recompute the last factor and do not store
+    const int f = (a.active != nullptr) ? a.active[slot] : slot;
     // ---- stage the table: one TMA bulk copy, completion on an mbarrier ----
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k1s_smem_u32(&mbar)), "r"(1) : "memory");
@@ -387,15 +470,20 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     }
     __syncthreads();
     // ---- epilogue: Vdmu = R e1 / T, Vddmu = R (e2 - e0 I) R / T (upper triangle mirrored), cost = e0 / T ----
-    const int nf = min(K1S_FPC, a.n - f0);
+    const int nf = min(K1S_FPC, nwork - f0);
+    const int* act = a.active;
     if (!FULL) {
-        if (threadIdx.x < nf) a.fcost[f0 + threadIdx.x] = tot[0][threadIdx.x] * sR[DIM * DIM][threadIdx.x];
+        if (threadIdx.x < nf) {
+            const int ff = act ? act[f0 + threadIdx.x] : f0 + (int)threadIdx.x;
+            a.fcost[ff] = tot[0][threadIdx.x] * sR[DIM * DIM][threadIdx.x];
+        }
+        k1s_finish_cta(a);
         return;
     }
     constexpr int NEP = DIM * DIM + DIM + 1;
     for (int idx = threadIdx.x; idx < nf * NEP; idx += K1S_THREADS) {
         const int l = idx / NEP, e = idx - l * NEP;
-        const int ff = f0 + l;
+        const int ff = act ? act[f0 + l] : f0 + l;
         const double invT = sR[DIM * DIM][l];
         const double e0 = tot[0][l];
         if (e < DIM * DIM) {
@@ -427,9 +515,10 @@ __global__ void __launch_bounds__(K1S_THREADS, k1s_minb(VAR))
     if (a.raw != nullptr) {
         for (int idx = threadIdx.x; idx < nf * NOUT; idx += K1S_THREADS) {
             const int l = idx / NOUT, e = idx - l * NOUT;
-            a.raw[(size_t)(f0 + l) * NOUT + e] = tot[e][l];
+            a.raw[(size_t)(act ? act[f0 + l] : f0 + l) * NOUT + e] = tot[e][l];
         }
     }
+    k1s_finish_cta(a);
 }
 
 }  // namespace gvib200

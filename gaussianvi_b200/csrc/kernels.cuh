@@ -976,6 +976,18 @@ __global__ void k_build_sdf_records(int rows, int cols, double thr, const double
     rec[idx] = v;
 }
 
+// free-space bound for CostPlanarHinge::all_zero: per 4 x 4 cell block the max of thr - (min corner distance of a cell)
+__global__ void k_build_sdf_coarse(int rows, int cols, double thr, const double* __restrict__ data, double* __restrict__ coarse) {
+    const int crows = (rows + 3) / 4, ccols = (cols + 3) / 4;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= crows * ccols) return;
+    const int R = idx % crows, C = idx / crows;
+    double lo = 1e300;  // min distance over the corners of the block's cells (upper indices clamped like the records)
+    for (int c = 4 * C; c <= min(4 * C + 4, cols - 1); ++c)
+        for (int r = 4 * R; r <= min(4 * R + 4, rows - 1); ++r) lo = fmin(lo, data[r + (size_t)c * rows]);
+    coarse[idx] = thr - lo;
+}
+
 // FP64 FMA micro-benchmark: the FP64 roofline denominator (not in MEASURED_PEAKS.json)
 __global__ void k_fp64_peak(int iters, double* out) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

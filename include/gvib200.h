@@ -273,6 +273,11 @@ typedef struct {
 int gvib200_profile_begin(gvib200_problem* prob);
 int gvib200_profile_end(gvib200_problem* prob, gvib200_profile* out);
 const char* gvib200_kernel_class_name(int kernel_class);
+/* Statistics of the free-space culling (problem option "cull", default on): GH factors whose sigma points were actually
+   evaluated by the sign-group kernel since the counter was last reset.  A factor is culled only when its cost functor
+   proves psi == 0 on the factor's whole sigma-point box (CostPlanarHinge: a conservative bound from the distance field);
+   its moments are then exactly zero, which is also what the evaluation would return -- results are bit-identical. */
+int gvib200_evaluated_factors(gvib200_problem* prob, long long* count, int reset);
 
 typedef struct {
     int num_states, dim_state, n_factors, n_gh_factors, n_linear_factors, chain_levels, chain_tiles, chain_tile_links;

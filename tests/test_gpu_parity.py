@@ -406,3 +406,28 @@ def test_three_level_chain_engine_long_chain(gpu_ctx):
     assert oc.lib().orc_inverse_gbp(S, d, Dc.ctypes.data_as(dp), Oc.ctypes.data_as(dp), rD.ctypes.data_as(dp), rO.ctypes.data_as(dp)) == 0
     assert rel(cD, np.transpose(rD, (0, 2, 1))) < 1e-11
     assert rel(cO, np.transpose(rO[:S - 1], (0, 2, 1))) < 1e-11
+
+
+def test_free_space_culling_is_bit_identical(gpu_ctx):
+    """Option "cull" (default on): factors whose sigma-point box lies provably in free space are not evaluated.  Their
+    moments are exactly zero either way, so five iterations with and without culling agree bit for bit -- and a good
+    part of the cfg3 factors is in fact culled."""
+    N = 3000
+    spec = problems.make_cfg3(N=N)
+    opts = capi.Problem.default_opts()
+    opts.reuse_accepted_sweep = 1
+    out = []
+    for cull in (1, 0):
+        p = problems.build_device_problem(gpu_ctx, spec)
+        p.set_option("cull", cull)
+        p.evaluated_factors(reset=True)
+        stats = p.optimize(5, opts)
+        n_eval = p.evaluated_factors()
+        covD, covO = p.covariance()
+        out.append((p.mean(), covD, covO, [s.cost for s in stats], n_eval))
+    (m1, d1, o1, c1, e1), (m0, d0, o0, c0, e0) = out
+    assert np.array_equal(m1, m0) and np.array_equal(d1, d0) and np.array_equal(o1, o0) and c1 == c0
+    sweeps = e0 // N
+    assert e0 == sweeps * N and sweeps >= 5          # without culling every sweep evaluates every factor
+    print("culling: evaluated", e1, "of", e0, "factor sweeps")
+    assert e1 < 0.8 * e0
