@@ -255,6 +255,10 @@ struct gvib200_problem {
     cudaEvent_t ev_host = nullptr;
     double *KlinD = nullptr, *KlinO = nullptr;
     // adjacency
+    // the same adjacency in ELL form (fixed width, -1 padded, [k][state]) when every state has few contributors: the
+    // assembly then needs one index load per contribution instead of a pointer chase
+    int *ell_v = nullptr, *ell_d = nullptr, *ell_dl = nullptr, *ell_o = nullptr, *ell_ol = nullptr;
+    int ell_nv = -1, ell_nd = 0, ell_no = 0;  // widths; ell_nv < 0: no ELL form
     int *vptr = nullptr, *voff = nullptr, *dptr = nullptr, *doff = nullptr, *dld = nullptr, *optr = nullptr,
         *ooff = nullptr, *old = nullptr;
     // chain engine (bt_cr.h): one plan, two workspaces so that the dmu solve and the candidate's selected inverse
@@ -273,7 +277,7 @@ struct gvib200_problem {
     double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_cull = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_cull = nullptr, ev_k1 = nullptr;
     // schedule (GVIGH::optimize locals)
     int iter = 0;
     bool is_lowtemp = true, converged = false;
@@ -935,7 +939,7 @@ static int dist_reduce(gvib200_problem* p, double* d_cost) {
 static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
-        const int nb = (int)std::min<size_t>(p->ctx->sm_count * 2, (n + 2047) / 2048);
+        const int nb = (int)std::min<size_t>(1024, (n + 1023) / 1024);  // <= 4 elements per thread
         const bool zc = (p->ctx->world == 1);
         LAUNCH(p, KC_SUM, k_total, nb, 256, 0, n, p->fcost[which], p->partial, p->d_counter, p->scal + which, 0.5,
                p->scal + 2 + which, p->d_flag, zc ? p->zc_dev : nullptr, which);
@@ -949,6 +953,12 @@ static void run_total(gvib200_problem* p, int which) {
 
 template <int D>
 static void launch_assemble(gvib200_problem* p, int which, bool alt) {
+    if (p->ell_nv >= 0) {
+        LAUNCH(p, KC_ASSEMBLE, (k_assemble_ell<D>), cdiv((long long)p->S * D, 128), 128, 0, p->S, p->ell_nv, p->ell_nd, p->ell_no, p->ell_v,
+               p->ell_d, p->ell_dl, p->ell_o, p->ell_ol, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, alt ? p->Vdmu2 : p->Vdmu,
+               alt ? p->VD2 : p->VD, alt ? p->VO2 : p->VO, alt ? p->rhs2 : p->rhs);
+        return;
+    }
     LAUNCH(p, KC_ASSEMBLE, (k_assemble<D>), cdiv((long long)p->S * D * D, 256), 256, 0, p->S, p->vptr, p->voff, p->dptr, p->doff, p->dld, p->optr,
            p->ooff, p->old, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, alt ? p->Vdmu2 : p->Vdmu, alt ? p->VD2 : p->VD,
            alt ? p->VO2 : p->VO, alt ? p->rhs2 : p->rhs);
@@ -1181,6 +1191,7 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_cull, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_k1, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_host, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
     p->ls = p->stream;
@@ -1207,7 +1218,7 @@ static void free_problem(gvib200_problem* p) {
         F(p->mu[i]); F(p->LD[i]); F(p->LO[i]); F(p->CD[i]); F(p->CO[i]); F(p->fcost[i]); F(p->fVdmu[i]); F(p->fVdd[i]);
     }
     F(p->scal); F(p->partial); F(p->d_flag); F(p->d_counter); F(p->Vdmu); F(p->VD); F(p->VO); F(p->rhs); F(p->Vdmu2); F(p->VD2); F(p->VO2); F(p->rhs2); F(p->dmu); F(p->KlinD); F(p->KlinO);
-    F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
+    F(p->ell_v); F(p->ell_d); F(p->ell_dl); F(p->ell_o); F(p->ell_ol); F(p->vptr); F(p->voff); F(p->dptr); F(p->doff); F(p->dld); F(p->optr); F(p->ooff); F(p->old); F(p->ws[0]); F(p->ws[1]);
     for (int i = 0; i < 2; ++i) {
         F(p->ws_mid[i]); F(p->ws_top[i]); F(p->dist_buf[i]);
     }
@@ -1226,6 +1237,7 @@ static void free_problem(gvib200_problem* p) {
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_pro) cudaEventDestroy(p->ev_pro);
     if (p->ev_cull) cudaEventDestroy(p->ev_cull);
+    if (p->ev_k1) cudaEventDestroy(p->ev_k1);
     if (p->ev_host) cudaEventDestroy(p->ev_host);
     if (p->ev_mu) cudaEventDestroy(p->ev_mu);
     if (p->stream2) cudaStreamDestroy(p->stream2);
@@ -1513,6 +1525,35 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     TRY(dev_upload(&p->optr, ptr, p->stream));
     TRY(dev_upload(&p->ooff, val, p->stream));
     TRY(dev_upload(&p->old, val2, p->stream));
+    {   // ELL form
+        auto width = [&](const std::vector<std::vector<int>>& ll) {
+            size_t w = 0;
+            for (auto& l : ll) w = std::max(w, l.size());
+            return (int)w;
+        };
+        const int nv = width(vl), nd = width(dl), no = width(ol);
+        if (nv <= 8 && nd <= 4 && no <= 4) {
+            auto ell = [&](const std::vector<std::vector<int>>& ll, int w, std::vector<int>& out) {
+                out.assign((size_t)std::max(w, 1) * S, -1);
+                for (int st = 0; st < S; ++st)
+                    for (size_t k = 0; k < ll[st].size(); ++k) out[k * S + st] = ll[st][k];
+            };
+            std::vector<int> e;
+            ell(vl, nv, e);
+            TRY(dev_upload(&p->ell_v, e, p->stream));
+            ell(dl, nd, e);
+            TRY(dev_upload(&p->ell_d, e, p->stream));
+            ell(dll, nd, e);
+            TRY(dev_upload(&p->ell_dl, e, p->stream));
+            ell(ol, no, e);
+            TRY(dev_upload(&p->ell_o, e, p->stream));
+            ell(oll, no, e);
+            TRY(dev_upload(&p->ell_ol, e, p->stream));
+            p->ell_nv = nv;
+            p->ell_nd = nd;
+            p->ell_no = no;
+        }
+    }
     // factor groups
     for (auto& g : p->gh) {
         TRY(dev_upload(&g.d_start, g.start, p->stream));
@@ -2003,17 +2044,35 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         }
         if (o.reuse_accepted_sweep) s.n_moment_sweeps++;
         else s.n_cost_sweeps++;
-        run_total(p, w);
-        // k_total hands the cost and the flags to the host through mapped memory; copies only where that is not valid
-        const bool zc = p->zc_ok[w] && p->zc_ok[p->cur];
-        if (!zc) CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         // speculation: if this trial is accepted its sweep is the next iteration's gradient sweep -- assemble it now,
         // into the second set of buffers, so that the host round trip below costs no device time
         const bool speculate = (o.reuse_accepted_sweep != 0);
-        TRY(read_flags(p, &flag_solve, &flag_inv, speculate ? w : -1, zc));
-        if (zc) {
+        const bool side_total = linear_forked && speculate && p->ctx->world == 1 && p->n_factors > 8192 && p->zc_ok[p->cur];
+        if (side_total) {
+            // the total cost (a short latency-bound kernel whose result only the host needs) moves to the side stream,
+            // next to the speculative assembly on the main stream; k_total hands cost and flags over in mapped memory
+            CUDA_TRY(cudaEventRecord(p->ev_k1, p->stream));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_k1, 0));
+            p->ls = p->stream2;
+            run_total(p, w);
+            p->ls = p->stream;
+            CUDA_TRY(cudaEventRecord(p->ev_host, p->stream2));
+            TRY(dispatch_assemble(p, w, true));
+            CUDA_TRY(cudaEventSynchronize(p->ev_host));
+            flag_solve = p->zc[2] != 0.0;
+            flag_inv = p->zc[3] != 0.0;
             p->h_scal[2] = p->zc[0];
             p->h_scal[3] = p->zc[1];
+        } else {
+            run_total(p, w);
+            // k_total hands the cost and the flags to the host through mapped memory; copies only where that is not valid
+            const bool zc = p->zc_ok[w] && p->zc_ok[p->cur];
+            if (!zc) CUDA_TRY(cudaMemcpyAsync(p->h_scal, p->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            TRY(read_flags(p, &flag_solve, &flag_inv, speculate ? w : -1, zc));
+            if (zc) {
+                p->h_scal[2] = p->zc[0];
+                p->h_scal[3] = p->zc[1];
+            }
         }
         if (cnt == 0) {
             cost_iter = p->h_scal[2 + p->cur];

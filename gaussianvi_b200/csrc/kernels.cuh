@@ -656,6 +656,62 @@ __global__ void __launch_bounds__(256) k_assemble(int S, const int* __restrict__
     }
 }
 
+// The same assembly over the ELL form of the adjacency ([k][state], -1 padded): one thread per (state, block column),
+// one coalesced index load per contribution instead of the pointer chase, D elements per thread.  Same summation order
+// as k_assemble (contributions in factor-id order on top of the constant block), so the results are bit-identical.
+template <int D>
+__global__ void __launch_bounds__(128) k_assemble_ell(int S, int nv, int nd, int no, const int* __restrict__ ev,
+                                                      const int* __restrict__ ed, const int* __restrict__ edl,
+                                                      const int* __restrict__ eo, const int* __restrict__ eol,
+                                                      const double* __restrict__ fVdmu, const double* __restrict__ fVdd,
+                                                      const double* __restrict__ KlinD, const double* __restrict__ KlinO,
+                                                      double* __restrict__ Vdmu, double* __restrict__ VD, double* __restrict__ VO,
+                                                      double* __restrict__ rhs) {
+    constexpr int DD = D * D;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(gid / D), j = (int)(gid - (long long)s * D);
+    if (s >= S) return;
+    const size_t cb = (size_t)s * DD + (size_t)j * D;  // first element of block column j of state s
+    double m[D], o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) m[i] = KlinD[cb + i];
+    const bool has_off = (s < S - 1);
+    if (has_off) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] = KlinO[cb + i];
+    }
+    for (int k = 0; k < nd; ++k) {
+        const int off = ed[(size_t)k * S + s];
+        if (off >= 0) {
+            const double* src = fVdd + off + (size_t)j * edl[(size_t)k * S + s];
+#pragma unroll
+            for (int i = 0; i < D; ++i) m[i] += src[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) VD[cb + i] = m[i];
+    if (has_off) {
+        for (int k = 0; k < no; ++k) {
+            const int off = eo[(size_t)k * S + s];
+            if (off >= 0) {
+                const double* src = fVdd + off + (size_t)j * eol[(size_t)k * S + s];
+#pragma unroll
+                for (int i = 0; i < D; ++i) o[i] += src[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) VO[cb + i] = o[i];
+    }
+    // thread j of the state gathers element j of Vdmu
+    double v = 0.0;
+    for (int k = 0; k < nv; ++k) {
+        const int off = ev[(size_t)k * S + s];
+        if (off >= 0) v += fVdmu[off + j];
+    }
+    Vdmu[(size_t)s * D + j] = v;
+    rhs[(size_t)s * D + j] = -v;
+}
+
 // Line-search candidate (NGDGH::onestep_linesearch, ngd/NGD-GH-impl.h:129-148):
 //   mu' = mu + a dmu,  Lambda' = Lambda + a (Vddmu - Lambda)
 __global__ void k_candidate(size_t nmu, size_t nD, size_t nO, double alpha, const double* __restrict__ mu,
@@ -693,25 +749,44 @@ __global__ void k_partial_sum(size_t n, const double* __restrict__ v, double* __
 }
 
 // Deterministic one-launch total: block b reduces a fixed contiguous slice of v into partial[b]; the block that
-// finishes last (device counter) adds the partials in index order: out[0] = sum(v) + half * extra[0].
+// finishes last (device counter) adds the partials in a fixed tree: out[0] = sum(v) + half * extra[0].
+// fixed-tree sum of one double per thread over a 256-thread block (shuffles inside a warp, then across the 8 warps);
+// the result is valid in thread 0
+__device__ __forceinline__ double block_sum_256(double v, double* sh8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 8) {
+        t = sh8[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0x000000ffu, t, o);
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restrict__ v, double* __restrict__ partial,
                                                unsigned* __restrict__ counter, const double* __restrict__ extra, double half,
                                                double* __restrict__ out, const int* __restrict__ dflag, double* zc, int which) {
-    __shared__ double sh[256];
+    __shared__ double sh8[8];
     __shared__ bool is_last;
+    // block b owns the fixed slice [b * per, (b + 1) * per); a thread takes (at most four) elements at stride 256, all
+    // loads in flight at once
     const size_t per = (n + gridDim.x - 1) / gridDim.x;
     const size_t lo = (size_t)blockIdx.x * per;
     const size_t hi = (lo + per < n) ? lo + per : n;
     double s = 0.0;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
+    for (size_t i = lo + threadIdx.x; i < hi; i += 1024) {
+        const double a0 = v[i];
+        const double a1 = (i + 256 < hi) ? v[i + 256] : 0.0;
+        const double a2 = (i + 512 < hi) ? v[i + 512] : 0.0;
+        const double a3 = (i + 768 < hi) ? v[i + 768] : 0.0;
+        s += (a0 + a1) + (a2 + a3);
     }
+    const double bs = block_sum_256(s, sh8);
     if (threadIdx.x == 0) {
-        partial[blockIdx.x] = sh[0];
+        partial[blockIdx.x] = bs;
         __threadfence();
         is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     }
@@ -720,14 +795,9 @@ __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restric
     __threadfence();
     double t = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(partial + i);
-    sh[threadIdx.x] = t;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
+    const double tot = block_sum_256(t, sh8);
     if (threadIdx.x == 0) {
-        const double total = sh[0] + (extra ? half * extra[0] : 0.0);
+        const double total = tot + (extra ? half * extra[0] : 0.0);
         out[0] = total;
         *counter = 0u;  // ready for the next launch
         if (zc != nullptr) {  // mapped host memory: the host reads the cost and the not-SPD flags without a copy
