@@ -447,22 +447,24 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     CrArgs<D> top = cr_bind<D>(p->plan_top, p->ws_top[slot], buf + L.Dt, buf + L.Ot, RHS ? buf + L.gt : nullptr, buf + L.xt,
                                buf + L.cDt, buf + L.cOt, a.notspd);
     p->flags_synced = false;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        TRY(cr_allow_smem(k_cr_mid_forward<D, RHS>, p->ctx->smem_optin - 5120));
+        TRY(cr_allow_smem(k_cr_dist_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
+        configured = true;
+    }
+    // 4 launches + one all-gather: tiles | separator sum + mid tile + boundary record | all-gather | chain of rank
+    // boundaries + seeds + mid tile back (+ log det) | tiles back
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
-    LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), 1, 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
-    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
-    LAUNCH(p, KC_OTHER, (k_cr_pack_boundary<D, RHS>), 1, 64, 0, mid, buf + L.send);
+    LAUNCH(p, KC_BT_TOP, (k_cr_mid_forward<D, RHS>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, a, mid, buf + L.D1, buf + L.O1,
+           buf + L.g1, buf + L.send);
     void* comm = (p->ls == p->stream2 && ctx->nccl_comm2) ? ctx->nccl_comm2 : ctx->nccl_comm;
     if (ctx->ncclAllGather(buf + L.send, buf + L.recv, (size_t)NB, /*ncclFloat64*/ 8, comm, p->ls) != 0)
         return fail(GVIB200_ENCCL, "chain pass: ncclAllGather failed");
-    LAUNCH(p, KC_OTHER, (k_cr_build_global<D>), 1, 256, 0, P, buf + L.recv, buf + L.Dt, buf + L.Ot, buf + L.gt);
-    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, p->plan_top.top_smem_bytes, top);
-    LAUNCH(p, KC_OTHER, (k_cr_seed_mid<D, RHS, SELINV>), 1, 64, 0, mid, ctx->rank, buf + L.xt, buf + L.cDt, buf + L.cOt);
-    LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), 1, CR_THREADS, p->plan_mid.tile_smem_bytes, mid);
+    LAUNCH(p, KC_BT_TOP, (k_cr_dist_top<D, RHS, SELINV>), 1, CR_THREADS,
+           std::max(p->plan_top.top_smem_bytes, p->plan_mid.tile_smem_bytes), P, ctx->rank, buf + L.recv, buf + L.Dt, buf + L.Ot,
+           buf + L.gt, top, mid, a.ld, pl.K, d_logdet);
     LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
-    if (d_logdet) {
-        // this rank's share of log det: its tiles + its mid tile; the chain of rank boundaries is counted by rank 0 only
-        LAUNCH(p, KC_SUM, k_sum3, 1, 256, 0, (size_t)pl.K, a.ld, mid.ld, ctx->rank == 0 ? top.ld : nullptr, d_logdet);
-    }
     return check_launch("chain_pass_dist");
 }
 
@@ -870,12 +872,17 @@ static LinearArgs linear_args(gvib200_problem* p, const LinGroup& g, const Sweep
     a.covO = t.cO;
     a.fcost = p->fcost[t.which] + g.first_id;
     a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
+    a.part = 3;
     return a;
 }
 
-static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
+// parts: 1 = covariance part, 2 = mean part, 3 = both (one after the other)
+static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full, int parts = 3) {
+  for (int part = 1; part <= 2; ++part) {
+    if (!(parts & part)) continue;
     for (auto& g : p->lin) {
         LinearArgs a;
+        a.part = part;
         a.n = g.n;
         a.dim = g.dim;
         a.m = g.m;
@@ -899,6 +906,7 @@ static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full) {
         else if (g.dim == 6 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<6, 6, 6>), cdiv(g.n, 128), 128, 0, a);
         else LAUNCH(p, KC_LINEAR, (k_linear<0, 0, 0>), cdiv(g.n, 128), 128, 0, a);
     }
+  }
     return check_launch("k_linear");
 }
 
@@ -930,7 +938,7 @@ static int dist_reduce(gvib200_problem* p, double* d_cost) {
     LAUNCH(p, KC_OTHER, k_red_pack, 1, 1, 0, d_cost, p->d_flag, p->red_buf);
     if (ctx->ncclAllReduce(p->red_buf, p->red_buf, 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, p->ls) != 0)
         return fail(GVIB200_ENCCL, "ncclAllReduce failed");
-    LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, d_cost, p->d_flag);
+    LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, d_cost, p->d_flag, (double*)nullptr, 0);
     p->flags_synced = true;
     return check_launch("dist_reduce");
 }
@@ -940,10 +948,21 @@ static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(1024, (n + 1023) / 1024);  // <= 4 elements per thread
-        const bool zc = (p->ctx->world == 1);
+        const bool single = (p->ctx->world == 1);
         LAUNCH(p, KC_SUM, k_total, nb, 256, 0, n, p->fcost[which], p->partial, p->d_counter, p->scal + which, 0.5,
-               p->scal + 2 + which, p->d_flag, zc ? p->zc_dev : nullptr, which);
-        p->zc_ok[which] = zc;
+               p->scal + 2 + which, p->d_flag, single ? p->zc_dev : nullptr, which, single ? nullptr : p->red_buf);
+        p->zc_ok[which] = true;
+        if (!single) {  // sum over the ranks, flags made global; the unpack kernel hands the result to the host (mapped memory)
+            gvib200_ctx* ctx = p->ctx;
+            if (ctx->ncclAllReduce(p->red_buf, p->red_buf, 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, p->ls) != 0) {
+                fail(GVIB200_ENCCL, "ncclAllReduce failed");
+                p->zc_ok[which] = false;
+                return;
+            }
+            LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, p->scal + 2 + which, p->d_flag, p->zc_dev, which);
+            p->flags_synced = true;
+        }
+        return;
     } else {
         LAUNCH(p, KC_SUM, k_sum, 1, 1024, 0, n, p->fcost[which], p->scal + which, 0.5, p->scal + 2 + which);
         p->zc_ok[which] = false;
@@ -2021,6 +2040,15 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             if (rc != 0) return rc;
             p->grads_valid = true;
             CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));  // candidate mean is complete
+            // covariance part of the closed-form linear factors (HBM bound): underneath the Jacobi prologue (FP64 bound)
+            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
+            p->ls = p->stream2;
+            {
+                SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
+                rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 1);
+            }
+            p->ls = p->stream;
+            if (rc != 0) return rc;
             TRY(run_prologue_only(p, w));
             CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_mu, 0));
             linear_forked = true;
@@ -2032,11 +2060,12 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         if (linear_forked) {
             // the linear factors start on the side stream once the candidate is complete and the (short, latency bound)
             // culling pass of the quadrature sweep is through; they then run underneath the moment kernel
-            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
+            // mean part of the linear factors: behind the (short, latency bound) culling pass, underneath the moment kernel.
+            // (Measured: a lowest-priority stream that only fills the moment kernel's last partial wave is no faster.)
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_cull, 0));
             p->ls = p->stream2;
             SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
-            const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0);
+            const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 2);
             p->ls = p->stream;
             if (rc != 0) return rc;
             CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));

@@ -439,6 +439,11 @@ struct LinearArgs {
     const double* covO;
     double* fcost;   // [n]
     double* fVdmu;   // [n][dim] or null (cost only)
+    // The closed form has a covariance part, (C/T) tr(A Sigma_k), and a mean part, (C/T) r^T Kinv r with r = Lambda mu - psi
+    // (and Vdmu).  part = 1 writes the covariance part into fcost, part = 2 adds the mean part to it and writes Vdmu: the
+    // two halves need different inputs (candidate covariance / candidate mean), which become available at different
+    // times of an iteration.  Every caller runs part 1 then part 2, so all paths share one arithmetic.
+    int part;
 };
 
 // DIM_, M_, SD_ > 0: compile-time shapes (fully unrolled); 0: taken from the arguments
@@ -450,6 +455,27 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
     constexpr int MAXD = DIM_ ? DIM_ : LIN_MAX_DIM, MAXM = M_ ? M_ : LIN_MAX_DIM;
     const size_t n = (size_t)a.n;
     const int s = a.start[f];
+    const double c_over_t = a.C[f] / a.T[f];
+    if (a.part == 1) {
+        // tr(A Sigma_k) = sum_i A_ii S_ii + 2 sum_{i<j} A_ij S_ij, Sigma_k assembled from the covariance blocks
+        const double* A = a.A + f;
+        double tr = 0.0;
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i)
+#pragma unroll
+            for (int j = i; j < MAXD; ++j)
+                if (i < dim && j < dim) {
+                    const int bi = i / sd, ii = i % sd, bj = j / sd, jj = j % sd;
+                    const double sij = (bi == bj) ? a.covD[(size_t)(s + bi) * sd * sd + ii + jj * sd]
+                                                  : a.covO[(size_t)s * sd * sd + ii + jj * sd];  // bi < bj: block (s, s+1)
+                    const double av = A[(size_t)e * n];
+                    tr = fma(i == j ? av : 2.0 * av, sij, tr);
+                    ++e;
+                }
+        a.fcost[f] = tr * c_over_t;
+        return;
+    }
     const double* L = a.Lambda + f;
     const double* Ki = a.Kinv + f;
     double mu[MAXD], r[MAXM], kr[MAXM];
@@ -476,7 +502,6 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
             kr[i] = v;
             q = fma(v, r[i], q);
         }
-    const double c_over_t = a.C[f] / a.T[f];
     if (a.fVdmu != nullptr) {
 #pragma unroll
         for (int k = 0; k < MAXD; ++k)
@@ -488,23 +513,7 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
                 a.fVdmu[(size_t)f * dim + k] = 2.0 * v * c_over_t;
             }
     }
-    // tr(A Sigma_k) = sum_i A_ii S_ii + 2 sum_{i<j} A_ij S_ij, Sigma_k assembled from the covariance blocks
-    const double* A = a.A + f;
-    double tr = 0.0;
-    int e = 0;
-#pragma unroll
-    for (int i = 0; i < MAXD; ++i)
-#pragma unroll
-        for (int j = i; j < MAXD; ++j)
-            if (i < dim && j < dim) {
-                const int bi = i / sd, ii = i % sd, bj = j / sd, jj = j % sd;
-                const double sij = (bi == bj) ? a.covD[(size_t)(s + bi) * sd * sd + ii + jj * sd]
-                                              : a.covO[(size_t)s * sd * sd + ii + jj * sd];  // bi < bj: block (s, s+1)
-                const double av = A[(size_t)e * n];
-                tr = fma(i == j ? av : 2.0 * av, sij, tr);
-                ++e;
-            }
-    a.fcost[f] = (tr + q) * c_over_t;
+    a.fcost[f] = fma(q, c_over_t, a.fcost[f]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -768,7 +777,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh8) {
 
 __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restrict__ v, double* __restrict__ partial,
                                                unsigned* __restrict__ counter, const double* __restrict__ extra, double half,
-                                               double* __restrict__ out, const int* __restrict__ dflag, double* zc, int which) {
+                                               double* __restrict__ out, const int* __restrict__ dflag, double* zc, int which,
+                                               double* __restrict__ red) {
     __shared__ double sh8[8];
     __shared__ bool is_last;
     // block b owns the fixed slice [b * per, (b + 1) * per); a thread takes (at most four) elements at stride 256, all
@@ -805,6 +815,12 @@ __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restric
             zc[2] = (double)dflag[0];
             zc[3] = (double)dflag[1];
             __threadfence_system();
+        }
+        if (red != nullptr) {  // multi-GPU: staging of the cost / flag all-reduce (k_red_pack folded in)
+            red[0] = total;
+            red[1] = (double)dflag[0];
+            red[2] = (double)dflag[1];
+            red[3] = 0.0;
         }
     }
 }
@@ -900,12 +916,10 @@ __device__ __forceinline__ void cr_backward_levels(const CrView<D>& v, const CrR
     }
 }
 
+// The three kernel bodies as device functions over caller-provided shared memory (dynamic `smem`, geometry `gm`,
+// reduction scratch `red`), so that the multi-GPU pass can chain several of them inside one single-CTA launch.
 template <int D, bool RHS>
-__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<D> a) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ CrGeom gm;
-    __shared__ double red[CR_THREADS];
-    const int tile = blockIdx.x;
+__device__ __forceinline__ void cr_dev_tile_forward(const CrArgs<D>& a, int tile, double* smem, CrGeom& gm, double* red) {
     const int n0 = tile * a.T;
     const int Tk = min(a.T, a.n - 1 - n0);
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
@@ -926,10 +940,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<
 }
 
 template <int D, bool RHS, bool SELINV>
-__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ CrGeom gm;
-    __shared__ double red[CR_THREADS];
+__device__ __forceinline__ void cr_dev_top(const CrArgs<D>& a, double* smem, CrGeom& gm, double* red) {
     const int nt = (a.K == 0) ? a.n : a.K + 1;  // nodes of the top chain
     if (threadIdx.x == 0) cr_make_geom(gm, nt - 1);
     __syncthreads();
@@ -964,10 +975,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
 }
 
 template <int D, bool RHS, bool SELINV>
-__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs<D> a) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ CrGeom gm;
-    const int tile = blockIdx.x;
+__device__ __forceinline__ void cr_dev_tile_backward(const CrArgs<D>& a, int tile, double* smem, CrGeom& gm) {
     const int n0 = tile * a.T;
     const int Tk = min(a.T, a.n - 1 - n0);
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
@@ -984,6 +992,73 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs
                                      a.xbase, a.xalpha, a.xout);
     __syncthreads();
     cr_stamp(clk0 + 20);
+}
+
+template <int D, bool RHS>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    cr_dev_tile_forward<D, RHS>(a, blockIdx.x, smem, gm, red);
+}
+
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    cr_dev_top<D, RHS, SELINV>(a, smem, gm, red);
+}
+
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_backward(const CrArgs<D> a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    cr_dev_tile_backward<D, RHS, SELINV>(a, blockIdx.x, smem, gm);
+}
+
+// Multi-GPU pass, the two single-CTA stages around the boundary all-gather, each ONE launch:
+//   k_cr_mid_forward  separator system of this rank's tiles summed (cr_sum_level) -> the "mid" tile over it eliminated ->
+//                     this rank's boundary record packed for the all-gather
+//   k_cr_dist_top     all boundary records -> chain of rank boundaries (cr_build_global) solved redundantly -> seeds of
+//                     the mid tile -> the mid tile walked back down (its results seed the real tiles) -> this rank's
+//                     share of log det
+// A stage only consumes what the same CTA wrote before the preceding __syncthreads().
+template <int D, bool RHS>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_mid_forward(const CrArgs<D> a, const CrArgs<D> mid, double* D1, double* O1,
+                                                                  double* g1, double* send) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    cr_sum_level<D, RHS>(a, D1, O1, g1, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cr_dev_tile_forward<D, RHS>(mid, 0, smem, gm, red);
+    __syncthreads();
+    cr_pack_boundary<D, RHS>(mid, send, threadIdx.x, blockDim.x);
+}
+
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1) k_cr_dist_top(int P, int rank, const double* recs, double* Dt, double* Ot, double* gt,
+                                                               const CrArgs<D> top, const CrArgs<D> mid, const double* tile_ld,
+                                                               int n_tile_ld, double* ldout) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm;
+    __shared__ double red[CR_THREADS];
+    cr_build_global<D>(P, recs, Dt, Ot, gt, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cr_dev_top<D, RHS, SELINV>(top, smem, gm, red);
+    __syncthreads();
+    cr_seed_mid<D, RHS, SELINV>(mid, rank, top.x, top.cD, top.cO, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cr_dev_tile_backward<D, RHS, SELINV>(mid, 0, smem, gm);
+    if (ldout != nullptr) {
+        // this rank's share of log det: its tiles + its mid tile; the chain of rank boundaries is counted by rank 0 only
+        __syncthreads();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < n_tile_ld; i += blockDim.x) t += tile_ld[i];
+        const double tot = cr_block_sum(t, red);
+        if (threadIdx.x == 0) ldout[0] = tot + mid.ld[0] + (rank == 0 ? top.ld[0] : 0.0);
+    }
 }
 
 // multi-GPU glue kernels (single small CTAs; the arithmetic is in bt_cr.h)
@@ -1024,10 +1099,16 @@ __global__ void k_red_pack(const double* cost, const int* flags, double* buf) {
     buf[2] = (double)flags[1];
     buf[3] = 0.0;
 }
-__global__ void k_red_unpack(const double* buf, double* cost, int* flags) {
+__global__ void k_red_unpack(const double* buf, double* cost, int* flags, double* zc, int which) {
     cost[0] = buf[0];
     flags[0] = buf[1] > 0.0 ? 1 : 0;
     flags[1] = buf[2] > 0.0 ? 1 : 0;
+    if (zc != nullptr) {  // mapped host memory, as in k_total
+        zc[which] = buf[0];
+        zc[2] = buf[1] > 0.0 ? 1.0 : 0.0;
+        zc[3] = buf[2] > 0.0 ? 1.0 : 0.0;
+        __threadfence_system();
+    }
 }
 
 // cell records for CostPlanarHinge from the column-major field (layout: cost_functors.cuh)
