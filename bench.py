@@ -37,6 +37,7 @@ DEG = 6
 N_NODES = 953
 FLOPS_FULL = 89     # per sigma point, full-moment sweep, d = 4, planar hinge
 FLOPS_COST = 61     # per sigma point, cost-only sweep
+K1_DRAM_BYTES_NCU = 14225408  # dram read + write bytes of one K1S launch (ncu --set full, profiles/r1_iteration_v5_ncu.txt)
 METRIC = "NGD iters/sec & sigma-pt evals/sec at N=100k factors, d=4, SpGH deg 6"
 UNIT = "NGD iters/s"
 CPU_SAMPLE_FACTORS = 10_000
@@ -370,7 +371,9 @@ def run_gpu(args, rank, world, local_rank):
                     "steps": e2e_steps, "call": "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks"},
             "roofline": {"bound": "fp64", "kernel": "k_moments<4, CostPlanarHinge, full> (K1)",
                          "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": K1_DRAM_BYTES_NCU,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_moments_sym per launch, ncu --set full "
+                                           "capture profiles/r1_iteration_v5_ncu.txt (bytes; the kernel is FP64 bound, not HBM bound)",
                          "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure",
                          "algorithmic_flops_per_launch": pts_launch * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],

@@ -277,7 +277,7 @@ struct gvib200_problem {
     double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_cull = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_k1 = nullptr;
     // schedule (GVIGH::optimize locals)
     int iter = 0;
     bool is_lowtemp = true, converged = false;
@@ -625,7 +625,6 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     if (a.active != nullptr) {
         if (full) LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
         else LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, false>), cdiv(g.n, 256), 256, 0, a);
-        CUDA_TRY(cudaEventRecord(p->ev_cull, p->ls));  // ngd_iterate starts the linear factors behind the culling pass
     }
     if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
     if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
@@ -1209,7 +1208,6 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_cull, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_k1, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_host, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
@@ -1255,7 +1253,6 @@ static void free_problem(gvib200_problem* p) {
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_pro) cudaEventDestroy(p->ev_pro);
-    if (p->ev_cull) cudaEventDestroy(p->ev_cull);
     if (p->ev_k1) cudaEventDestroy(p->ev_k1);
     if (p->ev_host) cudaEventDestroy(p->ev_host);
     if (p->ev_mu) cudaEventDestroy(p->ev_mu);
@@ -2060,9 +2057,9 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         if (linear_forked) {
             // the linear factors start on the side stream once the candidate is complete and the (short, latency bound)
             // culling pass of the quadrature sweep is through; they then run underneath the moment kernel
-            // mean part of the linear factors: behind the (short, latency bound) culling pass, underneath the moment kernel.
-            // (Measured: a lowest-priority stream that only fills the moment kernel's last partial wave is no faster.)
-            CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_cull, 0));
+            // mean part of the linear factors: as soon as the dmu solve (same stream) has delivered the candidate mean;
+            // it ends up underneath the moment kernel.  (Measured: neither holding it back behind the culling pass nor a
+            // lowest-priority stream that only fills the moment kernel's last partial wave is any faster.)
             p->ls = p->stream2;
             SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
             const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 2);
