@@ -398,6 +398,66 @@ using FixedGpPrior = NGDFactorizedLinear<FixedPriorGP>;    // gp/factorized_opts
 using LinearGpPrior = NGDFactorizedLinear<MinimumAccGP>;
 using LTVGpPrior = NGDFactorizedLinear<LTV_GP>;            // gp/factorized_opts_LTV.h
 
+// ------------------------------------------------------------------------------------------------ "_Cuda" aliases
+// The reference's own GPU path names its classes ..._Cuda and hands every nonlinear factor a CudaOperation_* object that
+// owns the distance field and the hinge parameters (helpers/CudaOperation.h:413-779, ngd/NGDFactorizedBaseGH_Cuda.h:25-50,
+// gp/factorized_opts_linear_Cuda.h:9-14).  Callers written against those names (VIMP's GPU planners) compile against the
+// stand-ins below; everything runs on the one device path of this library.  The reference's CudaOperation_* constructors
+// read their map from a file of the source tree (:463-468, :612-616); here the field is attached with set_sdf().
+struct QuadratureWeightsMap {};  // quadrature/SparseGHQuadratureWeights.h:16 -- the table lives in the library (gvib200_table_*)
+struct CudaOperation_PlanarPR {  // helpers/CudaOperation.h:452-531
+    CudaOperation_PlanarPR(double cost_sigma = 15.5, double epsilon = 0.5, double radius = 1) : _sigma(cost_sigma), _epsilon(epsilon), _radius(radius) {}
+    void set_sdf(const std::shared_ptr<PlanarSDF>& sdf) { _sdf = sdf; }
+    using CostClass = PlanarHingeCost;
+    CostClass cost_class() const { return CostClass{_sdf, _sigma, _epsilon, _radius}; }
+    double _sigma, _epsilon, _radius;
+    std::shared_ptr<PlanarSDF> _sdf;
+};
+struct CudaOperation_Quad {  // helpers/CudaOperation.h:534-607
+    CudaOperation_Quad(double cost_sigma = 15.5, double epsilon = 0.5, double radius = 1) : _sigma(cost_sigma), _epsilon(epsilon), _radius(radius) {}
+    void set_sdf(const std::shared_ptr<PlanarSDF>& sdf) { _sdf = sdf; }
+    using CostClass = QuadHingeCost;
+    CostClass cost_class() const { return CostClass{_sdf, _sigma, _epsilon, _radius}; }
+    double _sigma, _epsilon, _radius;
+    std::shared_ptr<PlanarSDF> _sdf;
+};
+struct CudaOperation_3dpR {  // helpers/CudaOperation.h:610-676
+    CudaOperation_3dpR(double cost_sigma = 15.5, double epsilon = 0.5, double radius = 1) : _sigma(cost_sigma), _epsilon(epsilon), _radius(radius) {}
+    void set_sdf(const std::shared_ptr<SignedDistanceField>& sdf) { _sdf = sdf; }
+    using CostClass = Hinge3DCost;
+    CostClass cost_class() const { return CostClass{_sdf, _sigma, _epsilon, _radius}; }
+    double _sigma, _epsilon, _radius;
+    std::shared_ptr<SignedDistanceField> _sdf;
+};
+
+// NGDFactorizedBaseGH_Cuda<CudaClass>(dimension, state_dim, gh_degree, num_states, start_index, cost_sigma, epsilon, radius,
+//                                     temperature, high_temperature, weight_sigpts_map_option, cuda_ptr)
+// ngd/NGDFactorizedBaseGH_Cuda.h:35-50.  The hinge parameters of the constructor win over the CudaClass object's, as in
+// the reference (the factor keeps its own _sigma / _epsilon / _radius).
+template <class CudaClass>
+class NGDFactorizedBaseGH_Cuda : public NGDFactorizedBaseGH<typename CudaClass::CostClass> {
+    using Cost = typename CudaClass::CostClass;
+    static Cost with_params(const CudaClass& c, double sigma, double epsilon, double radius) {
+        Cost k = c.cost_class();
+        k.sigma = sigma;
+        k.epsilon = epsilon;
+        k.radius = radius;
+        return k;
+    }
+
+public:
+    NGDFactorizedBaseGH_Cuda(int dimension, int state_dim, int gh_degree, int num_states, int start_index, double cost_sigma,
+                             double epsilon, double radius, double temperature, double high_temperature,
+                             std::shared_ptr<QuadratureWeightsMap> /*weight_sigpts_map_option*/, std::shared_ptr<CudaClass> cuda_ptr)
+        : NGDFactorizedBaseGH<Cost>(dimension, state_dim, gh_degree, nullptr, with_params(*cuda_ptr, cost_sigma, epsilon, radius),
+                                    num_states, start_index, temperature, high_temperature) {}
+    // hooks of the reference's GPU path (gvibase/GVIFactorizedBase_Cuda.h:153-189): nothing to do, the state is device resident
+    void cuda_init() {}
+    void cuda_free() {}
+};
+template <class Factor>
+using NGDFactorizedLinear_Cuda = NGDFactorizedLinear<Factor>;  // ngd/NGDFactorizedLinear_Cuda.h:28-41 (same constructor)
+
 // cost_fixed_gp / cost_linear_gp (gp/cost_functions.h:25-39): signature placeholders for source compatibility
 inline double cost_fixed_gp(const VectorXd&, const FixedPriorGP&) { return 0.0; }
 inline double cost_linear_gp(const VectorXd&, const MinimumAccGP&) { return 0.0; }
@@ -454,6 +514,19 @@ public:
     void set_niter_low_temperature(int v) { _opts.niters_lowtemp = v; }
     void set_niterations(int v) { _niters = v; }
     void set_reuse_accepted_sweep(bool v) { _opts.reuse_accepted_sweep = v ? 1 : 0; }
+    // hooks of the reference's GPU path (gvibase/GVI-GH-Cuda.h:140,223,392): the factors are classified and resident on the
+    // device by construction; the EMA of update_proposal (GVI-GH-Cuda-impl.h:112-114) is the identity at its default 1
+    void classify_factors() {}
+    void set_alpha(double alpha) {
+        if (alpha != 1.0) throw std::invalid_argument("set_alpha: only the reference default alpha = 1 (no EMA) is supported");
+    }
+    void time_test() {
+        build();
+        float ms[4] = {0, 0, 0, 0};
+        for (int stage = 0; stage < 4; ++stage) gvib200_check(gvib200_time_stage(_prob, stage, 10, &_opts, &ms[stage], nullptr), "time_test");
+        std::printf("time_test (ms / call): moment sweep %.4f  cost sweep %.4f  assemble + dmu solve %.4f  candidate + selected inverse %.4f\n",
+                    ms[0], ms[1], ms[2], ms[3]);
+    }
 
     void set_mu(const VectorXd& mean) {
         _mu0.assign(mean.data(), mean.data() + mean.size());

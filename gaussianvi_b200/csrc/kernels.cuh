@@ -740,23 +740,6 @@ __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __re
     if (i < n) out[i] = a[i] - b[i];
 }
 
-// Stage 1 of the deterministic two-stage sum: block b reduces a fixed contiguous slice of v.
-__global__ void k_partial_sum(size_t n, const double* __restrict__ v, double* __restrict__ partial) {
-    __shared__ double sh[256];
-    const size_t per = (n + gridDim.x - 1) / gridDim.x;
-    const size_t lo = (size_t)blockIdx.x * per;
-    const size_t hi = (lo + per < n) ? lo + per : n;
-    double s = 0.0;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += v[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
-
 // Deterministic one-launch total: block b reduces a fixed contiguous slice of v into partial[b]; the block that
 // finishes last (device counter) adds the partials in a fixed tree: out[0] = sum(v) + half * extra[0].
 // fixed-tree sum of one double per thread over a 256-thread block (shuffles inside a warp, then across the 8 warps);
@@ -1065,18 +1048,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_dist_top(int P, int rank, 
 template <int D, bool RHS>
 __global__ void k_cr_sum_level(const CrArgs<D> a, double* D1, double* O1, double* g1) {
     cr_sum_level<D, RHS>(a, D1, O1, g1, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-}
-template <int D, bool RHS>
-__global__ void k_cr_pack_boundary(const CrArgs<D> mid, double* rec) {
-    cr_pack_boundary<D, RHS>(mid, rec, threadIdx.x, blockDim.x);
-}
-template <int D>
-__global__ void k_cr_build_global(int P, const double* recs, double* Dt, double* Ot, double* gt) {
-    cr_build_global<D>(P, recs, Dt, Ot, gt, threadIdx.x, blockDim.x);
-}
-template <int D, bool RHS, bool SELINV>
-__global__ void k_cr_seed_mid(const CrArgs<D> mid, int rank, const double* xt, const double* cDt, const double* cOt) {
-    cr_seed_mid<D, RHS, SELINV>(mid, rank, xt, cDt, cOt, threadIdx.x, blockDim.x);
 }
 // out[0] = sum(v[0..n)) + a[0] + (b ? b[0] : 0), fixed order
 __global__ void k_sum3(size_t n, const double* __restrict__ v, const double* __restrict__ a, const double* __restrict__ b,

@@ -115,3 +115,31 @@ def test_robot_cost_classes_compile(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", str(ROOT / "gaussianvi_b200" / "cpp"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cuda_alias_api_compiles(tmp_path):
+    """callers written against the reference's `_Cuda` names (NGDFactorizedBaseGH_Cuda<CudaOperation_*>,
+    NGDFactorizedLinear_Cuda, classify_factors / set_alpha / cuda_init hooks) compile against the facade."""
+    src = tmp_path / "cuda_alias.cpp"
+    src.write_text('#include "ngd/NGDFactorizedBaseGH_Cuda.h"\n#include "ngd/NGD-GH-Cuda.h"\n'
+                   '#include "gp/factorized_opts_linear_Cuda.h"\n#include "helpers/CudaOperation.h"\n'
+                   'using namespace gvi;\n'
+                   'int main() {\n'
+                   '  auto cuda = std::make_shared<CudaOperation_PlanarPR>(15.5, 0.5, 1.0);\n'
+                   '  cuda->set_sdf(std::make_shared<PlanarSDF>());\n'
+                   '  using Col = NGDFactorizedBaseGH_Cuda<CudaOperation_PlanarPR>;\n'
+                   '  std::vector<std::shared_ptr<GVIFactorizedBase>> fs;\n'
+                   '  auto map = std::make_shared<QuadratureWeightsMap>();\n'
+                   '  auto f = std::make_shared<Col>(4, 4, 6, 10, 1, 15.5, 0.5, 1.0, 1.0, 10.0, map, cuda);\n'
+                   '  f->cuda_init(); f->cuda_free();\n'
+                   '  auto q = std::make_shared<CudaOperation_Quad>();\n'
+                   '  NGDFactorizedBaseGH_Cuda<CudaOperation_Quad> fq(6, 6, 3, 10, 1, 15.5, 0.5, 1.0, 1.0, 10.0, map, q);\n'
+                   '  auto r3 = std::make_shared<CudaOperation_3dpR>();\n'
+                   '  NGDFactorizedBaseGH_Cuda<CudaOperation_3dpR> f3(6, 6, 3, 10, 1, 15.5, 0.5, 1.0, 1.0, 10.0, map, r3);\n'
+                   '  std::vector<std::shared_ptr<Col>> v{f};\n'
+                   '  NGDGH<Col> opt(v, 4, 10);\n'
+                   '  opt.classify_factors(); opt.set_alpha(1.0);\n'
+                   '  return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", str(ROOT / "gaussianvi_b200" / "cpp"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
