@@ -431,3 +431,36 @@ def test_free_space_culling_is_bit_identical(gpu_ctx):
     assert e0 == sweeps * N and sweeps >= 5          # without culling every sweep evaluates every factor
     print("culling: evaluated", e1, "of", e0, "factor sweeps")
     assert e1 < 0.8 * e0
+
+
+@pytest.mark.parametrize("eps_radius,expect", [((0.001, 0.001), "all_culled"), ((40.0, 60.0), "none_culled")])
+def test_free_space_culling_extremes(gpu_ctx, eps_radius, expect):
+    """Threshold eps + r tiny: nearly every factor lies in free space (almost nothing is evaluated);
+    threshold larger than the field: nothing can be culled.  Both bit-identical to the run without culling; a second
+    hinge group with its own threshold rides along (two compacted lists)."""
+    N = 600
+    spec = problems.make_cfg3(N=N)
+    g = spec.groups[2]
+    g.params = capi.HingeParams(0.1 if expect == "all_culled" else 1e-4, eps_radius[0], eps_radius[1])
+    half = N // 2
+    start = np.asarray(g.start)
+    spec.groups[2] = problems.GhGroupSpec(g.kind, g.dim, g.deg, start[:half], g.params, 1.0, 10.0)
+    spec.groups.append(problems.GhGroupSpec(g.kind, g.dim, g.deg, start[half:], g.params, 1.0, 10.0))
+    opts = capi.Problem.default_opts()
+    opts.reuse_accepted_sweep = 1
+    res = []
+    for cull in (1, 0):
+        p = problems.build_device_problem(gpu_ctx, spec)
+        p.set_option("cull", cull)
+        p.evaluated_factors(reset=True)
+        stats = p.optimize(3, opts)
+        n_eval = p.evaluated_factors()
+        covD, covO = p.covariance()
+        res.append((p.mean(), covD, covO, [s.cost for s in stats], n_eval))
+    (m1, d1, o1, c1, e1), (m0, d0, o0, c0, e0) = res
+    assert np.array_equal(m1, m0) and np.array_equal(d1, d0) and np.array_equal(o1, o0) and c1 == c0
+    assert e0 > 0 and e0 % N == 0
+    if expect == "all_culled":   # (a few factors near a disc stay: the bound is conservative by up to a block of cells)
+        assert e1 < 0.3 * e0
+    else:
+        assert e1 == e0
