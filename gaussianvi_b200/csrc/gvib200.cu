@@ -1217,6 +1217,9 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
 }
 
 static void free_problem(gvib200_problem* p) {
+    // speculative work (the assembly of the last trial's sweep) may still be in flight on either stream
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->stream2) cudaStreamSynchronize(p->stream2);
     auto F = [](void* q) {
         if (q) cudaFree(q);
     };
