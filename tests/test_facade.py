@@ -27,7 +27,7 @@ def compile_example(name):
     return out
 
 
-@pytest.mark.parametrize("name", ["1d_example", "planar_chain", "1d_example_proxGVI"])
+@pytest.mark.parametrize("name", ["1d_example", "planar_chain", "1d_example_proxGVI", "point_robot_3d"])
 def test_facade_examples_compile(name):
     assert compile_example(name).exists()
 
@@ -143,3 +143,40 @@ def test_cuda_alias_api_compiles(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", str(ROOT / "gaussianvi_b200" / "cpp"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_facade_point_robot_3d_matches_ctypes_mirror_and_oracle(gpu_ctx):
+    """examples/point_robot_3d.cpp (the reference's _Cuda class names, 3-D SignedDistanceField through the facade) against the
+    same problem driven through the ctypes mirror and the oracle."""
+    S, niters, d, dt = 12, 5, 6, 0.3
+    exe = compile_example("point_robot_3d")
+    out = subprocess.run([str(exe), str(S), str(niters)], capture_output=True, text=True, check=True).stdout
+    costs = np.array([float(l.split()[2]) for l in out.splitlines() if l.startswith("cost")])
+    mean = np.array([float(l.split()[2]) for l in out.splitlines() if l.startswith("mean")])
+    nz, rows, cols, cell, origin = 40, 60, 80, 0.1, (-4.0, -3.0, -2.0)
+    z, y, x = np.meshgrid(origin[2] + cell * np.arange(nz), origin[1] + cell * np.arange(rows), origin[0] + cell * np.arange(cols),
+                          indexing="ij")
+    spec = problems.ProblemSpec(S=S, d=d)
+    spec.sdf3d = (np.sqrt(x * x + (y - 0.3) ** 2 + z * z) - 0.8, origin, cell)
+    start = np.array([-3.5, -2.5, -1.5, 0, 0, 0.0])
+    goal = np.array([3.0, 2.0, 1.0, 0, 0, 0.0])
+    spec.groups.append(problems.fixed_prior_group([0, S - 1], np.stack([start, goal]), 1e-4 * np.eye(d), d))
+    spec.groups.append(problems.minacc_group(S, 0.8 * np.eye(3), dt))
+    spec.groups.append(problems.GhGroupSpec(capi.COST_HINGE_3D, d, 3, np.arange(1, S - 1, dtype=np.int32),
+                                            capi.HingeParams(0.3, 0.5, 1.0), 1.0, 10.0))
+    t = np.linspace(0, 1, S)[:, None]
+    mu0 = start[None, :] * (1 - t) + goal[None, :] * t
+    mu0[:, 3:] = (goal[:3] - start[:3]) / ((S - 1) * dt)
+    spec.mu0 = mu0.reshape(-1)
+    spec.prec0_D = np.broadcast_to(10.0 * np.eye(d), (S, d, d)).copy()
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(niters=niters, step_size_base=0.55, niters_lowtemp=10)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    stats = p.optimize(niters, capi.Problem.default_opts())
+    assert len(costs) == niters
+    assert np.abs(costs - np.array([s.cost for s in stats])).max() / np.abs(costs).max() < 1e-12
+    assert np.abs(mean - p.mean()).max() / np.abs(mean).max() < 1e-12
+    ref = ob.build_oracle(spec, niters=niters)
+    ref.optimize()
+    assert np.abs(mean - ref.mean()).max() / np.abs(mean).max() < 1e-7
