@@ -274,7 +274,7 @@ struct gvib200_problem {
     double* ws_mid[2] = {nullptr, nullptr};
     double* ws_top[2] = {nullptr, nullptr};
     double* dist_buf[2] = {nullptr, nullptr};  // D1 | O1 | g1 | send | recv | Dt | Ot | gt | xt | cDt | cOt
-    double* red_buf = nullptr;                 // [4] cost / flag all-reduce staging
+    double* red_buf = nullptr;                 // [4 + 4 * world]: this rank's (cost, flag0, flag1, 0), then every rank's
     cudaStream_t stream2 = nullptr;  // side stream of the fork / join inside one iteration
     cudaStream_t ls = nullptr;       // stream the LAUNCH macro currently targets
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pro = nullptr, ev_mu = nullptr, ev_k1 = nullptr;
@@ -935,9 +935,10 @@ static int dist_reduce(gvib200_problem* p, double* d_cost) {
     gvib200_ctx* ctx = p->ctx;
     if (ctx->world <= 1) return 0;
     LAUNCH(p, KC_OTHER, k_red_pack, 1, 1, 0, d_cost, p->d_flag, p->red_buf);
-    if (ctx->ncclAllReduce(p->red_buf, p->red_buf, 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, p->ls) != 0)
-        return fail(GVIB200_ENCCL, "ncclAllReduce failed");
-    LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, d_cost, p->d_flag, (double*)nullptr, 0);
+    // an all-gather of the four doubles (cheaper than an all-reduce at this size) + a sum in rank order on every rank
+    if (ctx->ncclAllGather(p->red_buf, p->red_buf + 4, 4, /*ncclFloat64*/ 8, ctx->nccl_comm, p->ls) != 0)
+        return fail(GVIB200_ENCCL, "ncclAllGather (cost) failed");
+    LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, ctx->world, p->red_buf + 4, d_cost, p->d_flag, (double*)nullptr, 0);
     p->flags_synced = true;
     return check_launch("dist_reduce");
 }
@@ -953,12 +954,12 @@ static void run_total(gvib200_problem* p, int which) {
         p->zc_ok[which] = true;
         if (!single) {  // sum over the ranks, flags made global; the unpack kernel hands the result to the host (mapped memory)
             gvib200_ctx* ctx = p->ctx;
-            if (ctx->ncclAllReduce(p->red_buf, p->red_buf, 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, p->ls) != 0) {
-                fail(GVIB200_ENCCL, "ncclAllReduce failed");
+            if (ctx->ncclAllGather(p->red_buf, p->red_buf + 4, 4, /*ncclFloat64*/ 8, ctx->nccl_comm, p->ls) != 0) {
+                fail(GVIB200_ENCCL, "ncclAllGather (cost) failed");
                 p->zc_ok[which] = false;
                 return;
             }
-            LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, p->red_buf, p->scal + 2 + which, p->d_flag, p->zc_dev, which);
+            LAUNCH(p, KC_OTHER, k_red_unpack, 1, 1, 0, ctx->world, p->red_buf + 4, p->scal + 2 + which, p->d_flag, p->zc_dev, which);
             p->flags_synced = true;
         }
         return;
@@ -1699,7 +1700,7 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             CUDA_TRY(cudaMemsetAsync(p->dist_buf[i], 0, (L.total + 16) * sizeof(double), p->stream));
         }
     }
-    if (p->ctx->world > 1) TRY(dev_alloc(&p->red_buf, 8));
+    if (p->ctx->world > 1) TRY(dev_alloc(&p->red_buf, (size_t)4 * (p->ctx->world + 1)));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->finalized = true;
     return 0;

@@ -1063,21 +1063,28 @@ __global__ void k_sum3(size_t n, const double* __restrict__ v, const double* __r
     }
     if (threadIdx.x == 0) out[0] = sh[0] + a[0] + (b ? b[0] : 0.0);
 }
-// staging of the cost / flag all-reduce: buf = {cost, flag0, flag1, 0}; afterwards cost and flags are written back
+// staging of the cost / flag exchange: buf = {cost, flag0, flag1, 0}; after the all-gather cost and flags are written back
 __global__ void k_red_pack(const double* cost, const int* flags, double* buf) {
     buf[0] = cost[0];
     buf[1] = (double)flags[0];
     buf[2] = (double)flags[1];
     buf[3] = 0.0;
 }
-__global__ void k_red_unpack(const double* buf, double* cost, int* flags, double* zc, int which) {
-    cost[0] = buf[0];
-    flags[0] = buf[1] > 0.0 ? 1 : 0;
-    flags[1] = buf[2] > 0.0 ? 1 : 0;
+__global__ void k_red_unpack(int world, const double* all, double* cost, int* flags, double* zc, int which) {
+    // all: [world][4] = every rank's (cost, flag0, flag1, 0); summed in rank order, identically on every rank
+    double c = 0.0, f0 = 0.0, f1 = 0.0;
+    for (int r = 0; r < world; ++r) {
+        c += all[4 * r];
+        f0 += all[4 * r + 1];
+        f1 += all[4 * r + 2];
+    }
+    cost[0] = c;
+    flags[0] = f0 > 0.0 ? 1 : 0;
+    flags[1] = f1 > 0.0 ? 1 : 0;
     if (zc != nullptr) {  // mapped host memory, as in k_total
-        zc[which] = buf[0];
-        zc[2] = buf[1] > 0.0 ? 1.0 : 0.0;
-        zc[3] = buf[2] > 0.0 ? 1.0 : 0.0;
+        zc[which] = c;
+        zc[2] = f0 > 0.0 ? 1.0 : 0.0;
+        zc[3] = f1 > 0.0 ? 1.0 : 0.0;
         __threadfence_system();
     }
 }
