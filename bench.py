@@ -214,8 +214,10 @@ def run_gpu(args, rank, world, local_rank):
     opts.reuse_accepted_sweep = 1 if args.schedule == "reuse" else 0
     fp64_peak = ctx.fp64_peak_tflops()
 
-    # ---- warm-up, then snapshot the steady state the timed blocks rewind to
-    prob.iterate(opts)
+    # ---- set-up: one iteration (N > 1: a few more, so that both NCCL communicators have their connections and buffers
+    # established before anything is measured), then snapshot the steady state the timed blocks rewind to
+    for _ in range(1 if world == 1 else 6):
+        prob.iterate(opts)
     prob.snapshot_save()
     for _ in range(W):
         prob.iterate(opts)
