@@ -214,11 +214,15 @@ def run_gpu(args, rank, world, local_rank):
     opts.reuse_accepted_sweep = 1 if args.schedule == "reuse" else 0
     fp64_peak = ctx.fp64_peak_tflops()
 
-    # ---- set-up: one iteration (N > 1: a few more, so that both NCCL communicators have their connections and buffers
-    # established before anything is measured), then snapshot the steady state the timed blocks rewind to
-    for _ in range(1 if world == 1 else 6):
-        prob.iterate(opts)
+    # ---- set-up: one iteration, then snapshot the steady state the timed blocks rewind to.  N > 1: a few more iterations
+    # from that snapshot (rewound afterwards, fewer than the rewind interval) so that both NCCL communicators have their
+    # connections and buffers established before anything is measured
+    prob.iterate(opts)
     prob.snapshot_save()
+    if world > 1:
+        for _ in range(min(5, max(1, args.rewind_every - 1))):
+            prob.iterate(opts)
+        prob.snapshot_restore()
     for _ in range(W):
         prob.iterate(opts)
     prob.snapshot_restore()
