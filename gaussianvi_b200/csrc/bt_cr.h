@@ -183,12 +183,17 @@ GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, c
     for (int m = 0; m < D; ++m) ec.a[m] = (m == c) ? 1.0 : 0.0;
     chol_solve<D>(el.Gc, L, rd, Pjc);       // G = Dinv Pj
     chol_solve<D>(el.Hc, L, rd, el.Pirow);  // H = Dinv Pi^T
-    chol_solve<D>(Dic, L, rd, ec);
 #pragma unroll
     for (int m = 0; m < D; ++m) {
         rec.G[cr_rec(r, m + c * D, D * D)] = el.Gc.a[m];
         rec.H[cr_rec(r, m + c * D, D * D)] = el.Hc.a[m];
-        rec.Dinv[cr_rec(r, m + c * D, D * D)] = Dic.a[m];
+    }
+    // A pass is either a solve (RHS) or a selected inverse: the pivot inverse itself is only read by the Takahashi
+    // recursion (cr_bwd_selinv_compute), so a solve pass neither computes nor stores it.
+    if (!RHS) {
+        chol_solve<D>(Dic, L, rd, ec);
+#pragma unroll
+        for (int m = 0; m < D; ++m) rec.Dinv[cr_rec(r, m + c * D, D * D)] = Dic.a[m];
     }
     // right neighbour: Dn[k] -= Pj^T G
 #pragma unroll

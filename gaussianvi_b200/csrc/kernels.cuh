@@ -879,6 +879,7 @@ __device__ __forceinline__ bool cr_forward_levels(const CrView<D>& v, const CrRe
 template <int D, bool RHS, bool SELINV>
 __device__ __forceinline__ void cr_backward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base,
                                                    const CrGeom& gm, int clk0 = 0) {
+    static_assert(!(RHS && SELINV), "a pass is either a solve or a selected inverse (the forward phase of a solve keeps no pivot inverse)");
     const int per_round = blockDim.x / D;
     const int tn = threadIdx.x / D, c = threadIdx.x - tn * D;
     for (int l = gm.levels - 1; l >= 0; --l) {
