@@ -41,6 +41,7 @@ K1_DRAM_BYTES_NCU = 14225408  # dram read + write bytes of one K1S launch (ncu -
 METRIC = "NGD iters/sec & sigma-pt evals/sec at N=100k factors, d=4, SpGH deg 6"
 UNIT = "NGD iters/s"
 CPU_SAMPLE_FACTORS = 10_000
+WORKLOAD = "cfg3: NGD-GH hinge-SDF factors + LTV GP prior, d=4, N=100k factors, sparse-GH degree 6 (953 nodes)"
 
 
 def parse():
@@ -55,53 +56,107 @@ def parse():
     ap.add_argument("--factors", type=int, default=N_FACTORS, help="(development only) factors per GPU")
     ap.add_argument("--rewind-every", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-factors", type=int, default=int(os.environ.get("GVIB200_BENCH_CPU_FACTORS", "0")),
+                    help="(development / tests) factors of the CPU sample; default: chosen from a probe iteration")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(n_factors, steps, warmup, schedule):
+def cpu_arm(n_factors, steps, warmup, schedule, rewind_every=4):
     """Time the oracle's C restatement on a bounded sample of cfg3 (n_factors factors); returns
-    (iterations / s normalised to 100k factors, seconds per sample iteration, threads, T_ls, psi sweeps / iteration)."""
+    (iterations / s normalised to 100k factors, seconds per sample iteration, threads, T_ls, psi sweeps / iteration).
+
+    Like the GPU arm the state is rewound to a snapshot taken after one set-up iteration, every `rewind_every` steps,
+    so that every timed step does the same work.  With the reference's own arithmetic (schedule 0) the rewind is also
+    what keeps the run alive: NGDFactorizedLinear's O(dim^4) fourth-moment form of Vddmu (ngd/NGDFactorizedLinear.h:
+    107-119) feeds the rounding error of the pairwise marginal's inverse back into the next precision, the error grows
+    ~1000x per iteration and Vddmu stops being positive definite after 6 un-rewound iterations of this workload (the
+    algebraically identical closed form 2CA/T, which the GPU path and the lean schedule use, converges in 22)."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import gvi_oracle as o          # table generator of the oracle
     import gvi_oracle_c as oc       # the C restatement (CPU baseline; never part of the product path)
     from gaussianvi_b200 import problems
     spec = problems.make_cfg3(N=n_factors)
     c = oc.COracle(spec, o.table)
+    st = c.iterate(schedule=schedule)  # set-up iteration (also the snapshot the GPU arm rewinds to)
+    if st.status != 0 or not st.accepted:
+        raise RuntimeError(f"CPU oracle set-up iteration failed: status {st.status}, accepted {st.accepted}")
+    snap = c.snapshot()
+    rewind_every = max(1, int(rewind_every))
+    it = 0
+
+    def step():
+        nonlocal it
+        if it and it % rewind_every == 0:
+            c.restore(snap)
+        it += 1
+        return c.iterate(schedule=schedule)
+
     for _ in range(warmup):
-        c.iterate(schedule=schedule)
+        step()
+    c.restore(snap)
+    it = 0
     times, nb, sweeps = [], [], []
-    for _ in range(steps):
+    for k in range(steps):
+        restore = (it and it % rewind_every == 0)
         t = time.perf_counter()
-        st = c.iterate(schedule=schedule)
-        times.append(time.perf_counter() - t)
+        st = step()
+        times.append(time.perf_counter() - t)  # includes the (memcpy) rewind, as on the GPU
         nb.append(st.n_backtrack + 1)
         sweeps.append(st.n_psi_sweeps)
         if st.status != 0 or not st.accepted:
-            raise RuntimeError("CPU oracle iteration failed")
+            raise RuntimeError(f"CPU oracle iteration failed at timed step {k} ({(it - 1) % rewind_every + 1} iterations "
+                               f"after the snapshot{', rewound' if restore else ''}): status {st.status}, "
+                               f"accepted {st.accepted}, n_backtrack {st.n_backtrack}")
     t_iter = sum(times) / len(times)
     scale = n_factors / N_FACTORS
     return scale / t_iter, t_iter, oc.num_threads(), statistics.mean(nb), statistics.mean(sweeps)
+
+
+def cpu_sample_factors(steps, warmup, budget_s=150.0):
+    """The reference arm runs the TRUE 100k-factor workload when (steps + warmup) iterations fit `budget_s` on this
+    host (probed with one iteration at the 10k-factor sample: every stage is linear in the factor count), else the
+    10k-factor sample."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import gvi_oracle as o
+    import gvi_oracle_c as oc
+    from gaussianvi_b200 import problems
+    c = oc.COracle(problems.make_cfg3(N=CPU_SAMPLE_FACTORS), o.table)
+    c.iterate(schedule=0)
+    t = time.perf_counter()
+    c.iterate(schedule=0)
+    t10k = time.perf_counter() - t
+    est = t10k * (N_FACTORS / CPU_SAMPLE_FACTORS) * (steps + warmup + 1)
+    return (N_FACTORS if est <= budget_s else CPU_SAMPLE_FACTORS), t10k
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    value, t_iter, threads, tls, sweeps = cpu_arm(CPU_SAMPLE_FACTORS, steps, warmup, schedule=0)
+    n_sample, t_probe = cpu_sample_factors(steps, warmup)
+    if args.cpu_factors:
+        n_sample = args.cpu_factors
+    rewind = min(args.rewind_every, 4)
+    value, t_iter, threads, tls, sweeps = cpu_arm(n_sample, steps, warmup, schedule=0, rewind_every=rewind)
+    if n_sample == N_FACTORS:
+        sample = (f"one NGD iteration per step of the cfg3 generator at the full {N_FACTORS} factors ({N_FACTORS + 2} states)")
+    else:
+        sample = (f"one NGD iteration per step of the cfg3 generator at {n_sample} factors ({n_sample + 2} states; the full "
+                  f"size would need ~{t_probe * 10 * (steps + warmup + 1):.0f} s on this host); work is linear in the factor "
+                  f"count, value scaled by {n_sample}/{N_FACTORS}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": 1e3 * t_iter * (N_FACTORS / CPU_SAMPLE_FACTORS), "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": 1e3 * t_iter * (N_FACTORS / n_sample), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg3: NGD-GH hinge-SDF factors + LTV GP prior, d=4, N=100k factors, sparse-GH degree 6 (953 nodes)",
-                   "factors": N_FACTORS, "states": N_FACTORS + 2, "dim_state": 4, "gh_degree": DEG, "nodes": N_NODES},
+        "config": {"workload": WORKLOAD, "factors": N_FACTORS, "states": N_FACTORS + 2, "dim_state": 4, "gh_degree": DEG,
+                   "nodes": N_NODES, "rewind": f"host-side snapshot restore every {rewind} steps (inside the timed region)"},
         "sigma_pt_evals_per_s": value * N_FACTORS * N_NODES * sweeps,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"one NGD iteration per step of the cfg3 generator at {CPU_SAMPLE_FACTORS} factors "
-                                   f"({CPU_SAMPLE_FACTORS + 2} states), the reference's own schedule "
-                                   f"({sweeps:.0f} psi sweeps, (3+T_ls) chain inversions per iteration, T_ls={tls:.2f}); "
-                                   f"work is linear in the factor count, value scaled by {CPU_SAMPLE_FACTORS}/{N_FACTORS}",
-                         "seconds_per_sample_iteration": t_iter,
+                         "sample": sample + f"; the reference's own schedule ({sweeps:.0f} psi sweeps, (3+T_ls) chain "
+                                            f"inversions per iteration, T_ls={tls:.2f}) and arithmetic (three separate "
+                                            f"integrals per factor, O(dim^4) Vddmu loop of the linear factors)",
+                         "sample_factors": n_sample, "seconds_per_sample_iteration": t_iter,
                          "why_port": "the reference is header-only C++ on Eigen 3.4 + GSL + a MATLAB-generated table; none "
                                      "is in this image, so oracle/_ref cannot be built"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -343,26 +398,27 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     e2e_value = world * (N / N_FACTORS) * e2e_steps / e2e_s
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample: ~10-30 s of CPU work)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            v_ref, t_ref, threads, tls_c, sw_ref = cpu_arm(CPU_SAMPLE_FACTORS, 2, 1, schedule=0)
-            v_lean, t_lean, _, _, sw_lean = cpu_arm(CPU_SAMPLE_FACTORS, 2, 1, schedule=1)
-            cpu = {"value": v_ref, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"2 NGD iterations of the cfg3 generator at {CPU_SAMPLE_FACTORS} factors after 1 warm-up, "
-                             f"reference schedule ({sw_ref:.0f} psi sweeps / iteration); scaled by "
-                             f"{CPU_SAMPLE_FACTORS}/{N_FACTORS} (work is linear in the factor count)",
-                   "lean_schedule_value": v_lean, "lean_psi_sweeps": sw_lean}
-        except Exception as e:  # the baseline is reported, never required
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        n_cpu = args.cpu_factors or CPU_SAMPLE_FACTORS
+        v_ref, t_ref, threads, tls_c, sw_ref = cpu_arm(n_cpu, 8, 1, schedule=0)
+        v_lean, t_lean, _, _, sw_lean = cpu_arm(n_cpu, 8, 1, schedule=1)
+        cpu = {"value": v_ref, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"8 NGD iterations of the cfg3 generator at {n_cpu} factors after a set-up iteration and 1 warm-up "
+                         f"(state rewound every 4), reference schedule and arithmetic ({sw_ref:.0f} psi sweeps / iteration); "
+                         f"scaled by {n_cpu}/{N_FACTORS} (work is linear in the factor count)",
+               "sample_factors": n_cpu, "seconds_per_sample_iteration": t_ref,
+               "lean_schedule_value": v_lean, "lean_psi_sweeps": sw_lean,
+               "lean_note": "same C code with the GPU path's schedule: one fused moment sweep + T_ls cost sweeps, closed-form "
+                            "linear factors, (1+T_ls) chain inversions -- the hardware-only comparison"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3: NGD-GH hinge-SDF factors + LTV GP prior, d=4, N=100k factors, sparse-GH degree 6 (953 nodes)",
+            "config": {"workload": WORKLOAD,
                        "factors_per_gpu": N, "states_per_gpu": S, "dim_state": d, "gh_degree": DEG, "nodes": N_NODES,
                        "linear_factors_per_gpu": int(info.n_linear_factors), "schedule": args.schedule,
                        "T_ls_mean": tls, "parallelism": "1 GPU" if world == 1 else

@@ -1294,6 +1294,11 @@ extern "C" int gvib200_set_planar_sdf(gvib200_problem* p, int rows, int cols, do
     p->sdf_ox = ox;
     p->sdf_oy = oy;
     p->sdf_cell = cell;
+    // everything computed with the previous field is stale
+    p->sweep_valid = false;
+    p->asm_valid = false;
+    p->grads_valid = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
     return 0;
 }
 
@@ -1316,6 +1321,8 @@ extern "C" int gvib200_set_sdf3d(gvib200_problem* p, int rows, int cols, int nz,
     p->sdf3_cell = cell;
     p->sweep_valid = false;
     p->asm_valid = false;
+    p->grads_valid = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
     return 0;
 }
 
@@ -1376,7 +1383,8 @@ extern "C" int gvib200_add_linear_factors(gvib200_problem* p, int dim, int m, in
     if (!p || n < 1 || !start || !Lambda || !Psi || !mu_t || !Kinv || !C)
         return fail(GVIB200_EINVAL, "add_linear_factors: bad arguments");
     if (p->finalized) return fail(GVIB200_ESTATE, "add_linear_factors: problem already finalized");
-    if (dim % p->d != 0 || (dim / p->d != 1 && dim / p->d != 2) || dim > LIN_MAX_DIM || m > LIN_MAX_DIM || m < 1)
+    if (dim % p->d != 0 || (dim / p->d != 1 && dim / p->d != 2) || dim > LIN_MAX_DIM || m > LIN_MAX_DIM || m < 1 ||
+        kdim < 1)
         return fail(GVIB200_EINVAL, "add_linear_factors: unsupported dimensions");
     const int nst = dim / p->d;
     for (int i = 0; i < n; ++i)

@@ -170,6 +170,21 @@ class COracle:
                               C.byref(self.carried), C.byref(self.have_carry), C.byref(st))
         return st
 
+    def snapshot(self):
+        """Copy of the optimizer state (bench.py's CPU arm rewinds to it like the GPU arm does on the device)."""
+        return (self.mu.copy(), self.LD.copy(), self.LO.copy(), self.cD.copy(), self.cO.copy(), self.carried.value,
+                self.have_carry.value)
+
+    def restore(self, snap):
+        mu, LD, LO, cD, cO, carried, have = snap
+        self.mu[...] = mu
+        self.LD[...] = LD
+        self.LO[...] = LO
+        self.cD[...] = cD
+        self.cO[...] = cO
+        self.carried.value = carried
+        self.have_carry.value = have
+
     def mean(self):
         return self.mu.copy()
 

@@ -108,7 +108,7 @@ def test_bench_reference_arm_under_two_ranks():
     """bench.py --impl reference under torchrun semantics: rank 0 prints the line, the other rank exits 0 silently."""
     import json
     import subprocess
-    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", GVIB200_BENCH_CPU_FACTORS="2000")
     outs = []
     for rank in (0, 1):
         r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
@@ -119,3 +119,38 @@ def test_bench_reference_arm_under_two_ranks():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert outs[1] == ""
+
+
+def test_bench_reference_arm_at_the_drivers_arguments():
+    """The driver runs `bench.py --impl reference --steps 20 --warmup 5`: 25 iterations of the reference's own schedule
+    and arithmetic.  Un-rewound, the O(dim^4) Vddmu loop of the linear factors loses positive definiteness at iteration 6
+    of this workload (round 1's crash); the arm rewinds a host-side snapshot like the GPU arm rewinds on the device."""
+    import json
+    import subprocess
+    env = dict(os.environ, GVIB200_BENCH_CPU_FACTORS="10000")
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "20", "--warmup", "5"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip())
+    assert line["impl"] == "reference" and line["steps"] == 20 and line["warmup"] == 5 and line["value"] > 0
+    assert line["cpu_baseline"]["sample_factors"] == 10000 and line["e2e"]["value"] == line["value"]
+
+
+def test_c_oracle_faithful_linear_form_loses_spd_where_the_closed_form_converges():
+    """Documents WHY the rewind is needed: with the reference's fourth-moment form of the linear
+    factors' Vddmu (ngd/NGDFactorizedLinear.h:107-119) cfg3 at N = 2 000 stops being SPD within a dozen iterations, the
+    closed form 2CA/T (same algebra) keeps going."""
+    import gvi_oracle as o
+    import gvi_oracle_c as oc
+    from gaussianvi_b200 import problems
+    spec = problems.make_cfg3(N=2000)
+    lean = oc.COracle(spec, o.table)
+    for _ in range(12):
+        st = lean.iterate(schedule=1)
+        assert st.status == 0 and st.accepted
+    faithful = oc.COracle(spec, o.table)
+    status = [faithful.iterate(schedule=0).status for _ in range(12)]
+    assert status[0] == 0 and status[1] == 0 and status[2] == 0
+    assert any(s != 0 for s in status), status
