@@ -2116,11 +2116,16 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             cost_iter = p->h_scal[2 + p->cur];
             s.cost = cost_iter;
             if (flag_solve) {
+                // An indefinite Vddmu has no Cholesky factor: the step is not taken.  Everything the trial touched
+                // lives in the candidate buffers (mu / precision / covariance [w], the second V set), so the
+                // current state is exactly what it was; the iteration is not counted and the handle stays usable.
+                // (The reference hands the matrix to CG, ngd/NGD-GH-impl.h:59-60, and continues with whatever comes
+                // back; the oracle's direct solve reports it the same way as this library.)
                 s.status = GVIB200_ENOTSPD;
                 if (st) *st = s;
-                p->iter++;
+                p->grads_valid = false;
                 TRY(clear_flag(p));
-                return fail(GVIB200_ENOTSPD, "ngd_iterate: Vddmu is not positive definite");
+                return fail(GVIB200_ENOTSPD, "ngd_iterate: Vddmu is not positive definite (state unchanged)");
             }
         }
         const double new_cost = p->h_scal[2 + w];

@@ -630,6 +630,11 @@ int orc_assemble_V(const orc_problem* p, const double* mu, const double* cD, con
    order (GH group first here, then linear groups -- the sum is what matters), + 1/2 log det. */
 static int cost_value(const orc_problem* p, const double* mu, const double* LD, const double* LO, double* cD, double* cO,
                       double* fc, double* cost, orc_stats* st) {
+    /* a precision that is not positive definite: the reference's sum of log(LDLT pivots) is NaN and the comparison
+       `new_cost < cost_iter` (:99) is false -- the trial is rejected.  Same outcome (status -4 -> rejected by the caller)
+       without pushing the garbage covariances of an indefinite matrix through the factors (NaN sigma points). */
+    double ld = 0.0;
+    if (orc_block_solve(p->S, p->d, LD, LO, NULL, NULL, &ld)) return -4;
     if (orc_inverse_gbp(p->S, p->d, LD, LO, cD, cO)) return -4;
     st->n_inversions++;
     orc_factor_costs(p, mu, cD, cO, fc);
@@ -638,8 +643,6 @@ static int cost_value(const orc_problem* p, const double* mu, const double* LD, 
     for (int g = 0; g < p->n_lin_groups; ++g) nf += (size_t)p->lin[g].n;
     double v = 0.0;
     for (size_t i = 0; i < nf; ++i) v += fc[i];
-    double ld = 0.0;
-    if (orc_block_solve(p->S, p->d, LD, LO, NULL, NULL, &ld)) return -4;
     *cost = v + ld / 2;
     return 0;
 }

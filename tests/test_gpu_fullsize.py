@@ -116,3 +116,66 @@ def test_full_size_all_linear_chain_moves_towards_exact_posterior(gpu_ctx):
     pD, pO = p.precision()
     assert rel(pD, (1 - a) * spec.prec0_D + a * VD) < 1e-13
     assert rel(pO, (1 - a) * spec.prec0_O + a * VO) < 1e-13
+
+
+# ---------------------------------------------------------------- end-to-end parity at BASELINE.json's sizes
+def _run_vs_c_oracle(gpu_ctx, spec, niters, reuse, step_size_base=None):
+    """`niters` NGD iterations on the GPU and in the C oracle (lean schedule = the GPU path's arithmetic: closed-form
+    linear factors, direct block solve): per iteration the same decision and cost, at the end mu and the covariance
+    blocks within the north star's 1e-7."""
+    c = oc.COracle(spec, o.table)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    opts.niters_lowtemp = 1 << 30
+    opts.reuse_accepted_sweep = reuse
+    base = spec.meta.get("step_size_base", 0.55) if step_size_base is None else step_size_base
+    opts.step_size_base = base
+    for it in range(niters):
+        r = c.iterate(step_size_base=base, schedule=1)
+        s = p.iterate(opts)
+        assert r.status == 0 and s.status == 0, (it, r.status, s.status)
+        assert bool(s.accepted) == bool(r.accepted) and s.n_backtrack == r.n_backtrack, (it, s.n_backtrack, r.n_backtrack)
+        assert abs(s.cost - r.cost) < 1e-10 * max(1.0, abs(r.cost)), (it, s.cost, r.cost)
+    cD, cO = p.covariance()
+    rD, rO = c.cov_blocks()
+    e = (rel(p.mean(), c.mean()), rel(cD, rD), rel(cO, rO))
+    p.close()
+    return e
+
+
+@pytest.mark.parametrize("reuse", [1, 0])
+def test_cfg3_headline_size_ten_iterations_match_c_oracle(gpu_ctx, reuse):
+    """BASELINE config 3 at its full size: N = 100 000 hinge factors + 100 001 LTV factors, d = 4, degree 6."""
+    e = _run_vs_c_oracle(gpu_ctx, problems.make_cfg3(N=N_FULL), 10, reuse)
+    print("cfg3 N=100k, 10 iterations, reuse", reuse, ": rel err mu %.2e cov diag %.2e cov off %.2e" % e)
+    assert max(e) < 1e-7
+
+
+def test_cfg2_s1000_ten_iterations_match_c_oracle(gpu_ctx):
+    """BASELINE config 2 at its full size: all-linear 2-D point robot, S = 1000 (999 GP + 2 fixed + anchors)."""
+    spec = problems.make_cfg2(S=1000)
+    e = _run_vs_c_oracle(gpu_ctx, spec, 10, 0)
+    print("cfg2 S=1000, 10 iterations: rel err mu %.2e cov diag %.2e cov off %.2e" % e)
+    assert max(e) < 1e-7
+
+
+@pytest.mark.parametrize("closed_form", [False, True])
+def test_cfg4_s1001_prox_iterations_match_oracle(gpu_ctx, closed_form):
+    """BASELINE config 4 (Prox-GVI, dim-12 two-state factors, sparse GH degree 4 = 2649 nodes) at S = 1001: three
+    iterations against the NumPy oracle (proxgd/ProxGVI-GH-impl.h:124-205)."""
+    spec = problems.make_cfg4(S=1001, closed_form=closed_form)
+    p = problems.build_device_problem(gpu_ctx, spec, prox=True)
+    opts = capi.Problem.default_opts()
+    opts.step_size_base = spec.meta["step_size_base"]
+    opts.niters_lowtemp = spec.meta["niters_lowtemp"]
+    ref = ob.build_oracle_prox(spec, niters=3)
+    recs = ref.optimize()
+    stats = [p.prox_iterate(opts) for _ in range(3)]
+    for s, r in zip(stats, recs):
+        assert s.n_backtrack == r.n_backtrack and bool(s.accepted) == r.accepted
+        assert abs(s.cost - r.cost) < 1e-9 * max(1.0, abs(r.cost))
+    cD, cO = p.covariance()
+    e_mu = rel(p.mean(), ref.mean())
+    e_cov = rel(np.concatenate([cD.reshape(-1), cO.reshape(-1)]), np.concatenate([ref.cov.D.reshape(-1), ref.cov.O.reshape(-1)]))
+    print("prox cfg4 S=1001 closed_form", closed_form, "rel err mu", e_mu, "cov", e_cov)
+    assert e_mu < 1e-7 and e_cov < 1e-7
