@@ -54,6 +54,10 @@ def parse():
                     help="reuse: the accepted trial's full-moment sweep seeds the next iteration (identical results); "
                          "faithful: 1 moment sweep + T_ls cost sweeps per iteration")
     ap.add_argument("--factors", type=int, default=N_FACTORS, help="(development only) factors per GPU")
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg5"],
+                    help="cfg3: the headline chain (BASELINE configs[2]); cfg5: 4096 independent N=1k problems sharded "
+                         "over the GPUs (configs[4]) -- an extra bench line, the driver runs the default")
+    ap.add_argument("--problems", type=int, default=4096, help="cfg5: total number of independent problems")
     ap.add_argument("--rewind-every", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-factors", type=int, default=int(os.environ.get("GVIB200_BENCH_CPU_FACTORS", "0")),
@@ -470,6 +474,196 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ cfg5 (extra bench line)
+CFG5_N = 1000
+CFG5_METRIC = "independent-problem NGD iterations/s: 4096 problems of N=1k factors, d=4, SpGH deg 6, sharded over the GPUs"
+CFG5_UNIT = "problem-iterations/s"
+
+
+def cfg5_cpu(n_problems, steps, warmup, total):
+    """C oracle on a block-diagonal batch of `n_problems` problems (reference schedule and arithmetic, state rewound every
+    4 steps like cpu_arm); returns problem-iterations / s and a description."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import gvi_oracle as o
+    import gvi_oracle_c as oc
+    from gaussianvi_b200 import problems
+    c = oc.COracle(problems.make_cfg5(n_problems=n_problems, N=CFG5_N), o.table)
+    st = c.iterate(schedule=0)
+    if st.status != 0 or not st.accepted:
+        raise RuntimeError(f"cfg5 CPU oracle set-up iteration failed: status {st.status}")
+    snap = c.snapshot()
+    times = []
+    for k in range(warmup + steps):
+        if k and k % 4 == 0:
+            c.restore(snap)
+        t = time.perf_counter()
+        st = c.iterate(schedule=0)
+        if k >= warmup:
+            times.append(time.perf_counter() - t)
+        if st.status != 0 or not st.accepted:
+            raise RuntimeError(f"cfg5 CPU oracle iteration {k} failed: status {st.status}, accepted {st.accepted}")
+    t_iter = sum(times) / len(times)
+    return n_problems / t_iter, oc.num_threads(), (
+        f"{steps} NGD iterations of a batch of {n_problems} of the {total} problems after a set-up iteration and {warmup} "
+        f"warm-up (reference schedule and arithmetic, state rewound every 4); problems are independent, so "
+        f"problem-iterations/s does not depend on the batch size")
+
+
+def run_cfg5(args, rank, world, local_rank):
+    """BASELINE configs[4] / SURVEY 8(e) first bullet: `--problems` independent copies of the cfg3 generator at N = 1000
+    (seeds 1000 ...), sharded over the ranks as contiguous ranges; every rank runs its range as ONE block-diagonal batch
+    on its GPU.  No collective on the iteration path (strong scaling: the total is fixed)."""
+    K, W = max(1, args.steps), max(3, args.warmup)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, threads, sample = cfg5_cpu(8, K, max(0, args.warmup), args.problems)
+        print(json.dumps({
+            "impl": "reference", "metric": CFG5_METRIC, "value": v, "unit": CFG5_UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": max(0, args.warmup), "ms_per_step": 1e3 * args.problems / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg5: {args.problems} independent cfg3 problems of N={CFG5_N} factors"},
+            "cpu_baseline": {"value": v, "unit": CFG5_UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": CFG5_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import numpy as np
+    import torch
+    import gaussianvi_b200 as gv
+    from gaussianvi_b200 import problems
+    from gaussianvi_b200.dist import shard_problems
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    first, count = shard_problems(args.problems, rank, world)
+    ctx = gv.Context(local_rank)
+    t_build = time.perf_counter()
+    spec = problems.make_cfg5(n_problems=count, N=CFG5_N, first_seed=1000 + first, ctx=ctx)   # LTV set-up on the device
+    prob = problems.build_device_problem(ctx, spec)
+    t_build = time.perf_counter() - t_build
+    info = prob.info()
+    opts = gv.Problem.default_opts()
+    opts.niters_lowtemp = 1 << 30
+    opts.reuse_accepted_sweep = 1 if args.schedule == "reuse" else 0
+    prob.iterate(opts)
+    prob.snapshot_save()
+    for _ in range(W):
+        prob.iterate(opts)
+    prob.snapshot_restore()
+
+    def run_steps(k, collect=None):
+        for i in range(k):
+            if i and i % args.rewind_every == 0:
+                prob.snapshot_restore()
+            st = prob.iterate(opts)
+            if collect is not None:
+                collect.append(st)
+
+    sampler = ClockSampler(local_rank)
+    stats = []
+    barrier()
+    prob.evaluated_factors(reset=True)
+    l0 = ctx.launch_count()
+    sampler.start()
+    prob.timer_start()
+    run_steps(K, stats)
+    ms = prob.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ms = max_over_ranks(ms)
+    if not all(s.accepted and s.n_backtrack == 0 for s in stats):
+        raise SystemExit("bench.py: a timed cfg5 iteration was not accepted at the first trial")
+    n_eval = prob.evaluated_factors(reset=True)
+    value = args.problems * K / (ms * 1e-3)
+    # per-launch profile of the same steps (separate pass)
+    prob.snapshot_restore()
+    prob.profile_begin()
+    run_steps(K)
+    prof = prob.profile_end()
+    k1 = prof.get("k_moments<full>", (0, 0.0))
+    n_eval_prof = prob.evaluated_factors(reset=True)
+    k1_ms = k1[1] / max(k1[0], 1)
+    k1_tflops = n_eval_prof * N_NODES * FLOPS_FULL / max(k1[0], 1) / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+    fp64_peak = ctx.fp64_peak_tflops()
+    # end to end with host buffers
+    S, d = info.num_states, info.dim_state
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        t.numpy()[...] = a
+        return t.numpy()
+    mu_h = pinned(np.ascontiguousarray(spec.mu0, dtype=np.float64))
+    pD_h = pinned(np.ascontiguousarray(np.transpose(spec.prec0_D, (0, 2, 1))))
+    pO_h = pinned(np.ascontiguousarray(np.transpose(spec.prec0_O, (0, 2, 1))))
+    out_mu, out_cD, out_cO = pinned(np.zeros_like(mu_h)), pinned(np.zeros_like(pD_h)), pinned(np.zeros((max(S - 1, 1), d, d)))
+    e2e_steps = max(3, min(K, 6))
+    prob.set_state_raw(mu_h, pD_h, pO_h); prob.iterate(opts); prob.get_mean_into(out_mu); prob.get_cov_blocks_into(out_cD, out_cO)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prob.set_state_raw(mu_h, pD_h, pO_h)
+        prob.iterate(opts)
+        prob.get_mean_into(out_mu)
+        prob.get_cov_blocks_into(out_cD, out_cO)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, sample = cfg5_cpu(8, 6, 1, args.problems)
+        cpu = {"value": v, "unit": CFG5_UNIT, "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps({
+            "metric": CFG5_METRIC, "value": value, "unit": CFG5_UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cfg5: {args.problems} independent cfg3 problems (seeds 1000..) of N={CFG5_N} hinge factors, "
+                                   f"{CFG5_N + 2} states, d=4, sparse-GH degree 6",
+                       "problems_total": args.problems, "problems_per_gpu": count, "states_per_gpu": S,
+                       "factors_per_gpu": int(info.n_factors), "schedule": args.schedule,
+                       "parallelism": f"{world} rank(s): contiguous ranges of the problem index, one block-diagonal batch per GPU, "
+                                      f"no collective on the iteration path",
+                       "line_search": "one step size and the summed cost per batch (every timed iteration accepts the first trial, "
+                                      "where this equals the independent iterations)",
+                       "l2": "working set per iteration exceeds the 126 MB L2; no flush",
+                       "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)",
+                       "setup_s": t_build},
+            "iterations_per_s_per_batch": K / (ms * 1e-3),
+            "evaluated_factor_fraction": n_eval / float(info.n_gh_factors * sum(s.n_moment_sweeps + s.n_cost_sweeps for s in stats)),
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": args.problems * e2e_steps / e2e_s, "unit": CFG5_UNIT,
+                    "h2d_bytes_per_step": int(mu_h.nbytes + pD_h.nbytes + pO_h.nbytes),
+                    "d2h_bytes_per_step": int(out_mu.nbytes + out_cD.nbytes + pO_h.nbytes), "steps": e2e_steps,
+                    "call": "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks"},
+            "roofline": {"bound": "fp64", "kernel": "k_moments_sym<4, CostPlanarHinge, full> (K1)", "achieved": k1_tflops,
+                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak if fp64_peak else None,
+                         "traffic": None, "avg_launch_ms": k1_ms, "launches": k1[0],
+                         "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak)"},
+            "kernel_ms_per_step": {k: v[1] / K for k, v in sorted(prof.items())},
+            "cpu_baseline": cpu}), flush=True)
+    prob.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     # stdout carries ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are sent to
     # stderr for the whole run; the JSON line goes to the saved descriptor
@@ -487,6 +681,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "cfg5":
+        run_cfg5(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -22,6 +22,8 @@ COST_FIXED_GP = 4
 COST_QUADRATIC = 5
 COST_HINGE_3D = 6
 COST_QUAD_HINGE = 7
+COST_ARM_3D = 8
+ARM_MAX_DOF, ARM_MAX_SPHERES = 3, 12
 
 E_NOTSPD = -4
 
@@ -39,7 +41,7 @@ EXPORTS = [
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
-    "gvib200_evaluated_factors",
+    "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature",
 ]
 
 
@@ -51,7 +53,7 @@ class GviError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("step_size_base", C.c_double), ("backtrack_ratio", C.c_double), ("max_backtrack", C.c_int),
-                ("niters_lowtemp", C.c_int), ("reuse_accepted_sweep", C.c_int)]
+                ("niters_lowtemp", C.c_int), ("reuse_accepted_sweep", C.c_int), ("ema_alpha", C.c_double)]
 
 
 class IterStats(C.Structure):
@@ -83,6 +85,26 @@ class Stereo1DParams(C.Structure):
 
 class HingeParams(C.Structure):
     _fields_ = [("sigma", C.c_double), ("epsilon", C.c_double), ("radius", C.c_double)]
+
+
+class ArmParams(C.Structure):
+    """gvib200_arm_params: Denavit-Hartenberg arm with body spheres (helpers/CudaOperation.h:325-410, 680-779)."""
+    _fields_ = [("sigma", C.c_double), ("epsilon", C.c_double), ("n_dof", C.c_int), ("n_spheres", C.c_int),
+                ("a", C.c_double * ARM_MAX_DOF), ("alpha", C.c_double * ARM_MAX_DOF), ("d", C.c_double * ARM_MAX_DOF),
+                ("theta_bias", C.c_double * ARM_MAX_DOF), ("frames", C.c_int * ARM_MAX_SPHERES),
+                ("centers", (C.c_double * 3) * ARM_MAX_SPHERES), ("radii", C.c_double * ARM_MAX_SPHERES)]
+
+    @classmethod
+    def make(cls, a, alpha, d, theta_bias, frames, centers, radii, sigma=15.5, epsilon=0.5):
+        p = cls()
+        p.sigma, p.epsilon, p.n_dof, p.n_spheres = sigma, epsilon, len(a), len(frames)
+        for j in range(len(a)):
+            p.a[j], p.alpha[j], p.d[j], p.theta_bias[j] = a[j], alpha[j], d[j], theta_bias[j]
+        for i in range(len(frames)):
+            p.frames[i], p.radii[i] = int(frames[i]), radii[i]
+            for k in range(3):
+                p.centers[i][k] = centers[i][k]
+        return p
 
 
 _lib = None
@@ -238,6 +260,22 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.gvib200_launch_count(self.h))
+
+    def ltv_transition(self, A: np.ndarray, B: np.ndarray, delta_t: float, want_inverse: bool = True):
+        """Device-side LTV prior set-up (gvib200_ltv_transition; gp/LTV_prior.h:123-197): A [n, 4, ds, ds], B [n, 4, ds, nb]
+        piece-wise constant on the four quarter intervals -> Phi, Q (and Q^-1) as [n, ds, ds]."""
+        A = np.asarray(A, dtype=np.float64)
+        B = np.asarray(B, dtype=np.float64)
+        n, _, ds, _ = A.shape
+        nb = B.shape[3]
+        Ac = np.ascontiguousarray(np.transpose(A, (0, 1, 3, 2)))  # column-major blocks
+        Bc = np.ascontiguousarray(np.transpose(B, (0, 1, 3, 2)))
+        Phi, Q = np.zeros((n, ds, ds)), np.zeros((n, ds, ds))
+        Qi = np.zeros((n, ds, ds)) if want_inverse else None
+        _check(self.lib.gvib200_ltv_transition(self.h, n, ds, nb, _dp(Ac), _dp(Bc), C.c_double(delta_t), _dp(Phi), _dp(Q),
+                                               _dp(Qi) if want_inverse else None))
+        Phi, Q = np.transpose(Phi, (0, 2, 1)), np.transpose(Q, (0, 2, 1))
+        return (Phi, Q, np.transpose(Qi, (0, 2, 1))) if want_inverse else (Phi, Q)
 
     def selected_inverse(self, D: np.ndarray, O: np.ndarray):
         S, d = D.shape[0], D.shape[1]
@@ -457,6 +495,9 @@ class Problem:
         st = IterStats()
         _check(self.lib.gvib200_prox_iterate(self.h, C.byref(opts) if opts is not None else None, C.byref(st)))
         return st
+
+    def switch_to_high_temperature(self):
+        _check(self.lib.gvib200_switch_to_high_temperature(self.h))
 
     def reset_schedule(self):
         _check(self.lib.gvib200_reset_schedule(self.h))

@@ -17,8 +17,10 @@
 //
 // Host code only: matrices are Eigen's when <Eigen/Dense> is found, else the stand-in of gvi/matrix.h.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <map>
 #include <memory>
@@ -83,6 +85,17 @@ struct QuadHingeCost {
     double sigma = 15.5, epsilon = 0.5, radius = 1.0;
 };
 
+// cost_obstacle of CudaOperation_3dArm over ForwardKinematics, helpers/CudaOperation.h:325-410,751-770: a serial arm in
+// Denavit-Hartenberg form with body spheres; state = (joint angles, joint velocities), at most 3 joints (state blocks of the
+// chain engine go up to 6 x 6)
+struct Arm3DCost {
+    std::shared_ptr<SignedDistanceField> sdf;
+    VectorXd a, alpha, d, theta_bias, radii;
+    std::vector<int> frames;
+    MatrixXd centers;  // one row per sphere
+    double sigma = 15.5, epsilon = 0.5;
+};
+
 struct DeviceCostSpec {
     int kind = 0;
     std::vector<unsigned char> params;        // one struct (shared by the group)
@@ -140,6 +153,31 @@ struct DeviceCostTraits<Hinge3DCost> {
     static DeviceCostSpec spec(const Hinge3DCost& c) {
         gvib200_hinge_params p{c.sigma, c.epsilon, c.radius};
         return DeviceCostSpec{GVIB200_COST_HINGE_3D, pod_bytes(p), nullptr, c.sdf};
+    }
+};
+template <>
+struct DeviceCostTraits<Arm3DCost> {
+    static DeviceCostSpec spec(const Arm3DCost& c) {
+        gvib200_arm_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.sigma = c.sigma;
+        p.epsilon = c.epsilon;
+        p.n_dof = (int)c.a.size();
+        p.n_spheres = (int)c.frames.size();
+        if (p.n_dof > GVIB200_ARM_MAX_DOF || p.n_spheres > GVIB200_ARM_MAX_SPHERES)
+            throw std::invalid_argument("Arm3DCost: at most 3 joints and 12 body spheres");
+        for (int j = 0; j < p.n_dof; ++j) {
+            p.a[j] = c.a(j);
+            p.alpha[j] = c.alpha(j);
+            p.d[j] = c.d(j);
+            p.theta_bias[j] = c.theta_bias(j);
+        }
+        for (int i = 0; i < p.n_spheres; ++i) {
+            p.frames[i] = c.frames[(size_t)i];
+            p.radii[i] = c.radii(i);
+            for (int k = 0; k < 3; ++k) p.centers[i][k] = c.centers(i, k);
+        }
+        return DeviceCostSpec{GVIB200_COST_ARM_3D, pod_bytes(p), nullptr, c.sdf};
     }
 };
 template <>
@@ -216,6 +254,48 @@ inline MatrixXd expm(const MatrixXd& X) {
     }
     for (int s = 0; s < sq; ++s) E = E * E;
     return E;
+}
+// symmetric square root V sqrt(D) V^T of a symmetric PSD matrix (SelfAdjointEigenSolver::operatorSqrt,
+// quadrature/SparseGaussHermite.h:232-233) by cyclic Jacobi rotations -- host-side, for the sigmapts() accessor only
+inline MatrixXd sym_sqrt(const MatrixXd& A) {
+    const long n = A.rows();
+    MatrixXd M = A, V = MatrixXd::Identity(n, n);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (long q = 1; q < n; ++q)
+            for (long p = 0; p < q; ++p) off += M(p, q) * M(p, q);
+        if (off < 1e-300) break;
+        for (long q = 1; q < n; ++q)
+            for (long p = 0; p < q; ++p) {
+                if (M(p, q) == 0.0) continue;
+                const double theta = (M(q, q) - M(p, p)) / (2.0 * M(p, q));
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (long k = 0; k < n; ++k) {
+                    const double a = M(k, p), b = M(k, q);
+                    M(k, p) = c * a - sn * b;
+                    M(k, q) = sn * a + c * b;
+                }
+                for (long k = 0; k < n; ++k) {
+                    const double a = M(p, k), b = M(q, k);
+                    M(p, k) = c * a - sn * b;
+                    M(q, k) = sn * a + c * b;
+                }
+                for (long k = 0; k < n; ++k) {
+                    const double a = V(k, p), b = V(k, q);
+                    V(k, p) = c * a - sn * b;
+                    V(k, q) = sn * a + c * b;
+                }
+            }
+    }
+    MatrixXd S = MatrixXd::Zero(n, n);
+    for (long j = 0; j < n; ++j)
+        for (long i = 0; i < n; ++i) {
+            double v = 0.0;
+            for (long k = 0; k < n; ++k) v += V(i, k) * std::sqrt(M(k, k) > 0.0 ? M(k, k) : 0.0) * V(j, k);
+            S(i, j) = v;
+        }
+    return S;
 }
 }  // namespace detail
 
@@ -430,6 +510,39 @@ struct CudaOperation_3dpR {  // helpers/CudaOperation.h:610-676
     std::shared_ptr<SignedDistanceField> _sdf;
 };
 
+struct CudaOperation_3dArm {  // helpers/CudaOperation.h:680-793 (the distance field is attached with set_sdf, not read from a file)
+    CudaOperation_3dArm(const VectorXd& a, const VectorXd& alpha, const VectorXd& d, const VectorXd& theta_bias, const VectorXd& radii,
+                        const std::vector<int>& frames, const MatrixXd& centers, double cost_sigma = 15.5, double epsilon = 0.5)
+        : _sigma(cost_sigma), _epsilon(epsilon), _radius(0.0) {
+        _cost.a = a;
+        _cost.alpha = alpha;
+        _cost.d = d;
+        _cost.theta_bias = theta_bias;
+        _cost.radii = radii;
+        _cost.frames = frames;
+        _cost.centers = centers;
+    }
+    void set_sdf(const std::shared_ptr<SignedDistanceField>& sdf) { _cost.sdf = sdf; }
+    // The reference's factor constructor hands (cost_sigma, epsilon, radius) to every CudaOperation class; the arm takes its
+    // radii from the body spheres, so the `radius` member written by NGDFactorizedBaseGH_Cuda is accepted and unused.
+    struct CostClass : Arm3DCost {
+        double radius = 0.0;
+    };
+    CostClass cost_class() const {
+        CostClass k;
+        static_cast<Arm3DCost&>(k) = _cost;
+        k.sigma = _sigma;
+        k.epsilon = _epsilon;
+        return k;
+    }
+    double _sigma, _epsilon, _radius;
+    Arm3DCost _cost;
+};
+template <>
+struct DeviceCostTraits<CudaOperation_3dArm::CostClass> {
+    static DeviceCostSpec spec(const CudaOperation_3dArm::CostClass& c) { return DeviceCostTraits<Arm3DCost>::spec(c); }
+};
+
 // NGDFactorizedBaseGH_Cuda<CudaClass>(dimension, state_dim, gh_degree, num_states, start_index, cost_sigma, epsilon, radius,
 //                                     temperature, high_temperature, weight_sigpts_map_option, cuda_ptr)
 // ngd/NGDFactorizedBaseGH_Cuda.h:35-50.  The hinge parameters of the constructor win over the CudaClass object's, as in
@@ -517,8 +630,27 @@ public:
     // hooks of the reference's GPU path (gvibase/GVI-GH-Cuda.h:140,223,392): the factors are classified and resident on the
     // device by construction; the EMA of update_proposal (GVI-GH-Cuda-impl.h:112-114) is the identity at its default 1
     void classify_factors() {}
+    // EMA of an accepted proposal (gvibase/GVI-GH-Cuda.h:223, GVI-GH-Cuda-impl.h:112-114): alpha * new + (1 - alpha) * current
     void set_alpha(double alpha) {
-        if (alpha != 1.0) throw std::invalid_argument("set_alpha: only the reference default alpha = 1 (no EMA) is supported");
+        if (!(alpha > 0.0) || alpha > 1.0) throw std::invalid_argument("set_alpha: alpha must be in (0, 1]");
+        _opts.ema_alpha = alpha;
+    }
+    // gvibase/GVI-GH-GBP.h:187-194,218-224,261-267: bookkeeping members of the optimizer.  As in the reference the
+    // temperatures that enter the arithmetic are the factors' own (constructor arguments of every factor); the step size
+    // of set_step_size is not used by the back-tracking loop (step_size_base is), and stop_err is never read.
+    void set_step_size(double step_size) { _step_size = step_size; }
+    void set_stop_err(double stop_err) { _stop_err = stop_err; }
+    void set_temperature(double temperature) { _temperature = temperature; }
+    void set_high_temperature(double high_temp) { _high_temperature = high_temp; }
+    double temperature() const { return _temperature; }
+    void set_initial_precision_factor(double f) { _initial_precision_factor = f; }
+    void initilize_precision_matrix() { initilize_precision_matrix(_initial_precision_factor); }
+    // gvibase/GVI-GH-GBP-impl.h:18-27 (public, gvibase/GVI-GH-GBP.h:361): all factors take their high temperature now
+    void switch_to_high_temperature() {
+        build();
+        gvib200_check(gvib200_switch_to_high_temperature(_prob), "switch_to_high_temperature");
+        _temperature = _high_temperature;
+        _is_high_T = true;
     }
     void time_test() {
         build();
@@ -552,6 +684,7 @@ public:
         set_precision(P);
     }
     void initilize_precision_matrix(double initial_precision_factor) {  // (sic) gvibase/GVI-GH.h:201-204
+        _initial_precision_factor = initial_precision_factor;
         const int d = _dim_state, S = _num_states;
         _pd.assign((size_t)S * d * d, 0.0);
         _po.assign((size_t)(S > 1 ? S - 1 : 1) * d * d, 0.0);
@@ -620,7 +753,96 @@ public:
         return _prob;
     }
 
+    // ---- per-factor expectations (gvibase/GVI-GH-GBP.h:367-396), in the order the factors were handed over.  Nonlinear
+    // (GH) factors: the three integrals of the fused moment kernel at the current state.  Closed-form linear factors take
+    // no quadrature: E_Phis() returns their expected cost E_q[phi] = T * fact_cost_value (ngd/NGDFactorizedLinear.h:
+    // 122-129 stores exactly that in _E_Phi), the two matrix-valued lists hold an empty matrix for them.
+    std::vector<double> E_Phis() {
+        std::vector<double> e0;
+        std::vector<MatrixXd> e1, e2;
+        expectations(e0, e1, e2);
+        return e0;
+    }
+    std::vector<MatrixXd> E_xMuPhis() {
+        std::vector<double> e0;
+        std::vector<MatrixXd> e1, e2;
+        expectations(e0, e1, e2);
+        return e1;
+    }
+    std::vector<MatrixXd> E_xMuxMuTPhis() {
+        std::vector<double> e0;
+        std::vector<MatrixXd> e1, e2;
+        expectations(e0, e1, e2);
+        return e2;
+    }
+
+    // ---- 1-D cost surface (gvibase/GVI-GH-GBP.h:402-431): Z(j, i) = cost_value(mean_i, precision_j)
+    MatrixXd cost_map(const double& x_start, const double& x_end, const double& y_start, const double& y_end, const int& nmesh) {
+        if (_dim != 1) throw std::logic_error("cost_map: 1-D problems only");
+        build();
+        const double res_x = (x_end - x_start) / nmesh, res_y = (y_end - y_start) / nmesh;
+        MatrixXd Z = MatrixXd::Zero(nmesh, nmesh);
+        for (int i = 0; i < nmesh; ++i) {
+            const double m = x_start + i * res_x;
+            for (int j = 0; j < nmesh; ++j) {
+                const double prec = y_start + j * res_y;
+                double c = 0.0;
+                gvib200_check(gvib200_cost(_prob, &m, &prec, nullptr, &c, nullptr), "cost_map");
+                Z(j, i) = c;
+            }
+        }
+        return Z;
+    }
+    void save_costmap(std::string filename = "costmap.csv") {
+        const MatrixXd Z = cost_map(18, 25, 0.05, 1, 40);
+        gvib200_check(gvib200_csv_write(filename.c_str(), (int)Z.rows(), (int)Z.cols(), Z.data()), "save_costmap");
+    }
+
 protected:
+    void expectations(std::vector<double>& e0, std::vector<MatrixXd>& e1, std::vector<MatrixXd>& e2) {
+        build();
+        const size_t nf = _factors.size();
+        e0.assign(nf, 0.0);
+        e1.assign(nf, MatrixXd());
+        e2.assign(nf, MatrixXd());
+        // the library returns the GH factors' moments group by group in id order
+        std::vector<std::pair<int, size_t>> gh;  // (library id, caller index)
+        size_t n1 = 0, n2 = 0;
+        for (size_t i = 0; i < nf; ++i)
+            if (!_factors[i]->is_linear()) {
+                gh.emplace_back(_id_of_factor[i], i);
+                n1 += (size_t)_factors[i]->_dim;
+                n2 += (size_t)_factors[i]->_dim * _factors[i]->_dim;
+            }
+        std::sort(gh.begin(), gh.end());
+        if (!gh.empty()) {
+            std::vector<double> m0(gh.size()), m1(n1), m2(n2);
+            gvib200_check(gvib200_moments(_prob, m0.data(), m1.data(), m2.data()), "moments");
+            size_t o1 = 0, o2 = 0;
+            for (size_t k = 0; k < gh.size(); ++k) {
+                const size_t i = gh[k].second;
+                const int dim = _factors[i]->_dim;
+                e0[i] = m0[k];
+                e1[i] = MatrixXd::Zero(dim, 1);
+                e2[i] = MatrixXd::Zero(dim, dim);
+                for (int r = 0; r < dim; ++r) e1[i](r, 0) = m1[o1 + (size_t)r];
+                for (int c = 0; c < dim; ++c)
+                    for (int r = 0; r < dim; ++r) e2[i](r, c) = m2[o2 + (size_t)r + (size_t)c * dim];
+                o1 += (size_t)dim;
+                o2 += (size_t)dim * dim;
+            }
+        }
+        bool any_linear = false;
+        for (size_t i = 0; i < nf; ++i) any_linear = any_linear || _factors[i]->is_linear();
+        if (any_linear) {
+            std::vector<double> fc(nf);
+            double c = 0.0;
+            gvib200_check(gvib200_cost(_prob, nullptr, nullptr, nullptr, &c, fc.data()), "factor costs");
+            for (size_t i = 0; i < nf; ++i)
+                if (_factors[i]->is_linear())
+                    e0[i] = fc[(size_t)_id_of_factor[i]] * (_is_high_T ? _factors[i]->_high_temperature : _factors[i]->_temperature);
+        }
+    }
     template <class Mat>
     void pack_precision(const Mat& P, std::vector<double>& pd, std::vector<double>& po) const {
         const int d = _dim_state, S = _num_states;
@@ -760,6 +982,11 @@ protected:
             gvib200_check(gvib200_optimize(_prob, &_opts, _niters, _stats.data(), &done, nullptr, nullptr), "optimize");
         }
         _stats.resize((size_t)done);
+        for (auto& st : _stats)
+            if (st.switched_high_T) {
+                _is_high_T = true;
+                _temperature = _high_temperature;
+            }
         if (verbose)
             for (int i = 0; i < done; ++i) std::printf("iteration %d cost %.15g\n", i, _stats[(size_t)i].cost);
     }
@@ -770,6 +997,8 @@ protected:
     gvib200_trace _trace{};
     std::vector<double> _t_mean, _t_cov, _t_prec, _t_cov_off, _t_prec_off, _t_cost, _t_fac;
     double _temperature, _high_temperature;
+    double _step_size = 0.9, _stop_err = 1e-5, _initial_precision_factor = 100.0;  // gvibase/GVI-GH-GBP.h:54,93
+    bool _is_high_T = false;
     std::vector<std::shared_ptr<GVIFactorizedBase>> _factors;
     std::vector<int> _id_of_factor;
     gvib200_opts _opts;
@@ -855,7 +1084,26 @@ public:
     void update_mean(const VectorXd& mean) { _mean = mean; _dirty = true; }
     void update_P(const MatrixXd& P) { _P = P; _dirty = true; }
     void set_polynomial_deg(int deg) { _deg = deg; reset(); }
+    // quadrature/SparseGaussHermite.h:254-272
+    void update_dimension(int dim) { _dim = dim; reset(); }
+    void update_parameters(int deg, int dim, const VectorXd& mean, const MatrixXd& P) {
+        _deg = deg;
+        _dim = dim;
+        _mean = mean;
+        _P = P;
+        reset();
+    }
     VectorXd mean() const { return _mean; }
+    // sigma points X = Z sqrtm(P)^T + 1 mean^T (quadrature/SparseGaussHermite.h:231-243,275): the device kernel forms them
+    // on the fly and never stores them; this accessor rebuilds them on the host for inspection
+    MatrixXd sigmapts() const {
+        const MatrixXd Z = zeromeanpts();
+        const MatrixXd S = detail::sym_sqrt(_P);
+        MatrixXd X = Z * S.transpose();
+        for (long i = 0; i < X.rows(); ++i)
+            for (int c = 0; c < _dim; ++c) X(i, c) += _mean(c);
+        return X;
+    }
     // nodes of the rule (zero-mean sigma points) and weights, straight from the table generator
     MatrixXd zeromeanpts() const {
         const int n = gvib200_table_size(_dim, _deg);

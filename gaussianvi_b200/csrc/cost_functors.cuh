@@ -241,6 +241,78 @@ struct CostHinge3D {
     __device__ __forceinline__ double scale() const { return 0.25 * sigma; }
 };
 
+// CudaOperation_3dArm::cost_obstacle (helpers/CudaOperation.h:751-770) with ForwardKinematics (:325-410): a serial arm
+// described by Denavit-Hartenberg parameters (a, alpha, d, theta_bias per joint) carries body spheres (frame, centre in
+// that frame, radius); the state is (joint angles, joint velocities), the cost the sum over spheres of
+// sigma * max(0, eps + r_i - sd(p_i))^2 with p_i = T_0 ... T_frame(i) [centre_i; 1] and sd the trilinear lookup of the
+// 3-D SignedDistanceField (same lookup as CostHinge3D).  Two quirks of the reference are mirrored:
+//  * n_balls = theta.size() (:752): the number of spheres evaluated is the dimension of the factor's state vector (angles
+//    AND velocities), not the number of spheres the arm was given -- here min(that, n_spheres) so nothing is read out of
+//    bounds;
+//  * dh_matrix (:394-400) calls cosf / sinf: single-precision trigonometry of the double argument.  Mirrored as the
+//    correctly rounded single-precision value, float(cos(double(float(theta)))): this is what an exact cosf returns, and it
+//    is the same number on the device and in the CPU oracle (library cosf implementations differ in the last ulp).
+constexpr int ARM_MAX_DOF = 3;
+constexpr int ARM_MAX_SPHERES = 12;
+template <int NDOF>
+struct CostArm3D {
+    static constexpr int XD = 2 * NDOF;
+    GVIB200_SIMPLE_FUNCTOR_INTERFACE()
+    CostHinge3D field;  // distance field; its thr / sigma members are not used
+    double sigma, epsilon;
+    int n_spheres;
+    double a[ARM_MAX_DOF], ca[ARM_MAX_DOF], sa[ARM_MAX_DOF], d[ARM_MAX_DOF], bias[ARM_MAX_DOF];  // ca / sa: cosf / sinf of alpha
+    int frame[ARM_MAX_SPHERES];
+    double centre[ARM_MAX_SPHERES][3], radius[ARM_MAX_SPHERES];
+    static __device__ __forceinline__ double f32(double v) { return (double)(float)v; }
+    __device__ __forceinline__ double eval(const double* x, int f) const {
+        // cumulative transforms T_0 ... T_j, rows 0..2 of the 4x4 (the last row stays (0, 0, 0, 1))
+        double T[NDOF][12];
+        double cur[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+#pragma unroll
+        for (int j = 0; j < NDOF; ++j) {
+            const double th = f32(x[j] + bias[j]);
+            const double ct = f32(cos(th)), st = f32(sin(th));
+            // dh = [[ct, -st ca, st sa, a ct], [st, ct ca, -ct sa, a st], [0, sa, ca, d], [0, 0, 0, 1]]
+            const double m[12] = {ct, -st * ca[j], st * sa[j], a[j] * ct, st, ct * ca[j], -ct * sa[j], a[j] * st, 0.0, sa[j], ca[j], d[j]};
+            double nx[12];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double v = cur[4 * r + 0] * m[c] + cur[4 * r + 1] * m[4 + c] + cur[4 * r + 2] * m[8 + c];
+                    if (c == 3) v += cur[4 * r + 3];
+                    nx[4 * r + c] = v;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                cur[e] = nx[e];
+                T[j][e] = nx[e];
+            }
+        }
+        const int nb = min(2 * NDOF, n_spheres);
+        double cost = 0.0;
+        for (int i = 0; i < nb; ++i) {
+            const int fr = frame[i];
+            double pt[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                pt[r] = T[fr][4 * r + 3] + (T[fr][4 * r + 0] * centre[i][0] + T[fr][4 * r + 1] * centre[i][1] + T[fr][4 * r + 2] * centre[i][2]);
+            const CostHinge3D::Pending p = field.template begin<false>(pt, f);
+            const double fr_ = p.fr, fc = p.fc, fz = p.fz;
+            const double c00 = fma(fr_, p.v[1] - p.v[0], p.v[0]), c10 = fma(fr_, p.v[3] - p.v[2], p.v[2]);
+            const double c01 = fma(fr_, p.v[5] - p.v[4], p.v[4]), c11 = fma(fr_, p.v[7] - p.v[6], p.v[6]);
+            const double c0 = fma(fc, c10 - c00, c00), c1 = fma(fc, c11 - c01, c01);
+            const double sd = fma(fz, c1 - c0, c0);
+            const double t = epsilon + radius[i] - sd;
+            if (t >= 0.0) cost = fma(t, t, cost);  // sd > eps + r: no contribution (:760-763)
+        }
+        return cost;
+    }
+    __device__ __forceinline__ double scale() const { return sigma; }
+};
+
 // cost_linear_gp (gp/cost_functions.h:36-39 -> MinimumAccGP::cost gp/minimum_acc_prior.h:103-106,
 // LTV_GP::cost gp/LTV_prior.h:217-220): 1/2 (Phi th1 - th2)^T Qinv (Phi th1 - th2).
 // Per-factor parameters: Phi[DS*DS], Qinv[DS*DS] column-major.

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <map>
 #include <memory>
@@ -21,6 +22,7 @@
 #include "bt_cr_plan.h"
 #include "k1_sym.cuh"
 #include "kernels.cuh"
+#include "ltv_setup.cuh"
 #include "spgh_table.h"
 
 using namespace gvib200;
@@ -164,6 +166,10 @@ struct gvib200_ctx {
     int (*ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int rank = 0, world = 1;
     long long launches = 0;  // kernels launched through this ctx
+    // kernels whose function attributes (dynamic shared memory opt-in) were set on THIS context's device: the attributes
+    // are per device, so a process driving several contexts configures each of them
+    std::set<const void*> configured;
+    bool need_config(const void* kern) { return configured.insert(kern).second; }
 };
 
 struct GhGroup {
@@ -397,7 +403,8 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
 // chain engine drivers (tile-wise block cyclic reduction, bt_cr.h): three launches per pass
 // ------------------------------------------------------------------------------------------------
 template <class K>
-static int cr_allow_smem(K kern, size_t bytes) {
+static int cr_allow_smem(gvib200_ctx* ctx, K kern, size_t bytes) {
+    if (!ctx->need_config(reinterpret_cast<const void*>(kern))) return 0;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
@@ -447,12 +454,8 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     CrArgs<D> top = cr_bind<D>(p->plan_top, p->ws_top[slot], buf + L.Dt, buf + L.Ot, RHS ? buf + L.gt : nullptr, buf + L.xt,
                                buf + L.cDt, buf + L.cOt, a.notspd);
     p->flags_synced = false;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        TRY(cr_allow_smem(k_cr_mid_forward<D, RHS>, p->ctx->smem_optin - 5120));
-        TRY(cr_allow_smem(k_cr_dist_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
-        configured = true;
-    }
+    TRY(cr_allow_smem(ctx, k_cr_mid_forward<D, RHS>, ctx->smem_optin - 5120));
+    TRY(cr_allow_smem(ctx, k_cr_dist_top<D, RHS, SELINV>, ctx->smem_optin - 5120));
     // 4 launches + one all-gather: tiles | separator sum + mid tile + boundary record | all-gather | chain of rank
     // boundaries + seeds + mid tile back (+ log det) | tiles back
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
@@ -514,13 +517,9 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
         a.xalpha = fuse->xalpha;
         a.xout = fuse->xout;
     }
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        TRY(cr_allow_smem(k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 5120));
-        TRY(cr_allow_smem(k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
-        TRY(cr_allow_smem(k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
-        configured = true;
-    }
+    TRY(cr_allow_smem(p->ctx, k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 5120));
+    TRY(cr_allow_smem(p->ctx, k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
+    TRY(cr_allow_smem(p->ctx, k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
     if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (p->three_level) return chain_pass_3level<D, RHS, SELINV>(p, slot, a, d_logdet);
     a.ldout = d_logdet;  // the top kernel adds up the partial log determinants itself
@@ -614,13 +613,11 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     a.cost = cost;
     const int grid = cdiv(g.n, K1S_FPC);
     const size_t smem = (size_t)g.table->sym.ndata * sizeof(double);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    if (p->ctx->need_config(reinterpret_cast<const void*>(k_moments_sym<DIM, Cost, true>))) {
         CUDA_TRY(cudaFuncSetAttribute(k_moments_sym<DIM, Cost, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       K1S_MAX_DATA * (int)sizeof(double)));
         CUDA_TRY(cudaFuncSetAttribute(k_moments_sym<DIM, Cost, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       K1S_MAX_DATA * (int)sizeof(double)));
-        configured = true;
     }
     if (a.active != nullptr) {
         if (full) LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
@@ -797,6 +794,46 @@ static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bo
                 c.inv_cell = 1.0 / p->sdf3_cell;
                 c.thr = hp->epsilon + hp->radius;
                 c.sigma = hp->sigma;
+                return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
+            }
+            break;
+        }
+        case GVIB200_COST_ARM_3D: {
+            if constexpr (DIM == SD && (DIM == 4 || DIM == 6)) {
+                if (p->d_sdf3 == nullptr) return fail(GVIB200_ESTATE, "arm cost needs gvib200_set_sdf3d");
+                const auto* ap = reinterpret_cast<const gvib200_arm_params*>(g.params.data());
+                CostArm3D<DIM / 2> c;
+                c.field.data = p->d_sdf3;
+                c.field.rows = p->sdf3_rows;
+                c.field.cols = p->sdf3_cols;
+                c.field.nz = p->sdf3_nz;
+                c.field.ox = p->sdf3_o[0];
+                c.field.oy = p->sdf3_o[1];
+                c.field.oz = p->sdf3_o[2];
+                c.field.xmax = c.field.ox + (c.field.cols - 1.0) * p->sdf3_cell;
+                c.field.ymax = c.field.oy + (c.field.rows - 1.0) * p->sdf3_cell;
+                c.field.zmax = c.field.oz + (c.field.nz - 1.0) * p->sdf3_cell;
+                c.field.inv_cell = 1.0 / p->sdf3_cell;
+                c.field.thr = 0.0;
+                c.field.sigma = 0.0;
+                c.sigma = ap->sigma;
+                c.epsilon = ap->epsilon;
+                c.n_spheres = ap->n_spheres;
+                for (int j = 0; j < ARM_MAX_DOF; ++j) {
+                    const bool on = j < ap->n_dof;
+                    c.a[j] = on ? ap->a[j] : 0.0;
+                    c.d[j] = on ? ap->d[j] : 0.0;
+                    c.bias[j] = on ? ap->theta_bias[j] : 0.0;
+                    // cosf / sinf of alpha (helpers/CudaOperation.h:394-400), correctly rounded single precision
+                    c.ca[j] = on ? (double)(float)std::cos((double)(float)ap->alpha[j]) : 1.0;
+                    c.sa[j] = on ? (double)(float)std::sin((double)(float)ap->alpha[j]) : 0.0;
+                }
+                for (int i = 0; i < ARM_MAX_SPHERES; ++i) {
+                    const bool on = i < ap->n_spheres;
+                    c.frame[i] = on ? ap->frames[i] : 0;
+                    c.radius[i] = on ? ap->radii[i] : 0.0;
+                    for (int k = 0; k < 3; ++k) c.centre[i][k] = on ? ap->centers[i][k] : 0.0;
+                }
                 return launch_moments<DIM>(p, g, c, t.mu, SR, fc, fv, fm, raw, full, t.cD);
             }
             break;
@@ -1189,6 +1226,49 @@ extern "C" int gvib200_table_get(gvib200_ctx* ctx, int dim, int deg, double* nod
 }
 
 // ------------------------------------------------------------------------------------------------
+// C-ABI: device-side LTV prior set-up (gp/LTV_prior.h:123-197), ltv_setup.cuh
+// ------------------------------------------------------------------------------------------------
+extern "C" int gvib200_ltv_transition(gvib200_ctx* ctx, int n_links, int dim_state, int n_inputs, const double* A,
+                                      const double* B, double delta_t, double* Phi, double* Q, double* Qinv) {
+    if (!ctx || n_links < 1 || n_inputs < 1 || !A || !B || !Phi || !Q || !(delta_t > 0))
+        return fail(GVIB200_EINVAL, "ltv_transition: bad arguments");
+    if (!(dim_state == 2 || dim_state == 4 || dim_state == 6))
+        return fail(GVIB200_EINVAL, "ltv_transition: state dimension must be 2, 4 or 6");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t dd = (size_t)dim_state * dim_state, nA = (size_t)n_links * 4 * dd,
+                 nB = (size_t)n_links * 4 * dim_state * n_inputs, nO = (size_t)n_links * dd;
+    double *dA = nullptr, *dB = nullptr, *dO = nullptr;
+    auto cleanup = [&]() {
+        if (dA) cudaFree(dA);
+        if (dB) cudaFree(dB);
+        if (dO) cudaFree(dO);
+    };
+    auto body = [&]() -> int {
+        TRY(dev_alloc(&dA, nA));
+        TRY(dev_alloc(&dB, nB));
+        TRY(dev_alloc(&dO, 3 * nO));
+        CUDA_TRY(cudaMemcpy(dA, A, nA * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dB, B, nB * sizeof(double), cudaMemcpyHostToDevice));
+        const int block = 64, grid = cdiv(n_links, block);
+        double* dQi = Qinv ? dO + 2 * nO : nullptr;
+        switch (dim_state) {
+            case 2: k_ltv_transition<2><<<grid, block>>>(n_links, n_inputs, delta_t, dA, dB, dO, dO + nO, dQi); break;
+            case 4: k_ltv_transition<4><<<grid, block>>>(n_links, n_inputs, delta_t, dA, dB, dO, dO + nO, dQi); break;
+            default: k_ltv_transition<6><<<grid, block>>>(n_links, n_inputs, delta_t, dA, dB, dO, dO + nO, dQi); break;
+        }
+        ctx->launches++;
+        TRY(check_launch("k_ltv_transition"));
+        CUDA_TRY(cudaMemcpy(Phi, dO, nO * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(Q, dO + nO, nO * sizeof(double), cudaMemcpyDeviceToHost));
+        if (Qinv) CUDA_TRY(cudaMemcpy(Qinv, dO + 2 * nO, nO * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int rc = body();
+    cleanup();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI: problem definition
 // ------------------------------------------------------------------------------------------------
 extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_state, gvib200_problem** out) {
@@ -1351,6 +1431,19 @@ extern "C" int gvib200_add_gh_factors(gvib200_problem* p, int kind, int dim, int
         case GVIB200_COST_HINGE_3D:
         case GVIB200_COST_QUAD_HINGE: want = sizeof(gvib200_hinge_params); break;
         case GVIB200_COST_QUADRATIC: want = sizeof(double); break;
+        case GVIB200_COST_ARM_3D: {
+            want = sizeof(gvib200_arm_params);
+            if (params && bytes == want) {
+                const auto* ap = reinterpret_cast<const gvib200_arm_params*>(params);
+                if (ap->n_dof < 1 || ap->n_dof > GVIB200_ARM_MAX_DOF || 2 * ap->n_dof != dim || dim != p->d || ap->n_spheres < 1 ||
+                    ap->n_spheres > GVIB200_ARM_MAX_SPHERES)
+                    return fail(GVIB200_EINVAL, "add_gh_factors: arm cost needs dim = state dim = 2 n_dof, n_dof <= 3, 1..12 spheres");
+                for (int i = 0; i < ap->n_spheres; ++i)
+                    if (ap->frames[i] < 0 || ap->frames[i] >= ap->n_dof)
+                        return fail(GVIB200_EINVAL, "add_gh_factors: arm sphere frame out of range");
+            }
+            break;
+        }
         case GVIB200_COST_LINEAR_GP:
         case GVIB200_COST_FIXED_GP: want = cost_param_record(kind, dim) * n; break;
         default: return fail(GVIB200_EINVAL, "add_gh_factors: unknown cost kind");
@@ -1937,6 +2030,7 @@ extern "C" void gvib200_default_opts(gvib200_opts* o) {
     o->max_backtrack = 10;
     o->niters_lowtemp = 10;
     o->reuse_accepted_sweep = 0;
+    o->ema_alpha = 1.0;
 }
 
 // GVIGH::switch_to_high_temperature (gvibase/GVI-GH-GBP-impl.h:18-27)
@@ -2133,6 +2227,31 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         // a candidate precision that is not SPD has no finite cost: treat as a rejected trial
         const bool ok = (flag_inv == 0) && (new_cost < cost_iter);
         if (flag_inv) TRY(clear_flag(p));
+        if (ok && o.ema_alpha != 1.0) {
+            // EMA of the reference's GPU path (gvibase/GVI-GH-Cuda-impl.h:112-114): the proposal that is taken is
+            //   alpha * new + (1 - alpha) * current  =  mu + (alpha step) dmu,  Lambda + (alpha step)(Vddmu - Lambda),
+            // i.e. the candidate at the step alpha * step (whose cost is NOT evaluated: the trial at `step` decided).
+            // Rebuilt in the candidate buffers with its own selected inverse and factor marginals, then flipped.
+            TRY(launch_candidate(p, o.ema_alpha * step, 3));
+            TRY(clear_flag(p));
+            TRY(do_selinv(p, p->LD[w], p->LO[w], p->CD[w], p->CO[w], p->scal + w, 1));
+            TRY(run_prologue_only(p, w));
+            int f0 = 0, f1 = 0;
+            TRY(read_flags(p, &f0, &f1));
+            if (f0 | f1) {
+                TRY(clear_flag(p));
+                return fail(GVIB200_ENOTSPD, "ngd_iterate: the EMA proposal is not positive definite");
+            }
+            p->cur = w;
+            p->sweep_valid = false;
+            p->grads_valid = false;
+            p->asm_valid = false;
+            p->zc_ok[0] = p->zc_ok[1] = false;
+            s.accepted = 1;
+            s.step = step;
+            s.n_backtrack = cnt;
+            break;
+        }
         if (ok) {
             // update_proposal (ngd/NGD-GH-impl.h:151-156): the candidate's mu, precision, covariance and factor
             // marginals become current -- a buffer flip, everything is already on the device
@@ -2438,6 +2557,15 @@ extern "C" int gvib200_prox_optimize(gvib200_problem* p, const gvib200_opts* opt
         done++;
     }
     if (n_done) *n_done = done;
+    return 0;
+}
+
+extern "C" int gvib200_switch_to_high_temperature(gvib200_problem* p) {
+    if (!p || !p->finalized) return fail(GVIB200_ESTATE, "switch_to_high_temperature: problem not finalized");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    TRY(switch_to_high_temperature(p));
+    p->is_lowtemp = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
     return 0;
 }
 

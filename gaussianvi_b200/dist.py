@@ -49,3 +49,25 @@ def attach_nccl(ctx: "capi.Context", rank: int, world: int):
     capi._check(lib.gvib200_ctx_set_comm(ctx.h, comm, rank, world, path.encode()))
     ctx._nccl = (nccl, comm)
     return comm
+
+
+def shard_problems(n_problems: int, rank: int, world: int):
+    """Independent problems (BASELINE cfg5, SURVEY 8(e) first bullet) shard over the ranks as contiguous ranges of the
+    problem index; returns (first, count) of `rank`.  No collective touches the iteration path: every rank runs its range
+    as one block-diagonal batch, the results are gathered once at the end (gather_problem_results)."""
+    if not (0 <= rank < world) or n_problems < 0:
+        raise ValueError("shard_problems: bad arguments")
+    base, extra = divmod(n_problems, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def gather_problem_results(local, group=None):
+    """One gather of per-problem results (e.g. the final means [count, S*d]) at the end of a sharded cfg5 run:
+    returns the list of every rank's array on every rank (torch.distributed.all_gather_object; any backend)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [local]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    return out

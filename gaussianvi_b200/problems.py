@@ -8,6 +8,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
+import functools
+
 import numpy as np
 
 from . import capi
@@ -123,6 +125,7 @@ def ltv_transition_batch(A: np.ndarray, B: np.ndarray, delta_t: float):
 # ----------------------------------------------------------------------------------------------
 # ingredients
 # ----------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=4)
 def disc_layout(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
     rng = np.random.default_rng(seed)
     cx = rng.uniform(origin[0], origin[0] + (cols - 1) * cell, n_discs)
@@ -131,6 +134,7 @@ def disc_layout(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12,
     return cx, cy, rad
 
 
+@functools.lru_cache(maxsize=4)
 def disc_sdf(rows=300, cols=400, origin=(-20.0, -10.0), cell=0.1, n_discs=12, seed=7):
     """Analytic signed distance to `n_discs` discs on a rows x cols grid."""
     cx, cy, rad = disc_layout(rows, cols, origin, cell, n_discs, seed)
@@ -194,15 +198,13 @@ def minacc_group(S: int, Qc: np.ndarray, delta_t: float, T=1.0, T_high=10.0) -> 
                         C=np.full(n, 0.5), T=T, T_high=T_high)
 
 
-def ltv_group(S: int, delta_t: float, nominal: np.ndarray, seed=3, T=1.0, T_high=10.0):
-    """LTV_GP prior for i = 0..S-2 with the damped-oscillator dynamics of SURVEY 8(d) cfg3:
-    A(t) = [[0, I], [-w(t)^2 I, -c(t) I]], B = [0; I], w, c ~ U(1, 2) per quarter interval.
-    target_mean = -nominal (sign quirk of gp/LTV_prior.h:87-94: the prior is centred on -target_mean)."""
-    n = S - 1
-    dim = 2
-    ds = 4
+def ltv_system(n_links: int, seed: int):
+    """Damped-oscillator dynamics of SURVEY 8(d) cfg3 on the quarter intervals of `n_links` links:
+    A(t) = [[0, I], [-w(t)^2 I, -c(t) I]], B = [0; I], w, c ~ U(1, 2) per quarter interval (4 n_links + 1 draws each).
+    Returns hA [4 n + 1, 4, 4], hB [4 n + 1, 4, 2] (the reference's hA / hB vectors, gp/LTV_prior.h:42-60)."""
+    dim, ds = 2, 4
     rng = np.random.default_rng(seed)
-    nq = 4 * n + 1
+    nq = 4 * n_links + 1
     w = rng.uniform(1.0, 2.0, nq)
     c = rng.uniform(1.0, 2.0, nq)
     hA = np.zeros((nq, ds, ds))
@@ -211,10 +213,29 @@ def ltv_group(S: int, delta_t: float, nominal: np.ndarray, seed=3, T=1.0, T_high
     hA[:, dim:, dim:] = -c[:, None, None] * np.eye(dim)
     hB = np.zeros((nq, ds, dim))
     hB[:, dim:, :] = np.eye(dim)
-    idx = 4 * np.arange(n)[:, None] + np.arange(4)[None, :]
-    Phi, Q = ltv_transition_batch(hA[idx], hB[idx], delta_t)
+    return hA, hB
+
+
+def ltv_links(hA_q: np.ndarray, hB_q: np.ndarray, delta_t: float, ctx=None):
+    """Phi, Q, K^-1 = Q^-1 of links with quarter-interval dynamics hA_q [n, 4, ds, ds], hB_q [n, 4, ds, nb].
+    ctx = None: NumPy (Van Loan per quarter, ltv_transition_batch).  ctx = a capi.Context: the same on the device
+    (gvib200_ltv_transition) -- per-link scaling, so the result does not depend on the batching."""
+    if ctx is not None:
+        Phi, Q, Kinv = ctx.ltv_transition(hA_q, hB_q, delta_t)
+        return Phi, Q, 0.5 * (Kinv + np.transpose(Kinv, (0, 2, 1)))
+    Phi, Q = ltv_transition_batch(hA_q, hB_q, delta_t)
     Kinv = np.linalg.inv(Q)
-    Kinv = 0.5 * (Kinv + np.transpose(Kinv, (0, 2, 1)))
+    return Phi, Q, 0.5 * (Kinv + np.transpose(Kinv, (0, 2, 1)))
+
+
+def ltv_group(S: int, delta_t: float, nominal: np.ndarray, seed=3, T=1.0, T_high=10.0, ctx=None):
+    """LTV_GP prior for i = 0..S-2 with the damped-oscillator dynamics of SURVEY 8(d) cfg3 (ltv_system).
+    target_mean = -nominal (sign quirk of gp/LTV_prior.h:87-94: the prior is centred on -target_mean)."""
+    n = S - 1
+    ds = 4
+    hA, hB = ltv_system(n, seed)
+    idx = 4 * np.arange(n)[:, None] + np.arange(4)[None, :]
+    Phi, Q, Kinv = ltv_links(hA[idx], hB[idx], delta_t, ctx)
     Lam = np.concatenate([-Phi, np.broadcast_to(np.eye(ds), (n, ds, ds))], axis=2)
     Psi = -Lam
     target = -nominal
@@ -264,7 +285,7 @@ def make_cfg2(S: int = 1000, delta_t: float = 0.1, anchors_every: int = 10, prec
 
 
 def make_cfg3(N: int = 100_000, delta_t: float = 0.2, deg: int = 6, sigma: float = 0.1, prec0: float = 100.0,
-              seed: int = 3, clearance: Optional[float] = 0.6) -> ProblemSpec:
+              seed: int = 3, clearance: Optional[float] = 0.6, ctx=None) -> ProblemSpec:
     """Headline shape: S = N + 2 states, N single-state planar hinge-SDF factors (d = 4, sparse GH degree `deg`)
     at states 1..S-2, N + 1 LTV GP factors, two fixed priors."""
     d = 4
@@ -273,7 +294,7 @@ def make_cfg3(N: int = 100_000, delta_t: float = 0.2, deg: int = 6, sigma: float
     spec = ProblemSpec(S=S, d=d)
     spec.sdf = disc_sdf()
     spec.groups.append(fixed_prior_group([0, S - 1], np.stack([nominal[0], nominal[-1]]), 1e-4 * np.eye(d), d))
-    g, _, _, _ = ltv_group(S, delta_t, nominal, seed=seed)
+    g, _, _, _ = ltv_group(S, delta_t, nominal, seed=seed, ctx=ctx)
     spec.groups.append(g)
     spec.groups.append(GhGroupSpec(capi.COST_PLANAR_HINGE, d, deg, np.arange(1, S - 1, dtype=np.int32),
                                    capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
@@ -341,6 +362,23 @@ def _random_spd(rng, N, d, lo=1e-3, hi=1.0):
     return 0.5 * (Sigma + np.transpose(Sigma, (0, 2, 1)))
 
 
+def example_arm(n_dof: int = 3, sigma: float = 0.5, epsilon: float = 0.5) -> "capi.ArmParams":
+    """A small serial arm in Denavit-Hartenberg form for the CudaOperation_3dArm functor (helpers/CudaOperation.h:325-410,
+    680-779): link lengths ~1.2, alternating twists, body spheres spread over the links (more spheres than 2 n_dof, so the
+    reference's n_balls = theta.size() cap is exercised)."""
+    a = [1.2, 1.0, 0.8][:n_dof]
+    alpha = [np.pi / 2, -np.pi / 3, 0.4][:n_dof]
+    dd = [0.3, 0.0, 0.2][:n_dof]
+    bias = [0.1, -0.2, 0.3][:n_dof]
+    frames, centers, radii = [], [], []
+    for j in range(n_dof):
+        for k, t in enumerate((-0.8, -0.4, 0.0)):
+            frames.append(j)
+            centers.append([t * a[j], 0.05 * (k - 1), 0.02 * j])
+            radii.append(0.25 + 0.05 * ((j + k) % 3))
+    return capi.ArmParams.make(a, alpha, dd, bias, frames, centers, radii, sigma, epsilon)
+
+
 def make_factor_batch_functor(kind: int, N: int = 64, d: int = 6, deg: int = 3, sigma: float = 0.5, seed: int = 5) -> ProblemSpec:
     """Factor-batch input for the moment parity of the robot cost functors beyond the planar point robot:
     kind = COST_HINGE_3D (3-D point robot, x[0:3] position in a 3-D field) or COST_QUAD_HINGE (planar quadrotor
@@ -362,12 +400,16 @@ def make_factor_batch_functor(kind: int, N: int = 64, d: int = 6, deg: int = 3, 
         mu[:, 0] = rng.uniform(origin[0] - 1.0, origin[0] + (cols - 1) * cell + 1.0, N)
         mu[:, 1] = rng.uniform(origin[1] - 1.0, origin[1] + (rows - 1) * cell + 1.0, N)
         mu[:, 2] = rng.uniform(-np.pi, np.pi, N)
+    elif kind == capi.COST_ARM_3D:
+        spec.sdf3d = ball_sdf3d()
+        mu[:, :d // 2] = rng.uniform(-np.pi, np.pi, (N, d // 2))       # joint angles; velocities stay N(0, 1)
     else:
         raise ValueError(kind)
     Sigma = _random_spd(rng, N, d, 1e-3, 0.3)
     prec = np.linalg.inv(Sigma)
     prec = 0.5 * (prec + np.transpose(prec, (0, 2, 1)))
-    spec.groups.append(GhGroupSpec(kind, d, deg, np.arange(N, dtype=np.int32), capi.HingeParams(sigma, 0.5, 1.0), 1.0, 10.0))
+    params = example_arm(d // 2, sigma) if kind == capi.COST_ARM_3D else capi.HingeParams(sigma, 0.5, 1.0)
+    spec.groups.append(GhGroupSpec(kind, d, deg, np.arange(N, dtype=np.int32), params, 1.0, 10.0))
     spec.mu0 = mu.reshape(-1)
     spec.prec0_D = prec
     spec.prec0_O = np.zeros((N - 1, d, d))
@@ -507,13 +549,19 @@ def make_cfg4(S: int = 10_001, delta_t: float = 1.0, deg: int = 4, closed_form: 
     return spec
 
 
-def make_cfg5(n_problems: int = 64, N: int = 1000, first_seed: int = 1000, **kw) -> ProblemSpec:
+def make_cfg5(n_problems: int = 64, N: int = 1000, first_seed: int = 1000, ctx=None, **kw) -> ProblemSpec:
     """BASELINE.json configs[4]: independent copies of the cfg3 generator (seeds first_seed, first_seed + 1, ...) batched
     as ONE block-diagonal chain: problem b occupies the states [b (N+2), (b+1)(N+2)) and nothing couples consecutive
     problems (the off-diagonal block between them stays zero), so the chain engine, the sweeps and the assembly run over
     the whole batch in single launches.  The line search is shared by the batch (one step size, the summed cost); as long
-    as every problem would accept the same trial this is exactly the independent iteration."""
-    subs = [make_cfg3(N=N, seed=first_seed + b, **kw) for b in range(n_problems)]
+    as every problem would accept the same trial this is exactly the independent iteration.
+
+    ctx = a capi.Context: the LTV links of all problems are set up in one device launch (gvib200_ltv_transition) and the
+    batch is assembled without a per-problem Python loop -- what bench.py --config cfg5 uses for 4096 problems; every
+    problem is bit-identical to make_cfg3(N, seed=first_seed + b, ctx=ctx)."""
+    if ctx is not None and not kw:
+        return _make_cfg5_device(n_problems, N, first_seed, ctx)
+    subs = [make_cfg3(N=N, seed=first_seed + b, ctx=ctx, **kw) for b in range(n_problems)]
     Sb = subs[0].S
     d = subs[0].d
     out = ProblemSpec(S=Sb * n_problems, d=d)
@@ -534,4 +582,44 @@ def make_cfg5(n_problems: int = 64, N: int = 1000, first_seed: int = 1000, **kw)
                                            C=np.concatenate([np.broadcast_to(np.asarray(s.groups[gi].C, float), (len(s.groups[gi].start),)) for s in subs]),
                                            T=g0.T, T_high=g0.T_high))
     out.meta = dict(subs[0].meta, name="cfg5", n_problems=n_problems, states_per_problem=Sb)
+    return out
+
+
+def _make_cfg5_device(n_problems: int, N: int, first_seed: int, ctx) -> ProblemSpec:
+    """make_cfg5 without the per-problem loop: the problems share everything but the LTV dynamics (the seed only draws
+    w(t), c(t)), whose links are integrated in one device launch."""
+    base = make_cfg3(N=N, seed=first_seed, ctx=ctx)
+    Sb, d, n = base.S, base.d, base.S - 1
+    fixed0, ltv0, hinge0 = base.groups
+    idx = 4 * np.arange(n)[:, None] + np.arange(4)[None, :]
+    delta_t = 0.2  # make_cfg3's default
+    Phi = np.empty((n_problems * n, d, d))
+    Kinv = np.empty((n_problems * n, d, d))
+    CH = 128  # problems per device launch (bounds the host staging arrays)
+    for b0 in range(0, n_problems, CH):
+        nb_ = min(CH, n_problems - b0)
+        hA = np.empty((nb_ * n, 4, d, d))
+        hB = np.empty((nb_ * n, 4, d, 2))
+        for b in range(nb_):
+            a_, b_ = ltv_system(n, first_seed + b0 + b)
+            hA[b * n:(b + 1) * n] = a_[idx]
+            hB[b * n:(b + 1) * n] = b_[idx]
+        Phi[b0 * n:(b0 + nb_) * n], _, Kinv[b0 * n:(b0 + nb_) * n] = ltv_links(hA, hB, delta_t, ctx)
+    Lam = np.concatenate([-Phi, np.broadcast_to(np.eye(d), (n_problems * n, d, d))], axis=2)
+    off = (np.arange(n_problems, dtype=np.int64) * Sb)[:, None]
+    tile = lambda a: np.tile(a, (n_problems,) + (1,) * (a.ndim - 1))
+    out = ProblemSpec(S=Sb * n_problems, d=d)
+    out.sdf = base.sdf
+    out.mu0 = np.tile(base.mu0, n_problems)
+    out.prec0_D = tile(base.prec0_D)
+    out.prec0_O = np.zeros((out.S - 1, d, d))
+    out.groups.append(LinGroupSpec(start=(fixed0.start[None, :] + off).reshape(-1).astype(np.int32), Lambda=tile(fixed0.Lambda),
+                                   Psi=tile(fixed0.Psi), mu_t=tile(fixed0.mu_t), Kinv=tile(fixed0.Kinv),
+                                   C=np.tile(np.broadcast_to(np.asarray(fixed0.C, float), (len(fixed0.start),)), n_problems),
+                                   T=fixed0.T, T_high=fixed0.T_high))
+    out.groups.append(LinGroupSpec(start=(ltv0.start[None, :] + off).reshape(-1).astype(np.int32), Lambda=Lam, Psi=-Lam,
+                                   mu_t=tile(ltv0.mu_t), Kinv=Kinv, C=np.full(n_problems * n, 0.5), T=ltv0.T, T_high=ltv0.T_high))
+    out.groups.append(GhGroupSpec(hinge0.kind, hinge0.dim, hinge0.deg, (hinge0.start[None, :] + off).reshape(-1).astype(np.int32),
+                                  hinge0.params, hinge0.T, hinge0.T_high))
+    out.meta = dict(base.meta, name="cfg5", n_problems=n_problems, states_per_problem=Sb)
     return out

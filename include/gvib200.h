@@ -58,7 +58,14 @@ enum {
     GVIB200_COST_HINGE_3D = 6,
     /* CudaOperation_Quad::cost_obstacle_planar, helpers/CudaOperation.h:565-605: planar quadrotor (x, z, phi, ...), five
        check points along the body axis (L = 5), slope 5, over the PlanarSDF (params: gvib200_hinge_params) */
-    GVIB200_COST_QUAD_HINGE = 7
+    GVIB200_COST_QUAD_HINGE = 7,
+    /* CudaOperation_3dArm::cost_obstacle, helpers/CudaOperation.h:751-770, over ForwardKinematics :325-410 (Denavit-Hartenberg
+       chain with body spheres) and the 3-D SignedDistanceField (params: gvib200_arm_params; field set with gvib200_set_sdf3d).
+       The state is (joint angles, joint velocities): factor dim = state dim = 2 n_dof, n_dof <= 3 (the block-tridiagonal
+       engine holds state blocks up to 6 x 6, so a 7-DOF arm with 14-dimensional states is out of reach -- DESIGN.md 7).
+       Mirrored quirks: the number of spheres evaluated is min(2 n_dof, n_spheres) (n_balls = theta.size(), :752) and
+       dh_matrix's single-precision cosf / sinf (:394-400), as the correctly rounded single-precision values. */
+    GVIB200_COST_ARM_3D = 8
 };
 
 typedef struct {
@@ -68,6 +75,17 @@ typedef struct {
 typedef struct {
     double sigma, epsilon, radius; /* helpers/CudaOperation.h:456 defaults 15.5, 0.5, 1 */
 } gvib200_hinge_params;
+
+#define GVIB200_ARM_MAX_DOF 3
+#define GVIB200_ARM_MAX_SPHERES 12
+typedef struct {
+    double sigma, epsilon;                     /* helpers/CudaOperation.h:683-684 defaults 15.5, 0.5 */
+    int n_dof, n_spheres;
+    double a[GVIB200_ARM_MAX_DOF], alpha[GVIB200_ARM_MAX_DOF], d[GVIB200_ARM_MAX_DOF], theta_bias[GVIB200_ARM_MAX_DOF];
+    int frames[GVIB200_ARM_MAX_SPHERES];       /* joint frame of every body sphere */
+    double centers[GVIB200_ARM_MAX_SPHERES][3];/* centre in that frame (row per sphere, helpers/CudaOperation.h:343) */
+    double radii[GVIB200_ARM_MAX_SPHERES];
+} gvib200_arm_params;
 
 /* ---- context ---------------------------------------------------------------------- */
 int gvib200_ctx_create(int device, gvib200_ctx** out);
@@ -181,6 +199,9 @@ typedef struct {
     int reuse_accepted_sweep;/* 0: faithful schedule (1 moment sweep + T_ls cost sweeps / iteration);
                                 1: line-search sweeps compute full moments and the accepted trial's
                                    moments seed the next iteration (identical results, fewer sweeps) */
+    double ema_alpha;        /* GVIGH::_alpha of the reference's GPU path, default 1 (gvibase/GVI-GH-Cuda.h:78,223): an
+                                accepted trial takes alpha * new + (1 - alpha) * current for mean and precision
+                                (gvibase/GVI-GH-Cuda-impl.h:112-114)                              */
 } gvib200_opts;
 void gvib200_default_opts(gvib200_opts* opts);
 
@@ -242,6 +263,19 @@ int gvib200_prox_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib20
 int gvib200_prox_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats, int* n_done);
 /* reset the iteration counter / temperature phase (keeps the state) */
 int gvib200_reset_schedule(gvib200_problem* prob);
+/* GVIGH::switch_to_high_temperature (gvibase/GVI-GH-GBP-impl.h:18-27, public at gvibase/GVI-GH-GBP.h:361): every factor takes
+   its high temperature now; the optimizer will not switch again by itself */
+int gvib200_switch_to_high_temperature(gvib200_problem* prob);
+
+/* ---- device-side set-up of the LTV GP prior (gp/LTV_prior.h:123-197 compute_Phi_gsl / compute_Q_gsl with the piece-wise
+        constant A_function / system_param of :187-197), batched over links: one launch integrates
+        Phi' = A Phi, Q' = A Q + Q A^T + B B^T over [0, delta_t] for n_links links, A / B constant on each quarter interval.
+        Where the reference runs GSL rkf45 at tolerance 1e-12 per link on the host, each quarter is integrated exactly by
+        Van Loan's block exponential.  A: [n_links][4][dim_state x dim_state], B: [n_links][4][dim_state x n_inputs],
+        outputs [n_links][dim_state x dim_state], all column-major; Qinv (optional, may be NULL) = Q^-1 = the K^-1 of the
+        LTV_GP linear factor.  dim_state in {2, 4, 6}. */
+int gvib200_ltv_transition(gvib200_ctx* ctx, int n_links, int dim_state, int n_inputs, const double* A, const double* B,
+                           double delta_t, double* Phi, double* Q, double* Qinv);
 
 /* ---- stand-alone block-tridiagonal engine (GVIGH::inverse_GBP, GVI-GH-GBP-impl.h:245-305;
         EigenWrapper::inv_sparse helpers/EigenWrapper.h:336-381; SparseLDLT log det :234-238) -------- */

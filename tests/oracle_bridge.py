@@ -13,7 +13,8 @@ import gvi_oracle as o  # noqa: E402
 from gaussianvi_b200 import capi, problems  # noqa: E402
 
 
-SHARED_KINDS = (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC, capi.COST_HINGE_3D, capi.COST_QUAD_HINGE)
+SHARED_KINDS = (capi.COST_STEREO_1D, capi.COST_PLANAR_HINGE, capi.COST_QUADRATIC, capi.COST_HINGE_3D, capi.COST_QUAD_HINGE,
+                capi.COST_ARM_3D)
 
 
 def psi_for_group(spec, g, i):
@@ -37,6 +38,13 @@ def psi_for_group(spec, g, i):
         data, origin, cell = spec.sdf3d
         sdf = o.SignedDistanceField3D(np.asarray(origin), cell, data)
         return o.make_hinge3d_cost(sdf, g.params.sigma, g.params.epsilon, g.params.radius)
+    if g.kind == capi.COST_ARM_3D:
+        data, origin, cell = spec.sdf3d
+        sdf = o.SignedDistanceField3D(np.asarray(origin), cell, data)
+        q = g.params
+        nd, ns = q.n_dof, q.n_spheres
+        return o.make_arm_cost(sdf, list(q.a)[:nd], list(q.alpha)[:nd], list(q.d)[:nd], list(q.theta_bias)[:nd], list(q.frames)[:ns],
+                               [[q.centers[i][k] for k in range(3)] for i in range(ns)], list(q.radii)[:ns], q.sigma, q.epsilon)
     if g.kind == capi.COST_LINEAR_GP:
         ds = g.dim // 2
         rec = np.asarray(g.params).reshape(len(g.start), 2, ds, ds)

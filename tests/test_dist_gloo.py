@@ -154,3 +154,58 @@ def test_c_oracle_faithful_linear_form_loses_spd_where_the_closed_form_converges
     status = [faithful.iterate(schedule=0).status for _ in range(12)]
     assert status[0] == 0 and status[1] == 0 and status[2] == 0
     assert any(s != 0 for s in status), status
+
+
+def _cfg5_worker(rank, world, port, n_problems, N, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import gvi_oracle as o
+    import gvi_oracle_c as oc
+    from gaussianvi_b200 import problems
+    from gaussianvi_b200.dist import gather_problem_results, shard_problems
+    first, count = shard_problems(n_problems, rank, world)
+    spec = problems.make_cfg5(n_problems=count, N=N, first_seed=1000 + first)
+    c = oc.COracle(spec, o.table)
+    for _ in range(3):
+        st = c.iterate(schedule=1)
+        assert st.status == 0 and st.accepted and st.n_backtrack == 0
+    parts = gather_problem_results((first, count, c.mean().reshape(count, -1)))
+    if rank == 0:
+        out.put(parts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cfg5_problem_batch_shards_over_two_ranks_gloo():
+    """SURVEY 8(e), independent problems: contiguous ranges of the problem index per rank, no collective on the iteration
+    path, one gather at the end -- the gathered means equal the single-rank batch of all problems (CPU oracle on both
+    sides: this pins the host-side sharding / seeding logic that bench.py --config cfg5 uses)."""
+    import numpy as np
+    import torch.multiprocessing as mp
+    import gvi_oracle as o
+    import gvi_oracle_c as oc
+    from gaussianvi_b200 import problems
+    from gaussianvi_b200.dist import shard_problems
+    n_problems, N = 5, 30
+    assert [shard_problems(5, r, 2) for r in range(2)] == [(0, 3), (3, 2)]
+    assert [shard_problems(4096, r, 8) for r in (0, 7)] == [(0, 512), (3584, 512)]
+    assert sum(shard_problems(10, r, 4)[1] for r in range(4)) == 10
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_cfg5_worker, args=(r, 2, port, n_problems, N, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = oc.COracle(problems.make_cfg5(n_problems=n_problems, N=N), o.table)
+    for _ in range(3):
+        full.iterate(schedule=1)
+    want = full.mean().reshape(n_problems, -1)
+    got = np.zeros_like(want)
+    for first, count, mu in parts:
+        got[first:first + count] = mu
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()

@@ -27,7 +27,7 @@ def compile_example(name):
     return out
 
 
-@pytest.mark.parametrize("name", ["1d_example", "planar_chain", "1d_example_proxGVI", "point_robot_3d"])
+@pytest.mark.parametrize("name", ["1d_example", "planar_chain", "1d_example_proxGVI", "point_robot_3d", "ltv_chain"])
 def test_facade_examples_compile(name):
     assert compile_example(name).exists()
 
@@ -134,6 +134,10 @@ def test_cuda_alias_api_compiles(tmp_path):
                    '  f->cuda_init(); f->cuda_free();\n'
                    '  auto q = std::make_shared<CudaOperation_Quad>();\n'
                    '  NGDFactorizedBaseGH_Cuda<CudaOperation_Quad> fq(6, 6, 3, 10, 1, 15.5, 0.5, 1.0, 1.0, 10.0, map, q);\n'
+                   '  VectorXd v3 = VectorXd::Zero(3); std::vector<int> fr{0, 1, 2}; MatrixXd ctr = MatrixXd::Zero(3, 3);\n'
+                   '  auto arm = std::make_shared<CudaOperation_3dArm>(v3, v3, v3, v3, v3, fr, ctr, 15.5, 0.5);\n'
+                   '  arm->set_sdf(std::make_shared<SignedDistanceField>());\n'
+                   '  NGDFactorizedBaseGH_Cuda<CudaOperation_3dArm> fa(6, 6, 3, 10, 1, 15.5, 0.5, 0.0, 1.0, 10.0, map, arm);\n'
                    '  auto r3 = std::make_shared<CudaOperation_3dpR>();\n'
                    '  NGDFactorizedBaseGH_Cuda<CudaOperation_3dpR> f3(6, 6, 3, 10, 1, 15.5, 0.5, 1.0, 1.0, 10.0, map, r3);\n'
                    '  std::vector<std::shared_ptr<Col>> v{f};\n'
@@ -180,3 +184,103 @@ def test_facade_point_robot_3d_matches_ctypes_mirror_and_oracle(gpu_ctx):
     ref = ob.build_oracle(spec, niters=niters)
     ref.optimize()
     assert np.abs(mean - ref.mean()).max() / np.abs(mean).max() < 1e-7
+
+
+def _ltv_chain_spec(S):
+    """The problem of examples/ltv_chain.cpp as a neutral spec."""
+    d, dt = 4, 0.2
+    i = np.arange(S, dtype=np.float64)
+    nominal = np.stack([-6.0 + 12.0 * i / (S - 1), 5.0 + 3.5 * np.sin(3.0 * i / (S - 1)),
+                        np.full(S, 12.0 / ((S - 1) * dt)), 3.5 * 3.0 / ((S - 1) * dt) * np.cos(3.0 * i / (S - 1))], axis=1)
+    nq = 4 * (S - 1) + 1
+    q = np.arange(nq, dtype=np.float64)
+    w, c = 1.5 + 0.4 * np.sin(0.37 * q), 1.4 + 0.3 * np.cos(0.21 * q)
+    hA = np.zeros((nq, 4, 4))
+    hA[:, :2, 2:] = np.eye(2)
+    hA[:, 2:, :2] = -(w ** 2)[:, None, None] * np.eye(2)
+    hA[:, 2:, 2:] = -c[:, None, None] * np.eye(2)
+    hB = np.zeros((nq, 4, 2))
+    hB[:, 2:, :] = np.eye(2)
+    idx = 4 * np.arange(S - 1)[:, None] + np.arange(4)[None, :]
+    Phi, Q, Kinv = problems.ltv_links(hA[idx], hB[idx], dt)
+    Lam = np.concatenate([-Phi, np.broadcast_to(np.eye(d), (S - 1, d, d))], axis=2)
+    target = -nominal
+    spec = problems.ProblemSpec(S=S, d=d)
+    rows, cols, cell, origin = 120, 160, 0.25, (-20.0, -10.0)
+    X, Y = np.meshgrid(origin[0] + cell * np.arange(cols), origin[1] + cell * np.arange(rows))
+    spec.sdf = (np.hypot(X - 1.0, Y - 5.0) - 2.0, origin, cell)
+    spec.groups.append(problems.fixed_prior_group([0, S - 1], np.stack([nominal[0], nominal[-1]]), 1e-4 * np.eye(d), d))
+    spec.groups.append(problems.LinGroupSpec(start=np.arange(S - 1, dtype=np.int32), Lambda=Lam, Psi=-Lam,
+                                             mu_t=np.concatenate([target[:-1], target[1:]], axis=1), Kinv=Kinv, C=np.full(S - 1, 0.5)))
+    spec.groups.append(problems.GhGroupSpec(capi.COST_PLANAR_HINGE, d, 6, np.arange(1, S - 1, dtype=np.int32),
+                                            capi.HingeParams(0.1, 0.5, 1.0), 1.0, 10.0))
+    spec.mu0 = nominal.reshape(-1).copy()
+    spec.prec0_D = np.tile(100.0 * np.eye(d), (S, 1, 1))
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(step_size_base=0.55, niters_lowtemp=1 << 30)
+    return spec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alpha", [0.8, 1.0])
+def test_facade_ltv_chain_ema_and_accessors_match_mirror_and_oracle(gpu_ctx, alpha):
+    """examples/ltv_chain.cpp: facade LTV_GP (its own host-side Van Loan set-up) + _Cuda collision factors + the EMA update
+    set_alpha + E_Phis / switch_to_high_temperature / SparseGaussHermite::update_parameters / sigmapts, against the same
+    problem through the ctypes mirror (1e-9: the LTV blocks come from two implementations of the same exponential) and
+    the oracle with the EMA of gvibase/GVI-GH-Cuda-impl.h:112-114 (1e-7)."""
+    import gvi_oracle as o
+    S, niters = 30, 6
+    exe = compile_example("ltv_chain")
+    out = subprocess.run([str(exe), str(S), str(niters), str(alpha)], capture_output=True, text=True, check=True).stdout
+    lines = out.splitlines()
+    costs = np.array([float(l.split()[2]) for l in lines if l.startswith("cost ")])
+    mean = np.array([float(l.split()[2]) for l in lines if l.startswith("mean ")])
+    ephi = np.array([[float(x) for x in l.split()[2:]] for l in lines if l.startswith("ephi ")])
+    c_low, c_high, temp = (float(x) for x in [l for l in lines if l.startswith("costs ")][0].split()[1:5:1] if x != "temperature")
+    gh = [float(x) for x in [l for l in lines if l.startswith("gh ")][0].split()[1:]]
+    spec = _ltv_chain_spec(S)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    opts = capi.Problem.default_opts()
+    opts.niters_lowtemp = 1 << 30
+    opts.ema_alpha = alpha
+    stats = p.optimize(niters, opts)
+    assert len(costs) == niters and all(s.accepted for s in stats)
+    assert np.abs(costs - np.array([s.cost for s in stats])).max() < 1e-9 * np.abs(costs).max()
+    assert np.abs(mean - p.mean()).max() < 1e-9 * np.abs(mean).max()
+    ref = ob.build_oracle(spec, niters=niters)
+    ref.alpha = alpha
+    recs = ref.optimize()
+    assert all(r.accepted for r in recs)
+    assert np.abs(costs - np.array([r.cost for r in recs])).max() < 1e-8 * np.abs(costs).max()
+    assert np.abs(mean - ref.mean()).max() < 1e-7 * np.abs(mean).max()
+    # per-factor expectations in the caller's (interleaved) order
+    (E0, E1, E2), = p.moments()
+    c, fc = p.cost()
+    assert abs(c - c_low) < 1e-9 * abs(c)
+    k = 0
+    for i in range(S):
+        if i == 0:
+            assert abs(ephi[k, 0] - fc[0]) < 1e-9 * max(1.0, abs(fc[0])); k += 1
+        if i == S - 1:
+            assert abs(ephi[k, 0] - fc[1]) < 1e-9 * max(1.0, abs(fc[1])); k += 1
+        if i < S - 1:
+            assert abs(ephi[k, 0] - fc[2 + i]) < 1e-9 * max(1.0, abs(fc[2 + i])); k += 1
+        if 0 < i < S - 1:
+            j = i - 1
+            assert abs(ephi[k, 0] - E0[j]) <= 1e-10 * max(abs(E0[j]), 1e-300) + 1e-300
+            assert abs(ephi[k, 1] - E1[j, 0]) <= 1e-9 * np.abs(E1[j]).max() + 1e-300
+            assert abs(ephi[k, 2] - E2[j, 1, 1]) <= 1e-9 * np.abs(E2[j]).max() + 1e-300
+            k += 1
+    assert k == len(ephi)
+    p.switch_to_high_temperature()
+    c2, _ = p.cost()
+    assert abs(c2 - c_high) < 1e-9 * abs(c2) and temp == 10.0 and c2 != c
+    # SparseGaussHermite after update_parameters(deg 6, dim 4): 953 sigma points, moments vs the oracle
+    m4 = np.array([1.0, 3.5, 0.4, 0.6])
+    P4 = np.full((4, 4), 0.05) + np.diag([0.45, 0.55, 0.65, 0.75])
+    Z, w = o.table(4, 6)
+    psi = ob.psi_for_group(spec, spec.groups[2], 0)
+    r0, r1, r2 = o.moments(psi, m4, P4, Z, w)
+    assert int(gh[0]) == 953
+    assert abs(gh[1] - r0) < 1e-10 * abs(r0) and abs(gh[2] - r1[0]) < 1e-9 * np.abs(r1).max()
+    assert abs(gh[3] - m4[1]) < 1e-12 and abs(gh[4] - P4[1, 2]) < 1e-12

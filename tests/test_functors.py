@@ -56,16 +56,42 @@ def test_oracle_quadrotor_check_points():
     assert psi(np.array([[0.0, 0.0, np.pi / 2, 0, 0, 0]]))[0] == 0.0
 
 
+def test_oracle_arm_forward_kinematics():
+    """ForwardKinematics (helpers/CudaOperation.h:366-401) on cases with a closed form: a planar two-link arm (alpha = 0,
+    d = 0) puts the sphere at the classic (l1 c1 + l2 c12, l1 s1 + l2 s12, 0); n_balls is capped by the size of the state
+    vector (:752); the single-precision trigonometry is visible at the 1e-8 level and nowhere above."""
+    nz, rows, cols = 30, 40, 50
+    origin, cell = np.array([-2.5, -2.0, -1.5]), 0.1
+    z, y, x = np.meshgrid(origin[2] + cell * np.arange(nz), origin[1] + cell * np.arange(rows), origin[0] + cell * np.arange(cols),
+                          indexing="ij")
+    sdf = o.SignedDistanceField3D(origin, cell, 0.4 * x - 0.3 * y + 0.2 * z + 1.0)   # affine: the lookup is exact
+    l1, l2, th1, th2 = 1.0, 0.7, 0.3, -0.5
+    psi = o.make_arm_cost(sdf, [l1, l2], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0], frames=[1], centers=[[0.0, 0.0, 0.0]], radii=[3.0],
+                          sigma=2.0, eps=0.5)
+    px, py = l1 * np.cos(th1) + l2 * np.cos(th1 + th2), l1 * np.sin(th1) + l2 * np.sin(th1 + th2)
+    want = 2.0 * (3.5 - (0.4 * px - 0.3 * py + 1.0)) ** 2
+    got = psi(np.array([[th1, th2, 9.0, 9.0]]))[0]
+    assert abs(got - want) < 5e-7 * want and abs(got - want) > 0        # float trig: close, not equal
+    # three spheres but a 2-dimensional state vector: only the first two are evaluated
+    three = o.make_arm_cost(sdf, [l1], [0.0], [0.0], [0.0], frames=[0, 0, 0], centers=[[0, 0, 0], [-0.5, 0, 0], [-1.0, 0, 0]],
+                            radii=[3.0, 3.0, 3.0], sigma=1.0, eps=0.5)
+    two = o.make_arm_cost(sdf, [l1], [0.0], [0.0], [0.0], frames=[0, 0], centers=[[0, 0, 0], [-0.5, 0, 0]], radii=[3.0, 3.0],
+                          sigma=1.0, eps=0.5)
+    X = np.array([[0.4, 0.1]])
+    assert three(X)[0] == two(X)[0] > 0
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", [capi.COST_HINGE_3D, capi.COST_QUAD_HINGE])
-def test_moments_robot_functors(kind):
+@pytest.mark.parametrize("kind,d,deg", [(capi.COST_HINGE_3D, 6, 3), (capi.COST_QUAD_HINGE, 6, 3), (capi.COST_ARM_3D, 6, 3),
+                                        (capi.COST_ARM_3D, 4, 4)])
+def test_moments_robot_functors(kind, d, deg):
     import gaussianvi_b200 as gv
     ctx = gv.Context(0)
-    N, d, deg = 96, 6, 3
+    N = 96
     spec = problems.make_factor_batch_functor(kind, N=N, d=d, deg=deg)
     p = problems.build_device_problem(ctx, spec)
     (E0, E1, E2), = p.moments()
-    covD, _ = p.covariance()
+    covD = spec.meta["Sigma"]   # the generator's covariances: nothing read back from the GPU feeds the oracle
     psi = ob.psi_for_group(spec, spec.groups[0], 0)
     Z, w = o.table(d, deg)
     mu = spec.mu0.reshape(N, d)
@@ -113,3 +139,37 @@ def test_hinge3d_chain_matches_oracle():
     covD, covO = p.covariance()
     assert rel(covD, ref.covariance().D) < 1e-7
     assert all(s.accepted for s in stats)
+
+
+@pytest.mark.gpu
+def test_arm_chain_matches_oracle():
+    """A 3-DOF arm (state 6 = joint angles + velocities) under a min-acc prior with CudaOperation_3dArm collision factors
+    (helpers/CudaOperation.h:680-779): five NGD iterations on the device against the oracle."""
+    import gaussianvi_b200 as gv
+    ctx = gv.Context(0)
+    S, d, dt = 10, 6, 0.3
+    spec = problems.ProblemSpec(S=S, d=d)
+    spec.sdf3d = problems.ball_sdf3d()
+    start = np.array([-1.2, 0.4, 0.3, 0, 0, 0.0])
+    goal = np.array([1.0, -0.6, 1.1, 0, 0, 0.0])
+    spec.groups.append(problems.fixed_prior_group([0, S - 1], np.stack([start, goal]), 1e-4 * np.eye(d), d))
+    spec.groups.append(problems.minacc_group(S, 0.8 * np.eye(3), dt))
+    spec.groups.append(problems.GhGroupSpec(capi.COST_ARM_3D, d, 3, np.arange(1, S - 1, dtype=np.int32),
+                                            problems.example_arm(3, sigma=0.2), 1.0, 10.0))
+    t = np.linspace(0, 1, S)[:, None]
+    mu0 = start[None, :] * (1 - t) + goal[None, :] * t
+    mu0[:, 3:] = (goal[:3] - start[:3]) / ((S - 1) * dt)
+    spec.mu0 = mu0.reshape(-1)
+    spec.prec0_D = np.broadcast_to(10.0 * np.eye(d), (S, d, d)).copy()
+    spec.prec0_O = np.zeros((S - 1, d, d))
+    spec.meta = dict(niters=5, step_size_base=0.55, niters_lowtemp=10)
+    p = problems.build_device_problem(ctx, spec)
+    stats = p.optimize(5, gv.Problem.default_opts())
+    ref = ob.build_oracle(spec, niters=5)
+    recs = ref.optimize()
+    assert [bool(s.accepted) for s in stats] == [r.accepted for r in recs] and [s.n_backtrack for s in stats] == [r.n_backtrack for r in recs]
+    (E0, _, _), = p.moments()
+    assert (E0 > 0).sum() >= 2            # the arm does touch the obstacles
+    assert rel(p.mean(), ref.mean()) < 1e-7
+    covD, covO = p.covariance()
+    assert rel(covD, ref.covariance().D) < 1e-7

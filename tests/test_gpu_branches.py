@@ -24,11 +24,12 @@ def rel(a, b):
     return np.abs(a - b).max() / (den if den > 0 else 1.0)
 
 
-def run_regime(gpu_ctx, spec, niters, base, lowtemp, max_backtrack, reuse):
+def run_regime(gpu_ctx, spec, niters, base, lowtemp, max_backtrack, reuse, alpha=1.0):
     spec.meta["step_size_base"] = base
     spec.meta["niters_lowtemp"] = lowtemp
     ref = ob.build_oracle(spec, niters=niters)
     ref.set_max_iter_backtrack(max_backtrack)
+    ref.alpha = alpha
     recs = ref.optimize()
     p = problems.build_device_problem(gpu_ctx, spec)
     opts = capi.Problem.default_opts()
@@ -36,6 +37,7 @@ def run_regime(gpu_ctx, spec, niters, base, lowtemp, max_backtrack, reuse):
     opts.niters_lowtemp = lowtemp
     opts.max_backtrack = max_backtrack
     opts.reuse_accepted_sweep = reuse
+    opts.ema_alpha = alpha
     stats = p.optimize(niters, opts)
     return p, stats, ref, recs
 
@@ -112,6 +114,22 @@ def test_cfg3_chain_rejections_temperature_switch_and_convergence(gpu_ctx, base,
     assert sum(1 for r in recs if not r.accepted) == expect["exhausted"]
     e = check_path(p, stats, ref, recs, lowtemp, max_backtrack)
     print("cfg3 N=40 regime", base, lowtemp, max_backtrack, "reuse", reuse, "path", [(r.n_backtrack, int(r.accepted)) for r in recs], "err", e)
+
+
+@pytest.mark.parametrize("reuse", [0, 1])
+@pytest.mark.parametrize("alpha,base,lowtemp,max_backtrack,niters", [
+    (0.5, 0.55, 100, 10, 8),   # every first trial accepted, half of each step taken
+    (0.7, 2.2, 4, 5, 12),      # with rejections, the count switch and a final exhaustion (-> converged)
+])
+def test_ema_update_of_the_cuda_path(gpu_ctx, alpha, base, lowtemp, max_backtrack, niters, reuse):
+    """EMA of an accepted proposal, GVIGH::set_alpha of the reference's GPU path (gvibase/GVI-GH-Cuda.h:223,
+    GVI-GH-Cuda-impl.h:112-114): alpha * new + (1 - alpha) * current for mean and precision."""
+    p, stats, ref, recs = run_regime(gpu_ctx, problems.make_cfg3(N=40), niters, base, lowtemp, max_backtrack, reuse, alpha)
+    e = check_path(p, stats, ref, recs, lowtemp, max_backtrack)
+    # the EMA really is in effect: the same regime without it ends elsewhere
+    p1, _, _, _ = run_regime(gpu_ctx, problems.make_cfg3(N=40), niters, base, lowtemp, max_backtrack, reuse, 1.0)
+    assert rel(p1.mean(), p.mean()) > 1e-6
+    print("EMA alpha", alpha, "path", [(r.n_backtrack, int(r.accepted)) for r in recs], "err", e)
 
 
 def test_rejected_trial_with_culling_and_speculation_is_bit_identical(gpu_ctx):

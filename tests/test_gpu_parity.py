@@ -464,3 +464,54 @@ def test_free_space_culling_extremes(gpu_ctx, eps_radius, expect):
         assert e1 < 0.3 * e0
     else:
         assert e1 == e0
+
+
+# ---------------------------------------------------------------- device-side LTV prior set-up
+def test_device_ltv_transition_matches_numpy(gpu_ctx):
+    """gvib200_ltv_transition (one thread per link, Van Loan per quarter interval) against the NumPy set-up that stands
+    for gp/LTV_prior.h:123-197 in the generators: Phi, Q, Q^-1 of 3000 random damped-oscillator links."""
+    n = 3000
+    hA, hB = problems.ltv_system(n, seed=17)
+    idx = 4 * np.arange(n)[:, None] + np.arange(4)[None, :]
+    Phi, Q, Kinv = problems.ltv_links(hA[idx], hB[idx], 0.2, ctx=None)
+    dPhi, dQ, dKinv = problems.ltv_links(hA[idx], hB[idx], 0.2, ctx=gpu_ctx)
+    assert rel(dPhi, Phi) < 1e-13 and rel(dQ, Q) < 1e-13
+    assert max(rel(dKinv[k], Kinv[k]) for k in range(n)) < 1e-10   # kappa(Q) ~ 1e4
+    # a generic (non-commuting, full B) system of state dimension 6 against scipy's expm of the whole Van Loan matrix
+    from scipy.linalg import expm
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((5, 4, 6, 6))
+    B = rng.standard_normal((5, 4, 6, 3))
+    gPhi, gQ = gpu_ctx.ltv_transition(A, B, 0.4, want_inverse=False)
+    for f in range(5):
+        P, Qm = np.eye(6), np.zeros((6, 6))
+        for k in range(4):
+            M = np.zeros((12, 12))
+            M[:6, :6], M[:6, 6:], M[6:, 6:] = -A[f, k], B[f, k] @ B[f, k].T, A[f, k].T
+            E = expm(M * 0.1)
+            Pk = E[6:, 6:].T
+            Qm = Pk @ Qm @ Pk.T + Pk @ E[:6, 6:]
+            P = Pk @ P
+        assert rel(gPhi[f], P) < 1e-12 and rel(gQ[f], 0.5 * (Qm + Qm.T)) < 1e-12
+
+
+def test_cfg5_device_generated_batch_matches_independent_oracle_runs(gpu_ctx):
+    """The batch bench.py --config cfg5 builds (LTV links integrated on the device, no per-problem loop): every problem
+    is bit-identical to make_cfg3(seed = 1000 + b, ctx) and iterates like an independent oracle run of it."""
+    nb, N, niters = 4, 50, 5
+    spec = problems.make_cfg5(n_problems=nb, N=N, first_seed=1003, ctx=gpu_ctx)
+    Sb = spec.meta["states_per_problem"]
+    p = problems.build_device_problem(gpu_ctx, spec)
+    stats = p.optimize(niters, capi.Problem.default_opts())
+    assert all(s.accepted and s.n_backtrack == 0 for s in stats)
+    mu = p.mean().reshape(nb, -1)
+    cD, _ = p.covariance()
+    for b in range(nb):
+        sub = problems.make_cfg3(N=N, seed=1003 + b, ctx=gpu_ctx)
+        ltv_b = spec.groups[1]
+        assert np.array_equal(ltv_b.Kinv[b * (Sb - 1):(b + 1) * (Sb - 1)], sub.groups[1].Kinv)
+        assert np.array_equal(ltv_b.Lambda[b * (Sb - 1):(b + 1) * (Sb - 1)], sub.groups[1].Lambda)
+        ref = ob.build_oracle(sub, niters=niters)
+        ref.optimize()
+        assert rel(mu[b], ref.mean()) < FINAL_TOL
+        assert rel(cD[b * Sb:(b + 1) * Sb], ref.cov.D) < FINAL_TOL
