@@ -41,7 +41,7 @@ EXPORTS = [
     "gvib200_problem_set_option", "gvib200_prox_iterate", "gvib200_prox_optimize",
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
-    "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature",
+    "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature", "gvib200_ctx_mailbox_create", "gvib200_ctx_mailbox_connect",
 ]
 
 

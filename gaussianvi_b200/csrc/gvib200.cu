@@ -165,6 +165,14 @@ struct gvib200_ctx {
     int (*ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int rank = 0, world = 1;
+    // peer-memory mailbox (kernels.cuh "Multi-GPU exchange through peer memory"): when connected, the boundary records of
+    // the chain passes and the cost / flag exchange travel as NVLink stores issued by the kernels themselves -- no NCCL call
+    // on the iteration path
+    double* mbox = nullptr;
+    void* peer_mapped[MBOX_RANKS] = {};  // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
+    MboxPeers peers{};
+    bool mbox_on = false;
+    unsigned long long ep_rec[2] = {0, 0}, ep_cost = 0;  // epochs of the next exchange per slot / of the next cost exchange
     long long launches = 0;  // kernels launched through this ctx
     // kernels whose function attributes (dynamic shared memory opt-in) were set on THIS context's device: the attributes
     // are per device, so a process driving several contexts configures each of them
@@ -456,6 +464,22 @@ static int chain_pass_dist(gvib200_problem* p, int slot, const CrArgs<D>& a, dou
     p->flags_synced = false;
     TRY(cr_allow_smem(ctx, k_cr_mid_forward<D, RHS>, ctx->smem_optin - 5120));
     TRY(cr_allow_smem(ctx, k_cr_dist_top<D, RHS, SELINV>, ctx->smem_optin - 5120));
+    if (ctx->mbox_on) {
+        // 3 launches, like on one GPU: tiles | ONE single-CTA kernel in shared memory (separator chain reduced to this
+        // rank's two end nodes, boundary record pushed to the peers' mailboxes over NVLink, chain of rank boundaries,
+        // back up the separator chain, log det) | tiles back
+        TRY(cr_allow_smem(ctx, k_cr_dist_mid<D, RHS, SELINV>, ctx->smem_optin - 5120));
+        constexpr size_t DDc = (size_t)D * D;
+        const size_t smem_mid = (cr_top_doubles<D>(pl.K + 1) + cr_top_doubles<D>(P + 1) + (size_t)(P + 1) * NB + 4 * (P + 1) * DDc +
+                                 2 * (size_t)(P + 1) * D + 32) * sizeof(double);
+        if (smem_mid > ctx->smem_optin - 5120) return fail(GVIB200_EINVAL, "chain_pass_dist: separator chain too long for one CTA");
+        const unsigned long long epoch = ++ctx->ep_rec[slot & 1];
+        LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+        LAUNCH(p, KC_BT_TOP, (k_cr_dist_mid<D, RHS, SELINV>), 1, CR_THREADS, smem_mid, a, top, buf + L.send, buf + L.recv, buf + L.Dt,
+               buf + L.Ot, buf + L.gt, ctx->peers, slot & 1, epoch, d_logdet);
+        LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+        return check_launch("chain_pass_dist (mailbox)");
+    }
     // 4 launches + one all-gather: tiles | separator sum + mid tile + boundary record | all-gather | chain of rank
     // boundaries + seeds + mid tile back (+ log det) | tiles back
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
@@ -985,10 +1009,16 @@ static void run_total(gvib200_problem* p, int which) {
     const size_t n = (size_t)p->n_factors;
     if (n > 8192) {
         const int nb = (int)std::min<size_t>(1024, (n + 1023) / 1024);  // <= 4 elements per thread
-        const bool single = (p->ctx->world == 1);
+        const bool mailbox = (p->ctx->world > 1 && p->ctx->mbox_on);
+        const bool single = (p->ctx->world == 1) || mailbox;
+        MboxPeers peers = p->ctx->peers;
+        unsigned long long epoch = 0;
+        if (mailbox) epoch = ++p->ctx->ep_cost;
+        else peers.world = 1;
         LAUNCH(p, KC_SUM, k_total, nb, 256, 0, n, p->fcost[which], p->partial, p->d_counter, p->scal + which, 0.5,
-               p->scal + 2 + which, p->d_flag, single ? p->zc_dev : nullptr, which, single ? nullptr : p->red_buf);
+               p->scal + 2 + which, p->d_flag, single ? p->zc_dev : nullptr, which, single ? nullptr : p->red_buf, peers, epoch);
         p->zc_ok[which] = true;
+        if (mailbox) p->flags_synced = true;  // the cost exchange made the not-SPD flags global
         if (!single) {  // sum over the ranks, flags made global; the unpack kernel hands the result to the host (mapped memory)
             gvib200_ctx* ctx = p->ctx;
             if (ctx->ncclAllGather(p->red_buf, p->red_buf + 4, 4, /*ncclFloat64*/ 8, ctx->nccl_comm, p->ls) != 0) {
@@ -1083,6 +1113,9 @@ extern "C" int gvib200_ctx_destroy(gvib200_ctx* ctx) {
         if (kv.second->d_rows) cudaFree(kv.second->d_rows);
     for (auto& kv : ctx->tables)
         if (kv.second->d_sym) cudaFree(kv.second->d_sym);
+    for (int r = 0; r < MBOX_RANKS; ++r)
+        if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
+    if (ctx->mbox) cudaFree(ctx->mbox);
     delete ctx;
     return 0;
 }
@@ -1111,6 +1144,51 @@ extern "C" int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank,
     ctx->nccl_comm = nccl_comm;
     ctx->rank = rank;
     ctx->world = world;
+    return 0;
+}
+
+extern "C" int gvib200_ctx_mailbox_create(gvib200_ctx* ctx, void* handle_out, size_t handle_capacity) {
+    if (!ctx || !handle_out || handle_capacity < sizeof(cudaIpcMemHandle_t))
+        return fail(GVIB200_EINVAL, "mailbox_create: bad arguments (the handle needs 64 bytes)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->mbox) {
+        CUDA_TRY(cudaMalloc((void**)&ctx->mbox, MBOX_DOUBLES * sizeof(double)));
+        CUDA_TRY(cudaMemset(ctx->mbox, 0, MBOX_DOUBLES * sizeof(double)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->mbox));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return (int)sizeof(h);
+}
+
+extern "C" int gvib200_ctx_mailbox_connect(gvib200_ctx* ctx, int world, int rank, const void* handles, size_t handle_stride) {
+    if (!ctx || !handles || world < 2 || world > MBOX_RANKS || rank < 0 || rank >= world ||
+        handle_stride < sizeof(cudaIpcMemHandle_t))
+        return fail(GVIB200_EINVAL, "mailbox_connect: bad arguments (2..16 ranks)");
+    if (!ctx->mbox) return fail(GVIB200_ESTATE, "mailbox_connect: call gvib200_ctx_mailbox_create first");
+    if (ctx->world != world || ctx->rank != rank) return fail(GVIB200_ESTATE, "mailbox_connect: call gvib200_ctx_set_comm first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            ctx->peers.p[r] = ctx->mbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + (size_t)r * handle_stride, sizeof(h));
+        void* q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GVIB200_ECUDA, std::string("mailbox_connect: cudaIpcOpenMemHandle (rank ") + std::to_string(r) +
+                                           "): " + cudaGetErrorString(e));
+        }
+        ctx->peer_mapped[r] = q;
+        ctx->peers.p[r] = (double*)q;
+    }
+    ctx->peers.world = world;
+    ctx->peers.rank = rank;
+    ctx->mbox_on = !getenv("GVIB200_NO_MAILBOX");
     return 0;
 }
 
@@ -1759,7 +1837,9 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
     case D_: {                                                                                                 \
         int force_T = 0;                                                                                       \
         if (P > 1) { /* multi-GPU: always tiled, the separator chain goes through the mid level */            \
-            int K = std::min(p->ctx->sm_count, cr_max_top_nodes<D_>(smem) - 1);                                \
+            /* two SMs stay free of tile CTAs, as on one GPU: the single-CTA stage of one pass must not queue behind  \
+               the tile CTAs of the other pass */                                                              \
+            int K = std::min(std::max(1, p->ctx->sm_count - 2), cr_max_top_nodes<D_>(smem) - 1);               \
             K = std::max(1, std::min(K, S - 1));                                                               \
             force_T = std::max(2, std::min((S - 1 + K - 1) / K, cr_max_tile_links<D_>(smem)));                 \
         }                                                                                                      \
@@ -2179,7 +2259,8 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
         // speculation: if this trial is accepted its sweep is the next iteration's gradient sweep -- assemble it now,
         // into the second set of buffers, so that the host round trip below costs no device time
         const bool speculate = (o.reuse_accepted_sweep != 0);
-        const bool side_total = linear_forked && speculate && p->ctx->world == 1 && p->n_factors > 8192 && p->zc_ok[p->cur];
+        const bool side_total = linear_forked && speculate && (p->ctx->world == 1 || p->ctx->mbox_on) && p->n_factors > 8192 &&
+                                p->zc_ok[p->cur];
         if (side_total) {
             // the total cost (a short latency-bound kernel whose result only the host needs) moves to the side stream,
             // next to the speculative assembly on the main stream; k_total hands cost and flags over in mapped memory

@@ -758,10 +758,59 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh8) {
     return t;
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-GPU exchange through peer memory (NVLink / NVSwitch): every rank owns a "mailbox" in its device memory that its
+// peers map over CUDA IPC.  A rank PUSHES its record into every peer's mailbox with plain stores, publishes it with a
+// release store of the pass's epoch to the peer's flag word, and waits for the P flags of its own mailbox -- no NCCL call,
+// no host involvement, no extra launch: the exchange sits inside the single-CTA kernel that needs it.
+//   records     [slot][depth][rank][MBOX_REC]   boundary records of the chain passes (slot = workspace slot of the pass)
+//   rec flags   [slot][depth][rank]             epoch of the record held in that cell
+//   cost        [depth][rank][4]                (cost, flag0, flag1, 0) of a cost evaluation
+//   cost flags  [depth][rank]
+// Epochs only grow; a cell is reused every MBOX_DEPTH epochs.  Between two passes on the same slot lies at least one
+// cost exchange in which every rank waits for every other, so a writer is never more than one epoch ahead of a reader.
+// ------------------------------------------------------------------------------------------
+constexpr int MBOX_RANKS = 16;
+constexpr int MBOX_DEPTH = 4;
+constexpr int MBOX_REC = 256;  // doubles per boundary record cell (5 d^2 + 4 d = 204 at d = 6)
+constexpr size_t MBOX_OFF_REC = 0;
+constexpr size_t MBOX_OFF_RECFLAG = MBOX_OFF_REC + (size_t)2 * MBOX_DEPTH * MBOX_RANKS * MBOX_REC;
+constexpr size_t MBOX_OFF_COST = MBOX_OFF_RECFLAG + (size_t)2 * MBOX_DEPTH * MBOX_RANKS;
+constexpr size_t MBOX_OFF_COSTFLAG = MBOX_OFF_COST + (size_t)MBOX_DEPTH * MBOX_RANKS * 4;
+constexpr size_t MBOX_DOUBLES = MBOX_OFF_COSTFLAG + (size_t)MBOX_DEPTH * MBOX_RANKS;
+
+struct MboxPeers {
+    double* p[MBOX_RANKS];  // every rank's mailbox as mapped on THIS device (p[rank] is the local one)
+    int world, rank;
+};
+
+__device__ __forceinline__ void mbox_publish(double* cell, unsigned long long epoch) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(cell), "l"(epoch) : "memory");
+}
+// spin until the flag word carries `epoch`; gives up after ~2 s so that a dead peer cannot hang the device
+__device__ __forceinline__ bool mbox_wait(const double* cell, unsigned long long epoch) {
+    const long long t0 = clock64();
+    while (true) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(cell) : "memory");
+        if (v >= epoch) return true;
+        if (clock64() - t0 > 4000000000ll) return false;
+        __nanosleep(64);
+    }
+}
+
+// block_sum_256 leaves its result in thread 0: hand it to every thread (one more barrier)
+__device__ __forceinline__ double tot_bcast(double v, double* sh8) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh8[0] = v;
+    __syncthreads();
+    return sh8[0];
+}
+
 __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restrict__ v, double* __restrict__ partial,
                                                unsigned* __restrict__ counter, const double* __restrict__ extra, double half,
-                                               double* __restrict__ out, const int* __restrict__ dflag, double* zc, int which,
-                                               double* __restrict__ red) {
+                                               double* __restrict__ out, int* __restrict__ dflag, double* zc, int which,
+                                               double* __restrict__ red, const MboxPeers peers, unsigned long long epoch) {
     __shared__ double sh8[8];
     __shared__ bool is_last;
     // block b owns the fixed slice [b * per, (b + 1) * per); a thread takes (at most four) elements at stride 256, all
@@ -789,6 +838,48 @@ __global__ void __launch_bounds__(256) k_total(size_t n, const double* __restric
     double t = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(partial + i);
     const double tot = block_sum_256(t, sh8);
+    if (peers.world > 1) {
+        // multi-GPU: this rank's (cost, flags) go to every peer's mailbox, the P records come back, every rank forms the
+        // same rank-ordered sum; the host gets the result through mapped memory like on one GPU
+        __shared__ double rec[MBOX_RANKS][4];
+        __shared__ int bad;
+        const int P = peers.world, dq = (int)(epoch % MBOX_DEPTH);
+        if (threadIdx.x == 0) bad = 0;
+        const double total = tot_bcast(tot, sh8) + (extra ? half * extra[0] : 0.0);  // (barriers inside: all threads)
+        if ((int)threadIdx.x < P) {
+            double* dst = peers.p[threadIdx.x] + MBOX_OFF_COST + ((size_t)dq * MBOX_RANKS + peers.rank) * 4;
+            dst[0] = total;
+            dst[1] = (double)dflag[0];
+            dst[2] = (double)dflag[1];
+            dst[3] = 0.0;
+            __threadfence_system();
+            mbox_publish(peers.p[threadIdx.x] + MBOX_OFF_COSTFLAG + (size_t)dq * MBOX_RANKS + peers.rank, epoch);
+            const double* mine = peers.p[peers.rank];
+            if (!mbox_wait(mine + MBOX_OFF_COSTFLAG + (size_t)dq * MBOX_RANKS + threadIdx.x, epoch)) bad = 1;
+            const double* src = mine + MBOX_OFF_COST + ((size_t)dq * MBOX_RANKS + threadIdx.x) * 4;
+            for (int e = 0; e < 4; ++e) rec[threadIdx.x][e] = __ldcg(src + e);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = 0.0, f0 = bad ? 1.0 : 0.0, f1 = 0.0;
+            for (int r = 0; r < P; ++r) {
+                c += rec[r][0];
+                f0 += rec[r][1];
+                f1 += rec[r][2];
+            }
+            out[0] = c;
+            dflag[0] = f0 > 0.0 ? 1 : 0;
+            dflag[1] = f1 > 0.0 ? 1 : 0;
+            *counter = 0u;
+            if (zc != nullptr) {
+                zc[which] = c;
+                zc[2] = f0 > 0.0 ? 1.0 : 0.0;
+                zc[3] = f1 > 0.0 ? 1.0 : 0.0;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         const double total = tot + (extra ? half * extra[0] : 0.0);
         out[0] = total;
@@ -1043,6 +1134,143 @@ __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_dist_top(int P, int rank, 
         const double tot = cr_block_sum(t, red);
         if (threadIdx.x == 0) ldout[0] = tot + mid.ld[0] + (rank == 0 ? top.ld[0] : 0.0);
     }
+}
+
+// Multi-GPU pass, the single-CTA stage between the two tile launches, ONE launch that lives in shared memory like k_cr_top:
+//   separator system of this rank's tiles gathered (cr_top_load) and reduced by cyclic reduction down to its two end
+//   nodes, records in shared memory -> what is left on the end nodes IS this rank's boundary record: pushed into every
+//   peer's mailbox over NVLink -> all records in -> chain of rank boundaries (P + 1 nodes) solved redundantly in a second,
+//   small shared-memory region -> its results seed the two end nodes -> back substitution / Takahashi recursion up the
+//   separator chain -> separator results for the tiles' backward launch, this rank's share of log det.
+template <int D, bool RHS, bool SELINV>
+__global__ void __launch_bounds__(CR_THREADS, 1)
+    k_cr_dist_mid(const CrArgs<D> a, const CrArgs<D> top, double* send, double* recv, double* Dt, double* Ot, double* gt,
+                  const MboxPeers peers, int slot, unsigned long long epoch, double* ldout) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ CrGeom gm, gm2;
+    __shared__ double red[CR_THREADS];
+    __shared__ int timed_out;
+    constexpr int DD = D * D;
+    constexpr int NB = cr_boundary_doubles<D>();
+    const int P = peers.world, rank = peers.rank, dq = (int)(epoch % MBOX_DEPTH);
+    const int nt = a.K + 1;  // nodes of the separator chain
+    if (threadIdx.x == 0) {
+        cr_make_geom(gm, nt - 1);
+        timed_out = 0;
+    }
+    __syncthreads();
+    const CrView<D> v = cr_make_view<D>(smem, nt);
+    const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
+    CrRec<D> rec;
+    rec.G = v.g + (size_t)D * v.NS;
+    rec.H = rec.G + cr_rec_capacity(nrec, DD);
+    rec.Dinv = rec.H + cr_rec_capacity(nrec, DD);
+    rec.y = rec.Dinv + cr_rec_capacity(nrec, DD);
+    // everything about the chain of rank boundaries stays in shared memory too: the received records, the chain itself,
+    // its results, and the working arrays of its solve
+    double* srecv = rec.y + cr_rec_capacity(nrec, D);
+    double* ssend = srecv + (((size_t)P * NB + 1) & ~size_t(1));
+    double* sDt = ssend + ((NB + 1) & ~1);
+    double* sOt = sDt + (size_t)(P + 1) * DD;
+    double* sgt = sOt + (size_t)(P + 1) * DD;
+    double* sxt = sgt + (((size_t)(P + 1) * D + 1) & ~size_t(1));
+    double* scD = sxt + (((size_t)(P + 1) * D + 1) & ~size_t(1));
+    double* scO = scD + (size_t)(P + 1) * DD;
+    double* sld = scO + (size_t)(P + 1) * DD;
+    double* smem_top = sld + 2;
+    (void)send;
+    (void)recv;
+    (void)Dt;
+    (void)Ot;
+    (void)gt;
+    send = ssend;
+    recv = srecv;
+    Dt = sDt;
+    Ot = sOt;
+    gt = sgt;
+    CrArgs<D> tp = top;
+    tp.Dg = sDt;
+    tp.Og = sOt;
+    tp.g = sgt;
+    tp.x = sxt;
+    tp.cD = scD;
+    tp.cO = scO;
+    tp.ld = sld;
+    cr_top_load<D, RHS>(a, v, gm, threadIdx.x, blockDim.x);
+    __syncthreads();
+    LogDetAcc ld;
+    bool ok = cr_forward_levels<D, RHS>(v, rec, 0, gm, ld);
+    // boundary record [Dfirst | Dlast | CL | CR | O | gfirst | glast | gl | gr]: the reduced end nodes carry everything
+    for (int e = threadIdx.x; e < DD; e += blockDim.x) {
+        send[e] = v.Dn[(size_t)e * v.NS + 0];
+        send[DD + e] = v.Dn[(size_t)e * v.NS + 1];
+        send[2 * DD + e] = 0.0;
+        send[3 * DD + e] = 0.0;
+        send[4 * DD + e] = v.P[(size_t)e * v.NS + 0];
+    }
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        double* gv = send + 5 * DD;
+        gv[e] = RHS ? v.g[(size_t)e * v.NS + 0] : 0.0;
+        gv[D + e] = RHS ? v.g[(size_t)e * v.NS + 1] : 0.0;
+        gv[2 * D + e] = 0.0;
+        gv[3 * D + e] = 0.0;
+    }
+    __syncthreads();
+    // push the record into every rank's mailbox (the own one included), then publish it
+    const size_t cell = ((size_t)(slot * MBOX_DEPTH + dq) * MBOX_RANKS + rank);
+    for (int idx = threadIdx.x; idx < P * NB; idx += blockDim.x) {
+        const int r = idx / NB, e = idx - r * NB;
+        peers.p[r][MBOX_OFF_REC + cell * MBOX_REC + e] = send[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P) {
+        mbox_publish(peers.p[threadIdx.x] + MBOX_OFF_RECFLAG + cell, epoch);
+        const double* mine = peers.p[rank];
+        if (!mbox_wait(mine + MBOX_OFF_RECFLAG + (size_t)(slot * MBOX_DEPTH + dq) * MBOX_RANKS + threadIdx.x, epoch)) timed_out = 1;
+    }
+    __syncthreads();
+    {
+        const double* mine = peers.p[rank] + MBOX_OFF_REC + (size_t)(slot * MBOX_DEPTH + dq) * MBOX_RANKS * MBOX_REC;
+        for (int idx = threadIdx.x; idx < P * NB; idx += blockDim.x) {
+            const int r = idx / NB, e = idx - r * NB;
+            recv[idx] = __ldcg(mine + (size_t)r * MBOX_REC + e);  // written by the peers: not through L1
+        }
+    }
+    __syncthreads();
+    if (timed_out) {
+        if (threadIdx.x == 0) *a.notspd = 1;  // surfaces as an error on the host instead of a hang
+        return;
+    }
+    cr_build_global<D>(P, recv, Dt, Ot, gt, threadIdx.x, blockDim.x);
+    __syncthreads();
+    cr_dev_top<D, RHS, SELINV>(tp, smem_top, gm2, red);  // results: tp.x / tp.cD / tp.cO, tp.ld[0]
+    __syncthreads();
+    // seed the two end nodes of the separator chain with the results on this rank's boundaries
+    if (SELINV)
+        for (int e = threadIdx.x; e < DD; e += blockDim.x) {
+            v.Dn[(size_t)e * v.NS + 0] = tp.cD[(size_t)rank * DD + e];
+            v.Dn[(size_t)e * v.NS + 1] = tp.cD[(size_t)(rank + 1) * DD + e];
+            v.P[(size_t)e * v.NS + 0] = tp.cO[(size_t)rank * DD + e];
+        }
+    if (RHS)
+        for (int e = threadIdx.x; e < D; e += blockDim.x) {
+            v.g[(size_t)e * v.NS + 0] = tp.x[(size_t)rank * D + e];
+            v.g[(size_t)e * v.NS + 1] = tp.x[(size_t)(rank + 1) * D + e];
+        }
+    __syncthreads();
+    cr_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
+    cr_store_results<D, RHS, SELINV>(v, gm, nt, nt - 1, a.tx, a.tD, a.tO, 0, threadIdx.x, blockDim.x);
+    const double s = cr_block_sum(ld.value(), red);
+    if (ldout != nullptr) {
+        // this rank's share of log det: its tiles + its separator chain; the chain of rank boundaries is counted by rank 0
+        __syncthreads();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < a.K; i += blockDim.x) t += a.ld[i];
+        const double tot = cr_block_sum(t, red);
+        if (threadIdx.x == 0) ldout[0] = tot + s + (rank == 0 ? tp.ld[0] : 0.0);
+    }
+    if (!ok) *a.notspd = 1;
 }
 
 // multi-GPU glue kernels (single small CTAs; the arithmetic is in bt_cr.h)

@@ -24,7 +24,7 @@ def find_libnccl() -> str:
     raise ImportError("libnccl not found")
 
 
-def attach_nccl(ctx: "capi.Context", rank: int, world: int):
+def attach_nccl(ctx: "capi.Context", rank: int, world: int, mailbox: bool = True):
     """Create an NCCL communicator over the torch.distributed world and attach it to the gvib200 context."""
     import torch
     import torch.distributed as dist
@@ -48,7 +48,32 @@ def attach_nccl(ctx: "capi.Context", rank: int, world: int):
     lib = capi.load_library()
     capi._check(lib.gvib200_ctx_set_comm(ctx.h, comm, rank, world, path.encode()))
     ctx._nccl = (nccl, comm)
+    if mailbox and world > 1:
+        attach_mailbox(ctx, rank, world)
     return comm
+
+
+def attach_mailbox(ctx: "capi.Context", rank: int, world: int) -> bool:
+    """Peer-memory exchange: every rank's mailbox handle (CUDA IPC, 64 bytes) travels over torch.distributed, then each
+    rank maps its peers' mailboxes (gvib200_ctx_mailbox_create / _connect).  Returns False (and leaves the NCCL path in
+    place) when some rank cannot export or map a mailbox, e.g. GPUs without peer access."""
+    import torch.distributed as dist
+    lib = capi.load_library()
+    buf = C.create_string_buffer(64)
+    ok = lib.gvib200_ctx_mailbox_create(ctx.h, buf, C.c_size_t(64)) >= 0
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf.raw) if ok else None)
+    if any(h is None for h in handles):
+        return False
+    blob = C.create_string_buffer(b"".join(handles), 64 * world)
+    ok = lib.gvib200_ctx_mailbox_connect(ctx.h, world, rank, blob, C.c_size_t(64)) >= 0
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    if not any(flags):
+        return False
+    if not all(flags):
+        raise RuntimeError("gvib200 mailbox: some ranks connected and some did not: " + lib.gvib200_last_error().decode())
+    return True
 
 
 def shard_problems(n_problems: int, rank: int, world: int):

@@ -104,6 +104,15 @@ const char* gvib200_version(void);
    exchange 5 d^2 + 4 d doubles in one all-gather; per cost evaluation 4 doubles in one all-reduce.  All ranks must make
    the same sequence of calls. */
 int gvib200_ctx_set_comm(gvib200_ctx* ctx, void* nccl_comm, int rank, int world, const char* libnccl_path);
+/* Peer-memory exchange (optional, after gvib200_ctx_set_comm; one box, GPUs connected by NVLink / NVSwitch): every rank
+   creates a mailbox in its device memory and hands out its CUDA IPC handle (64 bytes), the handles of all ranks are
+   exchanged by the caller (any transport: the ctypes mirror uses torch.distributed) and given to _connect in rank order.
+   From then on the boundary records of the chain passes and the cost / flag exchange of a line-search trial are pushed
+   into the peers' mailboxes by the kernels themselves (plain NVLink stores + a release flag, polled by the consumer):
+   no NCCL call and no extra launch on the iteration path -- a multi-GPU block-tridiagonal pass is 3 launches like a
+   single-GPU one.  Without a connected mailbox the library falls back to the NCCL all-gathers.  Returns the handle size. */
+int gvib200_ctx_mailbox_create(gvib200_ctx* ctx, void* handle_out, size_t handle_capacity);
+int gvib200_ctx_mailbox_connect(gvib200_ctx* ctx, int world, int rank, const void* handles, size_t handle_stride);
 
 /* ---- sparse Gauss-Hermite tables (replaces the cereal map consumed at
         quadrature/SparseGaussHermite.h:138-166 and its MATLAB generator
