@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "bt_cr_plan.h"
+#include "k1_grp.cuh"
 #include "k1_sym.cuh"
 #include "kernels.cuh"
 #include "ltv_setup.cuh"
@@ -61,7 +62,79 @@ struct Table {
     SymTable sym;
     std::vector<double> sym_data;  // host copy of sym.data
     double* d_sym = nullptr;
+    bool grp_ok = false;           // the rule consists of full sign groups with <= K1G_KMAX non-zero coordinates (K1G)
+    GrpTable grp{};
+    int* d_grp_hdr = nullptr;
+    double* d_grp_val = nullptr;
 };
+
+// Sparse sign-group view of a rule for K1G (k1_grp.cuh): groups of 2^k sign combinations of (a_1 .. a_k) on k <= K1G_KMAX
+// coordinates with one common weight, sorted by decreasing k.  Returns false when the rule does not have that structure.
+static bool build_grp_table(const Table& t, std::vector<int>& hdr, std::vector<double>& val, GrpTable& gt) {
+    const int dim = t.dim, n = t.n;
+    if (dim > 255) return false;
+    struct Grp {
+        std::vector<int> c;
+        std::vector<double> a;
+        double w = 0.0;
+        int count = 0;
+        unsigned seen = 0;
+    };
+    std::map<std::vector<double>, Grp> groups;
+    gt = GrpTable();
+    gt.dim = dim;
+    for (int i = 0; i < n; ++i) {
+        std::vector<double> key(dim);
+        int k = 0, pat = 0;
+        for (int c = 0; c < dim; ++c) {
+            const double v = t.nodes[(size_t)i * dim + c];
+            key[c] = std::fabs(v);
+            if (v != 0.0) {
+                if (v < 0.0) pat |= 1 << k;
+                ++k;
+            }
+        }
+        if (k == 0) {
+            if (gt.has_origin) return false;
+            gt.has_origin = 1;
+            gt.w0 = t.w[i];
+            continue;
+        }
+        if (k > K1G_KMAX) return false;
+        auto it = groups.find(key);
+        if (it == groups.end()) {
+            Grp g;
+            for (int c = 0; c < dim; ++c)
+                if (key[c] != 0.0) {
+                    g.c.push_back(c);
+                    g.a.push_back(key[c]);
+                }
+            g.w = t.w[i];
+            it = groups.emplace(key, g).first;
+        }
+        Grp& g = it->second;
+        if (g.w != t.w[i] || (g.seen & (1u << pat))) return false;
+        g.seen |= 1u << pat;
+        g.count++;
+    }
+    std::vector<const Grp*> order;
+    for (auto& kv : groups) {
+        if (kv.second.count != (1 << kv.second.c.size())) return false;
+        order.push_back(&kv.second);
+    }
+    std::stable_sort(order.begin(), order.end(), [](const Grp* x, const Grp* y) { return x->c.size() > y->c.size(); });
+    hdr.clear();
+    val.clear();
+    for (const Grp* g : order) {
+        int h = (int)g->c.size();
+        for (size_t i = 0; i < g->c.size(); ++i) h |= g->c[i] << (4 + 8 * (int)i);
+        hdr.push_back(h);
+        for (int i = 0; i < 3; ++i) val.push_back(i < (int)g->a.size() ? g->a[(size_t)i] : 0.0);
+        val.push_back(g->w);
+    }
+    gt.n_groups = (int)order.size();
+    return gt.n_groups > 0;
+}
 
 // Sign-group view of a sparse-GH rule for K1S (k1_sym.cuh): every set of nodes sharing |xi| must be a full group of
 // 2^k sign combinations with one common weight.  Returns false when the rule does not have that structure.
@@ -396,6 +469,19 @@ static int get_table(gvib200_ctx* ctx, int dim, int deg, const Table** out) {
         }
         CUDA_TRY(cudaMalloc((void**)&t->d_rows, rows.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(t->d_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (dim > 4) {
+            std::vector<int> gh;
+            std::vector<double> gvv;
+            t->grp_ok = build_grp_table(*t, gh, gvv, t->grp);
+            if (t->grp_ok) {
+                CUDA_TRY(cudaMalloc((void**)&t->d_grp_hdr, gh.size() * sizeof(int)));
+                CUDA_TRY(cudaMalloc((void**)&t->d_grp_val, gvv.size() * sizeof(double)));
+                CUDA_TRY(cudaMemcpy(t->d_grp_hdr, gh.data(), gh.size() * sizeof(int), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(t->d_grp_val, gvv.data(), gvv.size() * sizeof(double), cudaMemcpyHostToDevice));
+                t->grp.hdr = t->d_grp_hdr;
+                t->grp.val = t->d_grp_val;
+            }
+        }
         t->sym_ok = build_sym_table(*t, t->sym);
         if (t->sym_ok) {
             CUDA_TRY(cudaMalloc((void**)&t->d_sym, t->sym_data.size() * sizeof(double)));
@@ -595,6 +681,15 @@ static int do_solve(gvib200_problem* p, const double* Dg, const double* Og, cons
 // ------------------------------------------------------------------------------------------------
 template <int DIM, int SD>
 static int launch_prologue(gvib200_problem* p, const GhGroup& g, const double* cD, const double* cO, double* SR) {
+    if constexpr (DIM > 4) {  // JG lanes per factor: parallel Jacobi in shared memory
+        constexpr int WD = 2 * DIM * DIM + 4 * ((DIM + 1) / 2) + 2 * DIM + 1;
+        constexpr int GPB = 256 / JG;
+        const size_t smem = (size_t)GPB * WD * sizeof(double);
+        if (p->ctx->need_config(reinterpret_cast<const void*>(k_prologue_warp<DIM, SD>)))
+            CUDA_TRY(cudaFuncSetAttribute(k_prologue_warp<DIM, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(p, KC_PROLOGUE, (k_prologue_warp<DIM, SD>), cdiv(g.n, GPB), 256, smem, g.n, g.d_start, cD, cO, SR);
+        return 0;
+    }
     const int block = (DIM <= 4) ? 128 : 32;
     LAUNCH(p, KC_PROLOGUE, (k_prologue<DIM, SD>), cdiv(g.n, block), block, 0, g.n, g.d_start, cD, cO, SR);
     return 0;
@@ -655,12 +750,51 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     return check_launch("k_moments_sym");
 }
 
+// K1G (k1_grp.cuh): factors of dimension > 4 on a rule made of sparse sign groups
+template <int DIM, class Cost>
+static int launch_moments_grp(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
+                              double* fcost, double* fVdmu, double* fVdd, double* raw, bool full) {
+    GrpArgs<Cost> a;
+    a.n = g.n;
+    a.state_dim = p->d;
+    a.start = g.d_start;
+    a.mu = mu;
+    a.SR = SR;
+    a.T = g.d_T;
+    a.fcost = fcost + g.first_id;
+    a.fVdmu = fVdmu + g.voff;
+    a.fVdd = fVdd + g.moff;
+    a.raw = raw;
+    a.cost = cost;
+    const GrpTable& tab = g.table->grp;
+    const size_t table_doubles = (size_t)4 * tab.n_groups + (size_t)(tab.n_groups + 1) / 2;
+    const size_t limit = std::min<size_t>(p->ctx->smem_optin, 227 * 1024) - 1024;
+    int warps = K1G_WARPS;
+    while (warps > 1 && (table_doubles + (size_t)warps * K1GCfg<DIM>::WARP_DOUBLES) * sizeof(double) > limit) --warps;
+    const size_t smem = (table_doubles + (size_t)warps * K1GCfg<DIM>::WARP_DOUBLES) * sizeof(double);
+    if (smem > limit) return fail(GVIB200_EINVAL, "K1G: the rule does not fit shared memory");
+    if (p->ctx->need_config(reinterpret_cast<const void*>(k_moments_grp<DIM, Cost, true>))) {
+        CUDA_TRY(cudaFuncSetAttribute(k_moments_grp<DIM, Cost, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        CUDA_TRY(cudaFuncSetAttribute(k_moments_grp<DIM, Cost, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    }
+    const int grid = std::max(1, std::min(cdiv(g.n, warps), p->ctx->sm_count));
+    if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
+    if (full) k_moments_grp<DIM, Cost, true><<<grid, warps * 32, smem, p->ls>>>(tab, a);
+    else k_moments_grp<DIM, Cost, false><<<grid, warps * 32, smem, p->ls>>>(tab, a);
+    if (p->profile) prof_end(p);
+    p->ctx->launches++;
+    return check_launch("k_moments_grp");
+}
+
 template <int DIM, class Cost>
 static int launch_moments(gvib200_problem* p, const GhGroup& g, const Cost& cost, const double* mu, const double* SR,
                           double* fcost, double* fVdmu, double* fVdd, double* raw, bool full, const double* covD) {
     if constexpr (DIM <= 4) {
         if (g.table->sym_ok && !p->force_generic_k1)
             return launch_moments_sym<DIM, Cost>(p, g, cost, mu, SR, fcost, fVdmu, fVdd, raw, full, covD);
+    } else {
+        if (g.table->grp_ok && !p->force_generic_k1)
+            return launch_moments_grp<DIM, Cost>(p, g, cost, mu, SR, fcost, fVdmu, fVdd, raw, full);
     }
     constexpr int XD = Cost::XD;
     constexpr int ROW = 2 * ((DIM + 1) / 2) + 1;  // doubles per node over all planes
@@ -1113,6 +1247,10 @@ extern "C" int gvib200_ctx_destroy(gvib200_ctx* ctx) {
         if (kv.second->d_rows) cudaFree(kv.second->d_rows);
     for (auto& kv : ctx->tables)
         if (kv.second->d_sym) cudaFree(kv.second->d_sym);
+    for (auto& kv : ctx->tables) {
+        if (kv.second->d_grp_hdr) cudaFree(kv.second->d_grp_hdr);
+        if (kv.second->d_grp_val) cudaFree(kv.second->d_grp_val);
+    }
     for (int r = 0; r < MBOX_RANKS; ++r)
         if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     if (ctx->mbox) cudaFree(ctx->mbox);
@@ -1228,6 +1366,8 @@ extern "C" int gvib200_table_set(gvib200_ctx* ctx, int dim, int deg, int n, cons
     auto it = ctx->tables.find(key);
     if (it != ctx->tables.end() && it->second->d_rows) cudaFree(it->second->d_rows);
     if (it != ctx->tables.end() && it->second->d_sym) cudaFree(it->second->d_sym);
+    if (it != ctx->tables.end() && it->second->d_grp_hdr) cudaFree(it->second->d_grp_hdr);
+    if (it != ctx->tables.end() && it->second->d_grp_val) cudaFree(it->second->d_grp_val);
     ctx->tables[key] = std::move(t);
     return 0;
 }

@@ -85,6 +85,166 @@ __global__ void k_prologue(int n, const int* __restrict__ start, const double* _
     }
 }
 
+// Group-cooperative symmetric eigendecomposition (parallel Jacobi, round-robin ordering): JG lanes work on one matrix, a warp
+// holds 32 / JG matrices.  A, V are N x N column-major in shared memory (one copy per group), on return V holds the
+// eigenvectors and the diagonal of A the eigenvalues.  A round applies N/2 rotations on disjoint index pairs at once: the
+// angles come from one state of the matrix, then the group's lanes split the column update A J (and V J) and the row update
+// J^T (A J).  For the factor dimensions above 4 (two-state factors: 8, 12; robot states: 6) one thread per factor spends its
+// time spilling a 12 x 12 matrix and leaves most of the machine idle (10^4 factors = 2 warps per SM); with 8 lanes per
+// factor the matrices live in shared memory and every lane has work in every phase.
+constexpr int JG = 32;  // lanes per matrix (measured at dim 12, 10^4 factors: 32 lanes 0.65 ms, 8 lanes 0.80 ms, one thread 1.26 ms per launch)
+template <int N>
+__device__ __forceinline__ void group_jacobi_eig(double* __restrict__ A, double* __restrict__ V, double* __restrict__ rot, int gl) {
+    constexpr int M = (N + 1) / 2;      // pairs per round
+    constexpr int NR = 2 * M - 1;       // rounds per sweep (odd N: one index sits out per round)
+    for (int e = gl; e < N * N; e += JG) V[e] = (e % N == e / N) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int e = gl; e < N * N; e += JG) {
+            const int i = e % N, j = e / N;
+            const double v = fabs(A[e]);
+            if (i == j) diag += v;
+            else if (i < j) off += v;
+        }
+#pragma unroll
+        for (int o = JG / 2; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            diag += __shfl_xor_sync(0xffffffffu, diag, o);
+        }
+        // the groups of a warp move in lock step: leave when all of them have converged (a converged matrix only sees
+        // identity rotations)
+        if (__all_sync(0xffffffffu, off <= 1e-300 || off <= 1e-22 * diag)) break;
+        for (int r = 0; r < NR; ++r) {
+            // circle method on 2 M positions (position 2 M - 1 is fixed; for odd N it is the idle slot)
+            for (int k = gl; k < M; k += JG) {
+                int p, q;
+                if (k == 0) {
+                    p = 2 * M - 1;
+                    q = r;
+                } else {
+                    p = (r + k) % NR;
+                    q = (r - k + NR) % NR;
+                }
+                if (p > q) {
+                    const int t = p;
+                    p = q;
+                    q = t;
+                }
+                double t = 0.0, c = 1.0, sn = 0.0;
+                if (q < N) jacobi_angle(A[p + p * N], A[q + q * N], A[p + q * N], t, c, sn);
+                else p = q = -1;  // idle pair
+                rot[4 * k + 0] = (double)p;
+                rot[4 * k + 1] = (double)q;
+                rot[4 * k + 2] = c;
+                rot[4 * k + 3] = sn;
+            }
+            __syncwarp();
+            // column update of A and V: (x_jp, x_jq) <- (c x_jp - s x_jq, s x_jp + c x_jq)
+            for (int task = gl; task < M * N; task += JG) {
+                const int k = task / N, j = task - k * N;
+                const int p = (int)rot[4 * k], q = (int)rot[4 * k + 1];
+                if (p < 0) continue;
+                const double c = rot[4 * k + 2], sn = rot[4 * k + 3];
+                const double ap = A[j + p * N], aq = A[j + q * N];
+                A[j + p * N] = fma(c, ap, -sn * aq);
+                A[j + q * N] = fma(sn, ap, c * aq);
+                const double vp = V[j + p * N], vq = V[j + q * N];
+                V[j + p * N] = fma(c, vp, -sn * vq);
+                V[j + q * N] = fma(sn, vp, c * vq);
+            }
+            __syncwarp();
+            // row update of A; the annihilated entries are set to exactly zero
+            for (int task = gl; task < M * N; task += JG) {
+                const int k = task / N, j = task - k * N;
+                const int p = (int)rot[4 * k], q = (int)rot[4 * k + 1];
+                if (p < 0) continue;
+                const double c = rot[4 * k + 2], sn = rot[4 * k + 3];
+                const double ap = A[p + j * N], aq = A[q + j * N];
+                double np_ = fma(c, ap, -sn * aq), nq = fma(sn, ap, c * aq);
+                if (j == q) np_ = 0.0;
+                if (j == p) nq = 0.0;
+                A[p + j * N] = np_;
+                A[q + j * N] = nq;
+            }
+            __syncwarp();
+        }
+        // keep A exactly symmetric (the two one-sided updates round differently)
+        for (int e = gl; e < N * N; e += JG) {
+            const int i = e % N, j = e / N;
+            if (i < j) {
+                const double v = 0.5 * (A[i + j * N] + A[j + i * N]);
+                A[i + j * N] = v;
+                A[j + i * N] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// K2 for factor dimensions above 4: JG lanes per factor (group_jacobi_eig), same outputs as k_prologue
+template <int DIM, int SD>
+__global__ void __launch_bounds__(256) k_prologue_warp(int n, const int* __restrict__ start, const double* __restrict__ covD,
+                                                       const double* __restrict__ covO, double* __restrict__ SR) {
+    constexpr int NS = DIM / SD;
+    static_assert(NS == 1 || NS == 2, "factors span one or two consecutive states");
+    constexpr int WD = 2 * DIM * DIM + 4 * ((DIM + 1) / 2) + 2 * DIM + 1;  // odd stride: the groups of a warp hit different banks
+    constexpr int GPB = 256 / JG;                                           // factors per CTA
+    extern __shared__ __align__(16) double sm[];
+    const int gl = threadIdx.x & (JG - 1), grp = threadIdx.x / JG;
+    // tail groups recompute the last factor and do not store (the groups of a warp run in lock step)
+    const int fraw = blockIdx.x * GPB + grp;
+    const int f = fraw < n ? fraw : n - 1;
+    double* A = sm + (size_t)grp * WD;
+    double* V = A + DIM * DIM;
+    double* rot = V + DIM * DIM;
+    double* sq = rot + 4 * ((DIM + 1) / 2);
+    double* isq = sq + DIM;
+    const int s = start[f];
+    for (int e = gl; e < DIM * DIM; e += JG) {
+        const int i = e % DIM, j = e / DIM;
+        const int bi = i / SD, bj = j / SD, li = i - bi * SD, lj = j - bj * SD;
+        double v;
+        if (bi == bj) v = covD[(size_t)(s + bi) * SD * SD + li + lj * SD];
+        else if (bi < bj) v = covO[(size_t)s * SD * SD + li + lj * SD];   // block (s, s+1)
+        else v = covO[(size_t)s * SD * SD + lj + li * SD];                 // its transpose
+        A[e] = v;
+    }
+    __syncwarp();
+    // the Jacobi iteration works on the symmetric part
+    for (int e = gl; e < DIM * DIM; e += JG) {
+        const int i = e % DIM, j = e / DIM;
+        if (i < j) {
+            const double v = 0.5 * (A[i + j * DIM] + A[j + i * DIM]);
+            A[i + j * DIM] = v;
+            A[j + i * DIM] = v;
+        }
+    }
+    __syncwarp();
+    group_jacobi_eig<DIM>(A, V, rot, gl);
+    for (int k = gl; k < DIM; k += JG) {
+        const double l = sqrt(A[k + k * DIM]);
+        sq[k] = l;
+        isq[k] = 1.0 / l;
+    }
+    __syncwarp();
+    if (fraw >= n) return;
+    double* out = SR + (size_t)f * 2 * DIM * DIM;
+    for (int e = gl; e < DIM * DIM; e += JG) {
+        const int i = e % DIM, j = e / DIM;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;  // one arithmetic for (i, j) and (j, i): exactly symmetric
+        double sv = 0.0, rv = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const double vv = V[hi + k * DIM] * V[lo + k * DIM];
+            sv = fma(vv, sq[k], sv);
+            rv = fma(vv, isq[k], rv);
+        }
+        out[e] = sv;
+        out[DIM * DIM + e] = rv;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: fused sigma-point / cost / moment kernel.  One warp per factor, lanes stride the nodes.
 //   x_i = mu_k + S_k xi_i                      quadrature/SparseGaussHermite.h:242

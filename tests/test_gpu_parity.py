@@ -515,3 +515,49 @@ def test_cfg5_device_generated_batch_matches_independent_oracle_runs(gpu_ctx):
         ref.optimize()
         assert rel(mu[b], ref.mean()) < FINAL_TOL
         assert rel(cD[b * Sb:(b + 1) * Sb], ref.cov.D) < FINAL_TOL
+
+
+# ---------------------------------------------------------------- K1G (sparse sign groups, dim > 4) vs the generic node loop
+@pytest.mark.parametrize("case", ["linear_gp_12", "hinge3d_6", "arm_6", "quad_hinge_6", "linear_gp_8"])
+def test_sparse_group_kernel_matches_generic_kernel(gpu_ctx, case):
+    """k_moments_grp (k1_grp.cuh: reduced coordinates, Walsh sums per sign group, lane-private accumulators) against
+    k_moments (node loop) on the same factors: moments, factor costs and the Vdmu / Vddmu epilogue to 1e-11."""
+    rng = np.random.default_rng(len(case))
+    if case.startswith("linear_gp"):
+        dim = int(case.split("_")[2])
+        spec = problems.make_cfg4(S=40) if dim == 12 else None
+        if spec is None:   # dim 8: two 4-dimensional states under a min-acc prior evaluated by quadrature
+            S, d = 30, 4
+            lin = problems.minacc_group(S, 0.8 * np.eye(2), 0.1)
+            Phi = -lin.Lambda[0][:, :d]
+            rec = np.concatenate([np.tile(Phi.T.reshape(-1), (S - 1, 1)), np.tile(lin.Kinv[0].T.reshape(-1), (S - 1, 1))], axis=1)
+            D, O = rand_spd_chain(rng, S, d)
+            spec = problems.ProblemSpec(S=S, d=d, groups=[problems.fixed_prior_group([0, S - 1], np.zeros((2, d)), np.eye(d), d),
+                                                          problems.GhGroupSpec(capi.COST_LINEAR_GP, 2 * d, 4, lin.start, rec)],
+                                        mu0=rng.standard_normal(S * d), prec0_D=D, prec0_O=O)
+        else:
+            D, O = rand_spd_chain(rng, spec.S, spec.d)   # a generic (correlated) state instead of the diagonal start
+            spec.prec0_D, spec.prec0_O = D, O
+            spec.mu0 = spec.mu0 + 0.3 * rng.standard_normal(spec.mu0.shape)
+    else:
+        kind = {"hinge3d_6": capi.COST_HINGE_3D, "arm_6": capi.COST_ARM_3D, "quad_hinge_6": capi.COST_QUAD_HINGE}[case]
+        spec = problems.make_factor_batch_functor(kind, N=200, d=6, deg=4)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    with_prior = case.startswith("linear_gp")   # a factor batch without a prior has no SPD Vddmu to solve with
+    mom_a = p.moments()
+    ca, fa = p.cost()
+    va = (p.gradients(), p.get_V())[1] if with_prior else ()
+    p.set_option("generic_k1", 1)
+    mom_b = p.moments()
+    cb, fb = p.cost()
+    vb = (p.gradients(), p.get_V())[1] if with_prior else ()
+    for (a0, a1, a2), (b0, b1, b2) in zip(mom_a, mom_b):
+        assert np.array_equal(a0 == 0, b0 == 0)
+        for f in range(len(a0)):
+            if b0[f] == 0:
+                continue
+            assert rel(a0[f], b0[f]) < 1e-11 and rel(a2[f], b2[f]) < 1e-11
+            assert np.abs(a1[f] - b1[f]).max() < 1e-11 * max(np.abs(b1[f]).max(), np.sqrt(np.abs(b2[f]).max() * abs(b0[f])), 1e-300)
+    assert rel(fa, fb) < 1e-11 and abs(ca - cb) < 1e-11 * abs(cb)
+    for x, y in zip(va, vb):
+        assert rel(x, y) < 1e-10

@@ -32,6 +32,12 @@ def run(name, spec, iters, prox=False, reuse=True):
         acc += step(opts).accepted
     ms = p.timer_stop() / iters
     info = p.info()
+    p.snapshot_restore()
+    p.profile_begin()
+    for i in range(4):
+        step(opts)
+    prof = p.profile_end()
+    print("    per-kernel ms / iteration:", {k: round(v[1] / 4, 4) for k, v in sorted(prof.items())})
     print(f"{name}: states {info.num_states} d {info.dim_state} GH factors {info.n_gh_factors} linear {info.n_linear_factors} "
           f"sigma points / sweep {info.sigma_points_per_sweep}: {ms:.4f} ms / iteration ({1e3 / ms:.0f} it/s), accepted {acc}/{iters}, "
           f"set-up {time.perf_counter() - t0:.1f} s", flush=True)
