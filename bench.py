@@ -258,8 +258,9 @@ def run_gpu(args, rank, world, local_rank):
     ctx = gv.Context(local_rank)
     if world > 1:
         # ONE chain of world * (N + 1) + 1 states cut along the time axis: every rank owns a contiguous segment of N (+1)
-        # hinge factors; per block-tridiagonal pass the ranks exchange their boundary blocks in one NCCL all-gather
-        # issued by the library; per cost evaluation one 4-double all-reduce
+        # hinge factors; per block-tridiagonal pass the ranks exchange their boundary records (96 doubles each) and per
+        # cost evaluation (cost, flags) through each other's peer-mapped mailboxes (NVLink stores issued by the kernels;
+        # NCCL all-gathers when no mailbox could be mapped)
         from gaussianvi_b200.dist import attach_nccl
         attach_nccl(ctx, rank, world)
         spec = problems.make_cfg3_segment(rank, world, N=N, deg=DEG)
@@ -282,6 +283,10 @@ def run_gpu(args, rank, world, local_rank):
         for _ in range(min(5, max(1, args.rewind_every - 1))):
             prob.iterate(opts)
         prob.snapshot_restore()
+    # clocks / throttle reasons are sampled from the warm-up on through every measured region of this run (the K timed
+    # steps alone last a few milliseconds: too short for more than one NVML sample)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         prob.iterate(opts)
     prob.snapshot_restore()
@@ -295,19 +300,16 @@ def run_gpu(args, rank, world, local_rank):
                 collect.append(st)
 
     # ---- device-resident timed region
-    sampler = ClockSampler(local_rank)
     stats = []
     barrier()
     prob.evaluated_factors(reset=True)
     l0 = ctx.launch_count()
-    sampler.start()
     t_wall = time.perf_counter()
     prob.timer_start()
     run_steps(K, stats)
     ms = prob.timer_stop()
     barrier()
     t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
     launches = ctx.launch_count() - l0
     ms = max_over_ranks(ms)
     tls = statistics.mean(s.n_backtrack + 1 for s in stats)
@@ -359,6 +361,49 @@ def run_gpu(args, rank, world, local_rank):
     prob.snapshot_restore()
     prob.iterate(opts)
     prob.snapshot_restore()
+    # ---- the same K steps with the reference's sweep schedule (1 moment sweep + T_ls cost sweeps per iteration, no reuse of
+    # the accepted trial's sweep): identical iterates, one more quadrature sweep per iteration
+    opts_f = gv.Problem.default_opts()
+    opts_f.niters_lowtemp = 1 << 30
+    opts_f.reuse_accepted_sweep = 0
+    for _ in range(3):
+        prob.iterate(opts_f)
+    prob.snapshot_restore()
+    barrier()
+    prob.timer_start()
+    for i in range(K):
+        if i and i % args.rewind_every == 0:
+            prob.snapshot_restore()
+        prob.iterate(opts_f)
+    ms_faithful = max_over_ranks(prob.timer_stop())
+    barrier()
+    value_faithful = world * (N / N_FACTORS) * 1e3 / (ms_faithful / K)
+    prob.snapshot_restore()
+    prob.iterate(opts)
+    prob.snapshot_restore()
+    # ---- strong scaling (N > 1): ONE chain of ~100k factors cut over the ranks, N_FACTORS / world hinge factors each
+    strong = None
+    if world > 1:
+        Ns = N // world
+        spec_s = problems.make_cfg3_segment(rank, world, N=Ns, deg=DEG)
+        prob_s = problems.build_device_problem(ctx, spec_s)
+        prob_s.iterate(opts)
+        prob_s.snapshot_save()
+        for _ in range(W):
+            prob_s.iterate(opts)
+        prob_s.snapshot_restore()
+        barrier()
+        prob_s.timer_start()
+        for i in range(K):
+            if i and i % args.rewind_every == 0:
+                prob_s.snapshot_restore()
+            st = prob_s.iterate(opts)
+        ms_s = max_over_ranks(prob_s.timer_stop())
+        barrier()
+        strong = {"value": 1e3 / (ms_s / K), "unit": UNIT, "ms_per_step": ms_s / K, "factors_total": Ns * world,
+                  "factors_per_gpu": Ns, "note": f"one chain of {world * (Ns + 1) + 1} states cut into {world} time segments"}
+        prob_s.close()
+    clocks = sampler.stop()
     prof_total = sum(v[1] for v in prof.values())
     # chain engine: algorithmic HBM bytes per block-tridiagonal pass (~8*8*d^2 per state per inversion)
     S, d = info.num_states, info.dim_state
@@ -427,8 +472,8 @@ def run_gpu(args, rank, world, local_rank):
                        "linear_factors_per_gpu": int(info.n_linear_factors), "schedule": args.schedule,
                        "T_ls_mean": tls, "parallelism": "1 GPU" if world == 1 else
                        f"{world} ranks: ONE chain of {world * (N + 1) + 1} states cut along the time axis, one contiguous segment "
-                       f"of ~{N} hinge factors per rank (weak scaling); per iteration 2 boundary all-gathers (100 doubles per rank) "
-                       f"+ 1 cost all-reduce over NCCL, issued by the library on the problem's stream",
+                       f"of ~{N} hinge factors per rank (weak scaling); per iteration 2 boundary exchanges (96 doubles per rank) + 1 cost / flag "
+                       f"exchange (4 doubles per rank) as NVLink peer stores issued by the kernels (mailboxes mapped over CUDA IPC)",
                        "l2": "working set per iteration (state, factor marginals, chain workspace, SDF: ~0.25 GB) exceeds the "
                              "126 MB L2; no flush",
                        "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)",
@@ -437,6 +482,11 @@ def run_gpu(args, rank, world, local_rank):
                                   "bit-identical (tests/test_gpu_parity.py::test_free_space_culling_is_bit_identical)"},
             "culling": {"evaluated_factor_fraction": eval_frac, "value_all_factors_evaluated": value_all,
                         "ms_per_step_all_factors_evaluated": ms_all / K},
+            "schedule_faithful": {"value": value_faithful, "ms_per_step": ms_faithful / K,
+                                  "note": "reuse_accepted_sweep = 0: the reference's 1 moment sweep + T_ls cost sweeps per "
+                                          "iteration (identical iterates); the headline value reuses the accepted trial's "
+                                          "full-moment sweep as the next iteration's gradient sweep"},
+            "strong_scaling": strong,
             "sigma_pt_evals_per_s": evals, "sigma_pt_evals_per_s_nominal": evals_nominal,
             "wall_ms_per_step": 1e3 * t_wall / K,
             "gpu_launches": int(launches),
