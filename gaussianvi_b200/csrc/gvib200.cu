@@ -1173,6 +1173,20 @@ static void run_total(gvib200_problem* p, int which) {
 
 template <int D>
 static void launch_assemble(gvib200_problem* p, int which, bool alt) {
+    if constexpr (D % 2 == 0) {
+        static const bool no_fast_env = getenv("GVIB200_NO_FAST_ASSEMBLE") != nullptr;  // development switch
+        if (p->ell_nv >= 0 && p->ell_nv <= 4 && p->ell_nd <= 1 && p->ell_no == 0 && !no_fast_env) {
+            double *oV = alt ? p->Vdmu2 : p->Vdmu, *oD = alt ? p->VD2 : p->VD, *oO = alt ? p->VO2 : p->VO, *oR = alt ? p->rhs2 : p->rhs;
+            const int grid = cdiv((long long)p->S * D, 128);
+            if (p->ell_nd == 1)
+                LAUNCH(p, KC_ASSEMBLE, (k_assemble_ell_fast<D, 4, 1>), grid, 128, 0, p->S, p->ell_v, p->ell_d, p->ell_dl, p->fVdmu[which],
+                       p->fVdd[which], p->KlinD, p->KlinO, oV, oD, oO, oR);
+            else
+                LAUNCH(p, KC_ASSEMBLE, (k_assemble_ell_fast<D, 4, 0>), grid, 128, 0, p->S, p->ell_v, p->ell_d, p->ell_dl, p->fVdmu[which],
+                       p->fVdd[which], p->KlinD, p->KlinO, oV, oD, oO, oR);
+            return;
+        }
+    }
     if (p->ell_nv >= 0) {
         LAUNCH(p, KC_ASSEMBLE, (k_assemble_ell<D>), cdiv((long long)p->S * D, 128), 128, 0, p->S, p->ell_nv, p->ell_nd, p->ell_no, p->ell_v,
                p->ell_d, p->ell_dl, p->ell_o, p->ell_ol, p->fVdmu[which], p->fVdd[which], p->KlinD, p->KlinO, alt ? p->Vdmu2 : p->Vdmu,
@@ -1878,11 +1892,11 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
                     for (size_t k = 0; k < ll[st].size(); ++k) out[k * S + st] = ll[st][k];
             };
             std::vector<int> e;
-            ell(vl, nv, e);
+            ell(vl, std::max(nv, 4), e);  // at least the widths k_assemble_ell_fast is compiled for (-1 padded)
             TRY(dev_upload(&p->ell_v, e, p->stream));
-            ell(dl, nd, e);
+            ell(dl, std::max(nd, 1), e);
             TRY(dev_upload(&p->ell_d, e, p->stream));
-            ell(dll, nd, e);
+            ell(dll, std::max(nd, 1), e);
             TRY(dev_upload(&p->ell_dl, e, p->stream));
             ell(ol, no, e);
             TRY(dev_upload(&p->ell_o, e, p->stream));

@@ -881,6 +881,72 @@ __global__ void __launch_bounds__(128) k_assemble_ell(int S, int nv, int nd, int
     rhs[(size_t)s * D + j] = -v;
 }
 
+// The same assembly with compile-time widths (NV <= 4 mean contributions, ND <= 1 diagonal and no off-diagonal block
+// contribution per state: every chain with single-state nonlinear factors, e.g. the headline shape): all index loads are
+// issued first, then all data loads as 16-byte vectors, so that a thread has its whole working set in flight at once
+// instead of one dependent pair after the other.  Same operands in the same order: bit-identical to k_assemble_ell.
+template <int D, int NV, int ND>
+__global__ void __launch_bounds__(128) k_assemble_ell_fast(int S, const int* __restrict__ ev, const int* __restrict__ ed,
+                                                           const int* __restrict__ edl, const double* __restrict__ fVdmu,
+                                                           const double* __restrict__ fVdd, const double* __restrict__ KlinD,
+                                                           const double* __restrict__ KlinO, double* __restrict__ Vdmu,
+                                                           double* __restrict__ VD, double* __restrict__ VO,
+                                                           double* __restrict__ rhs) {
+    static_assert(D % 2 == 0, "vector loads need an even block dimension");
+    constexpr int DD = D * D;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(gid / D), j = (int)(gid - (long long)s * D);
+    if (s >= S) return;
+    const size_t cb = (size_t)s * DD + (size_t)j * D;
+    int iv[NV > 0 ? NV : 1], id[ND > 0 ? ND : 1], il[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) iv[k] = __ldg(ev + (size_t)k * S + s);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        id[k] = __ldg(ed + (size_t)k * S + s);
+        il[k] = __ldg(edl + (size_t)k * S + s);
+    }
+    const bool has_off = (s < S - 1);
+    double2 m[D / 2], o[D / 2];
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) {
+        m[i] = __ldg(reinterpret_cast<const double2*>(KlinD + cb) + i);
+        o[i] = has_off ? __ldg(reinterpret_cast<const double2*>(KlinO + cb) + i) : make_double2(0.0, 0.0);
+    }
+    double c[ND > 0 ? ND : 1][D];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        // a factor block may start at an odd double (factor outputs are packed): scalar loads, predicated
+        const double* src = fVdd + (id[k] >= 0 ? (size_t)id[k] + (size_t)j * il[k] : 0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) c[k][i] = id[k] >= 0 ? __ldg(src + i) : 0.0;
+    }
+    double vv[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) vv[k] = iv[k] >= 0 ? __ldg(fVdmu + iv[k] + j) : 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+        if (id[k] >= 0) {
+#pragma unroll
+            for (int i = 0; i < D / 2; ++i) {
+                m[i].x += c[k][2 * i];
+                m[i].y += c[k][2 * i + 1];
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) reinterpret_cast<double2*>(VD + cb)[i] = m[i];
+    if (has_off) {
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) reinterpret_cast<double2*>(VO + cb)[i] = o[i];
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        if (iv[k] >= 0) v += vv[k];
+    Vdmu[(size_t)s * D + j] = v;
+    rhs[(size_t)s * D + j] = -v;
+}
+
 // Line-search candidate (NGDGH::onestep_linesearch, ngd/NGD-GH-impl.h:129-148):
 //   mu' = mu + a dmu,  Lambda' = Lambda + a (Vddmu - Lambda)
 __global__ void k_candidate(size_t nmu, size_t nD, size_t nO, double alpha, const double* __restrict__ mu,
