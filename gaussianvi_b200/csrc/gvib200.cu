@@ -1987,6 +1987,8 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
         int tiles_per_sm = 1;
         if (const char* e = getenv("GVIB200_TILES_PER_SM")) tiles_per_sm = std::max(1, atoi(e));
         if (const char* e = getenv("GVIB200_TILE_THREADS")) p->tile_threads = std::max(32, std::min(CR_THREADS, atoi(e)));
+        int long_tiles = 2;  // measured on cfg5 (1024 x 1002 states): 1 -> 3.79, 2 -> 3.64, 3 -> 3.89 ms per iteration
+        if (const char* e = getenv("GVIB200_LONG_TILES_PER_SM")) long_tiles = std::max(1, std::min(4, atoi(e)));
 #define PLAN_CASE(D_)                                                                                          \
     case D_: {                                                                                                 \
         int force_T = 0;                                                                                       \
@@ -1999,10 +2001,14 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
         }                                                                                                      \
         /* two SMs are left free of tile CTAs: the single-CTA top kernels of the two concurrent passes run there */ \
         ok = cr_make_plan<D_>(p->plan, S, tiles_per_sm * std::max(1, p->ctx->sm_count - 2), smem, force_T);    \
-        if (!ok && P == 1) { /* long chain: three levels (tiles -> tiles over the separator chain -> top) */   \
-            ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem, 0, true) &&                              \
+        if (!ok && P == 1) { /* long chain: three levels (tiles -> tiles over the separator chain -> top).  Many    \
+               waves of tiles: throughput counts, so `long_tiles` tile CTAs of 512 / long_tiles threads share an SM  \
+               (each with 1 / long_tiles of the shared memory) and overlap their latency-bound upper levels */  \
+            const size_t smem_tile = long_tiles > 1 ? (smem + 5120) / long_tiles - 5120 - 1024 : smem;         \
+            ok = cr_make_plan<D_>(p->plan, S, p->ctx->sm_count, smem_tile, 0, true) &&                         \
                  cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, p->ctx->sm_count, smem);                         \
             p->three_level = ok;                                                                               \
+            if (ok && long_tiles > 1) p->tile_threads = CR_THREADS / long_tiles;                               \
         }                                                                                                      \
         if (ok && P > 1)                                                                                       \
             ok = cr_make_plan<D_>(p->plan_mid, p->plan.K + 1, 1, smem, std::max(p->plan.K, 2)) &&              \

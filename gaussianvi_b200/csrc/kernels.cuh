@@ -99,7 +99,10 @@ __device__ __forceinline__ void group_jacobi_eig(double* __restrict__ A, double*
     constexpr int NR = 2 * M - 1;       // rounds per sweep (odd N: one index sits out per round)
     for (int e = gl; e < N * N; e += JG) V[e] = (e % N == e / N) ? 1.0 : 0.0;
     __syncwarp();
-    for (int sweep = 0; sweep < 16; ++sweep) {
+    // Quadratic convergence: a 12 x 12 SPD matrix is at rounding level after 5-6 sweeps; past that point rounding noise
+    // (~1e-17 relative) keeps re-filling the annihilated entries above jacobi_angle's `tiny` threshold, so the loop is
+    // bounded by a sweep count, with the exact exits for the easy cases (already diagonal / a sweep of identity rotations)
+    for (int sweep = 0; sweep < 8; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int e = gl; e < N * N; e += JG) {
             const int i = e % N, j = e / N;
@@ -114,7 +117,8 @@ __device__ __forceinline__ void group_jacobi_eig(double* __restrict__ A, double*
         }
         // the groups of a warp move in lock step: leave when all of them have converged (a converged matrix only sees
         // identity rotations)
-        if (__all_sync(0xffffffffu, off <= 1e-300 || off <= 1e-22 * diag)) break;
+        if (__all_sync(0xffffffffu, off <= 1e-300 || off <= 4e-17 * diag)) break;
+        bool rotated = false;  // some pair of this sweep was not already negligible (jacobi_angle's `tiny`)
         for (int r = 0; r < NR; ++r) {
             // circle method on 2 M positions (position 2 M - 1 is fixed; for odd N it is the idle slot)
             for (int k = gl; k < M; k += JG) {
@@ -134,6 +138,7 @@ __device__ __forceinline__ void group_jacobi_eig(double* __restrict__ A, double*
                 double t = 0.0, c = 1.0, sn = 0.0;
                 if (q < N) jacobi_angle(A[p + p * N], A[q + q * N], A[p + q * N], t, c, sn);
                 else p = q = -1;  // idle pair
+                rotated = rotated || (t != 0.0);
                 rot[4 * k + 0] = (double)p;
                 rot[4 * k + 1] = (double)q;
                 rot[4 * k + 2] = c;
@@ -169,6 +174,8 @@ __device__ __forceinline__ void group_jacobi_eig(double* __restrict__ A, double*
             }
             __syncwarp();
         }
+        // converged: a whole sweep of identity rotations (the off-diagonal part sits at rounding level and stays there)
+        if (!__any_sync(0xffffffffu, rotated)) break;
         // keep A exactly symmetric (the two one-sided updates round differently)
         for (int e = gl; e < N * N; e += JG) {
             const int i = e % N, j = e / N;
