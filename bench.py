@@ -2,23 +2,27 @@
 """bench.py -- the headline benchmark of BASELINE.json: NGD iterations / s (and sigma-point evaluations / s) of the
 factorized NGD-GVI hot path at N = 100 000 nonlinear factors, d = 4, sparse Gauss-Hermite degree 6 (953 nodes).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gvib200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gvib200|reference] [--config cfg3|cfg5]
 
 One "step" = one full NGD iteration (quadrature sweep(s) + precision assembly + block-tridiagonal solve + candidate +
 selected inverse / log det + line-search cost) of the synthetic cfg3 trajectory.
 
   value     whole-job NGD iterations / s with all state resident in HBM (gvib200_ngd_iterate), CUDA-event timed on the
             problem's stream, max over ranks.  At N > 1 every rank owns its own contiguous 100k-factor time segment
-            of one long chain (weak scaling, boundary blocks exchanged over NCCL); value = N_ranks * iterations / s, i.e.
-            iterations / s normalised to 100k factors.
+            of one long chain (weak scaling; the boundary records and the cost travel through peer-mapped mailboxes as
+            NVLink stores issued by the kernels); value = N_ranks * iterations / s, i.e. iterations / s normalised to
+            100k factors.  `strong_scaling` (N > 1): one 100k-factor chain cut over the ranks.
   e2e       the same iteration through the C-ABI with HOST buffers: per step set_state(mu, Lambda) from pinned host
             memory, one iteration, mean + covariance blocks read back.
   roofline  dominant kernel (the fused sigma-point / cost / moment kernel K1): algorithmic FP64 flops per launch
             (89 per sigma point) / average launch duration from per-launch CUDA events, against the FP64
             FMA peak measured live by a DFMA micro-benchmark (MEASURED_PEAKS.json carries no FP64 figure).
+  schedule_faithful / culling   the same steps with the reference's sweep schedule / with every factor evaluated.
   cpu_baseline  the oracle's C restatement (oracle/gvi_oracle_c.c, OpenMP) on a bounded sample of the same workload.
 
---impl reference times the CPU path alone (rank 0), with the reference's own schedule of one iteration.
+--impl reference times the CPU path alone (rank 0): the reference's own schedule and arithmetic of one iteration, state
+rewound from a host-side snapshot like the GPU arm, at the full 100k factors when that fits the time budget.
+--config cfg5: BASELINE configs[4], 4096 independent N=1k problems sharded over the GPUs (an extra bench line).
 """
 import argparse
 import json
@@ -37,7 +41,7 @@ DEG = 6
 N_NODES = 953
 FLOPS_FULL = 89     # per sigma point, full-moment sweep, d = 4, planar hinge
 FLOPS_COST = 61     # per sigma point, cost-only sweep
-K1_DRAM_BYTES_NCU = 14225408  # dram read + write bytes of one K1S launch (ncu --set full, profiles/r1_iteration_v5_ncu.txt)
+K1_DRAM_BYTES_NCU = 14230784  # dram read + write bytes of one K1S launch: STATIC figure from the ncu --set full capture profiles/r2_k1s_ncu.txt
 METRIC = "NGD iters/sec & sigma-pt evals/sec at N=100k factors, d=4, SpGH deg 6"
 UNIT = "NGD iters/s"
 CPU_SAMPLE_FACTORS = 10_000
@@ -497,7 +501,7 @@ def run_gpu(args, rank, world, local_rank):
                          "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": K1_DRAM_BYTES_NCU,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_moments_sym per launch, ncu --set full "
-                                           "capture profiles/r1_iteration_v5_ncu.txt (bytes; the kernel is FP64 bound, not HBM bound)",
+                                           "capture profiles/r2_k1s_ncu.txt -- a static figure of that capture, not measured in this run (bytes; the kernel is FP64 bound, not HBM bound)",
                          "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure",
                          "algorithmic_flops_per_launch": pts_launch * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],
