@@ -438,6 +438,7 @@ def run_gpu(args, rank, world, local_rank):
     e2e_steps = max(3, min(K, 12))
     h2d = mu_h.nbytes + pD_h.nbytes + pO_h.nbytes
     d2h = out_mu.nbytes + out_cD.nbytes + pO_h.nbytes
+    # (a) one handle, synchronous calls: upload, iterate, download one after the other
     prob.set_state_raw(mu_h, pD_h, pO_h); prob.iterate(opts); prob.get_mean_into(out_mu); prob.get_cov_blocks_into(out_cD, out_cO)
     barrier()
     t0 = time.perf_counter()
@@ -447,9 +448,49 @@ def run_gpu(args, rank, world, local_rank):
         prob.get_mean_into(out_mu)                 # D2H
         prob.get_cov_blocks_into(out_cD, out_cO)   # D2H
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * (N / N_FACTORS) * e2e_steps / e2e_s
+    e2e_sync_value = world * (N / N_FACTORS) * e2e_steps / e2e_sync_s
+    # (b) the same calls' asynchronous variants over several handles of the same problem (what a caller with a stream of
+    # independent planning problems does): every step still uploads ITS state from pinned host memory, runs one iteration
+    # and downloads ITS mean + covariance blocks, but the upload / download of one handle overlap the iteration of the
+    # other (both PCIe directions and the SMs busy at once).  Every result is checked against the synchronous one.
+    e2e_value, pipe_steps = e2e_sync_value, e2e_steps
+    # (N > 1: one handle only -- two handles of a distributed problem would interleave their peer-mailbox exchanges on
+    #  different streams, and the epoch order of those exchanges must be the same on every rank)
+    if world == 1:
+        NH = 2   # handles in flight (measured on the B200 box: 2 handles 775 it/s, 3 handles 708 -- the two PCIe directions
+                 # together move 57.6 MB per step at ~47 GB/s and do not speed each other up, so the step is transfer bound)
+        extra = [problems.build_device_problem(ctx, spec) for _ in range(NH - 1)]
+        ref_mu, ref_cD = out_mu.copy(), out_cD.copy()
+        handles = [(prob, (out_mu, out_cD, out_cO))]
+        for h in extra:
+            handles.append((h, (pinned(np.zeros_like(mu_h)), pinned(np.zeros_like(pD_h)), pinned(np.zeros((max(S - 1, 1), d, d))))))
+        for h, o in handles:                            # warm every handle up (first-use set-up of the new ones)
+            h.set_state_raw_async(mu_h, pD_h, pO_h); h.iterate(opts); h.get_mean_into_async(o[0]); h.get_cov_blocks_into_async(o[1], o[2])
+            h.sync()
+        pipe_steps = NH * e2e_steps
+        barrier()
+        t0 = time.perf_counter()
+        handles[0][0].set_state_raw_async(mu_h, pD_h, pO_h)
+        for i in range(pipe_steps):
+            h, o = handles[i % NH]
+            if i + 1 < pipe_steps:
+                handles[(i + 1) % NH][0].set_state_raw_async(mu_h, pD_h, pO_h)  # next step's H2D: overlaps this iteration
+            st = h.iterate(opts)                                                 # blocks on THIS handle's cost only
+            h.get_mean_into_async(o[0])                                          # D2H: overlaps the next iterations
+            h.get_cov_blocks_into_async(o[1], o[2])
+        for h, _ in handles:
+            h.sync()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_value = world * (N / N_FACTORS) * pipe_steps / e2e_s
+        for _, o in handles:
+            if not (np.array_equal(o[0], ref_mu) and np.array_equal(o[1], ref_cD)):
+                raise SystemExit("bench.py: a pipelined end-to-end step does not reproduce the synchronous result bit for bit")
+        for h in extra:
+            h.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample: ~10-30 s of CPU work)
     cpu = None
@@ -496,7 +537,14 @@ def run_gpu(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "call": "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks"},
+                    "steps": pipe_steps,
+                    "call": ("gvib200_set_state_async + gvib200_ngd_iterate + gvib200_get_mean_async + gvib200_get_cov_blocks_async "
+                             "per step, two handles alternating (the copies of one overlap the iteration of the other); every "
+                             "step uploads its state from pinned host memory and downloads its mean + covariance blocks")
+                            if world == 1 else "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks",
+                    "single_handle_synchronous": {"value": e2e_sync_value, "steps": e2e_steps,
+                                                  "call": "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + "
+                                                          "gvib200_get_cov_blocks, one after the other"}},
             "roofline": {"bound": "fp64", "kernel": "k_moments<4, CostPlanarHinge, full> (K1)",
                          "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": K1_DRAM_BYTES_NCU,

@@ -42,6 +42,8 @@ EXPORTS = [
     "gvib200_table_file_write", "gvib200_table_file_load", "gvib200_table_file_query", "gvib200_table_get",
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
     "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature", "gvib200_ctx_mailbox_create", "gvib200_ctx_mailbox_connect",
+    "gvib200_set_state_async", "gvib200_get_mean_async", "gvib200_get_prec_blocks_async", "gvib200_get_cov_blocks_async",
+    "gvib200_sync",
 ]
 
 
@@ -388,6 +390,19 @@ class Problem:
     # pinned buffers the library's cudaMemcpyAsync is a single DMA ----
     def set_state_raw(self, mu: np.ndarray, prec_diag: np.ndarray, prec_off: Optional[np.ndarray]):
         _check(self.lib.gvib200_set_state(self.h, _dp(mu), _dp(prec_diag), _dp(prec_off) if self.S > 1 else None))
+
+    # ---- asynchronous variants (pinned buffers): enqueued on the handle's stream, valid after sync() ----
+    def set_state_raw_async(self, mu: np.ndarray, prec_diag: np.ndarray, prec_off: Optional[np.ndarray]):
+        _check(self.lib.gvib200_set_state_async(self.h, _dp(mu), _dp(prec_diag), _dp(prec_off) if self.S > 1 else None))
+
+    def get_mean_into_async(self, mu: np.ndarray):
+        _check(self.lib.gvib200_get_mean_async(self.h, _dp(mu)))
+
+    def get_cov_blocks_into_async(self, diag: np.ndarray, off: np.ndarray):
+        _check(self.lib.gvib200_get_cov_blocks_async(self.h, _dp(diag), _dp(off)))
+
+    def sync(self):
+        _check(self.lib.gvib200_sync(self.h))
 
     def get_mean_into(self, mu: np.ndarray):
         _check(self.lib.gvib200_get_mean(self.h, _dp(mu)))

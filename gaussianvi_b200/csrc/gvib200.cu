@@ -369,6 +369,7 @@ struct gvib200_problem {
     int iter = 0;
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
+    bool pending_check = false;  // gvib200_set_state_async: the not-SPD flag of its selected inverse has not been read yet
     bool grads_valid = false;
     bool prox = false;              // Prox-GVI problem (option "prox" before finalize): linear factors get per-iteration
                                     // Vddmu blocks, no constant Klin, GH costs are not divided by a temperature
@@ -2050,17 +2051,34 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
 // ------------------------------------------------------------------------------------------------
 // C-ABI: state
 // ------------------------------------------------------------------------------------------------
-static int recompute_from_precision(gvib200_problem* p, int which) {
+static int recompute_from_precision(gvib200_problem* p, int which, bool async = false) {
     TRY(clear_flag(p));
     TRY(do_selinv(p, p->LD[which], p->LO[which], p->CD[which], p->CO[which], p->scal + which));
     TRY(run_prologue_only(p, which));
+    if (async) {  // the host does not wait: the flag is read by the next call that synchronises (resolve_pending)
+        p->pending_check = true;
+        return 0;
+    }
     int flag = 0;
     TRY(read_flag(p, &flag));
     if (flag) return fail(GVIB200_ENOTSPD, "precision matrix is not positive definite");
     return 0;
 }
 
-extern "C" int gvib200_set_state(gvib200_problem* p, const double* mu, const double* pd, const double* po) {
+// gvib200_set_state_async left its validity check open: wait for the upload + selected inverse and read the flag
+static int resolve_pending(gvib200_problem* p) {
+    if (!p->pending_check) return 0;
+    p->pending_check = false;
+    int flag = 0;
+    TRY(read_flag(p, &flag));
+    if (flag) {
+        p->has_state = false;
+        return fail(GVIB200_ENOTSPD, "precision matrix is not positive definite (gvib200_set_state_async)");
+    }
+    return 0;
+}
+
+static int set_state_impl(gvib200_problem* p, const double* mu, const double* pd, const double* po, bool async) {
     if (!p || !p->finalized) return fail(GVIB200_ESTATE, "set_state: problem not finalized");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
     const int S = p->S, d = p->d, c = p->cur;
@@ -2076,11 +2094,34 @@ extern "C" int gvib200_set_state(gvib200_problem* p, const double* mu, const dou
     p->sweep_valid = false;
     p->asm_valid = false;
     p->grads_valid = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
     if (pd || !p->has_state) {
         if (!pd) return fail(GVIB200_ESTATE, "set_state: the first call must provide a precision");
-        TRY(recompute_from_precision(p, c));
+        TRY(recompute_from_precision(p, c, async));
     }
     p->has_state = true;
+    return 0;
+}
+
+extern "C" int gvib200_set_state(gvib200_problem* p, const double* mu, const double* pd, const double* po) {
+    if (p && p->pending_check) TRY(resolve_pending(p));
+    return set_state_impl(p, mu, pd, po, false);
+}
+
+// Asynchronous variant for pipelines of independent problems: the uploads (from PINNED host memory), the selected inverse
+// and the factor marginals are enqueued on the problem's stream and the call returns; a precision that is not positive
+// definite is reported by the next gvib200_ngd_iterate / gvib200_prox_iterate / gvib200_get_* / gvib200_sync on this handle.
+extern "C" int gvib200_set_state_async(gvib200_problem* p, const double* mu, const double* pd, const double* po) {
+    if (p && p->pending_check) TRY(resolve_pending(p));
+    return set_state_impl(p, mu, pd, po, true);
+}
+
+extern "C" int gvib200_sync(gvib200_problem* p) {
+    if (!p) return fail(GVIB200_EINVAL, "sync: null handle");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    TRY(resolve_pending(p));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->stream2) CUDA_TRY(cudaStreamSynchronize(p->stream2));
     return 0;
 }
 
@@ -2090,36 +2131,46 @@ static int download(gvib200_problem* p, double* dst, const double* src, size_t n
     return 0;
 }
 
-extern "C" int gvib200_get_mean(gvib200_problem* p, double* mu) {
+static int get_mean_impl(gvib200_problem* p, double* mu, bool async) {
     if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_mean: no state");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (!async) TRY(resolve_pending(p));
     TRY(download(p, mu, p->mu[p->cur], (size_t)p->S * p->d));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (!async) CUDA_TRY(cudaStreamSynchronize(p->stream));
     return 0;
 }
-extern "C" int gvib200_get_prec_blocks(gvib200_problem* p, double* diag, double* off) {
-    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_prec_blocks: no state");
+static int get_blocks_impl(gvib200_problem* p, double* diag, double* off, bool cov, bool async) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get blocks: no state");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
+    if (!async) TRY(resolve_pending(p));
     const size_t dd = (size_t)p->d * p->d;
-    TRY(download(p, diag, p->LD[p->cur], p->S * dd));
-    TRY(download(p, off, p->LO[p->cur], (p->S - 1) * dd));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    TRY(download(p, diag, cov ? p->CD[p->cur] : p->LD[p->cur], p->S * dd));
+    TRY(download(p, off, cov ? p->CO[p->cur] : p->LO[p->cur], (p->S - 1) * dd));
+    if (!async) CUDA_TRY(cudaStreamSynchronize(p->stream));
     return 0;
+}
+extern "C" int gvib200_get_mean(gvib200_problem* p, double* mu) { return get_mean_impl(p, mu, false); }
+extern "C" int gvib200_get_prec_blocks(gvib200_problem* p, double* diag, double* off) {
+    return get_blocks_impl(p, diag, off, false, false);
 }
 extern "C" int gvib200_get_cov_blocks(gvib200_problem* p, double* diag, double* off) {
-    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "get_cov_blocks: no state");
-    CUDA_TRY(cudaSetDevice(p->ctx->device));
-    const size_t dd = (size_t)p->d * p->d;
-    TRY(download(p, diag, p->CD[p->cur], p->S * dd));
-    TRY(download(p, off, p->CO[p->cur], (p->S - 1) * dd));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    return 0;
+    return get_blocks_impl(p, diag, off, true, false);
+}
+// Asynchronous downloads into PINNED host memory: enqueued on the problem's stream behind everything already issued on the
+// handle; the buffers are valid after gvib200_sync (or any synchronous call on the handle).
+extern "C" int gvib200_get_mean_async(gvib200_problem* p, double* mu) { return get_mean_impl(p, mu, true); }
+extern "C" int gvib200_get_prec_blocks_async(gvib200_problem* p, double* diag, double* off) {
+    return get_blocks_impl(p, diag, off, false, true);
+}
+extern "C" int gvib200_get_cov_blocks_async(gvib200_problem* p, double* diag, double* off) {
+    return get_blocks_impl(p, diag, off, true, true);
 }
 
 // ------------------------------------------------------------------------------------------------
 // C-ABI: moments / cost / gradients
 // ------------------------------------------------------------------------------------------------
 static int ensure_sweep(gvib200_problem* p, bool want_raw) {
+    TRY(resolve_pending(p));
     if (p->sweep_valid && !want_raw) return 0;
     TRY(run_sweep(p, p->cur, false, true, want_raw));
     run_total(p, p->cur);
@@ -2309,6 +2360,7 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
     else gvib200_default_opts(&o);
     gvib200_iter_stats s;
     std::memset(&s, 0, sizeof(s));
+    TRY(resolve_pending(p));  // gvib200_set_state_async: its flag is read before this iteration clears it
     if (p->converged) {
         s.converged = 1;
         if (st) *st = s;
@@ -2720,6 +2772,7 @@ extern "C" int gvib200_prox_iterate(gvib200_problem* p, const gvib200_opts* opts
     else gvib200_default_opts(&o);
     gvib200_iter_stats s;
     std::memset(&s, 0, sizeof(s));
+    TRY(resolve_pending(p));
     if (p->iter == o.niters_lowtemp && p->is_lowtemp) {  // ProxGVI-GH-impl.h:130-133
         TRY(switch_to_high_temperature(p));
         p->is_lowtemp = false;

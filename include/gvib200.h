@@ -182,6 +182,19 @@ int gvib200_set_state(gvib200_problem* prob, const double* mu, const double* pre
 int gvib200_get_mean(gvib200_problem* prob, double* mu);                                 /* GVIGH::mean()       */
 int gvib200_get_prec_blocks(gvib200_problem* prob, double* diag, double* off);           /* GVIGH::precision()  */
 int gvib200_get_cov_blocks(gvib200_problem* prob, double* diag, double* off);            /* GVIGH::covariance() */
+/* Asynchronous variants of the same accessors for pipelines of independent problems (one handle each): the transfers use
+   PINNED host memory and are enqueued on the handle's stream, the call returns without waiting, so the upload / download
+   of one handle overlaps the iteration of another (both PCIe directions and the SMs busy at once).  set_state_async also
+   enqueues the selected inverse and the factor marginals; a precision that is not positive definite is reported
+   (GVIB200_ENOTSPD) by the next gvib200_ngd_iterate / gvib200_prox_iterate / synchronous accessor / gvib200_sync on that
+   handle.  Host buffers handed to the *_async getters are valid after gvib200_sync.  The reference has no counterpart: its
+   optimizer object owns host-side Eigen state (gvibase/GVI-GH-GBP.h:201-233) and its GPU path copies synchronously
+   (helpers/CudaOperation.cu, cudaMemcpy + cudaDeviceSynchronize per call). */
+int gvib200_set_state_async(gvib200_problem* prob, const double* mu, const double* prec_diag, const double* prec_off);
+int gvib200_get_mean_async(gvib200_problem* prob, double* mu);
+int gvib200_get_prec_blocks_async(gvib200_problem* prob, double* diag, double* off);
+int gvib200_get_cov_blocks_async(gvib200_problem* prob, double* diag, double* off);
+int gvib200_sync(gvib200_problem* prob);
 
 /* ---- per-factor quadrature moments at the current state: E_Phis / E_xMuPhis / E_xMuxMuTPhis
         (gvibase/GVI-GH-GBP.h:348-378; SparseGaussHermite::Integrate quadrature/SparseGaussHermite.h:197-221).
