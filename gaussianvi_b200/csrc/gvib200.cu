@@ -265,6 +265,8 @@ struct GhGroup {
     double* d_Thigh = nullptr;
     void* d_params = nullptr;
     double* d_SR[2] = {nullptr, nullptr};
+    bool sr_full[2] = {false, false};  // d_SR[b] holds S, R of EVERY factor at the state of buffer b (the fused culling +
+                                       // prologue pass only writes the factors it keeps)
     double* d_raw = nullptr;
     mutable int* d_active = nullptr;   // free-space culling: compacted list of the factors to evaluate
     mutable int* d_nactive = nullptr;  // [2]: list length, finished-CTA counter
@@ -369,6 +371,7 @@ struct gvib200_problem {
     int iter = 0;
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
+    const double* sweep_cO = nullptr;  // off-diagonal covariance blocks of the sweep being launched (fused culling + prologue)
     bool pending_check = false;  // gvib200_set_state_async: the not-SPD flag of its selected inverse has not been read yet
     bool grads_valid = false;
     bool prox = false;              // Prox-GVI problem (option "prox" before finalize): linear factors get per-iteration
@@ -385,6 +388,7 @@ struct gvib200_problem {
     size_t snap_doubles = 0;
     int snap_iter = 0, snap_cur = 0;
     bool snap_lowtemp = true, snap_sweep_valid = false;
+    std::vector<char> snap_sr_full;  // per GH group: sr_full of the snapshot's buffer
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -713,6 +717,8 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
     a.raw = raw;
     a.evaluated = p->d_evaluated;
     a.covD = covD;
+    a.covO = p->sweep_cO;
+    a.SR_out = const_cast<double*>(SR);
     a.xinorm = g.table->xinorm;
     a.active = nullptr;
     a.n_active = nullptr;
@@ -739,9 +745,14 @@ static int launch_moments_sym(gvib200_problem* p, const GhGroup& g, const Cost& 
         CUDA_TRY(cudaFuncSetAttribute(k_moments_sym<DIM, Cost, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       K1S_MAX_DATA * (int)sizeof(double)));
     }
-    if (a.active != nullptr) {
-        if (full) LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
-        else LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, false>), cdiv(g.n, 256), 256, 0, a);
+    if constexpr (Cost::CULL) if (a.active != nullptr) {
+        if (!g.sr_full[(SR == g.d_SR[1]) ? 1 : 0]) {  // S, R of the kept factors come from the culling pass itself
+            if (full) LAUNCH(p, KC_CULL, (k_cull_prologue_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
+            else LAUNCH(p, KC_CULL, (k_cull_prologue_sym<DIM, Cost, false>), cdiv(g.n, 256), 256, 0, a);
+        } else {
+            if (full) LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, true>), cdiv(g.n, 256), 256, 0, a);
+            else LAUNCH(p, KC_CULL, (k_cull_sym<DIM, Cost, false>), cdiv(g.n, 256), 256, 0, a);
+        }
     }
     if (p->profile) prof_begin(p, full ? KC_MOMENTS_FULL : KC_MOMENTS_COST);
     if (full) k_moments_sym<DIM, Cost, true><<<grid, K1S_THREADS, smem, p->ls>>>(g.table->sym, a);
@@ -867,8 +878,25 @@ template <int DIM, int SD>
 static int gh_group_run(gvib200_problem* p, GhGroup& g, const SweepTarget& t, bool prologue, bool sweep, bool full,
                         double* raw) {
     double* SR = g.d_SR[t.which];
-    if (prologue) TRY((launch_prologue<DIM, SD>(p, g, t.cD, t.cO, SR)));
+    // Hinge factors on the sign-group kernel with free-space culling: the culling pass of the sweep forms S, R itself, for the
+    // factors it keeps only (k_cull_prologue_sym) -- no separate prologue launch.  d_SR is then incomplete (sr_full), which
+    // only matters to a later sweep that runs without the fusion: it runs the full prologue first.
+    static const bool no_fused_env = getenv("GVIB200_NO_FUSED_PROLOGUE") != nullptr;  // development switch
+    const bool fused = g.kind == GVIB200_COST_PLANAR_HINGE && DIM >= 2 && DIM <= 4 && p->cull && !p->prox && g.table != nullptr &&
+                       g.table->sym_ok && !p->force_generic_k1 && !no_fused_env;
+    if (prologue) {
+        if (fused) {
+            g.sr_full[t.which] = false;
+        } else {
+            TRY((launch_prologue<DIM, SD>(p, g, t.cD, t.cO, SR)));
+            g.sr_full[t.which] = true;
+        }
+    } else if (sweep && !fused && !g.sr_full[t.which]) {
+        TRY((launch_prologue<DIM, SD>(p, g, t.cD, t.cO, SR)));
+        g.sr_full[t.which] = true;
+    }
     if (!sweep) return check_launch("k_prologue");
+    p->sweep_cO = t.cO;
     double* fc = p->fcost[t.which];
     double* fv = p->fVdmu[t.which];
     double* fm = p->fVdd[t.which];
@@ -1095,11 +1123,12 @@ static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full, int p
         a.fcost = p->fcost[t.which] + g.first_id;
         a.fVdmu = full ? p->fVdmu[t.which] + g.voff : nullptr;
         const int sd = p->d;
-        if (g.dim == 8 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<8, 4, 4>), cdiv(g.n, 128), 128, 0, a);
-        else if (g.dim == 4 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<4, 4, 4>), cdiv(g.n, 128), 128, 0, a);
-        else if (g.dim == 12 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<12, 6, 6>), cdiv(g.n, 128), 128, 0, a);
-        else if (g.dim == 6 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<6, 6, 6>), cdiv(g.n, 128), 128, 0, a);
-        else LAUNCH(p, KC_LINEAR, (k_linear<0, 0, 0>), cdiv(g.n, 128), 128, 0, a);
+        const int grid = cdiv(g.n, 128);
+        if (g.dim == 8 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<8, 4, 4>), grid, 128, 0, a);
+        else if (g.dim == 4 && g.m == 4 && sd == 4) LAUNCH(p, KC_LINEAR, (k_linear<4, 4, 4>), grid, 128, 0, a);
+        else if (g.dim == 12 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<12, 6, 6>), grid, 128, 0, a);
+        else if (g.dim == 6 && g.m == 6 && sd == 6) LAUNCH(p, KC_LINEAR, (k_linear<6, 6, 6>), grid, 128, 0, a);
+        else LAUNCH(p, KC_LINEAR, (k_linear<0, 0, 0>), grid, 128, 0, a);
     }
   }
     return check_launch("k_linear");
@@ -1917,7 +1946,12 @@ extern "C" int gvib200_problem_finalize(gvib200_problem* p) {
             CUDA_TRY(cudaMalloc(&g.d_params, g.params.size()));
             CUDA_TRY(cudaMemcpyAsync(g.d_params, g.params.data(), g.params.size(), cudaMemcpyHostToDevice, p->stream));
         }
-        for (int i = 0; i < 2; ++i) TRY(dev_alloc(&g.d_SR[i], (size_t)g.n * 2 * g.dim * g.dim));
+        for (int i = 0; i < 2; ++i) {
+            TRY(dev_alloc(&g.d_SR[i], (size_t)g.n * 2 * g.dim * g.dim));
+            // finite everywhere from the start: the entries of culled factors are never written by the fused culling + prologue
+            // pass and meet exactly-zero raw moments in k_raw_to_x
+            CUDA_TRY(cudaMemsetAsync(g.d_SR[i], 0, (size_t)g.n * 2 * g.dim * g.dim * sizeof(double), p->stream));
+        }
     }
     for (auto& g : p->lin) {
         TRY(dev_upload(&g.d_start, g.start, p->stream));
@@ -2435,7 +2469,9 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             if (rc != 0) return rc;
             p->grads_valid = true;
             CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));  // candidate mean is complete
-            // covariance part of the closed-form linear factors (HBM bound): underneath the Jacobi prologue (FP64 bound)
+            // covariance part of the closed-form linear factors (HBM bound), behind the solve pass on its stream.  (Measured and
+            // rejected: a third stream that starts it next to the backward half of the solve pass -- 0.400 -> 0.424 ms per
+            // iteration, although the per-launch timeline looked better.)
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
             p->ls = p->stream2;
             {
@@ -2964,6 +3000,8 @@ extern "C" int gvib200_snapshot_save(gvib200_problem* p) {
     p->snap_lowtemp = p->is_lowtemp;
     p->snap_cur = p->cur;
     p->snap_sweep_valid = p->sweep_valid;
+    p->snap_sr_full.clear();
+    for (auto& g : p->gh) p->snap_sr_full.push_back(g.sr_full[p->cur] ? 1 : 0);
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -2981,6 +3019,7 @@ extern "C" int gvib200_snapshot_restore(gvib200_problem* p) {
     p->iter = p->snap_iter;
     p->converged = false;
     p->sweep_valid = p->snap_sweep_valid;
+    for (size_t i = 0; i < p->gh.size() && i < p->snap_sr_full.size(); ++i) p->gh[i].sr_full[p->cur] = p->snap_sr_full[i] != 0;
     p->asm_valid = false;
     p->zc_ok[0] = p->zc_ok[1] = false;
     p->grads_valid = false;

@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include "cost_functors.cuh"
+#include "smallmat.h"
 
 namespace gvib200 {
 
@@ -80,6 +81,8 @@ struct SymArgs {
     double* raw;           // optional [n][1 + DIM + DIM*DIM]
     unsigned long long* evaluated;  // optional counter: factors whose sigma points were evaluated (not culled)
     const double* covD;    // marginal covariance blocks of the sweep's state (culling pass only)
+    const double* covO;    // off-diagonal covariance blocks (s, s+1) (fused culling + prologue pass only)
+    double* SR_out;        // fused culling + prologue pass: S, R of the factors that are kept (same array as SR)
     double xinorm;         // max ||xi||_2 over the rule's nodes
     // free-space culling (k_cull_sym): the factors to evaluate, compacted; null = all n factors in order
     int* active;           // [n] factor indices
@@ -344,6 +347,93 @@ __global__ void __launch_bounds__(256) k_cull_sym(const __grid_constant__ SymArg
         if (lane == __ffs(m) - 1) base = atomicAdd(a.n_active, __popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
         if (keep) a.active[base + __popc(m & ((1u << lane) - 1u))] = f;
+    }
+}
+
+// Free-space culling FUSED with the per-factor prologue (K2): the factors that survive the box test are compacted inside
+// the CTA and the first threads of the CTA -- dense warps -- form S = Sigma^1/2, R = Sigma^-1/2 for them (the same
+// extraction and the same sqrt_and_invsqrt as k_prologue: identical bits); culled factors get their exactly-zero outputs
+// and NO square root (nothing reads it: their raw moments are zero).  At the headline shape half of the Jacobi work
+// disappears and the other half no longer competes with the latency-bound solve pass for the SMs.  One atomic per CTA
+// appends the CTA's survivors to the global list.
+template <int DIM, class Cost, bool FULL>
+__global__ void __launch_bounds__(256) k_cull_prologue_sym(const __grid_constant__ SymArgs<Cost> a) {
+    constexpr int XD = Cost::XD;
+    constexpr int NOUT = 1 + DIM + DIM * DIM;
+    __shared__ int lst[256];
+    __shared__ int wcnt[8];
+    __shared__ int gbase;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+    bool keep = false;
+    if (f < a.n) {
+        const int s = a.start[f], sd = a.state_dim;
+        const double* mp = a.mu + (size_t)s * sd;
+        double lo[XD], hi[XD];
+#pragma unroll
+        for (int r = 0; r < XD; ++r) {
+            const int blk = r / sd, q = r - blk * sd;  // coordinate r lives in state s + blk
+            const double var = __ldg(a.covD + (size_t)(s + blk) * sd * sd + q + q * sd);
+            const double m = __ldg(mp + r);
+            const double rad = sqrt(fmax(var, 0.0)) * a.xinorm * (1.0 + 1e-12);
+            lo[r] = m - rad;
+            hi[r] = m + rad;
+        }
+        keep = !a.cost.all_zero(lo, hi);
+        if (!keep) a.fcost[f] = 0.0;
+    }
+    if (FULL) {
+        // the warp zeroes the outputs of its culled factors together: whole lines instead of 8-byte pieces
+        unsigned z = __ballot_sync(0xffffffffu, f < a.n && !keep);
+        const int fw = f - lane_;  // first factor of the warp
+        while (z != 0u) {
+            const int l = __ffs(z) - 1;
+            z &= z - 1u;
+            const size_t ff = (size_t)(fw + l);
+            for (int e = lane_; e < DIM * DIM; e += 32) a.fVdd[ff * DIM * DIM + e] = 0.0;
+            if (lane_ < DIM) a.fVdmu[ff * DIM + lane_] = 0.0;
+            if (a.raw != nullptr)
+                for (int e = lane_; e < NOUT; e += 32) a.raw[ff * NOUT + e] = 0.0;
+        }
+    }
+    // compaction inside the CTA (factor order preserved), one atomic per CTA for its place in the global list
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane_ == 0) wcnt[warp_] = __popc(m);
+    __syncthreads();
+    int before = 0, nk = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int c = wcnt[w];
+        if (w < warp_) before += c;
+        nk += c;
+    }
+    if (keep) lst[before + __popc(m & ((1u << lane_) - 1u))] = f;
+    if (threadIdx.x == 0) gbase = (nk > 0) ? atomicAdd(a.n_active, nk) : 0;
+    __syncthreads();
+    if ((int)threadIdx.x >= nk) return;
+    const int fk = lst[threadIdx.x];
+    a.active[gbase + threadIdx.x] = fk;
+    // ---- prologue of the kept factor fk (k_prologue: gvibase/GVIFactorizedBase.h:111-114, quadrature/SparseGaussHermite.h:231-233)
+    const int s = a.start[fk], sd = a.state_dim;
+    const size_t bs = (size_t)sd * sd;
+    Mat<DIM> Sig, S, R;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            const int bi = i / sd, ii = i - bi * sd, bj = j / sd, jj = j - bj * sd;
+            double v;
+            if (bi == bj) v = a.covD[(size_t)(s + bi) * bs + ii + jj * sd];
+            else if (bi < bj) v = a.covO[(size_t)s * bs + ii + jj * sd];  // block (s, s+1)
+            else v = a.covO[(size_t)s * bs + jj + ii * sd];               // its transpose
+            Sig(i, j) = v;
+        }
+    sqrt_and_invsqrt<DIM>(S, R, Sig);
+    double* out = a.SR_out + (size_t)fk * 2 * DIM * DIM;
+#pragma unroll
+    for (int e = 0; e < DIM * DIM; ++e) {
+        out[e] = S.a[e];
+        out[DIM * DIM + e] = R.a[e];
     }
 }
 
