@@ -2470,8 +2470,9 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             p->grads_valid = true;
             CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));  // candidate mean is complete
             // covariance part of the closed-form linear factors (HBM bound), behind the solve pass on its stream.  (Measured and
-            // rejected: a third stream that starts it next to the backward half of the solve pass -- 0.400 -> 0.424 ms per
-            // iteration, although the per-launch timeline looked better.)
+            // rejected, twice: starting it next to the backward half of the solve pass -- on a third stream, or on the main
+            // stream right behind the selected inverse -- makes the quadrature kernel a little faster and the iteration
+            // 0.402 -> 0.43 ms.)
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
             p->ls = p->stream2;
             {
