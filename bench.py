@@ -463,8 +463,11 @@ def run_gpu(args, rank, world, local_rank):
     # (N > 1: one handle only -- two handles of a distributed problem would interleave their peer-mailbox exchanges on
     #  different streams, and the epoch order of those exchanges must be the same on every rank)
     if world == 1:
-        NH = 2   # handles in flight (measured on the B200 box: 2 handles 775 it/s, 3 handles 708 -- the two PCIe directions
-                 # together move 57.6 MB per step at ~47 GB/s and do not speed each other up, so the step is transfer bound)
+        # handles in flight: one uploading, one iterating, one downloading (a handle's stream keeps its own download -> next
+        # upload -> selected inverse -> iteration in order).  Measured on the B200 box: 1 handle synchronous 545 it/s, 2
+        # handles 941, 3 handles 1149, 4 handles 1146 (compute bound: a step from a host-provided state costs two quadrature
+        # sweeps, a selected inverse and the factor marginals on top of the iteration's chain passes).
+        NH = int(os.environ.get("GVIB200_BENCH_E2E_HANDLES", "3"))
         extra = [problems.build_device_problem(ctx, spec) for _ in range(NH - 1)]
         ref_mu, ref_cD = out_mu.copy(), out_cD.copy()
         handles = [(prob, (out_mu, out_cD, out_cO))]
@@ -543,7 +546,7 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": pipe_steps,
                     "call": ("gvib200_set_state_async + gvib200_ngd_iterate + gvib200_get_mean_async + gvib200_get_cov_blocks_async "
-                             "per step, two handles alternating (the copies of one overlap the iteration of the other); every "
+                             "per step, three handles in rotation (one uploading, one iterating, one downloading); every "
                              "step uploads its state from pinned host memory and downloads its mean + covariance blocks")
                             if world == 1 else "gvib200_set_state + gvib200_ngd_iterate + gvib200_get_mean + gvib200_get_cov_blocks",
                     "single_handle_synchronous": {"value": e2e_sync_value, "steps": e2e_steps,

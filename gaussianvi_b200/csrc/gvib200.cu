@@ -342,6 +342,7 @@ struct gvib200_problem {
     double *Vdmu2 = nullptr, *VD2 = nullptr, *VO2 = nullptr, *rhs2 = nullptr;
     bool asm_valid = false;  // Vdmu / VD / VO / rhs hold the assembly of the sweep at the current state
     cudaEvent_t ev_host = nullptr;
+    cudaEvent_t ev_pending = nullptr;  // gvib200_set_state_async: upload + selected inverse + factor marginals are complete
     double *KlinD = nullptr, *KlinO = nullptr;
     // adjacency
     // the same adjacency in ELL form (fixed width, -1 padded, [k][state]) when every state has few contributors: the
@@ -1553,6 +1554,7 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pro, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_k1, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_host, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_pending, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_mu, cudaEventDisableTiming));
     p->ls = p->stream;
     *out = p.release();
@@ -1601,6 +1603,7 @@ static void free_problem(gvib200_problem* p) {
     if (p->ev_pro) cudaEventDestroy(p->ev_pro);
     if (p->ev_k1) cudaEventDestroy(p->ev_k1);
     if (p->ev_host) cudaEventDestroy(p->ev_host);
+    if (p->ev_pending) cudaEventDestroy(p->ev_pending);
     if (p->ev_mu) cudaEventDestroy(p->ev_mu);
     if (p->stream2) cudaStreamDestroy(p->stream2);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -2090,8 +2093,11 @@ static int recompute_from_precision(gvib200_problem* p, int which, bool async = 
     TRY(do_selinv(p, p->LD[which], p->LO[which], p->CD[which], p->CO[which], p->scal + which));
     TRY(run_prologue_only(p, which));
     if (async) {  // the host does not wait: the flag is read by the next call that synchronises (resolve_pending)
+        if (p->ctx->world > 1 && !p->flags_synced) TRY(dist_reduce(p, p->scal + 7));  // scal[7]: scratch
+        LAUNCH(p, KC_OTHER, k_flags_to_host, 1, 1, 0, p->d_flag, p->zc_dev + 4);
+        CUDA_TRY(cudaEventRecord(p->ev_pending, p->stream));
         p->pending_check = true;
-        return 0;
+        return check_launch("set_state_async");
     }
     int flag = 0;
     TRY(read_flag(p, &flag));
@@ -2103,8 +2109,8 @@ static int recompute_from_precision(gvib200_problem* p, int which, bool async = 
 static int resolve_pending(gvib200_problem* p) {
     if (!p->pending_check) return 0;
     p->pending_check = false;
-    int flag = 0;
-    TRY(read_flag(p, &flag));
+    CUDA_TRY(cudaEventSynchronize(p->ev_pending));
+    const int flag = p->zc[4] != 0.0;
     if (flag) {
         p->has_state = false;
         return fail(GVIB200_ENOTSPD, "precision matrix is not positive definite (gvib200_set_state_async)");

@@ -1526,6 +1526,12 @@ __global__ void k_sum3(size_t n, const double* __restrict__ v, const double* __r
     if (threadIdx.x == 0) out[0] = sh[0] + a[0] + (b ? b[0] : 0.0);
 }
 // staging of the cost / flag exchange: buf = {cost, flag0, flag1, 0}; after the all-gather cost and flags are written back
+// gvib200_set_state_async: the not-SPD flags of its selected inverse go to mapped host memory (no copy-engine transfer: a
+// small device-to-host copy would queue behind another handle's bulk download on the shared copy engine)
+__global__ void k_flags_to_host(const int* flags, double* zc_slot) {
+    zc_slot[0] = (double)(flags[0] | flags[1]);
+    __threadfence_system();
+}
 __global__ void k_red_pack(const double* cost, const int* flags, double* buf) {
     buf[0] = cost[0];
     buf[1] = (double)flags[0];
