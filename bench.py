@@ -744,6 +744,27 @@ def run_cfg5(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    # ---- the same batch with a line search PER PROBLEM (gvib200_set_batch / gvib200_batch_iterate: per-problem cost from the
+    # per-node log pivots, per-problem step sizes; exactly the independent optimizer objects of the reference also when
+    # the problems disagree about a trial)
+    Sb = spec.meta["states_per_problem"]
+    prob.snapshot_restore()
+    prob.set_batch(np.arange(count + 1, dtype=np.int32) * Sb)
+    for _ in range(3):
+        prob.batch_iterate(opts)
+    prob.snapshot_restore()
+    barrier()
+    prob.timer_start()
+    trials = 0
+    for i in range(K):
+        if i and i % args.rewind_every == 0:
+            prob.snapshot_restore()
+        sts, ntr = prob.batch_iterate(opts)
+        trials += ntr
+    ms_pp = max_over_ranks(prob.timer_stop())
+    barrier()
+    if not all(s_.accepted for s_ in sts):
+        raise SystemExit("bench.py: a timed per-problem iteration left a problem without an accepted trial")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, sample = cfg5_cpu(8, 6, 1, args.problems)
@@ -765,6 +786,10 @@ def run_cfg5(args, rank, world, local_rank):
                        "rewind": f"device-side snapshot restore every {args.rewind_every} steps (inside the timed region)",
                        "setup_s": t_build},
             "iterations_per_s_per_batch": K / (ms * 1e-3),
+            "per_problem_line_search": {"value": args.problems * K / (ms_pp * 1e-3), "unit": CFG5_UNIT, "ms_per_step": ms_pp / K,
+                                        "trial_sweeps_per_iteration": trials / K,
+                                        "call": "gvib200_set_batch + gvib200_batch_iterate (tests/test_gpu_batch.py: every "
+                                                "problem walks the path of its own independent oracle run)"},
             "evaluated_factor_fraction": n_eval / float(info.n_gh_factors * sum(s.n_moment_sweeps + s.n_cost_sweeps for s in stats)),
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": args.problems * e2e_steps / e2e_s, "unit": CFG5_UNIT,

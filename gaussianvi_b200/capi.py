@@ -43,7 +43,7 @@ EXPORTS = [
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
     "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature", "gvib200_ctx_mailbox_create", "gvib200_ctx_mailbox_connect",
     "gvib200_set_state_async", "gvib200_get_mean_async", "gvib200_get_prec_blocks_async", "gvib200_get_cov_blocks_async",
-    "gvib200_sync",
+    "gvib200_sync", "gvib200_set_batch", "gvib200_batch_iterate", "gvib200_batch_costs",
 ]
 
 
@@ -500,6 +500,24 @@ class Problem:
         _check(self.lib.gvib200_optimize_traced(self.h, C.byref(opts) if opts is not None else None, n_iters, 1 if prox else 0,
                                                 stats, C.byref(done), C.byref(rec.trace)))
         return [stats[i] for i in range(done.value)], rec
+
+    # ---- batches of independent problems, line search per problem ----
+    def set_batch(self, state_offsets):
+        off = np.ascontiguousarray(state_offsets, dtype=np.int32)
+        self._n_batch = len(off) - 1
+        _check(self.lib.gvib200_set_batch(self.h, self._n_batch, off.ctypes.data_as(_IP)))
+
+    def batch_iterate(self, opts: Optional[Opts] = None):
+        """One iteration of every problem of the batch; returns (per-problem IterStats list, trial sweeps of the batch)."""
+        stats = (IterStats * self._n_batch)()
+        nt = C.c_int()
+        _check(self.lib.gvib200_batch_iterate(self.h, C.byref(opts) if opts is not None else None, stats, C.byref(nt)))
+        return [stats[i] for i in range(self._n_batch)], nt.value
+
+    def batch_costs(self) -> np.ndarray:
+        out = np.zeros(self._n_batch)
+        _check(self.lib.gvib200_batch_costs(self.h, _dp(out)))
+        return out
 
     def evaluated_factors(self, reset: bool = True) -> int:
         v = C.c_longlong()

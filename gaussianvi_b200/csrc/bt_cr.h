@@ -76,7 +76,19 @@ struct CrView {
     double* Dn;  // [D*D][NS] Schur-updated diagonal blocks; after the forward pass reused for the covariance diagonal
     double* P;   // [D*D][NS] coupling of a node to its next alive node; reused for the covariance couplings
     double* g;   // [D][NS] right-hand side; reused for the solution
+    // optional per-node log det of the pivots (batches of independent problems need log det PER PROBLEM): local node j of
+    // this view is node min(ld_base + j ld_mul, ld_nmax) of its CrArgs level, which is chain node min(that ld_stride, ld_max)
+    double* ldnode = nullptr;
+    long long ld_base = 0, ld_mul = 1, ld_nmax = 0, ld_stride = 1, ld_max = 0;
 };
+template <int D>
+GVI_HD size_t cr_ld_index(const CrView<D>& v, int j) {
+    long long a = v.ld_base + (long long)j * v.ld_mul;
+    if (a > v.ld_nmax) a = v.ld_nmax;
+    a *= v.ld_stride;
+    if (a > v.ld_max) a = v.ld_max;
+    return (size_t)a;
+}
 
 template <int D>
 struct CrRec {
@@ -177,8 +189,26 @@ GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, c
     cr_ld_col<D>(Pjc, v.P, v.NS, sj, c);
     cr_ld_row<D>(el.Pirow, v.P, v.NS, el.si, c);
     symmetrize<D>(Dt);
-    LogDetAcc other;  // the pivots count once per node: worker 0 carries them
-    const bool ok = chol_factor<D>(L, rd, Dt, c == 0 ? ld : other);
+    // the pivots count once per node: worker 0 merges the node's product into its running one (and, for batches of
+    // independent problems, stores the node's own log det)
+    LogDetAcc nd;
+    const bool ok = chol_factor<D>(L, rd, Dt, nd);
+    if (c == 0) {
+        ld.m *= nd.m;
+        ld.e += nd.e;
+        ld.normalize();
+        if (v.ldnode != nullptr) v.ldnode[cr_ld_index<D>(v, j)] = ok ? nd.value() : nan("");
+    }
+    if (v.ldnode != nullptr && !ok) {
+        // Batch of independent problems: a pivot that is not positive has filled the factor with NaN.  A NaN would not
+        // stay inside its problem -- the exactly-zero coupling blocks between two problems turn 0 * NaN into NaN on the
+        // other side -- so the factor is replaced by zeros: everything downstream of this node is finite garbage, the
+        // node's log det is NaN and its problem's cost with it.
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) L.a[e] = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; ++m) rd[m] = 0.0;
+    }
 #pragma unroll
     for (int m = 0; m < D; ++m) ec.a[m] = (m == c) ? 1.0 : 0.0;
     chol_solve<D>(el.Gc, L, rd, Pjc);       // G = Dinv Pj
@@ -338,7 +368,18 @@ GVI_HD bool cr_top2(const CrView<D>& v, int T, LogDetAcc& ld) {
     Mat<D> A0, A1, P, I0, S1, G, Tm;
     cr_ld<D>(A0, v.Dn, v.NS, 0);
     symmetrize<D>(A0);
-    bool ok = spd_inverse<D>(I0, A0, ld);
+    bool ok;
+    if (v.ldnode != nullptr) {
+        LogDetAcc nd;
+        ok = spd_inverse<D>(I0, A0, nd);
+        v.ldnode[cr_ld_index<D>(v, 0)] = ok ? nd.value() : nan("");
+        if (!ok) mat_zero<D>(I0);  // finite garbage instead of NaN (see cr_fwd_A)
+        ld.m *= nd.m;
+        ld.e += nd.e;
+        ld.normalize();
+    } else {
+        ok = spd_inverse<D>(I0, A0, ld);
+    }
     Vec<D> g0, g1, y0, x1, tv;
     if (RHS) {
         cr_ldv<D>(g0, v.g, v.NS, 0);
@@ -356,7 +397,18 @@ GVI_HD bool cr_top2(const CrView<D>& v, int T, LogDetAcc& ld) {
 #pragma unroll
     for (int e = 0; e < D * D; ++e) A1.a[e] -= Tm.a[e];
     symmetrize<D>(A1);
-    ok = spd_inverse<D>(S1, A1, ld) && ok;  // Sigma_TT
+    if (v.ldnode != nullptr) {
+        LogDetAcc nd;
+        const bool ok1 = spd_inverse<D>(S1, A1, nd);  // Sigma_TT
+        ok = ok1 && ok;
+        v.ldnode[cr_ld_index<D>(v, T)] = ok1 ? nd.value() : nan("");
+        if (!ok1) mat_zero<D>(S1);
+        ld.m *= nd.m;
+        ld.e += nd.e;
+        ld.normalize();
+    } else {
+        ok = spd_inverse<D>(S1, A1, ld) && ok;  // Sigma_TT
+    }
     if (RHS) {
         cr_ldv<D>(g1, v.g, v.NS, 1);
         mtv<D>(tv, P, y0);
@@ -420,13 +472,20 @@ struct CrArgs {
     const double* xbase;
     double xalpha;
     double* xout;
+    // batches of independent problems (optional): alpha_node[i] replaces alpha for the blocks of node i of this level
+    // (diagonal block i and coupling (i, i+1)); ldnode receives the log det of every node's pivot block, node i of this
+    // level being chain node min(i ld_stride, ld_max)
+    const double* alpha_node;
+    double* ldnode;
+    long long ld_stride, ld_max;
 };
 
 template <int D>
 GVI_HD double cr_sys_diag(const CrArgs<D>& a, size_t idx) {
     double v = a.Dg[idx];
     if (a.Dg2 != nullptr) {
-        v = v + a.alpha * (a.Dg2[idx] - v);
+        const double al = a.alpha_node ? a.alpha_node[idx / (D * D)] : a.alpha;
+        v = v + al * (a.Dg2[idx] - v);
         a.Dout[idx] = v;
     }
     return v;
@@ -435,7 +494,8 @@ template <int D>
 GVI_HD double cr_sys_off(const CrArgs<D>& a, size_t idx) {
     double v = a.Og[idx];
     if (a.Og2 != nullptr) {
-        v = v + a.alpha * (a.Og2[idx] - v);
+        const double al = a.alpha_node ? a.alpha_node[idx / (D * D)] : a.alpha;
+        v = v + al * (a.Og2[idx] - v);
         a.Oout[idx] = v;
     }
     return v;
@@ -501,8 +561,9 @@ GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& g
                 const int node = idx / DD, e = idx - node * DD;
                 const int s = cr_slot(gm, node);
                 if (fused) {
-                    dv[u] = dv[u] + a.alpha * (d2[u] - dv[u]);
-                    ov[u] = ov[u] + a.alpha * (o2[u] - ov[u]);
+                    const double al = a.alpha_node ? a.alpha_node[n0 + node] : a.alpha;
+                    dv[u] = dv[u] + al * (d2[u] - dv[u]);
+                    ov[u] = ov[u] + al * (o2[u] - ov[u]);
                     if (node != 0 && node != Tk) a.Dout[g0 + idx] = dv[u];
                     if (node < Tk) a.Oout[g0 + idx] = ov[u];
                 }

@@ -141,6 +141,10 @@ inline CrArgs<D> cr_bind(const CrPlan& p, double* ws, const double* Dg, const do
     a.xbase = nullptr;
     a.xalpha = 0.0;
     a.xout = nullptr;
+    a.alpha_node = nullptr;
+    a.ldnode = nullptr;
+    a.ld_stride = 1;
+    a.ld_max = (long long)p.n - 1;
     return a;
 }
 

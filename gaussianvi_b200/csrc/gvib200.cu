@@ -373,6 +373,20 @@ struct gvib200_problem {
     bool is_lowtemp = true, converged = false;
     bool sweep_valid = false;  // fcost/fVdmu/fVdd[cur] hold a full moment sweep at the current state
     const double* sweep_cO = nullptr;  // off-diagonal covariance blocks of the sweep being launched (fused culling + prologue)
+    // batch of independent problems with a line search per problem (gvib200_set_batch / gvib200_batch_iterate)
+    struct Batch {
+        int P = 0, G = 0;
+        std::vector<int> soff;                 // [P + 1] first state of every problem
+        std::vector<int> sprob_h;              // [S] problem of every state
+        int *d_sprob = nullptr, *d_soff = nullptr, *d_seg = nullptr, *d_gfirst = nullptr;
+        double *d_step = nullptr, *d_alpha_node = nullptr, *d_ldn[2] = {nullptr, nullptr}, *d_ldn_solve = nullptr, *d_pcost = nullptr;
+        double* h_pcost = nullptr;             // pinned [P]
+        double* h_step = nullptr;              // pinned [P]
+        bool ldn_valid[2] = {false, false};    // d_ldn[b] holds the log pivots of buffer b's precision
+        bool cost_valid = false;               // cost_cur is the per-problem cost at the current state
+        std::vector<double> cost_cur;
+        std::vector<char> lowtemp, converged;
+    } batch;
     bool pending_check = false;  // gvib200_set_state_async: the not-SPD flag of its selected inverse has not been read yet
     bool grads_valid = false;
     bool prox = false;              // Prox-GVI problem (option "prox" before finalize): linear factors get per-iteration
@@ -595,6 +609,11 @@ static int chain_pass_3level(gvib200_problem* p, int slot, const CrArgs<D>& a, d
     const DistLayout L = dist_layout(D, pl.K, 1);
     double* buf = p->dist_buf[slot];
     CrArgs<D> mid = cr_bind<D>(pm, p->ws_mid[slot], buf + L.D1, buf + L.O1, RHS ? buf + L.g1 : nullptr, a.tx, a.tD, a.tO, a.notspd);
+    if (a.ldnode != nullptr) {  // node i of the mid level is separator i of the first level = chain node min(i T, n - 1)
+        mid.ldnode = a.ldnode;
+        mid.ld_stride = (long long)pl.T * a.ld_stride;
+        mid.ld_max = a.ld_max;
+    }
     LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), std::min(64, cdiv(pl.K + 1, 16)), 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
     if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
@@ -616,6 +635,8 @@ struct ChainFuse {
     const double* xbase = nullptr;
     double xalpha = 0.0;
     double* xout = nullptr;
+    const double* alpha_node = nullptr;  // per-state step size (batches of independent problems)
+    double* ldnode = nullptr;            // per-state log det of the pivot blocks
 };
 
 template <int D, bool RHS, bool SELINV>
@@ -632,6 +653,8 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
         a.xbase = fuse->xbase;
         a.xalpha = fuse->xalpha;
         a.xout = fuse->xout;
+        a.alpha_node = fuse->alpha_node;
+        a.ldnode = fuse->ldnode;
     }
     TRY(cr_allow_smem(p->ctx, k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 5120));
     TRY(cr_allow_smem(p->ctx, k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
@@ -1561,10 +1584,12 @@ extern "C" int gvib200_problem_create(gvib200_ctx* ctx, int num_states, int dim_
     return 0;
 }
 
+static void free_batch(gvib200_problem* p);
 static void free_problem(gvib200_problem* p) {
     // speculative work (the assembly of the last trial's sweep) may still be in flight on either stream
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->stream2) cudaStreamSynchronize(p->stream2);
+    free_batch(p);
     auto F = [](void* q) {
         if (q) cudaFree(q);
     };
@@ -2135,6 +2160,8 @@ static int set_state_impl(gvib200_problem* p, const double* mu, const double* pd
     p->asm_valid = false;
     p->grads_valid = false;
     p->zc_ok[0] = p->zc_ok[1] = false;
+    p->batch.ldn_valid[0] = p->batch.ldn_valid[1] = false;
+    p->batch.cost_valid = false;
     if (pd || !p->has_state) {
         if (!pd) return fail(GVIB200_ESTATE, "set_state: the first call must provide a precision");
         TRY(recompute_from_precision(p, c, async));
@@ -2654,6 +2681,291 @@ extern "C" int gvib200_optimize(gvib200_problem* p, const gvib200_opts* opts, in
 
 
 // ------------------------------------------------------------------------------------------------
+// C-ABI: batches of independent problems, line search PER PROBLEM.  The problems are concatenated block-diagonally into
+// one chain (nothing couples consecutive problems), so sweeps, assembly and chain passes run over the whole batch in single
+// launches; what is per problem is what GVIGH::optimize keeps per optimizer object (gvibase/GVI-GH-GBP-impl.h:33-130): the
+// cost (factor costs + log det / 2 of ITS precision), the back-tracking count and step size, the temperature phase and the
+// converged flag.  A trial is run for the whole batch with one step size per problem; problems that accepted keep their
+// step (their candidate is recomputed bit for bit), problems that rejected shrink theirs, problems that are through take
+// step 0 (candidate == current state) -- until every problem has accepted or exhausted its back-tracking.
+// ------------------------------------------------------------------------------------------------
+static void free_batch(gvib200_problem* p) {
+    auto& B = p->batch;
+    auto F = [](void* q) {
+        if (q) cudaFree(q);
+    };
+    F(B.d_sprob); F(B.d_soff); F(B.d_seg); F(B.d_gfirst); F(B.d_step); F(B.d_alpha_node); F(B.d_ldn[0]); F(B.d_ldn[1]);
+    F(B.d_ldn_solve); F(B.d_pcost);
+    if (B.h_pcost) cudaFreeHost(B.h_pcost);
+    if (B.h_step) cudaFreeHost(B.h_step);
+    B = gvib200_problem::Batch();
+}
+
+extern "C" int gvib200_set_batch(gvib200_problem* p, int n_problems, const int32_t* state_offsets) {
+    if (!p || !p->finalized) return fail(GVIB200_ESTATE, "set_batch: problem not finalized");
+    if (n_problems < 1 || !state_offsets) return fail(GVIB200_EINVAL, "set_batch: bad arguments");
+    if (p->prox) return fail(GVIB200_EINVAL, "set_batch: not available for Prox-GVI problems");
+    if (p->ctx->world > 1) return fail(GVIB200_EINVAL, "set_batch: a batch lives on one GPU (shard the problems over the ranks)");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    free_batch(p);
+    auto& B = p->batch;
+    const int P = n_problems, S = p->S, d = p->d;
+    if (state_offsets[0] != 0 || state_offsets[P] != S) return fail(GVIB200_EINVAL, "set_batch: offsets must run from 0 to num_states");
+    B.soff.assign(state_offsets, state_offsets + P + 1);
+    B.sprob_h.assign((size_t)S, 0);
+    for (int q = 0; q < P; ++q) {
+        if (B.soff[q + 1] <= B.soff[q]) return fail(GVIB200_EINVAL, "set_batch: offsets must increase");
+        for (int st = B.soff[q]; st < B.soff[q + 1]; ++st) B.sprob_h[(size_t)st] = q;
+    }
+    // every group's factors must be ordered by problem and must not span two problems
+    std::vector<int> seg, gfirst;
+    auto add_group = [&](const std::vector<int>& start, int span, int first_id) -> bool {
+        const int n = (int)start.size();
+        for (int f = 0; f < n; ++f) {
+            if (f && B.sprob_h[(size_t)start[f]] < B.sprob_h[(size_t)start[f - 1]]) return false;
+            if (B.sprob_h[(size_t)start[f]] != B.sprob_h[(size_t)(start[f] + span - 1)]) return false;
+        }
+        int f = 0;
+        for (int q = 0; q < P; ++q) {
+            seg.push_back(f);
+            while (f < n && B.sprob_h[(size_t)start[f]] == q) ++f;
+        }
+        seg.push_back(n);
+        gfirst.push_back(first_id);
+        return true;
+    };
+    for (auto& g : p->gh)
+        if (!add_group(g.start, std::max(1, g.dim / d), g.first_id))
+            return fail(GVIB200_EINVAL, "set_batch: factors must be ordered by problem and stay inside one problem");
+    for (auto& g : p->lin)
+        if (!add_group(g.start, std::max(1, g.dim / d), g.first_id))
+            return fail(GVIB200_EINVAL, "set_batch: factors must be ordered by problem and stay inside one problem");
+    B.P = P;
+    B.G = (int)gfirst.size();
+    TRY(dev_upload(&B.d_sprob, B.sprob_h, p->stream));
+    TRY(dev_upload(&B.d_soff, B.soff, p->stream));
+    TRY(dev_upload(&B.d_seg, seg, p->stream));
+    TRY(dev_upload(&B.d_gfirst, gfirst, p->stream));
+    TRY(dev_alloc(&B.d_step, (size_t)P));
+    TRY(dev_alloc(&B.d_alpha_node, (size_t)S));
+    TRY(dev_alloc(&B.d_ldn[0], (size_t)S));
+    TRY(dev_alloc(&B.d_ldn[1], (size_t)S));
+    TRY(dev_alloc(&B.d_ldn_solve, (size_t)S));
+    TRY(dev_alloc(&B.d_pcost, (size_t)P));
+    CUDA_TRY(cudaMallocHost((void**)&B.h_pcost, (size_t)P * sizeof(double)));
+    CUDA_TRY(cudaMallocHost((void**)&B.h_step, (size_t)P * sizeof(double)));
+    B.cost_cur.assign((size_t)P, 0.0);
+    B.lowtemp.assign((size_t)P, p->is_lowtemp ? 1 : 0);
+    B.converged.assign((size_t)P, 0);
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// per-problem sums of buffer `which`'s factor costs + log det / 2 (or, fcost_on = false, of the log pivots in `ldn` alone)
+static int batch_costs(gvib200_problem* p, int which, const double* ldn, bool fcost_on, double* host_out) {
+    auto& B = p->batch;
+    LAUNCH(p, KC_SUM, k_problem_costs, cdiv((long long)B.P * 32, 128), 128, 0, B.P, B.G, B.d_seg, B.d_gfirst,
+           fcost_on ? p->fcost[which] : nullptr, B.d_soff, ldn, fcost_on ? 0.5 : 1.0, B.d_pcost);
+    CUDA_TRY(cudaMemcpyAsync(host_out, B.d_pcost, (size_t)B.P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return check_launch("k_problem_costs");
+}
+
+// temperature switch of the problems marked in `mask` (GVIGH::switch_to_high_temperature, one optimizer object each)
+static int batch_switch_high_T(gvib200_problem* p, const std::vector<char>& mask) {
+    auto& B = p->batch;
+    for (auto& g : p->gh) {
+        for (int f = 0; f < g.n; ++f)
+            if (mask[(size_t)B.sprob_h[(size_t)g.start[f]]]) g.T[f] = g.Thigh[f];
+        CUDA_TRY(cudaMemcpyAsync(g.d_T, g.T.data(), g.T.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    for (auto& g : p->lin) {
+        for (int f = 0; f < g.n; ++f)
+            if (mask[(size_t)B.sprob_h[(size_t)g.start[f]]]) g.T[f] = g.Thigh[f];
+        CUDA_TRY(cudaMemcpyAsync(g.d_T, g.T.data(), g.T.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    TRY(upload_klin(p));
+    p->sweep_valid = false;
+    p->asm_valid = false;
+    p->grads_valid = false;
+    B.cost_valid = false;
+    return 0;
+}
+
+extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opts_in, gvib200_iter_stats* st, int* n_trials) {
+    if (!p || !p->has_state) return fail(GVIB200_ESTATE, "batch_iterate: no state");
+    auto& B = p->batch;
+    if (B.P < 1) return fail(GVIB200_ESTATE, "batch_iterate: call gvib200_set_batch first");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    gvib200_opts o;
+    if (opts_in) o = *opts_in;
+    else gvib200_default_opts(&o);
+    if (o.ema_alpha != 1.0) return fail(GVIB200_EINVAL, "batch_iterate: ema_alpha != 1 is not available for batches");
+    TRY(resolve_pending(p));
+    const int P = B.P, S = p->S, d = p->d;
+    std::vector<gvib200_iter_stats> stats((size_t)P);
+    std::memset(stats.data(), 0, stats.size() * sizeof(gvib200_iter_stats));
+    p->ls = p->stream;
+    // temperature switch at iteration niters_lowtemp (GVI-GH-GBP-impl.h:49-58), for every problem still at low temperature
+    if (p->iter == o.niters_lowtemp) {
+        std::vector<char> mask((size_t)P, 0);
+        bool any = false;
+        for (int q = 0; q < P; ++q)
+            if (B.lowtemp[q] && !B.converged[q]) {
+                mask[q] = 1;
+                B.lowtemp[q] = 0;
+                stats[q].switched_high_T = 1;
+                any = true;
+            }
+        if (any) TRY(batch_switch_high_T(p, mask));
+    }
+    TRY(clear_flag(p));
+    // sweep at the current state (kept from the accepted trial when reuse_accepted_sweep), per-problem cost_iter
+    TRY(ensure_sweep(p, false));
+    if (!B.ldn_valid[p->cur]) {
+        ChainFuse f;
+        f.ldnode = B.d_ldn[p->cur];
+        TRY(do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[p->cur], p->CO[p->cur], p->scal + p->cur, 1, &f));
+        B.ldn_valid[p->cur] = true;
+        B.cost_valid = false;
+    }
+    if (!B.cost_valid) {
+        TRY(batch_costs(p, p->cur, B.d_ldn[p->cur], true, B.h_pcost));
+        for (int q = 0; q < P; ++q) B.cost_cur[q] = B.h_pcost[q];
+        B.cost_valid = true;
+    }
+    if (!p->asm_valid) {
+        TRY(dispatch_assemble(p, p->cur));
+        p->asm_valid = true;
+    }
+    // dmu = -Vddmu^-1 Vdmu for the whole batch; a problem whose Vddmu is not SPD is left where it is (status ENOTSPD)
+    {
+        ChainFuse f;
+        f.ldnode = B.d_ldn_solve;
+        TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &f));
+        p->grads_valid = true;
+        TRY(batch_costs(p, p->cur, B.d_ldn_solve, false, B.h_pcost));
+    }
+    enum { RUN = 0, ACCEPTED, PARK, DONE };  // PARK: through, but one more trial with step 0 makes its candidate the current state
+    std::vector<int> phase((size_t)P, RUN), cnt((size_t)P, 0);
+    std::vector<double> step((size_t)P, o.step_size_base);
+    for (int q = 0; q < P; ++q) {
+        stats[q].cost = B.cost_cur[q];
+        stats[q].new_cost = B.cost_cur[q];
+        if (B.converged[q]) {
+            stats[q].converged = 1;
+            phase[q] = PARK;
+        } else if (!std::isfinite(B.h_pcost[q])) {
+            stats[q].status = GVIB200_ENOTSPD;
+            phase[q] = PARK;
+        }
+    }
+    TRY(clear_flag(p));  // the batch-wide flags say nothing about a single problem: the log pivots do
+    const int w = 1 - p->cur, c = p->cur;
+    int trials = 0;
+    while (true) {
+        for (int q = 0; q < P; ++q) {
+            if (phase[q] == RUN) step[q] *= o.backtrack_ratio;
+            B.h_step[q] = (phase[q] == RUN || phase[q] == ACCEPTED) ? step[q] : 0.0;
+        }
+        CUDA_TRY(cudaMemcpyAsync(B.d_step, B.h_step, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        LAUNCH(p, KC_CANDIDATE, k_batch_alpha, cdiv(S, 256), 256, 0, S, B.d_sprob, B.d_step, B.d_alpha_node);
+        LAUNCH(p, KC_CANDIDATE, k_batch_candidate_mu, cdiv((long long)S * d, 256), 256, 0, (size_t)S * d, d, B.d_alpha_node,
+               p->mu[c], p->dmu, p->mu[w]);
+        ChainFuse fi;
+        fi.Dg2 = p->VD;
+        fi.Og2 = p->VO;
+        fi.alpha_node = B.d_alpha_node;
+        fi.Dout = p->LD[w];
+        fi.Oout = p->LO[w];
+        fi.ldnode = B.d_ldn[w];
+        TRY(do_selinv(p, p->LD[c], p->LO[c], p->CD[w], p->CO[w], p->scal + w, 1, &fi));
+        TRY(run_prologue_only(p, w));
+        TRY(run_sweep(p, w, false, true, false));
+        TRY(batch_costs(p, w, B.d_ldn[w], true, B.h_pcost));
+        TRY(clear_flag(p));
+        ++trials;
+        bool again = false;
+        for (int q = 0; q < P; ++q) {
+            if (phase[q] == PARK) {
+                phase[q] = DONE;  // this trial ran it with step 0
+            } else if (phase[q] == RUN) {
+                const double nc = B.h_pcost[q];
+                stats[q].new_cost = nc;
+                if (nc < B.cost_cur[q]) {  // NaN (candidate precision not SPD) compares false: a rejected trial
+                    phase[q] = ACCEPTED;
+                    stats[q].accepted = 1;
+                    stats[q].step = step[q];
+                    stats[q].n_backtrack = cnt[q];
+                } else {
+                    cnt[q]++;
+                    if (cnt[q] > o.max_backtrack) {  // GVI-GH-GBP-impl.h:104-119
+                        stats[q].n_backtrack = cnt[q];
+                        if (B.lowtemp[q]) stats[q].switched_high_T = 1;
+                        else stats[q].converged = 1;
+                        phase[q] = PARK;
+                        again = true;
+                    } else {
+                        again = true;
+                    }
+                }
+            }
+        }
+        if (!again) break;
+    }
+    // every problem's candidate is now what it takes into the next iteration: the batch flips as one
+    std::vector<char> mask((size_t)P, 0);
+    bool any_switch = false, all_conv = true;
+    for (int q = 0; q < P; ++q) {
+        if (stats[q].accepted) B.cost_cur[q] = stats[q].new_cost;
+        if (stats[q].switched_high_T && B.lowtemp[q] && !stats[q].accepted) {
+            mask[q] = 1;
+            B.lowtemp[q] = 0;
+            any_switch = true;
+        }
+        if (stats[q].converged) B.converged[q] = 1;
+        all_conv = all_conv && B.converged[q];
+    }
+    p->cur = w;
+    B.ldn_valid[w] = true;
+    p->sweep_valid = true;
+    p->asm_valid = false;
+    p->grads_valid = false;
+    p->zc_ok[0] = p->zc_ok[1] = false;
+    run_total(p, w);  // the batch total (gvib200_cost etc. read it)
+    if (any_switch) TRY(batch_switch_high_T(p, mask));
+    p->converged = all_conv;
+    p->iter++;
+    if (st) std::memcpy(st, stats.data(), stats.size() * sizeof(gvib200_iter_stats));
+    if (n_trials) *n_trials = trials;
+    return check_launch("batch_iterate");
+}
+
+extern "C" int gvib200_batch_costs(gvib200_problem* p, double* cost_per_problem) {
+    if (!p || !p->has_state || p->batch.P < 1 || !cost_per_problem) return fail(GVIB200_ESTATE, "batch_costs: no batch / no state");
+    auto& B = p->batch;
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    TRY(resolve_pending(p));
+    p->ls = p->stream;
+    TRY(ensure_sweep(p, false));
+    if (!B.ldn_valid[p->cur]) {
+        ChainFuse f;
+        f.ldnode = B.d_ldn[p->cur];
+        TRY(clear_flag(p));
+        TRY(do_selinv(p, p->LD[p->cur], p->LO[p->cur], p->CD[p->cur], p->CO[p->cur], p->scal + p->cur, 1, &f));
+        B.ldn_valid[p->cur] = true;
+        B.cost_valid = false;
+    }
+    if (!B.cost_valid) {
+        TRY(batch_costs(p, p->cur, B.d_ldn[p->cur], true, B.h_pcost));
+        for (int q = 0; q < B.P; ++q) B.cost_cur[q] = B.h_pcost[q];
+        B.cost_valid = true;
+    }
+    for (int q = 0; q < B.P; ++q) cost_per_problem[q] = B.cost_cur[q];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI: result recorder (helpers/DataRecorder.h, banded)
 // ------------------------------------------------------------------------------------------------
 extern "C" int gvib200_optimize_traced(gvib200_problem* p, const gvib200_opts* opts, int n_iters, int prox,
@@ -3025,6 +3337,8 @@ extern "C" int gvib200_snapshot_restore(gvib200_problem* p) {
     TRY(snapshot_copy(p, false));
     p->iter = p->snap_iter;
     p->converged = false;
+    p->batch.ldn_valid[0] = p->batch.ldn_valid[1] = false;
+    p->batch.cost_valid = false;
     p->sweep_valid = p->snap_sweep_valid;
     for (size_t i = 0; i < p->gh.size() && i < p->snap_sr_full.size(); ++i) p->gh[i].sr_full[p->cur] = p->snap_sr_full[i] != 0;
     p->asm_valid = false;

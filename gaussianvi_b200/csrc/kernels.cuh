@@ -1232,7 +1232,13 @@ __device__ __forceinline__ void cr_dev_tile_forward(const CrArgs<D>& a, int tile
     const int Tk = min(a.T, a.n - 1 - n0);
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
     __syncthreads();
-    const CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    CrView<D> v = cr_make_view<D>(smem, a.T + 1);
+    v.ldnode = a.ldnode;
+    v.ld_base = n0;
+    v.ld_mul = 1;
+    v.ld_nmax = (long long)a.n - 1;
+    v.ld_stride = a.ld_stride;
+    v.ld_max = a.ld_max;
     const int clk0 = RHS ? 0 : 32;
     cr_stamp(clk0);
     cr_tile_load<D, RHS>(a, v, gm, n0, threadIdx.x, blockDim.x);
@@ -1252,7 +1258,13 @@ __device__ __forceinline__ void cr_dev_top(const CrArgs<D>& a, double* smem, CrG
     const int nt = (a.K == 0) ? a.n : a.K + 1;  // nodes of the top chain
     if (threadIdx.x == 0) cr_make_geom(gm, nt - 1);
     __syncthreads();
-    const CrView<D> v = cr_make_view<D>(smem, nt);
+    CrView<D> v = cr_make_view<D>(smem, nt);
+    v.ldnode = a.ldnode;
+    v.ld_base = 0;
+    v.ld_mul = (a.K == 0) ? 1 : a.T;  // the top chain of a tiled level consists of its separators k T (the last one is n - 1)
+    v.ld_nmax = (long long)a.n - 1;
+    v.ld_stride = a.ld_stride;
+    v.ld_max = a.ld_max;
     // elimination records of the top stay in shared memory
     const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
     CrRec<D> rec;
@@ -1526,6 +1538,48 @@ __global__ void k_sum3(size_t n, const double* __restrict__ v, const double* __r
     if (threadIdx.x == 0) out[0] = sh[0] + a[0] + (b ? b[0] : 0.0);
 }
 // staging of the cost / flag exchange: buf = {cost, flag0, flag1, 0}; after the all-gather cost and flags are written back
+// ------------------------------------------------------------------------------------------
+// Batches of independent problems with a line search PER PROBLEM (gvib200_batch_iterate): the problems are concatenated
+// block-diagonally into one chain, problem q owns the states [soff[q], soff[q+1]).
+// ------------------------------------------------------------------------------------------
+// per-state step size from the per-problem one
+__global__ void k_batch_alpha(int S, const int* __restrict__ sprob, const double* __restrict__ step_p, double* __restrict__ alpha_node) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) alpha_node[i] = step_p[sprob[i]];
+}
+// candidate mean mu' = mu + alpha(state) dmu
+__global__ void k_batch_candidate_mu(size_t n, int d, const double* __restrict__ alpha_node, const double* __restrict__ mu,
+                                     const double* __restrict__ dmu, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = mu[i] + alpha_node[i / d] * dmu[i];
+}
+// One warp per problem: sum of the problem's factor costs (group by group, the factors of a problem are a contiguous range
+// [seg[g][q], seg[g][q+1]) of every group) + half the sum of its nodes' log pivots.  Lane l takes the elements l, l + 32, ...
+// of each range relative to the range's start and the lanes meet in a fixed xor tree, so the value depends on the problem
+// alone -- not on where in the batch it sits.  fcost == nullptr: the log-pivot sum only (not finite = some pivot was not
+// positive: that problem's matrix is not SPD).
+__global__ void k_problem_costs(int P, int G, const int* __restrict__ seg, const int* __restrict__ gfirst,
+                                const double* __restrict__ fcost, const int* __restrict__ soff, const double* __restrict__ ldnode,
+                                double half, double* __restrict__ out) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= P) return;
+    double s = 0.0;
+    if (fcost != nullptr)
+        for (int g = 0; g < G; ++g) {
+            const int lo = seg[(size_t)g * (P + 1) + q], hi = seg[(size_t)g * (P + 1) + q + 1];
+            const double* fc = fcost + gfirst[g];
+            for (int i = lo + lane; i < hi; i += 32) s += fc[i];
+        }
+    double l = 0.0;
+    if (ldnode != nullptr)
+        for (int i = soff[q] + lane; i < soff[q + 1]; i += 32) l += ldnode[i];
+    s = fma(half, l, s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[q] = s;
+}
+
 // gvib200_set_state_async: the not-SPD flags of its selected inverse go to mapped host memory (no copy-engine transfer: a
 // small device-to-host copy would queue behind another handle's bulk download on the shared copy engine)
 __global__ void k_flags_to_host(const int* flags, double* zc_slot) {

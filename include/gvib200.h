@@ -289,6 +289,23 @@ int gvib200_reset_schedule(gvib200_problem* prob);
    its high temperature now; the optimizer will not switch again by itself */
 int gvib200_switch_to_high_temperature(gvib200_problem* prob);
 
+/* ---- batches of INDEPENDENT problems with a line search per problem.  The reference runs one optimizer object per problem
+        (GVIGH::optimize, gvibase/GVI-GH-GBP-impl.h:33-130: cost_iter, back-tracking count and step size, temperature phase
+        and the converged flag belong to the object); here the problems are concatenated block-diagonally into ONE chain
+        (problem q owns the states [state_offsets[q], state_offsets[q+1]), no factor and no coupling block crosses a
+        boundary, every group's factors are ordered by problem) so that sweeps, assembly and chain passes run over the whole
+        batch in single launches, and gvib200_batch_iterate keeps what is per object per problem: its cost (factor costs +
+        log det / 2 of ITS precision block, from the per-node log pivots of the chain engine), its step size and
+        back-tracking count, its temperature phase, its converged flag.  One call = one iteration of every problem that has
+        not converged; stats[q] is problem q's iteration record (status GVIB200_ENOTSPD: that problem's Vddmu has no Cholesky
+        factor, its state is unchanged); n_trials = trial sweeps the batch needed (the largest T_ls over the problems, +1
+        when some problem exhausted its back-tracking).  gvib200_ngd_iterate on the same handle remains the joint line
+        search (one step size, the summed cost).  ema_alpha != 1, Prox-GVI and multi-GPU chains are not available here. */
+int gvib200_set_batch(gvib200_problem* prob, int n_problems, const int32_t* state_offsets /* [n_problems + 1] */);
+int gvib200_batch_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats /* [n_problems] */,
+                          int* n_trials);
+int gvib200_batch_costs(gvib200_problem* prob, double* cost_per_problem /* [n_problems] */);
+
 /* ---- device-side set-up of the LTV GP prior (gp/LTV_prior.h:123-197 compute_Phi_gsl / compute_Q_gsl with the piece-wise
         constant A_function / system_param of :187-197), batched over links: one launch integrates
         Phi' = A Phi, Q' = A Q + Q A^T + B B^T over [0, delta_t] for n_links links, A / B constant on each quarter interval.
