@@ -170,7 +170,9 @@ struct CrElim {
 // Forward elimination of node j = (2t+1) 2^l, phase A: pivot factor, column c of the record, column c of the Schur
 // update of the RIGHT neighbour (every right neighbour is updated by exactly one elimination of the level and phase A
 // only reads blocks of j and the coupling of i, so phase A is race free).
-template <int D, bool RHS>
+// BATCH (batches of independent problems, gvib200_batch_iterate): the node's own log det goes to v.ldnode and a factor
+// that failed is replaced by zeros; the default instantiation is the plain elimination.
+template <int D, bool RHS, bool BATCH = false>
 GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm, int l, int t, int c,
                      CrElim<D>& el, LogDetAcc& ld) {
     const int j = (2 * t + 1) << l;
@@ -189,25 +191,31 @@ GVI_HD bool cr_fwd_A(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, c
     cr_ld_col<D>(Pjc, v.P, v.NS, sj, c);
     cr_ld_row<D>(el.Pirow, v.P, v.NS, el.si, c);
     symmetrize<D>(Dt);
-    // the pivots count once per node: worker 0 merges the node's product into its running one (and, for batches of
-    // independent problems, stores the node's own log det)
-    LogDetAcc nd;
-    const bool ok = chol_factor<D>(L, rd, Dt, nd);
-    if (c == 0) {
-        ld.m *= nd.m;
-        ld.e += nd.e;
-        ld.normalize();
-        if (v.ldnode != nullptr) v.ldnode[cr_ld_index<D>(v, j)] = ok ? nd.value() : nan("");
-    }
-    if (v.ldnode != nullptr && !ok) {
-        // Batch of independent problems: a pivot that is not positive has filled the factor with NaN.  A NaN would not
-        // stay inside its problem -- the exactly-zero coupling blocks between two problems turn 0 * NaN into NaN on the
-        // other side -- so the factor is replaced by zeros: everything downstream of this node is finite garbage, the
-        // node's log det is NaN and its problem's cost with it.
+    bool ok;
+    if constexpr (BATCH) {
+        // the pivots count once per node: worker 0 merges the node's product into its running one and stores the node's own
+        // log det
+        LogDetAcc nd;
+        ok = chol_factor<D>(L, rd, Dt, nd);
+        if (c == 0) {
+            ld.m *= nd.m;
+            ld.e += nd.e;
+            ld.normalize();
+            if (v.ldnode != nullptr) v.ldnode[cr_ld_index<D>(v, j)] = ok ? nd.value() : nan("");
+        }
+        if (!ok) {
+            // A pivot that is not positive has filled the factor with NaN.  A NaN would not stay inside its problem -- the
+            // exactly-zero coupling blocks between two problems turn 0 * NaN into NaN on the other side -- so the factor is
+            // replaced by zeros: everything downstream of this node is finite garbage, the node's log det is NaN and its
+            // problem's cost with it.
 #pragma unroll
-        for (int e = 0; e < D * D; ++e) L.a[e] = 0.0;
+            for (int e = 0; e < D * D; ++e) L.a[e] = 0.0;
 #pragma unroll
-        for (int m = 0; m < D; ++m) rd[m] = 0.0;
+            for (int m = 0; m < D; ++m) rd[m] = 0.0;
+        }
+    } else {
+        LogDetAcc other;  // the pivots count once per node: worker 0 carries them
+        ok = chol_factor<D>(L, rd, Dt, c == 0 ? ld : other);
     }
 #pragma unroll
     for (int m = 0; m < D; ++m) ec.a[m] = (m == c) ? 1.0 : 0.0;
@@ -363,13 +371,13 @@ GVI_HD void cr_bwd_selinv_store(const CrView<D>& v, const CrSel<D>& o, int c) {
 
 // The system left after all levels: nodes 0 and T (slots 0, 1) coupled by P[slot 0]; T == 0: a single node.
 // Solves it in place: v.g <- x (RHS), v.Dn <- Sigma diagonal blocks and v.P[0] <- Sigma_{0,T} (SELINV).
-template <int D, bool RHS, bool SELINV>
+template <int D, bool RHS, bool SELINV, bool BATCH = false>
 GVI_HD bool cr_top2(const CrView<D>& v, int T, LogDetAcc& ld) {
     Mat<D> A0, A1, P, I0, S1, G, Tm;
     cr_ld<D>(A0, v.Dn, v.NS, 0);
     symmetrize<D>(A0);
     bool ok;
-    if (v.ldnode != nullptr) {
+    if (BATCH && v.ldnode != nullptr) {
         LogDetAcc nd;
         ok = spd_inverse<D>(I0, A0, nd);
         v.ldnode[cr_ld_index<D>(v, 0)] = ok ? nd.value() : nan("");
@@ -397,7 +405,7 @@ GVI_HD bool cr_top2(const CrView<D>& v, int T, LogDetAcc& ld) {
 #pragma unroll
     for (int e = 0; e < D * D; ++e) A1.a[e] -= Tm.a[e];
     symmetrize<D>(A1);
-    if (v.ldnode != nullptr) {
+    if (BATCH && v.ldnode != nullptr) {
         LogDetAcc nd;
         const bool ok1 = spd_inverse<D>(S1, A1, nd);  // Sigma_TT
         ok = ok1 && ok;
@@ -480,21 +488,21 @@ struct CrArgs {
     long long ld_stride, ld_max;
 };
 
-template <int D>
+template <int D, bool BATCH = false>
 GVI_HD double cr_sys_diag(const CrArgs<D>& a, size_t idx) {
     double v = a.Dg[idx];
     if (a.Dg2 != nullptr) {
-        const double al = a.alpha_node ? a.alpha_node[idx / (D * D)] : a.alpha;
+        const double al = (BATCH && a.alpha_node) ? a.alpha_node[idx / (D * D)] : a.alpha;
         v = v + al * (a.Dg2[idx] - v);
         a.Dout[idx] = v;
     }
     return v;
 }
-template <int D>
+template <int D, bool BATCH = false>
 GVI_HD double cr_sys_off(const CrArgs<D>& a, size_t idx) {
     double v = a.Og[idx];
     if (a.Og2 != nullptr) {
-        const double al = a.alpha_node ? a.alpha_node[idx / (D * D)] : a.alpha;
+        const double al = (BATCH && a.alpha_node) ? a.alpha_node[idx / (D * D)] : a.alpha;
         v = v + al * (a.Og2[idx] - v);
         a.Oout[idx] = v;
     }
@@ -528,7 +536,7 @@ GVI_HD CrView<D> cr_make_view(double* sm, int nodes) {
 // element.
 constexpr int CR_UNROLL = 8;
 
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int n0, int tid, int nthreads) {
     constexpr int DD = D * D;
     const int Tk = gm.T;
@@ -561,7 +569,7 @@ GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& g
                 const int node = idx / DD, e = idx - node * DD;
                 const int s = cr_slot(gm, node);
                 if (fused) {
-                    const double al = a.alpha_node ? a.alpha_node[n0 + node] : a.alpha;
+                    const double al = (BATCH && a.alpha_node) ? a.alpha_node[n0 + node] : a.alpha;
                     dv[u] = dv[u] + al * (d2[u] - dv[u]);
                     ov[u] = ov[u] + al * (o2[u] - ov[u]);
                     if (node != 0 && node != Tk) a.Dout[g0 + idx] = dv[u];
@@ -598,14 +606,14 @@ GVI_HD void cr_tile_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& g
 }
 
 // what the tile hands to the top: its contributions to the two separators and their coupling
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 GVI_HD void cr_tile_store_reduced(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int tile, int n0, int tid,
                                   int nthreads) {
     constexpr int DD = D * D;
     const bool last = (tile == a.K - 1);
     for (int e = tid; e < DD; e += nthreads) {
-        a.rDn[(size_t)tile * DD + e] = cr_sys_diag<D>(a, (size_t)n0 * DD + e);
-        if (last) a.rDn[(size_t)a.K * DD + e] = cr_sys_diag<D>(a, (size_t)(a.n - 1) * DD + e);
+        a.rDn[(size_t)tile * DD + e] = cr_sys_diag<D, BATCH>(a, (size_t)n0 * DD + e);
+        if (last) a.rDn[(size_t)a.K * DD + e] = cr_sys_diag<D, BATCH>(a, (size_t)(a.n - 1) * DD + e);
         a.rCL[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 0];
         a.rCR[(size_t)tile * DD + e] = v.Dn[(size_t)e * v.NS + 1];
         a.rO[(size_t)tile * DD + e] = v.P[(size_t)e * v.NS + 0];
@@ -621,7 +629,7 @@ GVI_HD void cr_tile_store_reduced(const CrArgs<D>& a, const CrView<D>& v, const 
 }
 
 // top: gather the separator system (or, K == 0, the chain itself) into the working arrays
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 GVI_HD void cr_top_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm, int tid, int nthreads) {
     constexpr int DD = D * D;
     const int nt = gm.T + 1;  // nodes of the top
@@ -630,8 +638,8 @@ GVI_HD void cr_top_load(const CrArgs<D>& a, const CrView<D>& v, const CrGeom& gm
         const int s = cr_slot(gm, node);
         double dv;
         if (a.K == 0) {
-            dv = cr_sys_diag<D>(a, (size_t)node * DD + e);
-            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = cr_sys_off<D>(a, (size_t)node * DD + e);
+            dv = cr_sys_diag<D, BATCH>(a, (size_t)node * DD + e);
+            if (node < nt - 1) v.P[(size_t)e * v.NS + s] = cr_sys_off<D, BATCH>(a, (size_t)node * DD + e);
         } else {
             dv = a.rDn[(size_t)node * DD + e];
             if (node < a.K) dv += a.rCL[(size_t)node * DD + e];

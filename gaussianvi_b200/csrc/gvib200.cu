@@ -614,10 +614,17 @@ static int chain_pass_3level(gvib200_problem* p, int slot, const CrArgs<D>& a, d
         mid.ld_stride = (long long)pl.T * a.ld_stride;
         mid.ld_max = a.ld_max;
     }
-    LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+    const bool batch = (a.ldnode != nullptr || a.alpha_node != nullptr);  // per-node log det / step sizes (gvib200_batch_iterate)
+    if (batch) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS, true>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+    else LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     LAUNCH(p, KC_OTHER, (k_cr_sum_level<D, RHS>), std::min(64, cdiv(pl.K + 1, 16)), 256, 0, a, buf + L.D1, buf + L.O1, buf + L.g1);
-    if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
-    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pm.top_smem_bytes, mid);
+    if (batch) {
+        if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS, true>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
+        LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV, true>), 1, CR_THREADS, pm.top_smem_bytes, mid);
+    } else {
+        if (pm.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
+        LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pm.top_smem_bytes, mid);
+    }
     if (pm.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pm.K, CR_THREADS, pm.tile_smem_bytes, mid);
     LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     if (d_logdet) {
@@ -658,12 +665,22 @@ static int chain_pass(gvib200_problem* p, int slot, const double* Dg, const doub
     }
     TRY(cr_allow_smem(p->ctx, k_cr_tile_forward<D, RHS>, p->ctx->smem_optin - 5120));
     TRY(cr_allow_smem(p->ctx, k_cr_top<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
+    const bool batch = (a.ldnode != nullptr || a.alpha_node != nullptr);  // per-node log det / step sizes (gvib200_batch_iterate)
+    if (batch) {
+        TRY(cr_allow_smem(p->ctx, k_cr_tile_forward<D, RHS, true>, p->ctx->smem_optin - 5120));
+        TRY(cr_allow_smem(p->ctx, k_cr_top<D, RHS, SELINV, true>, p->ctx->smem_optin - 5120));
+    }
     TRY(cr_allow_smem(p->ctx, k_cr_tile_backward<D, RHS, SELINV>, p->ctx->smem_optin - 5120));
     if (p->ctx->world > 1) return chain_pass_dist<D, RHS, SELINV>(p, slot, a, d_logdet);
     if (p->three_level) return chain_pass_3level<D, RHS, SELINV>(p, slot, a, d_logdet);
     a.ldout = d_logdet;  // the top kernel adds up the partial log determinants itself
-    if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
-    LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
+    if (batch) {
+        if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS, true>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+        LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV, true>), 1, CR_THREADS, pl.top_smem_bytes, a);
+    } else {
+        if (pl.K > 0) LAUNCH(p, KC_BT_FORWARD, (k_cr_tile_forward<D, RHS>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
+        LAUNCH(p, KC_BT_TOP, (k_cr_top<D, RHS, SELINV>), 1, CR_THREADS, pl.top_smem_bytes, a);
+    }
     if (pl.K > 0) LAUNCH(p, KC_BT_BACK, (k_cr_tile_backward<D, RHS, SELINV>), pl.K, p->tile_threads, pl.tile_smem_bytes, a);
     return check_launch("chain_pass");
 }

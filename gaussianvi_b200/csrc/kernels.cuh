@@ -1178,7 +1178,7 @@ __device__ __forceinline__ double cr_block_sum(double v, double* red) {
 }
 
 // D workers per node (bt_cr.h): thread tid works on node tid / D of the round as worker tid % D
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 __device__ __forceinline__ bool cr_forward_levels(const CrView<D>& v, const CrRec<D>& rec, size_t rec_base, const CrGeom& gm,
                                                   LogDetAcc& ld, int clk0 = 0) {
     bool ok = true;
@@ -1190,7 +1190,7 @@ __device__ __forceinline__ bool cr_forward_levels(const CrView<D>& v, const CrRe
             const int t = base + tn;
             const bool on = (tn < per_round) && (t < cnt);
             CrElim<D> el;
-            if (on) ok = cr_fwd_A<D, RHS>(v, rec, rec_base, gm, l, t, c, el, ld) && ok;
+            if (on) ok = cr_fwd_A<D, RHS, BATCH>(v, rec, rec_base, gm, l, t, c, el, ld) && ok;
             __syncthreads();
             if (on) cr_fwd_B<D, RHS>(v, el, c);
             __syncthreads();
@@ -1226,45 +1226,49 @@ __device__ __forceinline__ void cr_backward_levels(const CrView<D>& v, const CrR
 
 // The three kernel bodies as device functions over caller-provided shared memory (dynamic `smem`, geometry `gm`,
 // reduction scratch `red`), so that the multi-GPU pass can chain several of them inside one single-CTA launch.
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 __device__ __forceinline__ void cr_dev_tile_forward(const CrArgs<D>& a, int tile, double* smem, CrGeom& gm, double* red) {
     const int n0 = tile * a.T;
     const int Tk = min(a.T, a.n - 1 - n0);
     if (threadIdx.x == 0) cr_make_geom(gm, Tk);
     __syncthreads();
     CrView<D> v = cr_make_view<D>(smem, a.T + 1);
-    v.ldnode = a.ldnode;
-    v.ld_base = n0;
-    v.ld_mul = 1;
-    v.ld_nmax = (long long)a.n - 1;
-    v.ld_stride = a.ld_stride;
-    v.ld_max = a.ld_max;
+    if constexpr (BATCH) {
+        v.ldnode = a.ldnode;
+        v.ld_base = n0;
+        v.ld_mul = 1;
+        v.ld_nmax = (long long)a.n - 1;
+        v.ld_stride = a.ld_stride;
+        v.ld_max = a.ld_max;
+    }
     const int clk0 = RHS ? 0 : 32;
     cr_stamp(clk0);
-    cr_tile_load<D, RHS>(a, v, gm, n0, threadIdx.x, blockDim.x);
+    cr_tile_load<D, RHS, BATCH>(a, v, gm, n0, threadIdx.x, blockDim.x);
     __syncthreads();
     cr_stamp(clk0 + 1);
     LogDetAcc ld;
-    const bool ok = cr_forward_levels<D, RHS>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld, clk0);
-    cr_tile_store_reduced<D, RHS>(a, v, gm, tile, n0, threadIdx.x, blockDim.x);
+    const bool ok = cr_forward_levels<D, RHS, BATCH>(v, a.rec, (size_t)tile * (a.T - 1), gm, ld, clk0);
+    cr_tile_store_reduced<D, RHS, BATCH>(a, v, gm, tile, n0, threadIdx.x, blockDim.x);
     const double s = cr_block_sum(ld.value(), red);
     if (threadIdx.x == 0) a.ld[tile] = s;
     if (!ok) *a.notspd = 1;
     cr_stamp(clk0 + 20);
 }
 
-template <int D, bool RHS, bool SELINV>
+template <int D, bool RHS, bool SELINV, bool BATCH = false>
 __device__ __forceinline__ void cr_dev_top(const CrArgs<D>& a, double* smem, CrGeom& gm, double* red) {
     const int nt = (a.K == 0) ? a.n : a.K + 1;  // nodes of the top chain
     if (threadIdx.x == 0) cr_make_geom(gm, nt - 1);
     __syncthreads();
     CrView<D> v = cr_make_view<D>(smem, nt);
-    v.ldnode = a.ldnode;
-    v.ld_base = 0;
-    v.ld_mul = (a.K == 0) ? 1 : a.T;  // the top chain of a tiled level consists of its separators k T (the last one is n - 1)
-    v.ld_nmax = (long long)a.n - 1;
-    v.ld_stride = a.ld_stride;
-    v.ld_max = a.ld_max;
+    if constexpr (BATCH) {
+        v.ldnode = a.ldnode;
+        v.ld_base = 0;
+        v.ld_mul = (a.K == 0) ? 1 : a.T;  // the top chain of a tiled level consists of its separators k T (the last one is n - 1)
+        v.ld_nmax = (long long)a.n - 1;
+        v.ld_stride = a.ld_stride;
+        v.ld_max = a.ld_max;
+    }
     // elimination records of the top stay in shared memory
     const size_t nrec = nt > 2 ? (size_t)(nt - 2) : 0;
     CrRec<D> rec;
@@ -1272,11 +1276,11 @@ __device__ __forceinline__ void cr_dev_top(const CrArgs<D>& a, double* smem, CrG
     rec.H = rec.G + cr_rec_capacity(nrec, D * D);
     rec.Dinv = rec.H + cr_rec_capacity(nrec, D * D);
     rec.y = rec.Dinv + cr_rec_capacity(nrec, D * D);
-    cr_top_load<D, RHS>(a, v, gm, threadIdx.x, blockDim.x);
+    cr_top_load<D, RHS, BATCH>(a, v, gm, threadIdx.x, blockDim.x);
     __syncthreads();
     LogDetAcc ld;
-    bool ok = cr_forward_levels<D, RHS>(v, rec, 0, gm, ld);
-    if (threadIdx.x == 0) ok = cr_top2<D, RHS, SELINV>(v, gm.T, ld) && ok;
+    bool ok = cr_forward_levels<D, RHS, BATCH>(v, rec, 0, gm, ld);
+    if (threadIdx.x == 0) ok = cr_top2<D, RHS, SELINV, BATCH>(v, gm.T, ld) && ok;
     __syncthreads();
     cr_backward_levels<D, RHS, SELINV>(v, rec, 0, gm);
     if (a.K == 0)
@@ -1314,20 +1318,20 @@ __device__ __forceinline__ void cr_dev_tile_backward(const CrArgs<D>& a, int til
     cr_stamp(clk0 + 20);
 }
 
-template <int D, bool RHS>
+template <int D, bool RHS, bool BATCH = false>
 __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_tile_forward(const CrArgs<D> a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ CrGeom gm;
     __shared__ double red[CR_THREADS];
-    cr_dev_tile_forward<D, RHS>(a, blockIdx.x, smem, gm, red);
+    cr_dev_tile_forward<D, RHS, BATCH>(a, blockIdx.x, smem, gm, red);
 }
 
-template <int D, bool RHS, bool SELINV>
+template <int D, bool RHS, bool SELINV, bool BATCH = false>
 __global__ void __launch_bounds__(CR_THREADS, 1) k_cr_top(const CrArgs<D> a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ CrGeom gm;
     __shared__ double red[CR_THREADS];
-    cr_dev_top<D, RHS, SELINV>(a, smem, gm, red);
+    cr_dev_top<D, RHS, SELINV, BATCH>(a, smem, gm, red);
 }
 
 template <int D, bool RHS, bool SELINV>
