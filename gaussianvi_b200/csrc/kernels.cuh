@@ -913,7 +913,8 @@ __global__ void __launch_bounds__(128) k_assemble_ell_fast(int S, const int* __r
         id[k] = __ldg(ed + (size_t)k * S + s);
         il[k] = __ldg(edl + (size_t)k * S + s);
     }
-    const bool has_off = (s < S - 1);
+    // VO == nullptr: no factor contributes an off-diagonal block and the caller reads the constant KlinO in place of VO
+    const bool has_off = (s < S - 1) && (VO != nullptr);
     double2 m[D / 2], o[D / 2];
 #pragma unroll
     for (int i = 0; i < D / 2; ++i) {
