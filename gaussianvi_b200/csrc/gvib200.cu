@@ -1141,10 +1141,10 @@ static LinearArgs linear_args(gvib200_problem* p, const LinGroup& g, const Sweep
     return a;
 }
 
-// parts: 1 = covariance part, 2 = mean part, 3 = both (one after the other)
+// parts: 1 = covariance part, 2 = mean part, 3 = both (one launch per group, same arithmetic)
 static int run_linear(gvib200_problem* p, const SweepTarget& t, bool full, int parts = 3) {
-  for (int part = 1; part <= 2; ++part) {
-    if (!(parts & part)) continue;
+  for (int part = 1; part <= 3; ++part) {
+    if (parts == 3 ? part != 3 : !(parts & part) || part == 3) continue;
     for (auto& g : p->lin) {
         LinearArgs a;
         a.part = part;
@@ -2534,11 +2534,15 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             // rejected, twice: starting it next to the backward half of the solve pass -- on a third stream, or on the main
             // stream right behind the selected inverse -- makes the quadrature kernel a little faster and the iteration
             // 0.402 -> 0.43 ms.)
+            // (Also measured and rejected here: both halves in ONE pass per group right behind the solve pass -- the linear
+            // factors' launches take half the time, 0.124 -> 0.064 ms per iteration, and the iteration 0.399 -> 0.406 ms.
+            // GVIB200_LINEAR_ONEPASS switches it on; every other caller of run_linear uses the one-pass form.)
+            static const bool lin_split_env = getenv("GVIB200_LINEAR_ONEPASS") == nullptr;
             CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_pro, 0));
             p->ls = p->stream2;
             {
                 SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
-                rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 1);
+                rc = run_linear(p, t, o.reuse_accepted_sweep != 0, lin_split_env ? 1 : 3);
             }
             p->ls = p->stream;
             if (rc != 0) return rc;
@@ -2556,11 +2560,14 @@ extern "C" int gvib200_ngd_iterate(gvib200_problem* p, const gvib200_opts* opts_
             // mean part of the linear factors: as soon as the dmu solve (same stream) has delivered the candidate mean;
             // it ends up underneath the moment kernel.  (Measured: neither holding it back behind the culling pass nor a
             // lowest-priority stream that only fills the moment kernel's last partial wave is any faster.)
-            p->ls = p->stream2;
-            SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
-            const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 2);
-            p->ls = p->stream;
-            if (rc != 0) return rc;
+            static const bool lin_split_env2 = getenv("GVIB200_LINEAR_ONEPASS") == nullptr;
+            if (lin_split_env2) {
+                p->ls = p->stream2;
+                SweepTarget t{p->mu[w], p->CD[w], p->CO[w], w};
+                const int rc = run_linear(p, t, o.reuse_accepted_sweep != 0, 2);
+                p->ls = p->stream;
+                if (rc != 0) return rc;
+            }
             CUDA_TRY(cudaEventRecord(p->ev_join, p->stream2));
             CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         }

@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
     const size_t n = (size_t)a.n;
     const int s = a.start[f];
     const double c_over_t = a.C[f] / a.T[f];
-    if (a.part == 1) {
+    double cov_part = 0.0;  // part 3: both halves in one pass, the covariance part stays in a register (same arithmetic:
+                            // the mean part is added to the ROUNDED product tr * c_over_t either way)
+    if (a.part == 1 || a.part == 3) {
         // tr(A Sigma_k) = sum_i A_ii S_ii + 2 sum_{i<j} A_ij S_ij, Sigma_k assembled from the covariance blocks
         const double* A = a.A + f;
         double tr = 0.0;
@@ -640,8 +642,11 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
                     tr = fma(i == j ? av : 2.0 * av, sij, tr);
                     ++e;
                 }
-        a.fcost[f] = tr * c_over_t;
-        return;
+        cov_part = tr * c_over_t;
+        if (a.part == 1) {
+            a.fcost[f] = cov_part;
+            return;
+        }
     }
     const double* L = a.Lambda + f;
     const double* Ki = a.Kinv + f;
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(128) k_linear(const LinearArgs a) {
                 a.fVdmu[(size_t)f * dim + k] = 2.0 * v * c_over_t;
             }
     }
-    a.fcost[f] = fma(q, c_over_t, a.fcost[f]);
+    a.fcost[f] = fma(q, c_over_t, a.part == 3 ? cov_part : a.fcost[f]);
 }
 
 // ------------------------------------------------------------------------------------------
