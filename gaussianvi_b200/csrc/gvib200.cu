@@ -3111,6 +3111,19 @@ extern "C" int gvib200_trace_save(const gvib200_trace* tr, int S, int d, int n_f
 // ------------------------------------------------------------------------------------------------
 template <int DIM>
 static void launch_prox_gh(gvib200_problem* p, const GhGroup& g, double eta, int which) {
+    if constexpr (DIM > 4) {  // one warp per factor, matrices in shared memory
+        static const bool thread_env = getenv("GVIB200_PROX_THREAD") != nullptr;  // development switch
+        if (!thread_env) {
+            constexpr int WD = 5 * DIM * DIM + 4 * ((DIM + 1) / 2) + DIM + 1;
+            constexpr int GPB = 256 / JG;
+            const size_t smem = (size_t)GPB * WD * sizeof(double);
+            if (p->ctx->need_config(reinterpret_cast<const void*>(k_prox_gh_warp<DIM>)))
+                cudaFuncSetAttribute(k_prox_gh_warp<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            LAUNCH(p, KC_OTHER, (k_prox_gh_warp<DIM>), cdiv(g.n, GPB), 256, smem, g.n, eta, g.d_raw, g.d_SR[which],
+                   p->fcost[which] + g.first_id, p->fVdmu[which] + g.voff, p->fVdd[which] + g.moff);
+            return;
+        }
+    }
     LAUNCH(p, KC_OTHER, (k_prox_gh<DIM>), cdiv(g.n, 64), 64, 0, g.n, eta, g.d_raw, g.d_SR[which],
            p->fcost[which] + g.first_id, p->fVdmu[which] + g.voff, p->fVdd[which] + g.moff);
 }

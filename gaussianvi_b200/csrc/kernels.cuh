@@ -728,6 +728,96 @@ __global__ void __launch_bounds__(64) k_prox_gh(int n, double eta, const double*
     fcost[f] = e0;
 }
 
+// The same epilogue for factor dimensions above 4 with one WARP per factor (the thread-per-factor form keeps eight 12 x 12
+// matrices per thread in local memory: 0.66 ms per launch at 10^4 dim-12 factors): the matrices live in shared memory,
+// the lanes split the entries of every product, the eigen-decomposition of H is the warp-parallel Jacobi of the prologue
+// (group_jacobi_eig).  Same formulas, the products in the same k order.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_prox_gh_warp(int n, double eta, const double* __restrict__ raw, const double* __restrict__ SR,
+                                                      double* __restrict__ fcost, double* __restrict__ fVdmu,
+                                                      double* __restrict__ fVdd) {
+    constexpr int DD = DIM * DIM;
+    constexpr int NOUT = 1 + DIM + DD;
+    constexpr int WD = 5 * DD + 4 * ((DIM + 1) / 2) + DIM + 1;  // odd stride
+    constexpr int GPB = 256 / JG;
+    extern __shared__ __align__(16) double sm[];
+    const int gl = threadIdx.x & (JG - 1), grp = threadIdx.x / JG;
+    const int fraw = blockIdx.x * GPB + grp;
+    const int f = fraw < n ? fraw : n - 1;  // tail groups recompute the last factor and do not store
+    double* S = sm + (size_t)grp * WD;
+    double* R = S + DD;
+    double* W1 = R + DD;
+    double* W2 = W1 + DD;
+    double* W3 = W2 + DD;
+    double* rot = W3 + DD;
+    double* lam = rot + 4 * ((DIM + 1) / 2);
+    const double* r = raw + (size_t)f * NOUT;
+    const double e0 = r[0];
+    for (int e = gl; e < DD; e += JG) {
+        S[e] = SR[(size_t)f * 2 * DD + e];
+        R[e] = SR[(size_t)f * 2 * DD + DD + e];
+        W1[e] = r[1 + DIM + e] - ((e % DIM) == (e / DIM) ? e0 : 0.0);  // E = e2 - e0 I
+    }
+    __syncwarp();
+    auto mul = [&](double* C, const double* A, const double* B, bool bt) {  // C = A B (bt: A B^T), lanes split the entries
+        for (int e = gl; e < DD; e += JG) {
+            const int i = e % DIM, j = e / DIM;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) v = fma(A[i + k * DIM], bt ? B[j + k * DIM] : B[k + j * DIM], v);
+            C[e] = v;
+        }
+        __syncwarp();
+    };
+    auto sym = [&](double* A) {
+        for (int e = gl; e < DD; e += JG) {
+            const int i = e % DIM, j = e / DIM;
+            if (i > j) {
+                const double v = 0.5 * (A[i + j * DIM] + A[j + i * DIM]);
+                A[i + j * DIM] = v;
+                A[j + i * DIM] = v;
+            }
+        }
+        __syncwarp();
+    };
+    mul(W2, R, W1, false);   // R E
+    mul(W3, W2, R, false);   // S_k = R E R
+    sym(W3);
+    for (int e = gl; e < DD; e += JG) W2[e] = ((e % DIM) == (e / DIM) ? 1.0 : 0.0) - eta * W3[e];  // M = I - eta S_k
+    __syncwarp();
+    mul(W1, S, S, false);    // Sigma = S S
+    mul(W3, W2, W1, false);  // T = M Sigma
+    mul(W1, W3, W2, true);   // H = T M^T
+    sym(W1);
+    group_jacobi_eig<DIM>(W1, W3, rot, gl);  // eigenvalues on the diagonal of W1, eigenvectors in W3
+    for (int k = gl; k < DIM; k += JG) {
+        const double l = W1[k + k * DIM];
+        const double disc = fma(l, l, 4.0 * eta * l);
+        lam[k] = 1.0 / (0.5 * l + eta + 0.5 * sqrt(disc > 0.0 ? disc : 0.0));
+    }
+    __syncwarp();
+    if (fraw >= n) return;
+    for (int e = gl; e < DD; e += JG) {
+        const int i0 = e % DIM, j0 = e / DIM;
+        const int i = i0 > j0 ? i0 : j0, j = i0 > j0 ? j0 : i0;  // one arithmetic for (i, j) and (j, i)
+        double v = 0.0, pij = 0.0, pji = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            v = fma(W3[i + k * DIM] * W3[j + k * DIM], lam[k], v);
+            pij = fma(R[i + k * DIM], R[k + j * DIM], pij);  // P = R R
+            pji = fma(R[j + k * DIM], R[k + i * DIM], pji);
+        }
+        fVdd[(size_t)f * DD + e] = (v - 0.5 * (pij + pji)) / eta;
+    }
+    for (int i = gl; i < DIM; i += JG) {
+        double b = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) b = fma(R[i + k * DIM], r[1 + k], b);
+        fVdmu[(size_t)f * DIM + i] = -b;
+    }
+    if (gl == 0) fcost[f] = e0;
+}
+
 template <int DIM, int M, int SD>
 __global__ void __launch_bounds__(64) k_prox_linear(const LinearArgs a, double eta, double* __restrict__ fVdd) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
