@@ -382,6 +382,7 @@ struct gvib200_problem {
         int *d_sprob = nullptr, *d_soff = nullptr, *d_seg = nullptr, *d_gfirst = nullptr;
         double *d_step = nullptr, *d_alpha_node = nullptr, *d_ldn[2] = {nullptr, nullptr}, *d_ldn_solve = nullptr, *d_pcost = nullptr;
         double* h_pcost = nullptr;             // pinned [P]
+        double *d_pcost2 = nullptr, *h_pcost2 = nullptr;  // per-problem log-pivot sums of the solve pass (SPD check of Vddmu)
         double* h_step = nullptr;              // pinned [P]
         bool ldn_valid[2] = {false, false};    // d_ldn[b] holds the log pivots of buffer b's precision
         bool cost_valid = false;               // cost_cur is the per-problem cost at the current state
@@ -2730,8 +2731,9 @@ static void free_batch(gvib200_problem* p) {
         if (q) cudaFree(q);
     };
     F(B.d_sprob); F(B.d_soff); F(B.d_seg); F(B.d_gfirst); F(B.d_step); F(B.d_alpha_node); F(B.d_ldn[0]); F(B.d_ldn[1]);
-    F(B.d_ldn_solve); F(B.d_pcost);
+    F(B.d_ldn_solve); F(B.d_pcost); F(B.d_pcost2);
     if (B.h_pcost) cudaFreeHost(B.h_pcost);
+    if (B.h_pcost2) cudaFreeHost(B.h_pcost2);
     if (B.h_step) cudaFreeHost(B.h_step);
     B = gvib200_problem::Batch();
 }
@@ -2787,7 +2789,9 @@ extern "C" int gvib200_set_batch(gvib200_problem* p, int n_problems, const int32
     TRY(dev_alloc(&B.d_ldn[1], (size_t)S));
     TRY(dev_alloc(&B.d_ldn_solve, (size_t)S));
     TRY(dev_alloc(&B.d_pcost, (size_t)P));
+    TRY(dev_alloc(&B.d_pcost2, (size_t)P));
     CUDA_TRY(cudaMallocHost((void**)&B.h_pcost, (size_t)P * sizeof(double)));
+    CUDA_TRY(cudaMallocHost((void**)&B.h_pcost2, (size_t)P * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void**)&B.h_step, (size_t)P * sizeof(double)));
     B.cost_cur.assign((size_t)P, 0.0);
     B.lowtemp.assign((size_t)P, p->is_lowtemp ? 1 : 0);
@@ -2873,13 +2877,25 @@ extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opt
         TRY(dispatch_assemble(p, p->cur));
         p->asm_valid = true;
     }
-    // dmu = -Vddmu^-1 Vdmu for the whole batch; a problem whose Vddmu is not SPD is left where it is (status ENOTSPD)
+    // dmu = -Vddmu^-1 Vdmu for the whole batch on the side stream, next to the first trial's selected inverse (whose candidate
+    // precision does not depend on dmu); the per-problem sums of its log pivots (not finite = that problem's Vddmu is not
+    // SPD) are read together with the first trial's costs: one host round trip per trial
+    TRY(clear_flag(p));  // the batch-wide flags say nothing about a single problem: the log pivots do
+    CUDA_TRY(cudaEventRecord(p->ev_fork, p->stream));
+    CUDA_TRY(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
+    p->ls = p->stream2;
     {
         ChainFuse f;
         f.ldnode = B.d_ldn_solve;
-        TRY(do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &f));
+        const int rc = do_solve(p, p->VD, p->VO, p->rhs, p->dmu, nullptr, 0, &f);
+        if (rc == 0)
+            LAUNCH(p, KC_SUM, k_problem_costs, cdiv((long long)P * 32, 128), 128, 0, P, B.G, B.d_seg, B.d_gfirst, (const double*)nullptr,
+                   B.d_soff, B.d_ldn_solve, 1.0, B.d_pcost2);
+        p->ls = p->stream;
+        if (rc != 0) return rc;
+        CUDA_TRY(cudaMemcpyAsync(B.h_pcost2, B.d_pcost2, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, p->stream2));
+        CUDA_TRY(cudaEventRecord(p->ev_mu, p->stream2));
         p->grads_valid = true;
-        TRY(batch_costs(p, p->cur, B.d_ldn_solve, false, B.h_pcost));
     }
     enum { RUN = 0, ACCEPTED, PARK, DONE };  // PARK: through, but one more trial with step 0 makes its candidate the current state
     std::vector<int> phase((size_t)P, RUN), cnt((size_t)P, 0);
@@ -2890,12 +2906,8 @@ extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opt
         if (B.converged[q]) {
             stats[q].converged = 1;
             phase[q] = PARK;
-        } else if (!std::isfinite(B.h_pcost[q])) {
-            stats[q].status = GVIB200_ENOTSPD;
-            phase[q] = PARK;
         }
     }
-    TRY(clear_flag(p));  // the batch-wide flags say nothing about a single problem: the log pivots do
     const int w = 1 - p->cur, c = p->cur;
     int trials = 0;
     while (true) {
@@ -2905,8 +2917,6 @@ extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opt
         }
         CUDA_TRY(cudaMemcpyAsync(B.d_step, B.h_step, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         LAUNCH(p, KC_CANDIDATE, k_batch_alpha, cdiv(S, 256), 256, 0, S, B.d_sprob, B.d_step, B.d_alpha_node);
-        LAUNCH(p, KC_CANDIDATE, k_batch_candidate_mu, cdiv((long long)S * d, 256), 256, 0, (size_t)S * d, d, B.d_alpha_node,
-               p->mu[c], p->dmu, p->mu[w]);
         ChainFuse fi;
         fi.Dg2 = p->VD;
         fi.Og2 = p->VO;
@@ -2916,12 +2926,23 @@ extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opt
         fi.ldnode = B.d_ldn[w];
         TRY(do_selinv(p, p->LD[c], p->LO[c], p->CD[w], p->CO[w], p->scal + w, 1, &fi));
         TRY(run_prologue_only(p, w));
+        if (trials == 0) CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_mu, 0));  // dmu (and the solve's log pivots on the host)
+        LAUNCH(p, KC_CANDIDATE, k_batch_candidate_mu, cdiv((long long)S * d, 256), 256, 0, (size_t)S * d, d, B.d_alpha_node,
+               p->mu[c], p->dmu, p->mu[w]);
         TRY(run_sweep(p, w, false, true, false));
         TRY(batch_costs(p, w, B.d_ldn[w], true, B.h_pcost));
         TRY(clear_flag(p));
         ++trials;
         bool again = false;
         for (int q = 0; q < P; ++q) {
+            if (trials == 1 && phase[q] == RUN && !std::isfinite(B.h_pcost2[q])) {
+                // this problem's Vddmu has no Cholesky factor: its step is not taken (whatever the trial produced from the
+                // garbage of its solve is discarded); one more trial with step 0 parks it at its current state
+                stats[q].status = GVIB200_ENOTSPD;
+                phase[q] = PARK;
+                again = true;
+                continue;
+            }
             if (phase[q] == PARK) {
                 phase[q] = DONE;  // this trial ran it with step 0
             } else if (phase[q] == RUN) {
