@@ -177,3 +177,41 @@ def test_per_problem_costs_on_tiled_and_three_level_chains(gpu_ctx, n_problems):
         assert rel(cD[a:b], c1) < 1e-11, q
     assert abs(pb.batch_costs().sum() - sum(s.new_cost for s in stats)) < 1e-12 * abs(sum(s.new_cost for s in stats))
     pb.close()
+
+
+def test_problem_with_indefinite_vddmu_is_reported_alone(gpu_ctx):
+    """One problem of the batch has a Vddmu without a Cholesky factor (sigma = 15.5 on a path through the obstacles, as in
+    test_gpu_branches.test_indefinite_vddmu_...): ITS status is GVIB200_ENOTSPD and its state stays where it is, every
+    iteration; its neighbours -- across whose boundary the garbage of its solve must not leak -- follow their own oracle."""
+    kws = [dict(N=25, sigma=15.5, clearance=1.2, seed=4), dict(N=30, sigma=15.5, clearance=None),
+           dict(N=35, sigma=15.5, clearance=1.5, seed=5)]
+    subs = [problems.make_cfg3(**kw) for kw in kws]
+    niters = 3
+    refs = {}
+    for q in (0, 2):
+        r = ob.build_oracle(subs[q], niters=niters)
+        refs[q] = (r, r.optimize())
+        assert all(x.accepted for x in refs[q][1])
+    spec, off = concat(subs)
+    p = problems.build_device_problem(gpu_ctx, spec)
+    p.set_batch(off)
+    opts = capi.Problem.default_opts()
+    opts.reuse_accepted_sweep = 1
+    mu0, cov0 = p.mean(), p.covariance()[0]
+    for it in range(niters):
+        stats, _ = p.batch_iterate(opts)
+        assert stats[1].status == capi.E_NOTSPD and not stats[1].accepted
+        for q in (0, 2):
+            r = refs[q][1][it]
+            assert stats[q].status == 0 and stats[q].accepted and stats[q].n_backtrack == r.n_backtrack
+            assert abs(stats[q].cost - r.cost) < 1e-9 * abs(r.cost), (q, it)
+    mu, cD = p.mean(), p.covariance()[0]
+    d = spec.d
+    a, b = off[1], off[2]
+    assert np.array_equal(mu[a * d:b * d], mu0[a * d:b * d])
+    assert rel(cD[a:b], cov0[a:b]) < 1e-13   # recomputed from the same precision, not copied
+    for q in (0, 2):
+        a, b = off[q], off[q + 1]
+        assert rel(mu[a * d:b * d], refs[q][0].mean()) < 1e-7, q
+        assert rel(cD[a:b], refs[q][0].cov.D) < 1e-7, q
+    p.close()
