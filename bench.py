@@ -563,7 +563,7 @@ def run_gpu(args, rank, world, local_rank):
                          "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": K1_DRAM_BYTES_NCU,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_moments_sym per launch, ncu --set full "
-                                           "capture profiles/r2_k1s_ncu.txt -- a static figure of that capture, not measured in this run (bytes; the kernel is FP64 bound, not HBM bound)",
+                                           "capture profiles/r2_k1s_ncu.txt (14.23 MB; the capture of the final code, profiles/r2_final_iteration_ncu.txt, shows the same) -- a static figure, not measured in this run (bytes; the kernel is FP64 bound, not HBM bound)",
                          "peak_source": "DFMA micro-benchmark run in this process (gvib200_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure",
                          "algorithmic_flops_per_launch": pts_launch * FLOPS_FULL, "avg_launch_ms": k1_ms, "launches": k1[0],
