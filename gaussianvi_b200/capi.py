@@ -43,7 +43,7 @@ EXPORTS = [
     "gvib200_optimize_traced", "gvib200_csv_write", "gvib200_trace_save", "gvib200_set_sdf3d",
     "gvib200_evaluated_factors", "gvib200_ltv_transition", "gvib200_switch_to_high_temperature", "gvib200_ctx_mailbox_create", "gvib200_ctx_mailbox_connect",
     "gvib200_set_state_async", "gvib200_get_mean_async", "gvib200_get_prec_blocks_async", "gvib200_get_cov_blocks_async",
-    "gvib200_sync", "gvib200_set_batch", "gvib200_batch_iterate", "gvib200_batch_costs",
+    "gvib200_sync", "gvib200_set_batch", "gvib200_batch_iterate", "gvib200_batch_costs", "gvib200_batch_optimize",
 ]
 
 
@@ -513,6 +513,13 @@ class Problem:
         nt = C.c_int()
         _check(self.lib.gvib200_batch_iterate(self.h, C.byref(opts) if opts is not None else None, stats, C.byref(nt)))
         return [stats[i] for i in range(self._n_batch)], nt.value
+
+    def batch_optimize(self, n_iters: int, opts: Optional[Opts] = None):
+        """Up to n_iters lock-step iterations of every problem; returns a list (per iteration) of per-problem IterStats lists."""
+        stats = (IterStats * (n_iters * self._n_batch))()
+        done = C.c_int()
+        _check(self.lib.gvib200_batch_optimize(self.h, C.byref(opts) if opts is not None else None, n_iters, stats, C.byref(done)))
+        return [[stats[it * self._n_batch + q] for q in range(self._n_batch)] for it in range(done.value)]
 
     def batch_costs(self) -> np.ndarray:
         out = np.zeros(self._n_batch)

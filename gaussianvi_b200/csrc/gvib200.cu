@@ -2997,6 +2997,25 @@ extern "C" int gvib200_batch_iterate(gvib200_problem* p, const gvib200_opts* opt
     return check_launch("batch_iterate");
 }
 
+// GVIGH::optimize of every problem of the batch: up to n_iters iterations (all problems iterate in lock step; a problem that
+// has converged stays where it is), stats[it * n_problems + q] = problem q's record of iteration it
+extern "C" int gvib200_batch_optimize(gvib200_problem* p, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats,
+                                      int* n_done) {
+    if (!p || !p->has_state || p->batch.P < 1) return fail(GVIB200_ESTATE, "batch_optimize: no batch / no state");
+    int done = 0;
+    for (int it = 0; it < n_iters; ++it) {
+        if (p->converged) break;
+        const int rc = gvib200_batch_iterate(p, opts, stats ? stats + (size_t)it * p->batch.P : nullptr, nullptr);
+        if (rc != 0) {
+            if (n_done) *n_done = done;
+            return rc;
+        }
+        done++;
+    }
+    if (n_done) *n_done = done;
+    return 0;
+}
+
 extern "C" int gvib200_batch_costs(gvib200_problem* p, double* cost_per_problem) {
     if (!p || !p->has_state || p->batch.P < 1 || !cost_per_problem) return fail(GVIB200_ESTATE, "batch_costs: no batch / no state");
     auto& B = p->batch;

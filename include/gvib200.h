@@ -304,6 +304,9 @@ int gvib200_switch_to_high_temperature(gvib200_problem* prob);
 int gvib200_set_batch(gvib200_problem* prob, int n_problems, const int32_t* state_offsets /* [n_problems + 1] */);
 int gvib200_batch_iterate(gvib200_problem* prob, const gvib200_opts* opts, gvib200_iter_stats* stats /* [n_problems] */,
                           int* n_trials);
+/* GVIGH::optimize (gvibase/GVI-GH-GBP-impl.h:33-130) of every problem: up to n_iters lock-step iterations, stops when every
+   problem has converged; stats[it * n_problems + q] is problem q's record of iteration it, *n_done the iterations run */
+int gvib200_batch_optimize(gvib200_problem* prob, const gvib200_opts* opts, int n_iters, gvib200_iter_stats* stats, int* n_done);
 int gvib200_batch_costs(gvib200_problem* prob, double* cost_per_problem /* [n_problems] */);
 
 /* ---- device-side set-up of the LTV GP prior (gp/LTV_prior.h:123-197 compute_Phi_gsl / compute_Q_gsl with the piece-wise
