@@ -3581,7 +3581,7 @@ extern "C" int gvib200_problem_info(gvib200_problem* p, gvib200_info* out) {
         out->sigma_points_per_sweep += (long long)g.n * g.table->n;
     }
     for (auto& g : p->lin) out->n_linear_factors += g.n;
-    out->chain_levels = p->plan.K > 0 ? 2 : 1;
+    out->chain_levels = p->three_level ? 3 : (p->plan.K > 0 ? 2 : 1);
     out->chain_tiles = p->plan.K;
     out->chain_tile_links = p->plan.T;
     return 0;

@@ -145,11 +145,11 @@ def test_agreeing_batch_equals_joint_line_search(gpu_ctx):
     pb.close()
 
 
-@pytest.mark.parametrize("n_problems", [8, 120])
+@pytest.mark.parametrize("n_problems", [8, 300])
 def test_per_problem_costs_on_tiled_and_three_level_chains(gpu_ctx, n_problems):
     """The per-node log pivots come out of every level of the chain engine (tiles, the separator chain's own tiles on a
     three-level plan, the top): per-problem costs of a long batch equal the costs of the same problems run one by one,
-    and two per-problem iterations reproduce the single-problem iterates (8 x 1002 states: tiled; 120 x 1002: three levels)."""
+    and two per-problem iterations reproduce the single-problem iterates (8 x 1002 states: tiled; 300 x 1002: three levels)."""
     N = 1000
     spec = problems.make_cfg5(n_problems=n_problems, N=N, ctx=gpu_ctx)
     Sb = spec.meta["states_per_problem"]
@@ -158,7 +158,7 @@ def test_per_problem_costs_on_tiled_and_three_level_chains(gpu_ctx, n_problems):
     opts.reuse_accepted_sweep = 1
     pb = problems.build_device_problem(gpu_ctx, spec)
     info = pb.info()
-    assert info.chain_tiles > 0
+    assert info.chain_tiles > 0 and info.chain_levels == (3 if n_problems == 300 else 2)
     pb.set_batch(off)
     c0 = pb.batch_costs()
     sample = sorted({0, 1, n_problems // 2, n_problems - 1})
